@@ -1,0 +1,146 @@
+/* modelardb_cuda.h -- C-ABI of the B200-native ModelarDB hot path (libmodelardb_cuda.so).
+ *
+ * This is the boundary a `modelardb_cuda` FFI crate binds (see INTEGRATION.md for the Rust side).
+ * Each entry point is the BATCH form of one function of the reference's `modelardb_compression`
+ * API (crates/modelardb_compression/src/lib.rs:26-34) or of one operator loop that calls it:
+ *
+ *   mdbcu_compress      <- try_compress_univariate_time_series   compression.rs:191-275, called per
+ *                          (series, field) by try_split_and_compress_univariate_time_series
+ *                          (compression.rs:147-179) and by the server's compressor thread
+ *                          (crates/modelardb_server/src/storage/uncompressed_data_manager.rs:563-581)
+ *   mdbcu_grid_count    <- len                                    models/mod.rs:98-124
+ *   mdbcu_grid          <- grid, looped over the rows of a batch  models/mod.rs:190-251,
+ *                          crates/modelardb_storage/src/query/grid_exec.rs:323-337
+ *   mdbcu_segment_sums  <- sum                                    models/mod.rs:129-184
+ *   mdbcu_aggregate     <- Model{Count,Min,Max,Sum,Avg}Accumulator::update_batch
+ *                          crates/modelardb_storage/src/optimizer/model_simple_aggregates.rs:345-585
+ *
+ * Conventions follow the reference's own C-API (crates/modelardb_embedded/src/capi.rs:56-80,
+ * 1148-1157; bindings/c/modelardb_embedded.h:73-199): every call returns 0 on success and 1 on
+ * failure, the message of the last failure on the calling thread is returned by
+ * mdbcu_last_error(), outputs are written through caller-supplied pointers, and memory produced
+ * by the library is released by a library call.  Where the reference would panic on a malformed
+ * segment row (models/mod.rs:170, :237; types.rs:315-319, :391, :405) these calls fail instead.
+ *
+ * Calls are blocking.  Every array argument lives in the memory space named by `space`:
+ * MDBCU_HOST (pageable or pinned host memory; the library stages it through the device) or
+ * MDBCU_DEVICE (device memory of the context's GPU; nothing crosses PCIe).  Scalars returned
+ * through pointers (totals) are always host memory.
+ *
+ * There is no CPU implementation behind this header: without a CUDA device every compute call
+ * fails with "no CUDA device".
+ */
+#ifndef MODELARDB_CUDA_H
+#define MODELARDB_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MDBCU_SUCCESS 0
+#define MDBCU_FAILURE 1
+
+/* ErrorBound (crates/modelardb_types/src/types.rs:299-335). */
+#define MDBCU_LOSSLESS 0
+#define MDBCU_ABSOLUTE 1 /* value > 0, finite */
+#define MDBCU_RELATIVE 2 /* 0 < percent <= 100 */
+
+/* Model type ids (crates/modelardb_compression/src/models/mod.rs:36-38). */
+#define MDBCU_PMC_MEAN 0
+#define MDBCU_SWING 1
+#define MDBCU_MACAQUE_V 2
+
+typedef enum { MDBCU_HOST = 0, MDBCU_DEVICE = 1 } mdbcu_space;
+
+typedef struct mdbcu_context mdbcu_context;   /* one GPU, one stream, reusable scratch */
+typedef struct mdbcu_segments mdbcu_segments; /* an owned batch of compressed segments */
+
+/* A batch of compressed segments: the columns of QUERY_COMPRESSED_SCHEMA
+ * (crates/modelardb_types/src/schemas.rs:40-52) as plain arrays.  The three BinaryView columns are
+ * Arrow LargeBinary style: row i is data[off[i] .. off[i+1]].  The `error` column is constant NaN
+ * (compression.rs:398, types.rs:265) and `field_column` / tags are constants per compress call
+ * (types.rs:492-516), so neither is carried. */
+typedef struct {
+    uint64_t n_segments;
+    const int8_t *model_type_id;
+    const int64_t *start_time;
+    const int64_t *end_time;
+    const float *min_value;
+    const float *max_value;
+    const uint64_t *timestamps_off; /* n_segments + 1 */
+    const uint8_t *timestamps_data;
+    const uint64_t *values_off;     /* n_segments + 1 */
+    const uint8_t *values_data;
+    const uint64_t *residuals_off;  /* n_segments + 1 */
+    const uint8_t *residuals_data;
+} mdbcu_segments_view;
+
+/* ---- library state ------------------------------------------------------------------------- */
+
+/* Message of the last failed call on this thread; valid until the next call on this thread. */
+const char *mdbcu_last_error(void);
+/* Number of visible CUDA devices (0 without a driver/GPU; never fails). */
+int mdbcu_device_count(void);
+/* Library version as "major.minor.patch". */
+const char *mdbcu_version(void);
+
+int mdbcu_context_create(int device, mdbcu_context **out);
+void mdbcu_context_destroy(mdbcu_context *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
+int mdbcu_context_set_stream(mdbcu_context *ctx, void *cuda_stream);
+/* The cudaStream_t the context launches on (for CUDA-event timing by the caller). */
+void *mdbcu_context_stream(mdbcu_context *ctx);
+/* Number of kernels this context has launched since it was created. */
+uint64_t mdbcu_context_launch_count(const mdbcu_context *ctx);
+
+/* ---- K1: compress -------------------------------------------------------------------------- */
+
+/* Compress n_units independent sorted (timestamps, values) slices; unit u is
+ * [unit_off[u], unit_off[u+1]) of `timestamps` / `values` and is compressed within the bound
+ * (eb_kind[u], eb_value[u]).  Each unit is one try_compress_univariate_time_series call: whole
+ * series for the bulk / embedded path, <= 65 536-point buffers for the server path.  An empty unit
+ * yields no segments (compression.rs:208-211).  Segment rows are ordered by unit, then time.
+ * Fails on invalid bounds (types.rs:312-334) or non-monotone unit_off. */
+int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timestamps,
+                   const float *values, const uint64_t *unit_off, uint64_t n_units,
+                   const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out);
+
+uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
+/* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off
+ * (nullable) receives a pointer to n_units + 1 row offsets: unit u produced rows
+ * [unit_seg_off[u], unit_seg_off[u+1]).  Pointers stay valid until mdbcu_segments_free. */
+int mdbcu_segments_get(mdbcu_segments *segments, mdbcu_space space, mdbcu_segments_view *view,
+                       const uint64_t **unit_seg_off);
+void mdbcu_segments_free(mdbcu_segments *segments);
+
+/* ---- K2: grid ------------------------------------------------------------------------------ */
+
+/* point_off (n_segments + 1, nullable) receives the exclusive prefix sum of len() per row;
+ * *total (host, nullable) the number of data points in the batch. */
+int mdbcu_grid_count(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments,
+                     uint64_t *point_off, uint64_t *total);
+/* Reconstruct every data point of every row, rows in order (grid_exec.rs:323-337 appends the same
+ * way).  Fails if the batch holds more than `capacity` points; *n_points (host) receives the count. */
+int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments,
+               int64_t *timestamps_out, float *values_out, uint64_t capacity, uint64_t *n_points);
+
+/* ---- K3: aggregates ------------------------------------------------------------------------ */
+
+/* Per-row `sum` exactly as models/mod.rs:129-184 computes it (f32). */
+int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments,
+                       float *sums_out);
+/* Fold rows [group_off[g], group_off[g+1]) into group g without materialising data points:
+ * count += len (i64), min/max fold the metadata columns from f32::MAX / f32::MIN with NaN-ignoring
+ * min/max, sum += (f64) per-row f32 sum.  group_off == NULL means one group over all rows
+ * (what the reference's rule rewrites); GROUP BY series passes unit_seg_off.  AVG = sum / count. */
+int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments,
+                    const uint64_t *group_off, uint64_t n_groups, int64_t *count, float *min,
+                    float *max, double *sum);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MODELARDB_CUDA_H */

@@ -1,0 +1,414 @@
+// mdb_compress.cuh -- per-thread bodies of the compress kernels, K1.
+//
+// try_compress_univariate_time_series (compression.rs:191-275) is a greedy, strictly ordered
+// segmenter: segment k+1 starts where segment k ended, and a rejected start index is re-fitted from
+// the next index.  One unit (one call of the reference function) is therefore one chain; units are
+// independent.  The work is split in two so that the byte columns can be allocated exactly:
+//   pass 1  compress_fit_unit:   runs the chain, writes one fixed-size SegRecord per segment row
+//                                (model, boundaries, metadata, and the byte LENGTH of each of the
+//                                three binary columns, obtained by running the encoders on a counter);
+//   pass 2  compress_emit_segment: one thread per segment row re-runs the encoders on a writer at the
+//                                offsets given by an exclusive scan of those lengths.
+#pragma once
+
+#include "mdb_device.cuh"
+
+namespace mdb {
+
+constexpr uint32_t RESIDUAL_VALUES_MAX_LENGTH = 255; // compression.rs:38
+
+// Upper bound on the number of segment rows of a unit of n points: a stored model covers >= 8 points
+// (29/len <= 4, compression.rs:238), a separate MacaqueV row follows a model only with > 255 residuals
+// (compression.rs:320), plus one leading MacaqueV row.
+MDB_DEV uint64_t max_segments_of_unit(uint64_t n) { return n == 0 ? 0 : n / 8 + n / 264 + 2; }
+
+struct SegRecord {           // 48 bytes
+    uint32_t start_index;    // first point of the row, relative to the unit
+    uint32_t model_end_index;// last point represented by the model (== res_end_index for MacaqueV rows)
+    uint32_t res_end_index;  // last point of the row (model + residuals)
+    uint32_t ts_len;         // byte length of the `timestamps` column
+    uint32_t val_len;        // byte length of the `values` column
+    uint32_t res_len;        // byte length of the `residuals` column
+    float min_value, max_value;
+    float model_last_value;  // seed of the residual encoder (types.rs:270-278)
+    uint8_t values[8];       // `values` of PMC-Mean / Swing rows (types.rs:283-370)
+    int8_t model_type_id;
+    uint8_t regular;         // timestamps of the row are regular
+    uint8_t pad[2];
+};
+static_assert(sizeof(SegRecord) == 48, "SegRecord layout");
+
+// ------------------------------------------------------------------------------------------------
+// model fitting
+// ------------------------------------------------------------------------------------------------
+
+struct PMCMean { // pmc_mean.rs:31-93
+    float min_value, max_value;
+    double sum_of_values;
+    uint32_t length;
+    MDB_DEV void init() {
+        min_value = max_value = __uint_as_float(0x7fc00000u);
+        sum_of_values = 0.0;
+        length = 0;
+    }
+    MDB_DEV bool fit_value(const ErrorBound &eb, float value) { // pmc_mean.rs:58-75
+        float next_min = rust_minf(min_value, value);
+        float next_max = rust_maxf(max_value, value);
+        double next_sum = __dadd_rn(sum_of_values, (double)value);
+        uint32_t next_length = length + 1;
+        float average = __double2float_rn(__ddiv_rn(next_sum, (double)next_length));
+        if (is_value_within_error_bound(eb, next_min, average) && is_value_within_error_bound(eb, next_max, average)) {
+            min_value = next_min; max_value = next_max; sum_of_values = next_sum; length = next_length;
+            return true;
+        }
+        return false;
+    }
+    MDB_DEV float model() const { return __double2float_rn(__ddiv_rn(sum_of_values, (double)length)); }
+};
+
+struct Swing { // swing.rs:34-259
+    int64_t start_time, end_time;
+    double first_value;
+    double upper_slope, upper_intercept, lower_slope, lower_intercept;
+    double mse_numerator, mse_denominator;
+    uint32_t length;
+    MDB_DEV void init() {
+        start_time = end_time = 0;
+        first_value = upper_slope = upper_intercept = lower_slope = lower_intercept = (double)__uint_as_float(0x7fc00000u);
+        mse_numerator = mse_denominator = 0.0;
+        length = 0;
+    }
+
+    MDB_DEV bool fit_data_point(const ErrorBound &eb, int64_t timestamp, float value_f32) { // swing.rs:101-198
+        double value = (double)value_f32;
+        double maximum_deviation = maximum_allowed_deviation(eb, value);
+        if (length == 0) {
+            start_time = timestamp; end_time = timestamp; first_value = value; length = 1;
+            return true;
+        }
+        bool first_finite = !(first_value != first_value) && !isinf(first_value);
+        bool value_finite = !(value != value) && !isinf(value);
+        if (!first_finite || !value_finite) {
+            if (equal_or_nan(first_value, value)) {
+                end_time = timestamp;
+                upper_slope = upper_intercept = lower_slope = lower_intercept = value;
+                length += 1;
+                return true;
+            }
+            return false;
+        }
+        if (length == 1) {
+            end_time = timestamp;
+            compute_slope_and_intercept(start_time, first_value, timestamp, __dadd_rn(value, maximum_deviation),
+                                        upper_slope, upper_intercept);
+            compute_slope_and_intercept(start_time, first_value, timestamp, __dsub_rn(value, maximum_deviation),
+                                        lower_slope, lower_intercept);
+            length = 2;
+            return true;
+        }
+        double t = (double)timestamp;
+        double upper = __dadd_rn(__dmul_rn(upper_slope, t), upper_intercept);
+        double lower = __dadd_rn(__dmul_rn(lower_slope, t), lower_intercept);
+        if (__dadd_rn(upper, maximum_deviation) < value || __dsub_rn(lower, maximum_deviation) > value) return false;
+        end_time = timestamp;
+        if (__dsub_rn(upper, maximum_deviation) > value)
+            compute_slope_and_intercept(start_time, first_value, timestamp, __dadd_rn(value, maximum_deviation),
+                                        upper_slope, upper_intercept);
+        if (__dadd_rn(lower, maximum_deviation) < value)
+            compute_slope_and_intercept(start_time, first_value, timestamp, __dsub_rn(value, maximum_deviation),
+                                        lower_slope, lower_intercept);
+        // swing.rs:212-228 (0.0 is added when value == first_value)
+        double num = 0.0, den = 0.0;
+        if (!equal_or_nan(first_value, value)) {
+            double dt = (double)(timestamp - start_time);
+            num = __dmul_rn(__dsub_rn(value, first_value), dt);
+            den = __dmul_rn(dt, dt);
+        }
+        mse_numerator = __dadd_rn(mse_numerator, num);
+        mse_denominator = __dadd_rn(mse_denominator, den);
+        length += 1;
+        return true;
+    }
+    MDB_DEV void model(float &first_out, float &last_out) const { // swing.rs:246-259
+        double projected = __ddiv_rn(mse_numerator, mse_denominator);
+        double slope = rust_maxd(lower_slope, rust_mind(projected, upper_slope));
+        double last = __dadd_rn(__dmul_rn(slope, (double)(end_time - start_time)), first_value);
+        first_out = __double2float_rn(first_value);
+        last_out = __double2float_rn(last);
+    }
+};
+
+struct FittedModel { // CompressedSegmentBuilder, types.rs:148-166
+    uint32_t start_index, end_index;
+    float min_value, max_value, model_last_value, bytes_per_value;
+    int8_t model_type_id;
+    uint8_t values_len; // Swing: 0 -> [] (first < last), 1 -> [0]
+};
+
+// Tracks, as the chain first touches each point of the unit, whether any sampling-interval change has
+// been seen so far.  While none has, every row is regular (a sub-range of a regular range is regular)
+// and timestamps_encoded_len needs no scan of its own; this avoids a second pass over the timestamps.
+struct RegularityTracker {
+    uint32_t max_seen;   // highest index visited so far
+    int64_t ts_max_seen; // its timestamp
+    int64_t delta0;
+    bool irregular;
+    MDB_DEV void init(const int64_t *ts) { max_seen = 0; ts_max_seen = ts[0]; delta0 = 0; irregular = false; }
+    MDB_DEV void visit(uint32_t i, int64_t t) { // visits are contiguous: i <= max_seen + 1
+        if (i <= max_seen) return;
+        int64_t delta = t - ts_max_seen;
+        if (i == 1) delta0 = delta;
+        else if (delta != delta0) irregular = true;
+        max_seen = i;
+        ts_max_seen = t;
+    }
+};
+
+// fit_next_model (compression.rs:280-301) + ModelBuilder (types.rs:61-144).
+MDB_DEV FittedModel fit_next_model(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t start,
+                                   uint32_t n, RegularityTracker &trk) {
+    PMCMean pmc; pmc.init();
+    Swing swing; swing.init();
+    bool pmc_ok = true, swing_ok = true;
+    uint32_t i = start;
+    while ((pmc_ok || swing_ok) && i < n) {
+        float value = values[i];
+        int64_t t = ts[i];
+        trk.visit(i, t);
+        if (pmc_ok) pmc_ok = pmc.fit_value(eb, value);
+        if (swing_ok) swing_ok = swing.fit_data_point(eb, t, value);
+        i++;
+    }
+    FittedModel m;
+    m.start_index = start;
+    float pmc_bpv = __fdiv_rn(29.0f, (float)pmc.length);    // pmc_mean.rs:83-87
+    float swing_bpv = __fdiv_rn(30.0f, (float)swing.length); // swing.rs:236-239
+    if (swing_bpv < pmc_bpv) { // min_by keeps the first minimum: PMC-Mean wins ties (types.rs:90-94)
+        float first, last;
+        swing.model(first, last);
+        m.model_type_id = SWING;
+        m.end_index = start + swing.length - 1;
+        m.min_value = rust_minf(first, last);
+        m.max_value = rust_maxf(first, last);
+        m.values_len = (first < last) ? 0 : 1;
+        m.model_last_value = last;
+        m.bytes_per_value = swing_bpv;
+    } else {
+        float value = pmc.model();
+        m.model_type_id = PMC_MEAN;
+        m.end_index = start + pmc.length - 1;
+        m.min_value = m.max_value = m.model_last_value = value;
+        m.values_len = 0;
+        m.bytes_per_value = pmc_bpv;
+    }
+    return m;
+}
+
+// ------------------------------------------------------------------------------------------------
+// encoders shared by the sizing pass (Sink = BitCounter) and the emit pass (Sink = BitWriter)
+// ------------------------------------------------------------------------------------------------
+
+// MacaqueV over values[lo..=hi]; seeded -> compress_values_without_first (macaque_v.rs:92-97),
+// else compress_values with the first value raw (macaque_v.rs:76-88).
+template <typename Sink>
+MDB_DEV void macaque_v_encode(const ErrorBound &eb, const float *values, uint32_t lo, uint32_t hi, bool seeded,
+                              float seed, Sink &sink, float &min_out, float &max_out) {
+    MacaqueVEncoder enc;
+    enc.init();
+    uint32_t i = lo;
+    if (seeded) enc.last_value = seed;
+    else enc.first_raw(values[i++], sink);
+    for (; i <= hi; i++) enc.compress_value_xor_last_value(eb, values[i], sink);
+    min_out = enc.min_value;
+    max_out = enc.max_value;
+}
+
+MDB_DEV void put_le(uint8_t *p, float f) {
+    uint32_t b = __float_as_uint(f);
+    p[0] = (uint8_t)b; p[1] = (uint8_t)(b >> 8); p[2] = (uint8_t)(b >> 16); p[3] = (uint8_t)(b >> 24);
+}
+
+// types.rs:283-303; returns the length written to out[0..8)
+MDB_DEV uint32_t encode_values_for_pmc_mean(float min_value, float max_value, float res_min, float res_max, uint8_t *out) {
+    if (min_value > res_min) {
+        if (max_value >= res_max) { out[0] = 1; return 1; }
+        put_le(out, min_value);
+        return 4;
+    }
+    return 0;
+}
+
+// types.rs:325-370
+MDB_DEV uint32_t encode_values_for_swing(float min_value, float max_value, bool min_value_is_first, float res_min,
+                                         float res_max, uint8_t *out) {
+    if (res_min < min_value && max_value < res_max) {
+        if (min_value_is_first) { put_le(out, min_value); put_le(out + 4, max_value); }
+        else { put_le(out, max_value); put_le(out + 4, min_value); }
+        return 8;
+    } else if (res_min < min_value) {
+        out[0] = min_value_is_first ? 0 : 1;
+        put_le(out + 1, min_value);
+        return 5;
+    } else if (max_value < res_max) {
+        out[0] = min_value_is_first ? 2 : 3;
+        put_le(out + 1, max_value);
+        return 5;
+    } else if (!min_value_is_first) {
+        out[0] = 0;
+        return 1;
+    }
+    return 0;
+}
+
+// Byte length of compress_residual_timestamps(ts[lo..=hi]) (timestamps.rs:56-73) and whether regular.
+MDB_DEV uint32_t timestamps_encoded_len(const int64_t *ts, uint32_t lo, uint32_t hi, bool known_regular, uint8_t &regular) {
+    uint64_t n = (uint64_t)hi - lo + 1;
+    regular = 1;
+    if (n <= 2) return 0;
+    if (known_regular || are_uncompressed_timestamps_regular(ts + lo, n)) return regular_timestamps_bytes(n);
+    regular = 0;
+    BitCounter c;
+    compress_irregular_residual_timestamps(ts + lo, n, c);
+    return (uint32_t)c.bytes();
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 1: the chain
+// ------------------------------------------------------------------------------------------------
+
+struct UnitTotals { uint64_t ts_bytes, val_bytes, res_bytes; };
+
+// CompressedSegmentBuilder::finish (types.rs:197-267) as a record.
+MDB_DEV void record_model_segment(const ErrorBound &eb, const FittedModel &m, uint32_t res_end, const int64_t *ts,
+                                  const float *values, bool unit_regular, SegRecord &rec) {
+    rec.start_index = m.start_index;
+    rec.model_end_index = m.end_index;
+    rec.res_end_index = res_end;
+    rec.model_type_id = m.model_type_id;
+    rec.model_last_value = m.model_last_value;
+    rec.min_value = m.min_value;
+    rec.max_value = m.max_value;
+    rec.pad[0] = rec.pad[1] = 0;
+    for (int k = 0; k < 8; k++) rec.values[k] = 0;
+    rec.val_len = m.values_len; // Swing [0] or []
+    rec.res_len = 0;
+    rec.ts_len = timestamps_encoded_len(ts, m.start_index, res_end, unit_regular, rec.regular);
+    if (m.end_index < res_end) {
+        BitCounter c;
+        float res_min, res_max;
+        macaque_v_encode(eb, values, m.end_index + 1, res_end, true, m.model_last_value, c, res_min, res_max);
+        if (m.model_type_id == PMC_MEAN)
+            rec.val_len = encode_values_for_pmc_mean(m.min_value, m.max_value, res_min, res_max, rec.values);
+        else
+            rec.val_len = encode_values_for_swing(m.min_value, m.max_value, m.values_len == 0, res_min, res_max, rec.values);
+        rec.min_value = rust_minf(m.min_value, res_min);
+        rec.max_value = rust_maxf(m.max_value, res_max);
+        rec.res_len = (uint32_t)c.bytes() + 1; // + the count byte (types.rs:250)
+    }
+}
+
+// compress_and_store_residuals_in_a_separate_segment (compression.rs:367-400) as a record.
+MDB_DEV void record_macaque_v_segment(const ErrorBound &eb, uint32_t lo, uint32_t hi, const int64_t *ts,
+                                      const float *values, bool unit_regular, SegRecord &rec) {
+    rec.start_index = lo;
+    rec.model_end_index = hi;
+    rec.res_end_index = hi;
+    rec.model_type_id = MACAQUE_V;
+    rec.model_last_value = 0.0f;
+    rec.pad[0] = rec.pad[1] = 0;
+    for (int k = 0; k < 8; k++) rec.values[k] = 0;
+    rec.res_len = 0;
+    rec.ts_len = timestamps_encoded_len(ts, lo, hi, unit_regular, rec.regular);
+    BitCounter c;
+    macaque_v_encode(eb, values, lo, hi, false, 0.0f, c, rec.min_value, rec.max_value);
+    rec.val_len = (uint32_t)c.bytes();
+}
+
+// store_compressed_segments_with_model_and_or_residuals (compression.rs:310-362). Returns rows written.
+MDB_DEV uint32_t store_segments(const ErrorBound &eb, bool have_model, const FittedModel &m, uint32_t res_end,
+                                const int64_t *ts, const float *values, bool unit_regular, SegRecord *recs) {
+    if (have_model) {
+        if (res_end - m.end_index <= RESIDUAL_VALUES_MAX_LENGTH) {
+            record_model_segment(eb, m, res_end, ts, values, unit_regular, recs[0]);
+            return 1;
+        }
+        record_model_segment(eb, m, m.end_index, ts, values, unit_regular, recs[0]);
+        record_macaque_v_segment(eb, m.end_index + 1, res_end, ts, values, unit_regular, recs[1]);
+        return 2;
+    }
+    record_macaque_v_segment(eb, 0, res_end, ts, values, unit_regular, recs[0]);
+    return 1;
+}
+
+// try_compress_univariate_time_series (compression.rs:191-275) over one unit. `recs` has room for
+// max_segments_of_unit(n) records. Returns the number of segment rows.
+MDB_DEV uint32_t compress_fit_unit(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t n,
+                                   SegRecord *recs, UnitTotals &totals) {
+    totals.ts_bytes = totals.val_bytes = totals.res_bytes = 0;
+    if (n == 0) return 0;
+    RegularityTracker trk;
+    trk.init(ts);
+    uint32_t n_rows = 0;
+    uint32_t current_start_index = 0;
+    bool have_previous = false;
+    FittedModel previous_model;
+    previous_model.start_index = previous_model.end_index = 0;
+    while (current_start_index < n) {
+        FittedModel model = fit_next_model(eb, ts, values, current_start_index, n, trk);
+        if (model.bytes_per_value <= 4.0f) { // compression.rs:238
+            if (current_start_index > 0)
+                n_rows += store_segments(eb, have_previous, previous_model, current_start_index - 1, ts, values,
+                                         !trk.irregular, recs + n_rows);
+            current_start_index = model.end_index + 1;
+            previous_model = model;
+            have_previous = true;
+        } else {
+            current_start_index += 1; // this point becomes a residual; refit from the next one
+        }
+    }
+    n_rows += store_segments(eb, have_previous, previous_model, n - 1, ts, values, !trk.irregular, recs + n_rows);
+    for (uint32_t k = 0; k < n_rows; k++) {
+        totals.ts_bytes += recs[k].ts_len;
+        totals.val_bytes += recs[k].val_len;
+        totals.res_bytes += recs[k].res_len;
+    }
+    return n_rows;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pass 2: emit one segment row
+// ------------------------------------------------------------------------------------------------
+
+MDB_DEV void compress_emit_segment(const ErrorBound &eb, const SegRecord &rec, const int64_t *ts, const float *values,
+                                   uint8_t *ts_out, uint8_t *val_out, uint8_t *res_out) {
+    // timestamps (timestamps.rs:56-155)
+    uint64_t n = (uint64_t)rec.res_end_index - rec.start_index + 1;
+    if (rec.ts_len) {
+        if (rec.regular) {
+            for (uint32_t k = 0; k < rec.ts_len; k++) ts_out[rec.ts_len - 1 - k] = (uint8_t)(n >> (8 * k));
+        } else {
+            BitWriter w(ts_out);
+            compress_irregular_residual_timestamps(ts + rec.start_index, n, w);
+            w.finish(true);
+        }
+    }
+    // values
+    if (rec.model_type_id == MACAQUE_V) {
+        BitWriter w(val_out);
+        float mn, mx;
+        macaque_v_encode(eb, values, rec.start_index, rec.res_end_index, false, 0.0f, w, mn, mx);
+        w.finish(false);
+    } else {
+        for (uint32_t k = 0; k < rec.val_len; k++) val_out[k] = rec.values[k];
+    }
+    // residuals (types.rs:219-254)
+    if (rec.res_len) {
+        BitWriter w(res_out);
+        float mn, mx;
+        macaque_v_encode(eb, values, rec.model_end_index + 1, rec.res_end_index, true, rec.model_last_value, w, mn, mx);
+        w.finish(false);
+        res_out[rec.res_len - 1] = (uint8_t)(rec.res_end_index - rec.model_end_index);
+    }
+}
+
+} // namespace mdb

@@ -1,0 +1,157 @@
+// emu.cc -- DEBUGGING HARNESS, not a product path and not a fallback.
+//
+// The build container has no GPU, and a gpurun round trip takes minutes.  This file compiles the
+// per-thread kernel bodies of modelardb_rs_b200/csrc/mdb_{grid,aggregate,compress}.cuh for the host
+// (MDB_DEV -> inline, intrinsics -> mdb_host_shim.h) and steps them in plain loops, so that logic
+// errors in those bodies are caught by `pytest -m "not gpu"` before GPU time is spent.  What it cannot
+// cover -- launch geometry, scans, shared-memory tiling, warp primitives, the C-ABI -- is covered by
+// the `-m gpu` tests.  Nothing under modelardb_rs_b200/ links or loads this.
+#include <cstdint>
+#include <cstring>
+#include <vector>
+
+#include "../../modelardb_rs_b200/csrc/mdb_aggregate.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_compress.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_grid.cuh"
+
+using namespace mdb;
+
+struct EmuSegments {
+    std::vector<int8_t> model_type_id;
+    std::vector<int64_t> start_time, end_time;
+    std::vector<float> min_value, max_value;
+    std::vector<uint64_t> ts_off, val_off, res_off, unit_seg_off;
+    std::vector<uint8_t> ts_data, val_data, res_data;
+};
+
+extern "C" {
+
+EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t *unit_off, uint64_t n_units,
+                          const uint8_t *eb_kind, const float *eb_value) {
+    EmuSegments *out = new EmuSegments();
+    std::vector<std::vector<SegRecord>> recs(n_units);
+    out->unit_seg_off.assign(n_units + 1, 0);
+    for (uint64_t u = 0; u < n_units; u++) { // pass 1: one "thread" per unit
+        uint64_t n = unit_off[u + 1] - unit_off[u];
+        recs[u].resize(max_segments_of_unit(n));
+        ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        UnitTotals totals;
+        uint32_t rows = compress_fit_unit(eb, ts + unit_off[u], values + unit_off[u], (uint32_t)n, recs[u].data(), totals);
+        recs[u].resize(rows);
+        out->unit_seg_off[u + 1] = out->unit_seg_off[u] + rows;
+    }
+    uint64_t S = out->unit_seg_off[n_units];
+    out->model_type_id.resize(S); out->start_time.resize(S); out->end_time.resize(S);
+    out->min_value.resize(S); out->max_value.resize(S);
+    out->ts_off.assign(S + 1, 0); out->val_off.assign(S + 1, 0); out->res_off.assign(S + 1, 0);
+    for (uint64_t u = 0; u < n_units; u++) // gather + scans
+        for (size_t k = 0; k < recs[u].size(); k++) {
+            uint64_t r = out->unit_seg_off[u] + k;
+            const SegRecord &rec = recs[u][k];
+            out->model_type_id[r] = rec.model_type_id;
+            out->start_time[r] = ts[unit_off[u] + rec.start_index];
+            out->end_time[r] = ts[unit_off[u] + rec.res_end_index];
+            out->min_value[r] = rec.min_value;
+            out->max_value[r] = rec.max_value;
+            out->ts_off[r + 1] = out->ts_off[r] + rec.ts_len;
+            out->val_off[r + 1] = out->val_off[r] + rec.val_len;
+            out->res_off[r + 1] = out->res_off[r] + rec.res_len;
+        }
+    out->ts_data.assign(out->ts_off[S] + 1, 0xAA);
+    out->val_data.assign(out->val_off[S] + 1, 0xAA);
+    out->res_data.assign(out->res_off[S] + 1, 0xAA);
+    for (uint64_t u = 0; u < n_units; u++) { // pass 2: one "thread" per row
+        ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        for (size_t k = 0; k < recs[u].size(); k++) {
+            uint64_t r = out->unit_seg_off[u] + k;
+            compress_emit_segment(eb, recs[u][k], ts + unit_off[u], values + unit_off[u],
+                                  out->ts_data.data() + out->ts_off[r], out->val_data.data() + out->val_off[r],
+                                  out->res_data.data() + out->res_off[r]);
+        }
+    }
+    return out;
+}
+
+uint64_t emu_segments_len(const EmuSegments *s) { return s->model_type_id.size(); }
+void emu_segments_view(const EmuSegments *s, SegmentsView *v, const uint64_t **unit_seg_off) {
+    v->n_segments = s->model_type_id.size();
+    v->model_type_id = s->model_type_id.data();
+    v->start_time = s->start_time.data();
+    v->end_time = s->end_time.data();
+    v->min_value = s->min_value.data();
+    v->max_value = s->max_value.data();
+    v->timestamps_off = s->ts_off.data();
+    v->timestamps_data = s->ts_data.data();
+    v->values_off = s->val_off.data();
+    v->values_data = s->val_data.data();
+    v->residuals_off = s->res_off.data();
+    v->residuals_data = s->res_data.data();
+    if (unit_seg_off) *unit_seg_off = s->unit_seg_off.data();
+}
+void emu_segments_free(EmuSegments *s) { delete s; }
+
+// Returns total points or (uint64_t)-1 on a malformed row. point_off: S+1.
+uint64_t emu_grid_count(const SegmentsView *v, uint64_t *point_off) {
+    uint64_t total = 0;
+    for (uint64_t s = 0; s < v->n_segments; s++) {
+        SegDesc d;
+        uint32_t len = grid_prepare_segment(*v, s, d);
+        if (d.flags & F_MALFORMED) return (uint64_t)-1;
+        if (point_off) point_off[s] = total;
+        total += len;
+    }
+    if (point_off) point_off[v->n_segments] = total;
+    return total;
+}
+
+uint64_t emu_grid(const SegmentsView *v, int64_t *ts_out, float *val_out, uint64_t capacity) {
+    uint64_t S = v->n_segments;
+    std::vector<SegDesc> desc(S);
+    std::vector<uint64_t> po(S + 1, 0);
+    for (uint64_t s = 0; s < S; s++) { // prepare + scan
+        uint32_t len = grid_prepare_segment(*v, s, desc[s]);
+        if (desc[s].flags & F_MALFORMED) return (uint64_t)-1;
+        po[s + 1] = po[s] + len;
+    }
+    if (po[S] > capacity) return (uint64_t)-1;
+    std::memset(ts_out, 0xAA, po[S] * 8);
+    std::memset(val_out, 0xAA, po[S] * 4);
+    for (uint64_t s = 0; s < S; s++) // tile kernel: one "thread" per output point
+        for (uint64_t p = po[s]; p < po[s + 1]; p++) grid_point(desc[s], (uint32_t)(p - po[s]), ts_out, val_out, p);
+    for (uint64_t s = 0; s < S; s++) // sequential kernel
+        if (desc[s].flags & F_SEQUENTIAL)
+            grid_sequential_segment(*v, s, desc[s], po[s], (uint32_t)(po[s + 1] - po[s]), ts_out, val_out);
+    return po[S];
+}
+
+int emu_segment_sums(const SegmentsView *v, float *sums, uint64_t *counts) {
+    for (uint64_t s = 0; s < v->n_segments; s++) {
+        uint64_t c;
+        float sum;
+        if (!aggregate_segment(*v, s, c, sum)) return 1;
+        sums[s] = sum;
+        if (counts) counts[s] = c;
+    }
+    return 0;
+}
+
+int emu_aggregate(const SegmentsView *v, const uint64_t *group_off, uint64_t n_groups, int64_t *count, float *mn,
+                  float *mx, double *sum) {
+    uint64_t whole[2] = {0, v->n_segments};
+    if (!group_off) { group_off = whole; n_groups = 1; }
+    for (uint64_t g = 0; g < n_groups; g++) {
+        GroupAgg acc = group_agg_identity();
+        for (uint64_t s = group_off[g]; s < group_off[g + 1]; s++) {
+            uint64_t c;
+            float sm;
+            if (!aggregate_segment(*v, s, c, sm)) return 1;
+            GroupAgg row;
+            row.count = (int64_t)c; row.min = v->min_value[s]; row.max = v->max_value[s]; row.sum = (double)sm;
+            acc = group_agg_combine(acc, row);
+        }
+        count[g] = acc.count; mn[g] = acc.min; mx[g] = acc.max; sum[g] = acc.sum;
+    }
+    return 0;
+}
+
+} // extern "C"

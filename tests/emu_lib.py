@@ -1,0 +1,119 @@
+"""Builds and binds tests/emu/emu.cc: the per-thread kernel bodies stepped on the host.
+
+Debugging harness for the GPU-less build container (see emu.cc); the GPU tests are the parity tests.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from oracle import mdb_oracle as O
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SRC = os.path.join(_HERE, "emu", "emu.cc")
+_SO = os.path.join(_HERE, "emu", "libmdb_emu.so")
+_CSRC = os.path.join(os.path.dirname(_HERE), "modelardb_rs_b200", "csrc")
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    deps = [_SRC] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                               "-x", "c++", _SRC, "-o", _SO])
+    L = C.CDLL(_SO)
+    vp, u64 = C.c_void_p, C.c_uint64
+    L.emu_compress.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.emu_compress.restype = vp
+    L.emu_segments_len.argtypes = [vp]
+    L.emu_segments_len.restype = u64
+    L.emu_segments_view.argtypes = [vp, C.POINTER(O._View), C.POINTER(vp)]
+    L.emu_segments_view.restype = None
+    L.emu_segments_free.argtypes = [vp]
+    L.emu_grid_count.argtypes = [C.POINTER(O._View), vp]
+    L.emu_grid_count.restype = u64
+    L.emu_grid.argtypes = [C.POINTER(O._View), vp, vp, u64]
+    L.emu_grid.restype = u64
+    L.emu_segment_sums.argtypes = [C.POINTER(O._View), vp, vp]
+    L.emu_segment_sums.restype = C.c_int
+    L.emu_aggregate.argtypes = [C.POINTER(O._View), vp, u64, vp, vp, vp, vp]
+    L.emu_aggregate.restype = C.c_int
+    _lib = L
+    return L
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def compress(ts, values, unit_off=None, eb=(0, 0.0)) -> O.Segments:
+    ts = np.ascontiguousarray(ts, np.int64)
+    vals = np.ascontiguousarray(values, np.float32)
+    if unit_off is None:
+        unit_off = np.array([0, len(ts)], np.uint64)
+    unit_off = np.ascontiguousarray(unit_off, np.uint64)
+    n_units = len(unit_off) - 1
+    if isinstance(eb, tuple):
+        eb = [eb] * n_units
+    kinds = np.array([e[0] for e in eb], np.uint8)
+    evals = np.array([e[1] for e in eb], np.float32)
+    L = lib()
+    h = L.emu_compress(_p(ts), _p(vals), _p(unit_off), n_units, _p(kinds), _p(evals))
+    v = O._View()
+    uso = C.c_void_p()
+    L.emu_segments_view(h, C.byref(v), C.byref(uso))
+    n = v.n_segments
+
+    def arr(ptr, count, dt):
+        if count == 0 or not ptr:
+            return np.zeros(0, dt)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+
+    cols = dict(model_type_id=arr(v.model_type_id, n, np.int8), start_time=arr(v.start_time, n, np.int64),
+                end_time=arr(v.end_time, n, np.int64), min_value=arr(v.min_value, n, np.float32),
+                max_value=arr(v.max_value, n, np.float32), timestamps_off=arr(v.timestamps_off, n + 1, np.uint64),
+                values_off=arr(v.values_off, n + 1, np.uint64), residuals_off=arr(v.residuals_off, n + 1, np.uint64))
+    cols["timestamps_data"] = arr(v.timestamps_data, int(cols["timestamps_off"][-1]), np.uint8)
+    cols["values_data"] = arr(v.values_data, int(cols["values_off"][-1]), np.uint8)
+    cols["residuals_data"] = arr(v.residuals_data, int(cols["residuals_off"][-1]), np.uint8)
+    cols["unit_seg_off"] = arr(uso.value, n_units + 1, np.uint64)
+    L.emu_segments_free(h)
+    return O.Segments(**cols)
+
+
+def grid(seg: O.Segments):
+    off = np.zeros(len(seg) + 1, np.uint64)
+    v = seg.view()
+    total = lib().emu_grid_count(C.byref(v), _p(off))
+    if total == 2**64 - 1:
+        raise ValueError("malformed segment")
+    ts = np.empty(total, np.int64)
+    val = np.empty(total, np.float32)
+    n = lib().emu_grid(C.byref(v), _p(ts), _p(val), total)
+    assert n == total
+    return ts, val, off
+
+
+def segment_sums(seg: O.Segments):
+    sums = np.empty(len(seg), np.float32)
+    counts = np.empty(len(seg), np.uint64)
+    v = seg.view()
+    if lib().emu_segment_sums(C.byref(v), _p(sums), _p(counts)) != 0:
+        raise ValueError("malformed segment")
+    return sums, counts
+
+
+def aggregate(seg: O.Segments, group_off=None):
+    g = 1 if group_off is None else len(group_off) - 1
+    count = np.zeros(g, np.int64)
+    mn, mx = np.zeros(g, np.float32), np.zeros(g, np.float32)
+    sm = np.zeros(g, np.float64)
+    v = seg.view()
+    go = None if group_off is None else np.ascontiguousarray(group_off, np.uint64)
+    if lib().emu_aggregate(C.byref(v), None if go is None else _p(go), g, _p(count), _p(mn), _p(mx), _p(sm)) != 0:
+        raise ValueError("malformed segment")
+    return count, mn, mx, sm

@@ -1,0 +1,99 @@
+"""Seeded workloads and comparison helpers shared by the CPU (kernel-body emulation) and GPU parity tests.
+
+Every case is (name, timestamps, values, unit_off, error_bounds).  They cover the shapes the reference's
+tests use (compression.rs:421-863: constant / linear / random, regular / irregular, lossless / abs / rel)
+plus the five BASELINE.json configs at sizes the oracle finishes in seconds, plus the edge cases:
+empty and 1/2/3-point units, ragged units, NaN / inf / signed zeros, > 255 residual runs, all models.
+"""
+import numpy as np
+
+from modelardb_rs_b200 import synthetic as syn
+
+LOSSLESS = (0, 0.0)
+
+
+def _cat(units):
+    ts = np.concatenate([u[0] for u in units]) if units else np.zeros(0, np.int64)
+    vals = np.concatenate([u[1] for u in units]) if units else np.zeros(0, np.float32)
+    off = np.zeros(len(units) + 1, np.uint64)
+    off[1:] = np.cumsum([len(u[0]) for u in units])
+    return ts.astype(np.int64), vals.astype(np.float32), off
+
+
+def small_cases():
+    cases = []
+    for irregular in (False, True):
+        for noise in (None, (1.0, 1.05)):
+            for eb in (LOSSLESS, (1, 5.0), (2, 5.0)):
+                ts, v = syn.mixed_series(6000, 31 + int(irregular), irregular=irregular, noise=noise)
+                cases.append((f"mixed-irr{int(irregular)}-noise{noise is not None}-eb{eb}", ts, v,
+                              np.array([0, len(ts)], np.uint64), [eb]))
+    # epoch-scale timestamps: cancellation-sensitive Swing arithmetic (quirk Q1)
+    for eb in (LOSSLESS, (2, 1.0), (2, 10.0), (1, 0.5)):
+        ts, v, off = syn.multi_series(6, 5000, 2, "sine")
+        cases.append((f"sine-epoch-eb{eb}", ts, v, off, [eb] * 6))
+        ts, v, off = syn.multi_series(6, 5000, 3, "walk")
+        cases.append((f"walk-epoch-eb{eb}", ts, v, off, [eb] * 6))
+    ts, v, off = syn.multi_series(4, 4000, 5, "walk", irregular=True)
+    cases.append(("walk-irregular-rel1", ts, v, off, [(2, 1.0)] * 4))
+    ts, v, off = syn.multi_series(4, 4000, 5, "sine", irregular=True)
+    cases.append(("sine-irregular-rel1", ts, v, off, [(2, 1.0)] * 4))
+    # ragged / tiny / empty units, one bound per unit
+    units, ebs = [], []
+    rng = np.random.default_rng(9)
+    for k, n in enumerate([0, 1, 2, 3, 7, 8, 9, 15, 16, 17, 0, 263, 264, 265, 1000, 1, 0]):
+        t = syn.regular_timestamps(n) if k % 2 == 0 else syn.irregular_timestamps(max(n, 1), 100 + k)[:n]
+        if k % 3 == 0:
+            v = syn.sine_noise(n, 200 + k)
+        elif k % 3 == 1:
+            v = rng.uniform(-1e3, 1e3, n).astype(np.float32)
+        else:
+            v = np.full(n, 42.5, np.float32)
+        units.append((t, v))
+        ebs.append([LOSSLESS, (1, 1.0), (2, 5.0)][k % 3])
+    ts, v, off = _cat(units)
+    cases.append(("ragged-units", ts, v, off, ebs))
+    # special values
+    sp = np.array([0.0, -0.0, 0.0, -0.0, np.nan, np.nan, np.inf, np.inf, -np.inf, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0,
+                   1.0, np.nan, 3.0, np.float32(1e-45), np.float32(-1e-45), 3.4e38, -3.4e38] * 20, np.float32)
+    for eb in (LOSSLESS, (1, 1.0), (2, 10.0)):
+        cases.append((f"specials-eb{eb}", syn.regular_timestamps(len(sp)), sp, np.array([0, len(sp)], np.uint64), [eb]))
+    # a model followed by > 255 incompressible points -> separate MacaqueV row (compression.rs:329-349)
+    v = np.concatenate([np.full(50, 7.0, np.float32), rng.uniform(-1e6, 1e6, 700).astype(np.float32),
+                        np.full(50, 9.0, np.float32), rng.uniform(-1e6, 1e6, 255).astype(np.float32),
+                        np.full(20, 1.0, np.float32), rng.uniform(-1e6, 1e6, 256).astype(np.float32)])
+    for eb in (LOSSLESS, (2, 1.0)):
+        cases.append((f"long-residual-runs-eb{eb}", syn.regular_timestamps(len(v)), v, np.array([0, len(v)], np.uint64), [eb]))
+    # lossy MacaqueV with tiny / huge bounds (rewrite position wraps, macaque_v.rs:333-336)
+    v = rng.uniform(-1e3, 1e3, 600).astype(np.float32)
+    for eb in ((1, 1e-10), (1, 1e10), (2, 1e-6), (2, 100.0), (1, 3.0e38)):
+        cases.append((f"lossy-extreme-eb{eb}", syn.regular_timestamps(len(v)), v, np.array([0, len(v)], np.uint64), [eb]))
+    return cases
+
+
+def assert_segments_equal(a, b, where=""):
+    """Bit-exact comparison of two segment batches (oracle.Segments-like objects)."""
+    assert len(a) == len(b), f"{where}: {len(a)} vs {len(b)} segments"
+    for col in ("model_type_id", "start_time", "end_time", "timestamps_off", "values_off", "residuals_off",
+                "timestamps_data", "values_data", "residuals_data"):
+        x, y = getattr(a, col), getattr(b, col)
+        if not np.array_equal(x, y):
+            bad = np.flatnonzero(x != y)[:5] if len(x) == len(y) else "length"
+            raise AssertionError(f"{where}: column {col} differs at {bad}")
+    for col in ("min_value", "max_value"):
+        x, y = getattr(a, col).view(np.uint32), getattr(b, col).view(np.uint32)
+        if not np.array_equal(x, y):
+            bad = np.flatnonzero(x != y)[:5]
+            raise AssertionError(f"{where}: column {col} differs (bit pattern) at rows {bad}: "
+                                 f"{getattr(a, col)[bad]} vs {getattr(b, col)[bad]}")
+    if a.unit_seg_off is not None and b.unit_seg_off is not None:
+        assert np.array_equal(a.unit_seg_off, b.unit_seg_off), f"{where}: unit_seg_off differs"
+
+
+def assert_f32_bits_equal(x, y, where=""):
+    x, y = np.asarray(x, np.float32).view(np.uint32), np.asarray(y, np.float32).view(np.uint32)
+    assert len(x) == len(y), f"{where}: length {len(x)} vs {len(y)}"
+    if not np.array_equal(x, y):
+        bad = np.flatnonzero(x != y)
+        raise AssertionError(f"{where}: {len(bad)} of {len(x)} values differ, first at {bad[:5]}: "
+                             f"{x.view(np.float32)[bad[:5]]} vs {y.view(np.float32)[bad[:5]]}")
