@@ -1,0 +1,94 @@
+"""ctypes binding of libmodelardb_cuda.so (include/modelardb_cuda.h).
+
+There is no fallback: if the library is missing, or there is no CUDA device, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmodelardb_cuda.so")
+
+HOST, DEVICE = 0, 1
+
+# Every symbol include/modelardb_cuda.h declares (tests check the .so exports exactly these).
+SYMBOLS = (
+    "mdbcu_last_error", "mdbcu_device_count", "mdbcu_version",
+    "mdbcu_context_create", "mdbcu_context_destroy", "mdbcu_context_set_stream", "mdbcu_context_stream",
+    "mdbcu_context_launch_count",
+    "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
+    "mdbcu_grid_count", "mdbcu_grid", "mdbcu_segment_sums", "mdbcu_aggregate",
+)
+
+
+class ModelarDbCudaError(RuntimeError):
+    """A call through the C-ABI returned MDBCU_FAILURE; the message is mdbcu_last_error()."""
+
+
+class SegmentsView(C.Structure):
+    _fields_ = [
+        ("n_segments", C.c_uint64),
+        ("model_type_id", C.c_void_p),
+        ("start_time", C.c_void_p),
+        ("end_time", C.c_void_p),
+        ("min_value", C.c_void_p),
+        ("max_value", C.c_void_p),
+        ("timestamps_off", C.c_void_p),
+        ("timestamps_data", C.c_void_p),
+        ("values_off", C.c_void_p),
+        ("values_data", C.c_void_p),
+        ("residuals_off", C.c_void_p),
+        ("residuals_data", C.c_void_p),
+    ]
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ModelarDbCudaError(
+            f"{LIB_PATH} is missing: build it with `python -m modelardb_rs_b200.build` "
+            "(there is no CPU implementation to fall back to)")
+    L = C.CDLL(LIB_PATH)
+    vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
+    L.mdbcu_last_error.restype = C.c_char_p
+    L.mdbcu_version.restype = C.c_char_p
+    L.mdbcu_device_count.restype = i32
+    L.mdbcu_context_create.argtypes = [i32, C.POINTER(vp)]
+    L.mdbcu_context_create.restype = i32
+    L.mdbcu_context_destroy.argtypes = [vp]
+    L.mdbcu_context_destroy.restype = None
+    L.mdbcu_context_set_stream.argtypes = [vp, vp]
+    L.mdbcu_context_set_stream.restype = i32
+    L.mdbcu_context_stream.argtypes = [vp]
+    L.mdbcu_context_stream.restype = vp
+    L.mdbcu_context_launch_count.argtypes = [vp]
+    L.mdbcu_context_launch_count.restype = u64
+    L.mdbcu_compress.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, C.POINTER(vp)]
+    L.mdbcu_compress.restype = i32
+    L.mdbcu_segments_len.argtypes = [vp]
+    L.mdbcu_segments_len.restype = u64
+    L.mdbcu_segments_get.argtypes = [vp, i32, C.POINTER(SegmentsView), C.POINTER(vp)]
+    L.mdbcu_segments_get.restype = i32
+    L.mdbcu_segments_free.argtypes = [vp]
+    L.mdbcu_segments_free.restype = None
+    L.mdbcu_grid_count.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, C.POINTER(u64)]
+    L.mdbcu_grid_count.restype = i32
+    L.mdbcu_grid.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, vp, u64, C.POINTER(u64)]
+    L.mdbcu_grid.restype = i32
+    L.mdbcu_segment_sums.argtypes = [vp, i32, C.POINTER(SegmentsView), vp]
+    L.mdbcu_segment_sums.restype = i32
+    L.mdbcu_aggregate.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, u64, vp, vp, vp, vp]
+    L.mdbcu_aggregate.restype = i32
+    _lib = L
+    return L
+
+
+def check(rc: int):
+    if rc != 0:
+        raise ModelarDbCudaError(lib().mdbcu_last_error().decode("utf-8", "replace"))

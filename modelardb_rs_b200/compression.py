@@ -1,0 +1,397 @@
+"""Host-side mirror of the reference's `modelardb_compression` API over the C-ABI.
+
+Names, argument meaning and error behaviour follow crates/modelardb_compression/src/lib.rs:26-34:
+`try_compress_univariate_time_series`, `grid`, `sum`, `len`, `is_value_within_error_bound`'s ErrorBound
+type, `MODEL_TYPE_COUNT` / `MODEL_TYPE_NAMES`.  Every function here calls libmodelardb_cuda.so; nothing
+is computed in Python.  Inputs may be numpy arrays (host space: the library stages them through the
+GPU) or torch CUDA tensors (device space: nothing crosses PCIe).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _native
+from ._native import DEVICE, HOST, ModelarDbCudaError, SegmentsView
+
+PMC_MEAN_ID, SWING_ID, MACAQUE_V_ID = 0, 1, 2           # models/mod.rs:36-38
+MODEL_TYPE_COUNT = 3                                     # models/mod.rs:41
+MODEL_TYPE_NAMES = ["pmc_mean", "swing", "macaque_v"]    # models/mod.rs:44
+UNCOMPRESSED_DATA_BUFFER_CAPACITY = 64 * 1024            # modelardb_server/src/storage/mod.rs:58
+
+_COLUMNS = ("model_type_id", "start_time", "end_time", "min_value", "max_value", "timestamps_off",
+            "timestamps_data", "values_off", "values_data", "residuals_off", "residuals_data")
+_DTYPES = dict(model_type_id=np.int8, start_time=np.int64, end_time=np.int64, min_value=np.float32,
+               max_value=np.float32, timestamps_off=np.uint64, timestamps_data=np.uint8, values_off=np.uint64,
+               values_data=np.uint8, residuals_off=np.uint64, residuals_data=np.uint8)
+
+
+@dataclass(frozen=True)
+class ErrorBound:
+    """modelardb_types/src/types.rs:299-335."""
+    kind: int
+    value: float = 0.0
+
+    @staticmethod
+    def lossless() -> "ErrorBound":
+        return ErrorBound(0, 0.0)
+
+    @staticmethod
+    def try_new_absolute(value: float) -> "ErrorBound":
+        if not math.isfinite(value) or value <= 0.0:
+            raise ValueError("An absolute error bound must be a positive finite value.")
+        return ErrorBound(1, float(value))
+
+    @staticmethod
+    def try_new_relative(percentage: float) -> "ErrorBound":
+        if not (0.0 < percentage <= 100.0):
+            raise ValueError("A relative error bound must be a positive value that is at most 100.0%.")
+        return ErrorBound(2, float(percentage))
+
+
+Lossless = ErrorBound.lossless()
+
+
+def _is_torch(x) -> bool:
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x) -> int:
+    if x is None:
+        return 0
+    if _is_torch(x):
+        return x.data_ptr()
+    return x.ctypes.data
+
+
+class Context:
+    """One GPU, one stream (mdbcu_context)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _native.check(_native.lib().mdbcu_context_create(device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if self._h:
+            _native.lib().mdbcu_context_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def stream(self) -> int:
+        return _native.lib().mdbcu_context_stream(self._h) or 0
+
+    def set_stream(self, cuda_stream: int):
+        _native.check(_native.lib().mdbcu_context_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    @property
+    def launch_count(self) -> int:
+        return _native.lib().mdbcu_context_launch_count(self._h)
+
+
+_default_contexts = {}
+
+
+def default_context(device: int = 0) -> Context:
+    if device not in _default_contexts:
+        _default_contexts[device] = Context(device)
+    return _default_contexts[device]
+
+
+class HostSegments:
+    """A batch of compressed segments in host memory: the columns of QUERY_COMPRESSED_SCHEMA
+    (modelardb_types/src/schemas.rs:40-52) as numpy arrays, binary columns as offsets + data."""
+
+    def __init__(self, unit_seg_off=None, **cols):
+        for c in _COLUMNS:
+            setattr(self, c, np.ascontiguousarray(cols[c], dtype=_DTYPES[c]))
+        self.unit_seg_off = unit_seg_off
+
+    def __len__(self):
+        return len(self.model_type_id)
+
+    def view(self) -> SegmentsView:
+        v = SegmentsView()
+        v.n_segments = len(self)
+        for c in _COLUMNS:
+            setattr(v, c, getattr(self, c).ctypes.data)
+        return v
+
+    space = HOST
+
+    def row(self, i: int) -> dict:
+        def sl(off, data):
+            return data[int(off[i]): int(off[i + 1])].tobytes()
+        return dict(model_type_id=int(self.model_type_id[i]), start_time=int(self.start_time[i]),
+                    end_time=int(self.end_time[i]), timestamps=sl(self.timestamps_off, self.timestamps_data),
+                    min_value=self.min_value[i], max_value=self.max_value[i],
+                    values=sl(self.values_off, self.values_data), residuals=sl(self.residuals_off, self.residuals_data))
+
+    def segment_bytes(self) -> int:
+        return int(29 * len(self) + len(self.timestamps_data) + len(self.values_data) + len(self.residuals_data))
+
+    def slice(self, lo: int, hi: int) -> "HostSegments":
+        """Rows [lo, hi) as an independent batch (offsets rebased)."""
+        cols = {c: getattr(self, c)[lo:hi] for c in ("model_type_id", "start_time", "end_time", "min_value", "max_value")}
+        for name in ("timestamps", "values", "residuals"):
+            off = getattr(self, name + "_off")
+            a, b = int(off[lo]), int(off[hi])
+            cols[name + "_off"] = off[lo:hi + 1] - off[lo]
+            cols[name + "_data"] = getattr(self, name + "_data")[a:b]
+        return HostSegments(**cols)
+
+
+class CompressedSegments:
+    """An owned device-resident batch produced by compress (mdbcu_segments)."""
+
+    space = DEVICE
+
+    def __init__(self, handle: C.c_void_p, ctx: Context, n_units: int):
+        self._h = handle
+        self.ctx = ctx
+        self.n_units = n_units
+
+    def __len__(self):
+        return _native.lib().mdbcu_segments_len(self._h)
+
+    def free(self):
+        if self._h:
+            _native.lib().mdbcu_segments_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def _get(self, space: int):
+        v = SegmentsView()
+        uso = C.c_void_p()
+        _native.check(_native.lib().mdbcu_segments_get(self._h, space, C.byref(v), C.byref(uso)))
+        return v, uso.value
+
+    def view(self) -> SegmentsView:
+        return self._get(DEVICE)[0]
+
+    def unit_seg_off_device_ptr(self) -> int:
+        return self._get(DEVICE)[1] or 0
+
+    def to_host(self) -> HostSegments:
+        v, uso = self._get(HOST)
+        n = v.n_segments
+
+        def arr(ptr, count, dt):
+            if count == 0 or not ptr:
+                return np.zeros(0, dt)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+
+        cols = {}
+        for c in ("model_type_id", "start_time", "end_time", "min_value", "max_value"):
+            cols[c] = arr(getattr(v, c), n, _DTYPES[c])
+        for name in ("timestamps", "values", "residuals"):
+            off = arr(getattr(v, name + "_off"), n + 1, np.uint64)
+            cols[name + "_off"] = off
+            cols[name + "_data"] = arr(getattr(v, name + "_data"), int(off[-1]) if len(off) else 0, np.uint8)
+        return HostSegments(unit_seg_off=arr(uso, self.n_units + 1, np.uint64), **cols)
+
+
+def _space_of(*arrays) -> int:
+    kinds = {_is_torch(a) for a in arrays if a is not None}
+    if len(kinds) > 1:
+        raise ValueError("mixing numpy (host) and torch (device) arrays in one call")
+    if kinds == {True}:
+        for a in arrays:
+            if a is not None and not a.is_cuda:
+                raise ValueError("torch tensors must live on the GPU; pass numpy arrays for host memory")
+            if a is not None and not a.is_contiguous():
+                raise ValueError("tensors must be contiguous")
+        return DEVICE
+    return HOST
+
+
+def _bounds(error_bound, n_units: int):
+    if isinstance(error_bound, ErrorBound):
+        error_bound = [error_bound] * n_units
+    if len(error_bound) != n_units:
+        raise ValueError("one error bound per unit is required")
+    return (np.array([e.kind for e in error_bound], np.uint8), np.array([e.value for e in error_bound], np.float32))
+
+
+def compress(timestamps, values, unit_off=None, error_bound=Lossless, ctx: Optional[Context] = None) -> CompressedSegments:
+    """Batch form of try_compress_univariate_time_series (compression.rs:191-275): unit u is the slice
+    [unit_off[u], unit_off[u+1]) and is compressed independently."""
+    ctx = ctx or default_context()
+    if len(timestamps) != len(values):
+        # compression.rs:202-206
+        raise ModelarDbCudaError("Uncompressed timestamps and uncompressed values have different lengths.")
+    space = _space_of(timestamps, values)
+    if space == HOST:
+        timestamps = np.ascontiguousarray(timestamps, np.int64)
+        values = np.ascontiguousarray(values, np.float32)
+        if unit_off is None:
+            unit_off = np.array([0, len(timestamps)], np.uint64)
+        unit_off = np.ascontiguousarray(unit_off, np.uint64)
+        n_units = len(unit_off) - 1
+        kinds, ebv = _bounds(error_bound, n_units)
+    else:
+        import torch
+        if timestamps.dtype != torch.int64 or values.dtype != torch.float32:
+            raise ValueError("device inputs must be int64 timestamps and float32 values")
+        if unit_off is None:
+            unit_off = torch.tensor([0, len(timestamps)], dtype=torch.int64, device=timestamps.device)
+        n_units = len(unit_off) - 1
+        if isinstance(error_bound, tuple) and _is_torch(error_bound[0]):
+            kinds, ebv = error_bound  # already on the device
+        else:
+            k, v = _bounds(error_bound, n_units)
+            kinds = torch.from_numpy(k).to(timestamps.device)
+            ebv = torch.from_numpy(v).to(timestamps.device)
+    out = C.c_void_p()
+    _native.check(_native.lib().mdbcu_compress(ctx._h, space, _ptr(timestamps), _ptr(values), _ptr(unit_off), n_units,
+                                               _ptr(kinds), _ptr(ebv), C.byref(out)))
+    return CompressedSegments(out, ctx, n_units)
+
+
+def try_compress_univariate_time_series(uncompressed_timestamps, uncompressed_values, error_bound: ErrorBound = Lossless,
+                                        ctx: Optional[Context] = None) -> HostSegments:
+    """compression.rs:191-275 for one series, returning the segment batch in host memory."""
+    seg = compress(uncompressed_timestamps, uncompressed_values, None, error_bound, ctx)
+    try:
+        return seg.to_host()
+    finally:
+        seg.free()
+
+
+def split_into_buffers(n_points_per_series: Sequence[int], capacity: int = UNCOMPRESSED_DATA_BUFFER_CAPACITY) -> np.ndarray:
+    """unit_off for the server ingestion path: every series is cut into buffers of at most `capacity`
+    points before compression (modelardb_server/src/storage/mod.rs:58,
+    uncompressed_data_manager.rs:530-581)."""
+    offs = [0]
+    pos = 0
+    for n in n_points_per_series:
+        end = pos + int(n)
+        while pos < end:
+            pos = min(end, pos + capacity)
+            offs.append(pos)
+    return np.array(offs, np.uint64)
+
+
+def _view_of(segments):
+    return segments.view(), segments.space
+
+
+def grid_count(segments, ctx: Optional[Context] = None):
+    """len() per row (models/mod.rs:98-124) as an exclusive prefix sum: returns (point_off, total)."""
+    ctx = ctx or getattr(segments, "ctx", None) or default_context()
+    v, space = _view_of(segments)
+    total = C.c_uint64()
+    if space == HOST:
+        off = np.zeros(v.n_segments + 1, np.uint64)
+    else:
+        import torch
+        off = torch.zeros(v.n_segments + 1, dtype=torch.int64, device=f"cuda:{ctx.device}")
+    _native.check(_native.lib().mdbcu_grid_count(ctx._h, space, C.byref(v), _ptr(off), C.byref(total)))
+    return off, total.value
+
+
+def grid(segments, timestamps_out=None, values_out=None, ctx: Optional[Context] = None):
+    """grid() over every row of the batch, rows in order (models/mod.rs:190-251, grid_exec.rs:323-337).
+    Returns (timestamps, values) trimmed to the number of data points."""
+    ctx = ctx or getattr(segments, "ctx", None) or default_context()
+    v, space = _view_of(segments)
+    if timestamps_out is None:
+        _, total = grid_count(segments, ctx)
+        if space == HOST:
+            timestamps_out = np.empty(total, np.int64)
+            values_out = np.empty(total, np.float32)
+        else:
+            import torch
+            dev = f"cuda:{ctx.device}"
+            timestamps_out = torch.empty(total, dtype=torch.int64, device=dev)
+            values_out = torch.empty(total, dtype=torch.float32, device=dev)
+    n = C.c_uint64()
+    _native.check(_native.lib().mdbcu_grid(ctx._h, space, C.byref(v), _ptr(timestamps_out), _ptr(values_out),
+                                           len(timestamps_out), C.byref(n)))
+    return timestamps_out[: n.value], values_out[: n.value]
+
+
+def segment_sums(segments, ctx: Optional[Context] = None):
+    """sum() per row (models/mod.rs:129-184)."""
+    ctx = ctx or getattr(segments, "ctx", None) or default_context()
+    v, space = _view_of(segments)
+    if space == HOST:
+        out = np.empty(v.n_segments, np.float32)
+    else:
+        import torch
+        out = torch.empty(v.n_segments, dtype=torch.float32, device=f"cuda:{ctx.device}")
+    _native.check(_native.lib().mdbcu_segment_sums(ctx._h, space, C.byref(v), _ptr(out)))
+    return out
+
+
+def aggregate(segments, group_off=None, ctx: Optional[Context] = None):
+    """COUNT / MIN / MAX / SUM per group of rows without materialising data points
+    (model_simple_aggregates.rs:345-585). Returns (count i64, min f32, max f32, sum f64)."""
+    ctx = ctx or getattr(segments, "ctx", None) or default_context()
+    v, space = _view_of(segments)
+    if isinstance(group_off, tuple):  # (raw pointer in the batch's memory space, n_groups)
+        group_off, g = group_off
+    else:
+        g = 1 if group_off is None else len(group_off) - 1
+    if space == HOST:
+        if group_off is not None and not isinstance(group_off, int):
+            group_off = np.ascontiguousarray(group_off, np.uint64)
+        count, mn, mx, sm = np.zeros(g, np.int64), np.zeros(g, np.float32), np.zeros(g, np.float32), np.zeros(g, np.float64)
+    else:
+        import torch
+        dev = f"cuda:{ctx.device}"
+        count = torch.zeros(g, dtype=torch.int64, device=dev)
+        mn = torch.zeros(g, dtype=torch.float32, device=dev)
+        mx = torch.zeros(g, dtype=torch.float32, device=dev)
+        sm = torch.zeros(g, dtype=torch.float64, device=dev)
+    gp = group_off if isinstance(group_off, int) else _ptr(group_off)
+    _native.check(_native.lib().mdbcu_aggregate(ctx._h, space, C.byref(v), gp, g if group_off is not None else 1,
+                                                _ptr(count), _ptr(mn), _ptr(mx), _ptr(sm)))
+    return count, mn, mx, sm
+
+
+# Row-wise forms with the reference's names and argument order (models/mod.rs:98, :129-138, :190-201).
+def _one_row(model_type_id, start_time, end_time, timestamps, min_value, max_value, values, residuals) -> HostSegments:
+    u8 = lambda b: np.frombuffer(bytes(b), np.uint8).copy()
+    return HostSegments(
+        model_type_id=np.array([model_type_id], np.int8), start_time=np.array([start_time], np.int64),
+        end_time=np.array([end_time], np.int64), min_value=np.array([min_value], np.float32),
+        max_value=np.array([max_value], np.float32),
+        timestamps_off=np.array([0, len(timestamps)], np.uint64), timestamps_data=u8(timestamps),
+        values_off=np.array([0, len(values)], np.uint64), values_data=u8(values),
+        residuals_off=np.array([0, len(residuals)], np.uint64), residuals_data=u8(residuals))
+
+
+def len_(start_time: int, end_time: int, timestamps: bytes, ctx: Optional[Context] = None) -> int:
+    """models/mod.rs:98-124."""
+    row = _one_row(PMC_MEAN_ID, start_time, end_time, timestamps, 0.0, 0.0, b"", b"")
+    return grid_count(row, ctx)[1]
+
+
+def sum_(model_type_id, start_time, end_time, timestamps, min_value, max_value, values, residuals,
+         ctx: Optional[Context] = None) -> np.float32:
+    """models/mod.rs:129-184."""
+    row = _one_row(model_type_id, start_time, end_time, timestamps, min_value, max_value, values, residuals)
+    return segment_sums(row, ctx)[0]
+
+
+def grid_row(model_type_id, start_time, end_time, timestamps, min_value, max_value, values, residuals,
+             ctx: Optional[Context] = None):
+    """models/mod.rs:190-251 for a single row: returns (timestamps, values)."""
+    row = _one_row(model_type_id, start_time, end_time, timestamps, min_value, max_value, values, residuals)
+    return grid(row, ctx=ctx)

@@ -1,0 +1,1018 @@
+// mdb_cuda.cu -- kernels and C-ABI of libmodelardb_cuda.so (include/modelardb_cuda.h), sm_100a.
+//
+// Kernel inventory (DESIGN.md has the roofline of each):
+//   scan_*                exclusive prefix sums (point offsets, row offsets, byte offsets)
+//   k_grid_prepare        one thread per segment row -> SegDesc + point count (+ worklist of serial rows)
+//   k_grid_tile_index     first segment row of every 2048-point output tile
+//   k_grid_tile           one thread per OUTPUT POINT: streaming, coalesced writes of timestamps/values
+//   k_grid_sequential     irregular timestamps, MacaqueV values, residuals (serial per row)
+//   k_agg_segments        one thread per row: COUNT and SUM of the row from its model
+//   k_agg_partial/final   deterministic in-order tree reduction per group
+//   k_compress_fit        one thread per unit: greedy PMC-Mean/Swing segmentation -> SegRecords
+//   k_compress_gather     row metadata + per-row byte lengths in final row order
+//   k_compress_emit       one thread per row: MacaqueTS / MacaqueV byte columns
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/modelardb_cuda.h"
+#include "mdb_aggregate.cuh"
+#include "mdb_compress.cuh"
+#include "mdb_grid.cuh"
+
+using namespace mdb;
+
+// ------------------------------------------------------------------------------------------------
+// errors, context, buffers
+// ------------------------------------------------------------------------------------------------
+
+static thread_local std::string g_last_error;
+
+static int fail(const std::string &msg) {
+    g_last_error = msg;
+    return MDBCU_FAILURE;
+}
+
+#define CUDA_TRY(expr)                                                                              \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess)                                                                      \
+            return fail(std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
+    } while (0)
+
+struct mdbcu_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    uint64_t launches = 0;
+    int sm_count = 148;
+};
+
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
+    do {                                                                 \
+        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        (ctx)->launches++;                                               \
+    } while (0)
+
+// Stream-ordered device buffer (cudaMallocAsync: after warm-up this is a pool hit, not a driver call).
+template <typename T> struct DBuf {
+    T *p = nullptr;
+    cudaStream_t s = nullptr;
+    DBuf() = default;
+    DBuf(const DBuf &) = delete;
+    DBuf &operator=(const DBuf &) = delete;
+    ~DBuf() { release(); }
+    cudaError_t alloc(size_t n, cudaStream_t stream) {
+        release();
+        s = stream;
+        return cudaMallocAsync((void **)&p, (n ? n : 1) * sizeof(T), stream);
+    }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    T *take() { T *q = p; p = nullptr; return q; }
+};
+
+struct Status {            // zeroed before each call
+    unsigned int bad;      // some row / unit was malformed
+    unsigned int n_seq;    // rows in the serial worklist
+    unsigned long long first_bad;
+};
+
+static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// exclusive scan: out[i] = sum(in[0..i)), out[n] = total.  Three small kernels; the inputs here are
+// per-row / per-unit counters, two to three orders of magnitude smaller than the point data.
+// ------------------------------------------------------------------------------------------------
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 16;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ uint64_t block_exclusive_scan(uint64_t x, uint64_t &block_total) {
+    __shared__ uint64_t warp_sums[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint64_t incl = x;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint64_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += y;
+    }
+    if (lane == 31) warp_sums[warp] = incl;
+    __syncthreads();
+    uint64_t warp_prefix = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < SCAN_THREADS / 32; w++) {
+        uint64_t s = warp_sums[w];
+        if (w < warp) warp_prefix += s;
+        total += s;
+    }
+    __syncthreads();
+    block_total = total;
+    return warp_prefix + incl - x;
+}
+
+template <typename T> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_block_sums(const T *in, uint64_t n, uint64_t *block_sums) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK;
+    uint64_t sum = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint64_t i = base + (uint64_t)k * SCAN_THREADS + threadIdx.x; // coalesced
+        if (i < n) sum += in[i];
+    }
+    uint64_t total;
+    block_exclusive_scan(sum, total);
+    if (threadIdx.x == 0) block_sums[blockIdx.x] = total;
+}
+
+// single block: in-place exclusive scan of block_sums[0..nb), total to block_sums[nb]
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_sums(uint64_t *block_sums, uint64_t nb) {
+    __shared__ uint64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (uint64_t base = 0; base < nb; base += SCAN_THREADS) {
+        uint64_t i = base + threadIdx.x;
+        uint64_t x = i < nb ? block_sums[i] : 0;
+        uint64_t total;
+        uint64_t excl = block_exclusive_scan(x, total);
+        uint64_t carry = carry_s;
+        if (i < nb) block_sums[i] = carry + excl;
+        __syncthreads();
+        if (threadIdx.x == 0) carry_s = carry + total;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) block_sums[nb] = carry_s;
+}
+
+template <typename T> __global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const T *in, uint64_t n, const uint64_t *block_sums, uint64_t *out) {
+    uint64_t base = (uint64_t)blockIdx.x * SCAN_BLOCK + (uint64_t)threadIdx.x * SCAN_ITEMS;
+    uint64_t v[SCAN_ITEMS];
+    uint64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint64_t i = base + k;
+        v[k] = i < n ? (uint64_t)in[i] : 0;
+        sum += v[k];
+    }
+    uint64_t total;
+    uint64_t run = block_sums[blockIdx.x] + block_exclusive_scan(sum, total);
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        uint64_t i = base + k;
+        if (i < n) out[i] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == gridDim.x - 1 && threadIdx.x == 0) out[n] = block_sums[gridDim.x];
+}
+
+// out must hold n + 1 entries. Leaves the total in out[n] (device).
+template <typename T> static int exclusive_scan(mdbcu_context *ctx, const T *in, uint64_t n, uint64_t *out) {
+    if (n == 0) {
+        CUDA_TRY(cudaMemsetAsync(out, 0, sizeof(uint64_t), ctx->stream));
+        return MDBCU_SUCCESS;
+    }
+    unsigned int nb = div_up(n, SCAN_BLOCK);
+    DBuf<uint64_t> block_sums;
+    CUDA_TRY(block_sums.alloc((size_t)nb + 1, ctx->stream));
+    LAUNCH(ctx, k_scan_block_sums<T>, nb, SCAN_THREADS, 0, in, n, block_sums.p);
+    LAUNCH(ctx, k_scan_sums, 1, SCAN_THREADS, 0, block_sums.p, (uint64_t)nb);
+    LAUNCH(ctx, k_scan_apply<T>, nb, SCAN_THREADS, 0, in, n, block_sums.p, out);
+    CUDA_TRY(cudaGetLastError());
+    return MDBCU_SUCCESS;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: grid
+// ------------------------------------------------------------------------------------------------
+
+constexpr int TILE_THREADS = 256;
+constexpr int TILE_POINTS_PER_THREAD = 8;
+constexpr int TILE = TILE_THREADS * TILE_POINTS_PER_THREAD; // 2048 output points per block
+
+__device__ __forceinline__ void report_bad(Status *status, uint64_t index) {
+    atomicExch(&status->bad, 1u);
+    atomicMin(&status->first_bad, (unsigned long long)index);
+}
+
+__global__ void __launch_bounds__(256) k_grid_prepare(SegmentsView v, SegDesc *desc, uint32_t *len, uint32_t *worklist, Status *status) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool serial = false;
+    if (s < v.n_segments) {
+        SegDesc d;
+        uint32_t n = grid_prepare_segment(v, s, d);
+        desc[s] = d;
+        len[s] = n;
+        if (d.flags & F_MALFORMED) report_bad(status, s);
+        serial = (d.flags & F_SEQUENTIAL) != 0;
+    }
+    // warp-aggregated append to the worklist of rows that need the serial kernel
+    unsigned int mask = __ballot_sync(0xffffffffu, serial);
+    if (mask) {
+        int lane = threadIdx.x & 31;
+        int leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&status->n_seq, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (serial) worklist[base + __popc(mask & ((1u << lane) - 1))] = (uint32_t)s;
+    }
+}
+
+// tile_first[t] = the row that contains output point t * TILE
+__global__ void __launch_bounds__(256) k_grid_tile_index(const uint64_t *point_off, uint64_t n_segments, uint32_t *tile_first) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_segments) return;
+    uint64_t a = point_off[s], b = point_off[s + 1];
+    for (uint64_t t = (a + TILE - 1) / TILE; t * TILE < b; t++) tile_first[t] = (uint32_t)s;
+}
+
+// One block per tile of 2048 consecutive output points.  The rows overlapping the tile are found with
+// head flags + a block-wide max-scan in shared memory (no per-point binary search), then every thread
+// writes points tid, tid + 256, ... so that each warp store covers 128 B of values / 256 B of timestamps.
+__global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__restrict__ desc, const uint64_t *__restrict__ point_off,
+                                                            const uint32_t *__restrict__ tile_first, uint64_t n_segments,
+                                                            uint64_t total, int64_t *__restrict__ ts_out, float *__restrict__ val_out) {
+    __shared__ uint64_t po_s[TILE + 2];      // point offsets of the rows overlapping the tile
+    __shared__ uint16_t seg_of[TILE];        // local row index of every point of the tile
+    __shared__ uint32_t warp_max[TILE_THREADS / 32];
+
+    const uint64_t tile_start = (uint64_t)blockIdx.x * TILE;
+    const uint64_t tile_end = min(total, tile_start + TILE);
+    const uint64_t s0 = tile_first[blockIdx.x];
+    const int tid = threadIdx.x;
+
+    for (int p = tid; p < TILE; p += TILE_THREADS) seg_of[p] = 0;
+    __syncthreads();
+    // Stage point_off[s0 ..] until it passes the end of the tile (rows have >= 1 point, so at most
+    // TILE + 1 rows overlap) and drop a head flag where each row i >= 1 starts inside the tile.
+    for (int base = 0; base < TILE + 2; base += TILE_THREADS) {
+        int i = base + tid;
+        uint64_t x = ~0ull;
+        if (i < TILE + 2) {
+            if (s0 + i <= n_segments) x = point_off[s0 + i];
+            po_s[i] = x;
+            if (i >= 1 && x < tile_end) seg_of[x - tile_start] = (uint16_t)i;
+        }
+        if (!__syncthreads_or(tid == TILE_THREADS - 1 && x < tile_end)) break;
+    }
+    __syncthreads();
+    // inclusive max-scan over seg_of: thread owns 8 consecutive entries
+    uint32_t loc[TILE_POINTS_PER_THREAD];
+    uint32_t run = 0;
+#pragma unroll
+    for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) {
+        run = max(run, (uint32_t)seg_of[tid * TILE_POINTS_PER_THREAD + k]);
+        loc[k] = run;
+    }
+    uint32_t incl = run;
+    const int lane = tid & 31, warp = tid >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl = max(incl, y);
+    }
+    if (lane == 31) warp_max[warp] = incl;
+    uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
+    if (lane == 0) prev = 0;
+    __syncthreads();
+    for (int w = 0; w < warp; w++) prev = max(prev, warp_max[w]);
+#pragma unroll
+    for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) seg_of[tid * TILE_POINTS_PER_THREAD + k] = (uint16_t)max(prev, loc[k]);
+    __syncthreads();
+
+#pragma unroll
+    for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) {
+        int p = tid + k * TILE_THREADS;
+        uint64_t gp = tile_start + p;
+        if (gp < tile_end) {
+            uint32_t i = seg_of[p];
+            const SegDesc d = desc[s0 + i];
+            grid_point(d, (uint32_t)(gp - po_s[i]), ts_out, val_out, gp);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(128) k_grid_sequential(SegmentsView v, const SegDesc *desc, const uint64_t *point_off, const uint32_t *worklist,
+                                                         uint32_t n_work, int64_t *ts_out, float *val_out) {
+    uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_work) return;
+    uint64_t s = worklist[w];
+    uint64_t base = point_off[s];
+    grid_sequential_segment(v, s, desc[s], base, (uint32_t)(point_off[s + 1] - base), ts_out, val_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: aggregates
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *seg_count, float *seg_sum, Status *status) {
+    uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= v.n_segments) return;
+    uint64_t c;
+    float sum;
+    if (!aggregate_segment(v, s, c, sum)) report_bad(status, s);
+    if (seg_count) seg_count[s] = c;
+    seg_sum[s] = sum;
+}
+
+constexpr int AGG_THREADS = 256;
+
+// In-order tree reduction of a block's per-thread partials (thread t holds rows EARLIER than t + 1).
+__device__ __forceinline__ GroupAgg block_reduce_in_order(GroupAgg a) {
+    __shared__ GroupAgg warp_part[AGG_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        GroupAgg o;
+        o.count = __shfl_down_sync(0xffffffffu, a.count, d);
+        o.min = __shfl_down_sync(0xffffffffu, a.min, d);
+        o.max = __shfl_down_sync(0xffffffffu, a.max, d);
+        o.sum = __shfl_down_sync(0xffffffffu, a.sum, d);
+        if (lane + d < 32) a = group_agg_combine(a, o);
+    }
+    if (lane == 0) warp_part[warp] = a;
+    __syncthreads();
+    GroupAgg r = warp_part[0];
+    if (threadIdx.x == 0)
+        for (int w = 1; w < AGG_THREADS / 32; w++) r = group_agg_combine(r, warp_part[w]);
+    __syncthreads();
+    return r; // valid in thread 0
+}
+
+// Block (part, group): folds the part-th contiguous slice of the group's rows.
+__global__ void __launch_bounds__(AGG_THREADS) k_agg_partial(const uint64_t *group_off, uint64_t n_groups, uint64_t n_rows_all, uint32_t parts,
+                                                             const uint64_t *seg_count, const float *seg_sum, const float *min_value,
+                                                             const float *max_value, GroupAgg *partial) {
+    for (uint64_t g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        uint64_t lo = group_off ? group_off[g] : 0, hi = group_off ? group_off[g + 1] : n_rows_all;
+        hi = min(hi, n_rows_all); // never read past the batch, whatever the caller passed
+        lo = min(lo, hi);
+        uint64_t rows = hi - lo;
+        uint64_t part = blockIdx.x;
+        uint64_t plo = lo + rows * part / parts, phi = lo + rows * (part + 1) / parts;
+        uint64_t prow = phi - plo;
+        // thread t folds the t-th contiguous chunk, in row order
+        uint64_t tlo = plo + prow * threadIdx.x / AGG_THREADS, thi = plo + prow * (threadIdx.x + 1) / AGG_THREADS;
+        GroupAgg a = group_agg_identity();
+        for (uint64_t s = tlo; s < thi; s++) {
+            GroupAgg row;
+            row.count = (int64_t)seg_count[s];
+            row.min = min_value[s];
+            row.max = max_value[s];
+            row.sum = (double)seg_sum[s];
+            a = group_agg_combine(a, row);
+        }
+        a = block_reduce_in_order(a);
+        if (threadIdx.x == 0) partial[g * parts + part] = a;
+    }
+}
+
+__global__ void __launch_bounds__(AGG_THREADS) k_agg_final(const GroupAgg *partial, uint64_t n_groups, uint32_t parts, int64_t *count, float *mn,
+                                                           float *mx, double *sum) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    GroupAgg a = partial[g * parts];
+    for (uint32_t p = 1; p < parts; p++) a = group_agg_combine(a, partial[g * parts + p]);
+    count[g] = a.count;
+    mn[g] = a.min;
+    mx[g] = a.max;
+    sum[g] = a.sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: compress
+// ------------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) k_unit_caps(const uint64_t *unit_off, uint64_t n_units, const uint8_t *eb_kind, const float *eb_value,
+                                                   uint64_t *caps, Status *status) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint64_t a = unit_off[u], b = unit_off[u + 1];
+    bool ok = b >= a && (b - a) < 0xFFFFFFFFull;
+    uint8_t kind = eb_kind[u];
+    float value = eb_value[u];
+    // ErrorBound::try_new_absolute / try_new_relative (modelardb_types/src/types.rs:312-334)
+    if (kind == KIND_ABSOLUTE) ok = ok && value > 0.0f && !isinf(value) && value == value;
+    else if (kind == KIND_RELATIVE) ok = ok && value > 0.0f && value <= 100.0f;
+    else if (kind != KIND_LOSSLESS) ok = false;
+    if (!ok) report_bad(status, u);
+    caps[u] = ok ? max_segments_of_unit(b - a) : 0;
+}
+
+// One thread per unit; 32-thread blocks spread the chains over all SMs.
+__global__ void __launch_bounds__(32) k_compress_fit(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                     uint64_t n_units, const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                     const uint64_t *__restrict__ rec_base, SegRecord *recs, uint32_t *unit_rows) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint64_t a = unit_off[u];
+    uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    UnitTotals totals;
+    unit_rows[u] = compress_fit_unit(eb, ts + a, values + a, n, recs + rec_base[u], totals);
+}
+
+// One warp per unit: row metadata and byte lengths in final row order.
+__global__ void __launch_bounds__(256) k_compress_gather(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off, uint64_t n_units,
+                                                         const uint64_t *__restrict__ rec_base, const SegRecord *__restrict__ recs,
+                                                         const uint64_t *__restrict__ unit_seg_off, int8_t *model_type_id, int64_t *start_time,
+                                                         int64_t *end_time, float *min_value, float *max_value, uint32_t *ts_len,
+                                                         uint32_t *val_len, uint32_t *res_len, uint32_t *row_unit) {
+    uint64_t u = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (u >= n_units) return;
+    const int lane = threadIdx.x & 31;
+    uint64_t r0 = unit_seg_off[u], rows = unit_seg_off[u + 1] - r0;
+    const SegRecord *urecs = recs + rec_base[u];
+    const int64_t *uts = ts + unit_off[u];
+    for (uint64_t k = lane; k < rows; k += 32) {
+        SegRecord rec = urecs[k];
+        uint64_t r = r0 + k;
+        model_type_id[r] = rec.model_type_id;
+        start_time[r] = uts[rec.start_index];
+        end_time[r] = uts[rec.res_end_index];
+        min_value[r] = rec.min_value;
+        max_value[r] = rec.max_value;
+        ts_len[r] = rec.ts_len;
+        val_len[r] = rec.val_len;
+        res_len[r] = rec.res_len;
+        row_unit[r] = (uint32_t)u;
+    }
+}
+
+__global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                      const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                      const uint64_t *__restrict__ rec_base, const SegRecord *__restrict__ recs,
+                                                      const uint64_t *__restrict__ unit_seg_off, const uint32_t *__restrict__ row_unit, uint64_t n_rows,
+                                                      const uint64_t *__restrict__ ts_off, uint8_t *ts_data, const uint64_t *__restrict__ val_off,
+                                                      uint8_t *val_data, const uint64_t *__restrict__ res_off, uint8_t *res_data) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t u = row_unit[r];
+    SegRecord rec = recs[rec_base[u] + (r - unit_seg_off[u])];
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    uint64_t a = unit_off[u];
+    compress_emit_segment(eb, rec, ts + a, values + a, ts_data + ts_off[r], val_data + val_off[r], res_data + res_off[r]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+
+struct mdbcu_segments {
+    mdbcu_context *ctx = nullptr;
+    uint64_t n_segments = 0, n_units = 0;
+    // device columns
+    int8_t *model_type_id = nullptr;
+    int64_t *start_time = nullptr, *end_time = nullptr;
+    float *min_value = nullptr, *max_value = nullptr;
+    uint64_t *ts_off = nullptr, *val_off = nullptr, *res_off = nullptr, *unit_seg_off = nullptr;
+    uint8_t *ts_data = nullptr, *val_data = nullptr, *res_data = nullptr;
+    uint64_t ts_bytes = 0, val_bytes = 0, res_bytes = 0;
+    // lazily made host copy
+    bool have_host = false;
+    std::vector<int8_t> h_model_type_id;
+    std::vector<int64_t> h_start_time, h_end_time;
+    std::vector<float> h_min_value, h_max_value;
+    std::vector<uint64_t> h_ts_off, h_val_off, h_res_off, h_unit_seg_off;
+    std::vector<uint8_t> h_ts_data, h_val_data, h_res_data;
+};
+
+static SegmentsView to_device_view(const mdbcu_segments_view *v) {
+    SegmentsView d;
+    d.n_segments = v->n_segments;
+    d.model_type_id = v->model_type_id;
+    d.start_time = v->start_time;
+    d.end_time = v->end_time;
+    d.min_value = v->min_value;
+    d.max_value = v->max_value;
+    d.timestamps_off = v->timestamps_off;
+    d.timestamps_data = v->timestamps_data;
+    d.values_off = v->values_off;
+    d.values_data = v->values_data;
+    d.residuals_off = v->residuals_off;
+    d.residuals_data = v->residuals_data;
+    return d;
+}
+
+// Device copy of a HOST-space segment batch.
+struct StagedSegments {
+    DBuf<int8_t> model_type_id;
+    DBuf<int64_t> start_time, end_time;
+    DBuf<float> min_value, max_value;
+    DBuf<uint64_t> ts_off, val_off, res_off;
+    DBuf<uint8_t> ts_data, val_data, res_data;
+    SegmentsView view;
+};
+
+template <typename T> static cudaError_t upload(DBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
+    cudaError_t e = dst.alloc(n, s);
+    if (e != cudaSuccess) return e;
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
+}
+
+template <typename T> static cudaError_t download(std::vector<T> &dst, const T *src, size_t n, cudaStream_t s) {
+    dst.resize(n);
+    if (n == 0) return cudaSuccess;
+    return cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, s);
+}
+
+static int stage_segments(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *v, StagedSegments &st) {
+    if (!v) return fail("segments view is null");
+    uint64_t S = v->n_segments;
+    if (S > 0xFFFFFFF0ull) return fail("more than 2^32 segment rows in one batch");
+    if (space == MDBCU_DEVICE) {
+        st.view = to_device_view(v);
+        return MDBCU_SUCCESS;
+    }
+    cudaStream_t s = ctx->stream;
+    if (S && (!v->timestamps_off || !v->values_off || !v->residuals_off)) return fail("offset column is null");
+    uint64_t tb = S ? v->timestamps_off[S] : 0, vb = S ? v->values_off[S] : 0, rb = S ? v->residuals_off[S] : 0;
+    CUDA_TRY(upload(st.model_type_id, v->model_type_id, S, s));
+    CUDA_TRY(upload(st.start_time, v->start_time, S, s));
+    CUDA_TRY(upload(st.end_time, v->end_time, S, s));
+    CUDA_TRY(upload(st.min_value, v->min_value, S, s));
+    CUDA_TRY(upload(st.max_value, v->max_value, S, s));
+    CUDA_TRY(upload(st.ts_off, v->timestamps_off, S ? S + 1 : 0, s));
+    CUDA_TRY(upload(st.val_off, v->values_off, S ? S + 1 : 0, s));
+    CUDA_TRY(upload(st.res_off, v->residuals_off, S ? S + 1 : 0, s));
+    CUDA_TRY(upload(st.ts_data, v->timestamps_data, tb, s));
+    CUDA_TRY(upload(st.val_data, v->values_data, vb, s));
+    CUDA_TRY(upload(st.res_data, v->residuals_data, rb, s));
+    st.view.n_segments = S;
+    st.view.model_type_id = st.model_type_id.p;
+    st.view.start_time = st.start_time.p;
+    st.view.end_time = st.end_time.p;
+    st.view.min_value = st.min_value.p;
+    st.view.max_value = st.max_value.p;
+    st.view.timestamps_off = st.ts_off.p;
+    st.view.timestamps_data = st.ts_data.p;
+    st.view.values_off = st.val_off.p;
+    st.view.values_data = st.val_data.p;
+    st.view.residuals_off = st.res_off.p;
+    st.view.residuals_data = st.res_data.p;
+    return MDBCU_SUCCESS;
+}
+
+static int check_ctx(mdbcu_context *ctx) {
+    if (!ctx) return fail("context is null");
+    CUDA_TRY(cudaSetDevice(ctx->device));
+    return MDBCU_SUCCESS;
+}
+
+static int read_status(mdbcu_context *ctx, const Status *d_status, Status &h, const char *what) {
+    CUDA_TRY(cudaMemcpyAsync(&h, d_status, sizeof(Status), cudaMemcpyDeviceToHost, ctx->stream));
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (h.bad) return fail(std::string("malformed ") + what + " " + std::to_string(h.first_bad));
+    return MDBCU_SUCCESS;
+}
+
+static int new_status(mdbcu_context *ctx, DBuf<Status> &st) {
+    CUDA_TRY(st.alloc(1, ctx->stream));
+    Status init;
+    init.bad = 0;
+    init.n_seq = 0;
+    init.first_bad = ~0ull;
+    // tiny H2D of a stack value: cudaMemcpyAsync from pageable memory returns after staging the copy
+    CUDA_TRY(cudaMemcpyAsync(st.p, &init, sizeof(Status), cudaMemcpyHostToDevice, ctx->stream));
+    return MDBCU_SUCCESS;
+}
+
+extern "C" {
+
+const char *mdbcu_last_error(void) { return g_last_error.c_str(); }
+
+const char *mdbcu_version(void) { return "0.1.0"; }
+
+int mdbcu_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int mdbcu_context_create(int device, mdbcu_context **out) {
+    if (!out) return fail("out is null");
+    *out = nullptr;
+    int n = mdbcu_device_count();
+    if (n == 0) return fail("no CUDA device: libmodelardb_cuda has no CPU implementation");
+    if (device < 0 || device >= n) return fail("device index out of range");
+    CUDA_TRY(cudaSetDevice(device));
+    mdbcu_context *ctx = new mdbcu_context();
+    ctx->device = device;
+    cudaError_t e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return fail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
+    }
+    ctx->own_stream = true;
+    cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    // keep freed blocks in the pool: steady-state calls then never reach the driver allocator
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    *out = ctx;
+    return MDBCU_SUCCESS;
+}
+
+void mdbcu_context_destroy(mdbcu_context *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int mdbcu_context_set_stream(mdbcu_context *ctx, void *cuda_stream) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+    return MDBCU_SUCCESS;
+}
+
+void *mdbcu_context_stream(mdbcu_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+
+uint64_t mdbcu_context_launch_count(const mdbcu_context *ctx) { return ctx ? ctx->launches : 0; }
+
+// ---- K2 ------------------------------------------------------------------------------------------
+
+// Shared front half of grid_count / grid: descriptors, point offsets, worklist. Leaves h_status/total on host.
+struct GridPlan {
+    DBuf<SegDesc> desc;
+    DBuf<uint32_t> len, worklist;
+    DBuf<uint64_t> point_off;
+    DBuf<Status> status;
+    Status h_status;
+    uint64_t total = 0;
+};
+
+static int grid_plan(mdbcu_context *ctx, const SegmentsView &v, GridPlan &pl) {
+    uint64_t S = v.n_segments;
+    cudaStream_t s = ctx->stream;
+    CUDA_TRY(pl.desc.alloc(S, s));
+    CUDA_TRY(pl.len.alloc(S, s));
+    CUDA_TRY(pl.worklist.alloc(S, s));
+    CUDA_TRY(pl.point_off.alloc(S + 1, s));
+    if (new_status(ctx, pl.status)) return MDBCU_FAILURE;
+    if (S) LAUNCH(ctx, k_grid_prepare, div_up(S, 256), 256, 0, v, pl.desc.p, pl.len.p, pl.worklist.p, pl.status.p);
+    if (exclusive_scan<uint32_t>(ctx, pl.len.p, S, pl.point_off.p)) return MDBCU_FAILURE;
+    CUDA_TRY(cudaMemcpyAsync(&pl.total, pl.point_off.p + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    if (read_status(ctx, pl.status.p, pl.h_status, "segment row")) return MDBCU_FAILURE;
+    return MDBCU_SUCCESS;
+}
+
+int mdbcu_grid_count(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, uint64_t *point_off, uint64_t *total) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    StagedSegments st;
+    if (stage_segments(ctx, space, segments, st)) return MDBCU_FAILURE;
+    GridPlan pl;
+    if (grid_plan(ctx, st.view, pl)) return MDBCU_FAILURE;
+    if (point_off) {
+        CUDA_TRY(cudaMemcpyAsync(point_off, pl.point_off.p, (st.view.n_segments + 1) * sizeof(uint64_t),
+                                 space == MDBCU_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    }
+    if (total) *total = pl.total;
+    return MDBCU_SUCCESS;
+}
+
+int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, int64_t *timestamps_out, float *values_out,
+               uint64_t capacity, uint64_t *n_points) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    StagedSegments st;
+    if (stage_segments(ctx, space, segments, st)) return MDBCU_FAILURE;
+    GridPlan pl;
+    if (grid_plan(ctx, st.view, pl)) return MDBCU_FAILURE;
+    if (n_points) *n_points = pl.total;
+    if (pl.total > capacity) return fail("grid: batch holds " + std::to_string(pl.total) + " data points, capacity is " + std::to_string(capacity));
+    if (pl.total == 0) return MDBCU_SUCCESS;
+    if (!timestamps_out || !values_out) return fail("grid: output pointer is null");
+    cudaStream_t s = ctx->stream;
+    uint64_t S = st.view.n_segments;
+
+    int64_t *d_ts = timestamps_out;
+    float *d_val = values_out;
+    DBuf<int64_t> ts_buf;
+    DBuf<float> val_buf;
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(ts_buf.alloc(pl.total, s));
+        CUDA_TRY(val_buf.alloc(pl.total, s));
+        d_ts = ts_buf.p;
+        d_val = val_buf.p;
+    }
+    unsigned int n_tiles = div_up(pl.total, TILE);
+    DBuf<uint32_t> tile_first;
+    CUDA_TRY(tile_first.alloc(n_tiles, s));
+    LAUNCH(ctx, k_grid_tile_index, div_up(S, 256), 256, 0, pl.point_off.p, S, tile_first.p);
+    LAUNCH(ctx, k_grid_tile, n_tiles, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, d_ts, d_val);
+    if (pl.h_status.n_seq)
+        LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p,
+               (uint32_t)pl.h_status.n_seq, d_ts, d_val);
+    CUDA_TRY(cudaGetLastError());
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(timestamps_out, d_ts, pl.total * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(values_out, d_val, pl.total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MDBCU_SUCCESS;
+}
+
+// ---- K3 ------------------------------------------------------------------------------------------
+
+int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, float *sums_out) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    StagedSegments st;
+    if (stage_segments(ctx, space, segments, st)) return MDBCU_FAILURE;
+    uint64_t S = st.view.n_segments;
+    if (S == 0) return MDBCU_SUCCESS;
+    if (!sums_out) return fail("segment_sums: output pointer is null");
+    cudaStream_t s = ctx->stream;
+    DBuf<Status> status;
+    if (new_status(ctx, status)) return MDBCU_FAILURE;
+    DBuf<float> sum_buf;
+    float *d_sum = sums_out;
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(sum_buf.alloc(S, s));
+        d_sum = sum_buf.p;
+    }
+    LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, status.p);
+    CUDA_TRY(cudaGetLastError());
+    if (space == MDBCU_HOST) CUDA_TRY(cudaMemcpyAsync(sums_out, d_sum, S * sizeof(float), cudaMemcpyDeviceToHost, s));
+    Status h;
+    return read_status(ctx, status.p, h, "segment row");
+}
+
+int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, const uint64_t *group_off, uint64_t n_groups,
+                    int64_t *count, float *min, float *max, double *sum) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (!group_off) n_groups = 1;
+    if (n_groups == 0) return MDBCU_SUCCESS;
+    if (!count || !min || !max || !sum) return fail("aggregate: output pointer is null");
+    StagedSegments st;
+    if (stage_segments(ctx, space, segments, st)) return MDBCU_FAILURE;
+    uint64_t S = st.view.n_segments;
+    cudaStream_t s = ctx->stream;
+
+    DBuf<uint64_t> group_off_buf;
+    const uint64_t *d_group_off = group_off;
+    if (group_off && space == MDBCU_HOST) {
+        if (group_off[n_groups] > S) return fail("aggregate: group_off exceeds the number of rows");
+        CUDA_TRY(upload(group_off_buf, group_off, n_groups + 1, s));
+        d_group_off = group_off_buf.p;
+    }
+    DBuf<Status> status;
+    if (new_status(ctx, status)) return MDBCU_FAILURE;
+    DBuf<uint64_t> seg_count;
+    DBuf<float> seg_sum;
+    CUDA_TRY(seg_count.alloc(S, s));
+    CUDA_TRY(seg_sum.alloc(S, s));
+    if (S) LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, seg_count.p, seg_sum.p, status.p);
+
+    // parts per group: enough blocks to fill the GPU when there are few large groups
+    uint64_t avg_rows = S / n_groups + 1;
+    uint32_t parts = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(1, avg_rows / 4096));
+    if (n_groups >= (uint64_t)ctx->sm_count * 8) parts = 1;
+    DBuf<GroupAgg> partial;
+    CUDA_TRY(partial.alloc(n_groups * parts, s));
+    dim3 grid(parts, (unsigned int)std::min<uint64_t>(n_groups, 65535));
+    LAUNCH(ctx, k_agg_partial, grid, AGG_THREADS, 0, d_group_off, n_groups, S, parts, seg_count.p, seg_sum.p, st.view.min_value,
+           st.view.max_value, partial.p);
+
+    DBuf<int64_t> count_buf;
+    DBuf<float> min_buf, max_buf;
+    DBuf<double> sum_buf;
+    int64_t *d_count = count;
+    float *d_min = min, *d_max = max;
+    double *d_sum = sum;
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(count_buf.alloc(n_groups, s));
+        CUDA_TRY(min_buf.alloc(n_groups, s));
+        CUDA_TRY(max_buf.alloc(n_groups, s));
+        CUDA_TRY(sum_buf.alloc(n_groups, s));
+        d_count = count_buf.p; d_min = min_buf.p; d_max = max_buf.p; d_sum = sum_buf.p;
+    }
+    LAUNCH(ctx, k_agg_final, div_up(n_groups, AGG_THREADS), AGG_THREADS, 0, partial.p, n_groups, parts, d_count, d_min, d_max, d_sum);
+    CUDA_TRY(cudaGetLastError());
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(cudaMemcpyAsync(count, d_count, n_groups * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(min, d_min, n_groups * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(max, d_max, n_groups * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaMemcpyAsync(sum, d_sum, n_groups * sizeof(double), cudaMemcpyDeviceToHost, s));
+    }
+    Status h;
+    return read_status(ctx, status.p, h, "segment row");
+}
+
+// ---- K1 ------------------------------------------------------------------------------------------
+
+uint64_t mdbcu_segments_len(const mdbcu_segments *segments) { return segments ? segments->n_segments : 0; }
+
+void mdbcu_segments_free(mdbcu_segments *sg) {
+    if (!sg) return;
+    if (sg->ctx) {
+        cudaSetDevice(sg->ctx->device);
+        cudaStream_t s = sg->ctx->stream;
+        void *ptrs[] = {sg->model_type_id, sg->start_time, sg->end_time, sg->min_value, sg->max_value, sg->ts_off, sg->val_off,
+                        sg->res_off, sg->unit_seg_off, sg->ts_data, sg->val_data, sg->res_data};
+        for (void *p : ptrs)
+            if (p) cudaFreeAsync(p, s);
+    }
+    delete sg;
+}
+
+int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_view *view, const uint64_t **unit_seg_off) {
+    if (!sg || !view) return fail("segments or view is null");
+    if (check_ctx(sg->ctx)) return MDBCU_FAILURE;
+    uint64_t S = sg->n_segments;
+    if (space == MDBCU_DEVICE) {
+        view->n_segments = S;
+        view->model_type_id = sg->model_type_id;
+        view->start_time = sg->start_time;
+        view->end_time = sg->end_time;
+        view->min_value = sg->min_value;
+        view->max_value = sg->max_value;
+        view->timestamps_off = sg->ts_off;
+        view->timestamps_data = sg->ts_data;
+        view->values_off = sg->val_off;
+        view->values_data = sg->val_data;
+        view->residuals_off = sg->res_off;
+        view->residuals_data = sg->res_data;
+        if (unit_seg_off) *unit_seg_off = sg->unit_seg_off;
+        return MDBCU_SUCCESS;
+    }
+    if (!sg->have_host) {
+        cudaStream_t s = sg->ctx->stream;
+        CUDA_TRY(download(sg->h_model_type_id, sg->model_type_id, S, s));
+        CUDA_TRY(download(sg->h_start_time, sg->start_time, S, s));
+        CUDA_TRY(download(sg->h_end_time, sg->end_time, S, s));
+        CUDA_TRY(download(sg->h_min_value, sg->min_value, S, s));
+        CUDA_TRY(download(sg->h_max_value, sg->max_value, S, s));
+        CUDA_TRY(download(sg->h_ts_off, sg->ts_off, S + 1, s));
+        CUDA_TRY(download(sg->h_val_off, sg->val_off, S + 1, s));
+        CUDA_TRY(download(sg->h_res_off, sg->res_off, S + 1, s));
+        CUDA_TRY(download(sg->h_unit_seg_off, sg->unit_seg_off, sg->n_units + 1, s));
+        CUDA_TRY(download(sg->h_ts_data, sg->ts_data, sg->ts_bytes, s));
+        CUDA_TRY(download(sg->h_val_data, sg->val_data, sg->val_bytes, s));
+        CUDA_TRY(download(sg->h_res_data, sg->res_data, sg->res_bytes, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        sg->have_host = true;
+    }
+    view->n_segments = S;
+    view->model_type_id = sg->h_model_type_id.data();
+    view->start_time = sg->h_start_time.data();
+    view->end_time = sg->h_end_time.data();
+    view->min_value = sg->h_min_value.data();
+    view->max_value = sg->h_max_value.data();
+    view->timestamps_off = sg->h_ts_off.data();
+    view->timestamps_data = sg->h_ts_data.data();
+    view->values_off = sg->h_val_off.data();
+    view->values_data = sg->h_val_data.data();
+    view->residuals_off = sg->h_res_off.data();
+    view->residuals_data = sg->h_res_data.data();
+    if (unit_seg_off) *unit_seg_off = sg->h_unit_seg_off.data();
+    return MDBCU_SUCCESS;
+}
+
+int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timestamps, const float *values, const uint64_t *unit_off,
+                   uint64_t n_units, const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (!out) return fail("compress: out is null");
+    *out = nullptr;
+    if (n_units > 0xFFFFFFF0ull) return fail("compress: more than 2^32 units");
+    if (n_units && (!unit_off || !eb_kind || !eb_value)) return fail("compress: unit_off / eb_kind / eb_value is null");
+    cudaStream_t s = ctx->stream;
+
+    // total number of points: unit_off[0] .. unit_off[n_units]
+    uint64_t first = 0, last = 0;
+    if (n_units) {
+        if (space == MDBCU_HOST) {
+            first = unit_off[0];
+            last = unit_off[n_units];
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(&first, unit_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(&last, unit_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        if (last < first) return fail("compress: unit_off is not monotone");
+    }
+    uint64_t n_points = last; // arrays are indexed by absolute unit_off values
+    if (n_points && (!timestamps || !values)) return fail("compress: timestamps / values is null");
+
+    DBuf<int64_t> ts_buf;
+    DBuf<float> val_buf;
+    DBuf<uint64_t> off_buf;
+    DBuf<uint8_t> kind_buf;
+    DBuf<float> ebv_buf;
+    const int64_t *d_ts = timestamps;
+    const float *d_val = values;
+    const uint64_t *d_off = unit_off;
+    const uint8_t *d_kind = eb_kind;
+    const float *d_ebv = eb_value;
+    if (space == MDBCU_HOST && n_units) {
+        CUDA_TRY(upload(ts_buf, timestamps, n_points, s));
+        CUDA_TRY(upload(val_buf, values, n_points, s));
+        CUDA_TRY(upload(off_buf, unit_off, n_units + 1, s));
+        CUDA_TRY(upload(kind_buf, eb_kind, n_units, s));
+        CUDA_TRY(upload(ebv_buf, eb_value, n_units, s));
+        d_ts = ts_buf.p; d_val = val_buf.p; d_off = off_buf.p; d_kind = kind_buf.p; d_ebv = ebv_buf.p;
+    }
+
+    mdbcu_segments *sg = new mdbcu_segments();
+    sg->ctx = ctx;
+    sg->n_units = n_units;
+    auto bail = [&](int rc) { mdbcu_segments_free(sg); return rc; };
+#define TRY_SG(expr)                                                                       \
+    do {                                                                                   \
+        cudaError_t e_ = (expr);                                                           \
+        if (e_ != cudaSuccess) {                                                           \
+            fail(std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
+            return bail(MDBCU_FAILURE);                                                    \
+        }                                                                                  \
+    } while (0)
+
+    TRY_SG(cudaMallocAsync((void **)&sg->unit_seg_off, (n_units + 1) * sizeof(uint64_t), s));
+    if (n_units == 0) {
+        TRY_SG(cudaMemsetAsync(sg->unit_seg_off, 0, sizeof(uint64_t), s));
+        TRY_SG(cudaMallocAsync((void **)&sg->ts_off, sizeof(uint64_t), s));
+        TRY_SG(cudaMallocAsync((void **)&sg->val_off, sizeof(uint64_t), s));
+        TRY_SG(cudaMallocAsync((void **)&sg->res_off, sizeof(uint64_t), s));
+        TRY_SG(cudaMemsetAsync(sg->ts_off, 0, sizeof(uint64_t), s));
+        TRY_SG(cudaMemsetAsync(sg->val_off, 0, sizeof(uint64_t), s));
+        TRY_SG(cudaMemsetAsync(sg->res_off, 0, sizeof(uint64_t), s));
+        TRY_SG(cudaStreamSynchronize(s));
+        *out = sg;
+        return MDBCU_SUCCESS;
+    }
+
+    // pass 1: worst-case record table, one chain per unit
+    DBuf<Status> status;
+    if (new_status(ctx, status)) return bail(MDBCU_FAILURE);
+    DBuf<uint64_t> caps, rec_base;
+    TRY_SG(caps.alloc(n_units, s));
+    TRY_SG(rec_base.alloc(n_units + 1, s));
+    LAUNCH(ctx, k_unit_caps, div_up(n_units, 256), 256, 0, d_off, n_units, d_kind, d_ebv, caps.p, status.p);
+    if (exclusive_scan<uint64_t>(ctx, caps.p, n_units, rec_base.p)) return bail(MDBCU_FAILURE);
+    Status h;
+    if (read_status(ctx, status.p, h, "unit (bad unit_off or error bound)")) return bail(MDBCU_FAILURE);
+    uint64_t rec_cap = (n_points - first) / 8 + (n_points - first) / 264 + 2 * n_units;
+    DBuf<SegRecord> recs;
+    DBuf<uint32_t> unit_rows;
+    TRY_SG(recs.alloc(rec_cap, s));
+    TRY_SG(unit_rows.alloc(n_units, s));
+    LAUNCH(ctx, k_compress_fit, div_up(n_units, 32), 32, 0, d_ts, d_val, d_off, n_units, d_kind, d_ebv, rec_base.p, recs.p, unit_rows.p);
+    if (exclusive_scan<uint32_t>(ctx, unit_rows.p, n_units, sg->unit_seg_off)) return bail(MDBCU_FAILURE);
+    uint64_t S = 0;
+    TRY_SG(cudaMemcpyAsync(&S, sg->unit_seg_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaStreamSynchronize(s));
+    TRY_SG(cudaGetLastError());
+    sg->n_segments = S;
+
+    // row metadata in final order + byte offsets of the three binary columns
+    TRY_SG(cudaMallocAsync((void **)&sg->model_type_id, (S ? S : 1) * sizeof(int8_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->start_time, (S ? S : 1) * sizeof(int64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->end_time, (S ? S : 1) * sizeof(int64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->min_value, (S ? S : 1) * sizeof(float), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->max_value, (S ? S : 1) * sizeof(float), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->ts_off, (S + 1) * sizeof(uint64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->val_off, (S + 1) * sizeof(uint64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->res_off, (S + 1) * sizeof(uint64_t), s));
+    DBuf<uint32_t> ts_len, val_len, res_len, row_unit;
+    TRY_SG(ts_len.alloc(S, s));
+    TRY_SG(val_len.alloc(S, s));
+    TRY_SG(res_len.alloc(S, s));
+    TRY_SG(row_unit.alloc(S, s));
+    LAUNCH(ctx, k_compress_gather, div_up(n_units * 32, 256), 256, 0, d_ts, d_off, n_units, rec_base.p, recs.p, sg->unit_seg_off,
+           sg->model_type_id, sg->start_time, sg->end_time, sg->min_value, sg->max_value, ts_len.p, val_len.p, res_len.p, row_unit.p);
+    if (exclusive_scan<uint32_t>(ctx, ts_len.p, S, sg->ts_off)) return bail(MDBCU_FAILURE);
+    if (exclusive_scan<uint32_t>(ctx, val_len.p, S, sg->val_off)) return bail(MDBCU_FAILURE);
+    if (exclusive_scan<uint32_t>(ctx, res_len.p, S, sg->res_off)) return bail(MDBCU_FAILURE);
+    TRY_SG(cudaMemcpyAsync(&sg->ts_bytes, sg->ts_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaMemcpyAsync(&sg->val_bytes, sg->val_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaMemcpyAsync(&sg->res_bytes, sg->res_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaStreamSynchronize(s));
+
+    // pass 2: byte columns
+    TRY_SG(cudaMallocAsync((void **)&sg->ts_data, sg->ts_bytes ? sg->ts_bytes : 1, s));
+    TRY_SG(cudaMallocAsync((void **)&sg->val_data, sg->val_bytes ? sg->val_bytes : 1, s));
+    TRY_SG(cudaMallocAsync((void **)&sg->res_data, sg->res_bytes ? sg->res_bytes : 1, s));
+    if (S)
+        LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, rec_base.p, recs.p, sg->unit_seg_off, row_unit.p, S,
+               sg->ts_off, sg->ts_data, sg->val_off, sg->val_data, sg->res_off, sg->res_data);
+    TRY_SG(cudaGetLastError());
+    TRY_SG(cudaStreamSynchronize(s));
+#undef TRY_SG
+    *out = sg;
+    return MDBCU_SUCCESS;
+}
+
+} // extern "C"
