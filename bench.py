@@ -1,0 +1,472 @@
+#!/usr/bin/env python
+"""Benchmark of the ModelarDB hot path on B200: compress -> grid -> aggregate of synthetic multi-series data.
+
+Workload (BASELINE.json configs[1]): time series of 1 M f32 points each (sine + noise, regular 1 ms
+timestamps at epoch scale), 1 % relative error bound, compress + full grid decompression (+ the
+model aggregates GROUP BY series).  The 10 000-series table (10^10 points, 120 GB raw) does not fit
+one GPU next to its own reconstruction, so it is streamed in slabs of --series series; one "step" is
+one slab through compress -> grid -> aggregate.  With --gpus N every rank processes its own slab
+(weak scaling, series are independent; only the per-series aggregates are gathered over NCCL).
+
+One JSON line is printed by rank 0 (see the driver contract in the task statement):
+  value     data points/s with inputs resident in HBM (device space of the C-ABI)
+  e2e       the same through the C-ABI with HOST buffers (pinned), H2D/D2H inside the timed region
+  roofline  the dominant kernel against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle (a C++ port of the reference's Rust) on this box's host cores, bounded sample
+
+`--impl reference` times that CPU port alone with all host threads on the same workload shape.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+EPOCH_US = 1_600_000_000_000_000
+STEP_US = 1000
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=5)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--series", type=int, default=1000, help="series per slab (per GPU)")
+    p.add_argument("--points", type=int, default=1_000_000, help="points per series")
+    p.add_argument("--eb", default="rel:1.0", help="lossless | abs:X | rel:X")
+    p.add_argument("--units", default="series", choices=["series", "buffers"],
+                   help="series: one compress unit per series (bulk / embedded path); "
+                        "buffers: 65 536-point buffers (server ingestion path)")
+    p.add_argument("--kind", default="sine", choices=["sine", "walk"])
+    p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
+    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    return p.parse_args()
+
+
+def parse_eb(text):
+    if text == "lossless":
+        return (0, 0.0)
+    kind, val = text.split(":")
+    return ({"abs": 1, "rel": 2}[kind], float(val))
+
+
+# ----------------------------------------------------------------------------------------------- data
+
+def gen_values_device(torch, n_series, n_points, seed, kind, device):
+    """Per-series sine + noise (or random walk) as f32, generated on the device in chunks of series."""
+    out = torch.empty(n_series * n_points, dtype=torch.float32, device=device)
+    g = torch.Generator(device=device).manual_seed(seed)
+    i = torch.arange(n_points, device=device, dtype=torch.float64)
+    chunk = max(1, min(n_series, (64 << 20) // max(1, n_points)))
+    for s0 in range(0, n_series, chunk):
+        k = min(chunk, n_series - s0)
+        if kind == "sine":
+            base = 50.0 + 100.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            amp = 1.0 + 19.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            period = 500.0 + 1500.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            phase = 6.28 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            v = base + amp * torch.sin(2.0 * torch.pi * i / period + phase)
+            v += 0.1 * torch.randn(k, n_points, device=device, generator=g, dtype=torch.float64)
+        else:
+            v = 100.0 + torch.cumsum(torch.randn(k, n_points, device=device, generator=g, dtype=torch.float64), dim=1)
+        out[s0 * n_points:(s0 + k) * n_points] = v.to(torch.float32).reshape(-1)
+        del v
+    return out
+
+
+def gen_values_host(n_series, n_points, seed, kind):
+    from modelardb_rs_b200 import synthetic as syn
+    rng = np.random.default_rng(seed)
+    out = np.empty(n_series * n_points, np.float32)
+    for s in range(n_series):
+        sl = slice(s * n_points, (s + 1) * n_points)
+        if kind == "sine":
+            out[sl] = syn.sine_noise(n_points, seed + s, base=float(rng.uniform(50, 150)), amp=float(rng.uniform(1, 20)),
+                                     period=float(rng.uniform(500, 2000)), phase=float(rng.uniform(0, 6.28)))
+        else:
+            out[sl] = syn.random_walk(n_points, seed + s)
+    return out
+
+
+def unit_offsets(n_series, n_points, units):
+    from modelardb_rs_b200.compression import split_into_buffers
+    if units == "series":
+        return (np.arange(n_series + 1, dtype=np.uint64) * np.uint64(n_points)).astype(np.uint64)
+    return split_into_buffers([n_points] * n_series)
+
+
+# ----------------------------------------------------------------------------------------------- clocks
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ----------------------------------------------------------------------------------------------- CPU arm
+
+def cpu_port_throughput(n_series, n_points, eb, kind, units, threads, seed=4242):
+    """Times the CPU port of the reference (the oracle) on `n_series` series: compress -> grid -> aggregate,
+    series partitioned statically over `threads` threads.  Returns (points/s, per-stage seconds)."""
+    from oracle import mdb_oracle as oracle
+    vals = gen_values_host(n_series, n_points, seed, kind)
+    ts = np.tile(EPOCH_US + STEP_US * np.arange(n_points, dtype=np.int64), n_series)
+    off = unit_offsets(n_series, n_points, units)
+    t0 = time.perf_counter()
+    seg = oracle.compress(ts, vals, off, eb=eb, n_threads=threads)
+    t1 = time.perf_counter()
+    oracle.grid(seg, n_threads=threads)
+    t2 = time.perf_counter()
+    oracle.aggregate(seg, seg.unit_seg_off, n_threads=threads)
+    t3 = time.perf_counter()
+    n = n_series * n_points
+    return n / (t3 - t0), {"compress_s": t1 - t0, "grid_s": t2 - t1, "aggregate_s": t3 - t2}
+
+
+def cpu_sample_size(n_points, threads, budget_s):
+    # the port does ~8 M points/s/thread over compress+grid+aggregate; one series per thread at least
+    per_thread_points = 6e6 * budget_s
+    k = max(1, int(per_thread_points // n_points))
+    return threads * k
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's own algorithm on the host cores.  The reference is Rust and cannot
+    be built in this image (no cargo/rustc), so this is its C++ port (oracle/), all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    eb = parse_eb(args.eb)
+    threads = os.cpu_count() or 1
+    n_series = cpu_sample_size(args.points, threads, min(args.cpu_seconds, 15.0))
+    # bounded: each step is ~15 s of CPU work, so cap the number of steps to keep the run to a few minutes
+    warm, steps = min(args.warmup, 1), min(args.steps, 5)
+    times = []
+    stages = None
+    for step in range(warm + steps):
+        rate, stages = cpu_port_throughput(n_series, args.points, eb, args.kind, args.units, threads, seed=4242 + step)
+        if step >= warm:
+            times.append(n_series * args.points / rate)
+    ms = 1000.0 * sum(times) / len(times)
+    value = n_series * args.points / (ms / 1000.0)
+    sample = f"{n_series} series x {args.points} points per step ({args.eb}, units={args.units})"
+    line = {
+        "impl": "reference", "metric": "compress+grid+aggregate data points/s", "value": value, "unit": "points/s",
+        "n_gpus": args.gpus, "steps": len(times), "warmup": warm, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 values, f64 fitting, i64 timestamps",
+        "data": "synthetic",
+        "config": workload_config(args, per_gpu_series=n_series),
+        "cpu_baseline": {"value": value, "unit": "points/s", "cores": threads, "kind": "port", "sample": sample,
+                         "stages_s": stages},
+        "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, per_gpu_series):
+    return {
+        "workload": f"BASELINE.json configs[1] streamed in slabs: {per_gpu_series} series x {args.points} points per GPU per step, "
+                    f"{args.kind}+noise f32, regular 1 ms timestamps, error bound {args.eb}, compress + full grid + aggregates GROUP BY series",
+        "series_per_gpu_per_step": per_gpu_series, "points_per_series": args.points, "error_bound": args.eb,
+        "compress_units": args.units, "l2": "inputs (12 B/point x slab) far larger than the 126 MB L2; no flush needed",
+        "parallelism": f"series sharded over {args.gpus} GPU(s), no data-path collective; per-series aggregates all-gathered",
+    }
+
+
+# ----------------------------------------------------------------------------------------------- GPU arm
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from modelardb_rs_b200 import compression as mc
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path has no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    device = f"cuda:{local_rank}"
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device(device))
+
+    eb_t = parse_eb(args.eb)
+    eb = mc.ErrorBound(*eb_t)
+    n_series, n_points = args.series, args.points
+    n = n_series * n_points
+
+    ctx = mc.Context(local_rank)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=device)
+
+    # ---- inputs resident in HBM
+    vals = gen_values_device(torch, n_series, n_points, 1000 + rank, args.kind, device)
+    ts = (EPOCH_US + STEP_US * torch.arange(n_points, device=device, dtype=torch.int64)).repeat(n_series)
+    off_np = unit_offsets(n_series, n_points, args.units)
+    off = torch.from_numpy(off_np.astype(np.int64)).to(device)
+    n_units = len(off_np) - 1
+    kinds = torch.full((n_units,), eb.kind, dtype=torch.uint8, device=device)
+    ebv = torch.full((n_units,), eb.value, dtype=torch.float32, device=device)
+    series_group_off = None  # group rows by series = by unit (units=series) or by runs of units
+    ts_out = torch.empty(n, dtype=torch.int64, device=device)
+    val_out = torch.empty(n, dtype=torch.float32, device=device)
+    torch.cuda.synchronize()
+
+    stage_ms = {"compress": [], "grid": [], "aggregate": []}
+    seg_bytes_last = [0, 0]
+
+    def step(record):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+        ev[0].record(stream)
+        seg = mc.compress(ts, vals, off, (kinds, ebv), ctx)
+        ev[1].record(stream)
+        mc.grid(seg, ts_out, val_out, ctx)
+        ev[2].record(stream)
+        if args.units == "series":
+            group = (seg.unit_seg_off_device_ptr(), n_units)
+        else:
+            group = series_group_off_of(seg)
+        count, mn, mx, sm = mc.aggregate(seg, group, ctx)
+        if world > 1:  # only the per-series aggregate partials travel (disjoint groups -> all-gather)
+            with torch.cuda.stream(stream):
+                for t in (count, mn, mx, sm):
+                    g = torch.empty(world * t.numel(), dtype=t.dtype, device=device)
+                    dist.all_gather_into_tensor(g, t)
+        ev[3].record(stream)
+        if record:
+            ev[3].synchronize()
+            stage_ms["compress"].append(ev[0].elapsed_time(ev[1]))
+            stage_ms["grid"].append(ev[1].elapsed_time(ev[2]))
+            stage_ms["aggregate"].append(ev[2].elapsed_time(ev[3]))
+            h = seg.to_host() if not seg_bytes_last[0] else None
+            if h is not None:
+                seg_bytes_last[0] = h.segment_bytes()
+                seg_bytes_last[1] = len(h)
+        seg.free()
+        return count
+
+    def series_group_off_of(seg):
+        # units=buffers: a series is a run of consecutive units; its rows are [uso[first unit], uso[last unit + 1])
+        per_series = n_units // n_series
+        idx = torch.arange(0, n_units + 1, per_series, device=device)
+        # view the library-owned array through torch without copying it to the host
+        uso = _wrap_device_i64(torch, seg.unit_seg_off_device_ptr(), n_units + 1, device)
+        with torch.cuda.stream(stream):
+            return uso[idx].contiguous()
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step(True)
+    e1.record(stream)
+    e1.synchronize()
+    barrier()
+    clock_info = clocks.stop()
+    total_ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    kstats = ctx.kernel_stats()
+    ctx.set_profiling(False)
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = float(t.item())
+    ms_per_step = total_ms / args.steps
+    value = world * n * args.steps / (total_ms / 1000.0)
+
+    # ---- e2e: same path through the C-ABI with HOST (pinned) buffers
+    e2e = None
+    if not args.no_e2e:
+        es, esteps = min(args.e2e_series, n_series), args.e2e_steps
+        en = es * n_points
+        h_ts = torch.empty(en, dtype=torch.int64).pin_memory()
+        h_vals = torch.empty(en, dtype=torch.float32).pin_memory()
+        h_ts.copy_(ts[:en])
+        h_vals.copy_(vals[:en])
+        h_ts_out = torch.empty(en, dtype=torch.int64).pin_memory()
+        h_val_out = torch.empty(en, dtype=torch.float32).pin_memory()
+        e_off = unit_offsets(es, n_points, args.units)
+        e_units = len(e_off) - 1
+        e_group = e_off_group = None
+        if args.units == "series":
+            e_group_sel = None
+        h2d = d2h = 0
+
+        def e2e_step():
+            nonlocal h2d, d2h
+            seg = mc.compress(h_ts.numpy(), h_vals.numpy(), e_off, [eb] * e_units, ctx)
+            host_seg = seg.to_host()                      # what the Rust caller gets back: the RecordBatch columns
+            seg.free()
+            mc.grid(host_seg, h_ts_out.numpy(), h_val_out.numpy(), ctx)
+            uso = host_seg.unit_seg_off
+            group = uso if args.units == "series" else uso[:: (e_units // es)]
+            res = mc.aggregate(host_seg, group, ctx)
+            seg_b = host_seg.segment_bytes() + 3 * 8 * (len(host_seg) + 1)
+            h2d = 12 * en + 2 * seg_b                      # raw points in; segments in again for grid and aggregate
+            d2h = seg_b + 12 * en + 24 * len(res[0])       # segments out; reconstructed points out; aggregates out
+            return res
+
+        for _ in range(1):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(esteps):
+            e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * en * esteps / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "series_per_gpu_per_step": es, "steps": esteps,
+               "note": "numpy views of pinned host tensors passed to the C-ABI in MDBCU_HOST space; wall clock, max over ranks"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy bandwidth)"
+    else:
+        peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (6.65 TB/s)"
+    seg_bytes, n_rows = seg_bytes_last
+    algo_bytes = {  # per launch
+        "k_compress_fit": 12 * n + 48 * n_rows,       # reads every point once; writes one 48 B record per row
+        "k_grid_tile": seg_bytes + 12 * n,            # reads the segments; writes 12 B per point
+        "k_grid_sequential": seg_bytes + 12 * n,
+        "k_agg_segments": seg_bytes,
+        "k_compress_emit": seg_bytes,
+    }
+    dominant = max(kstats.items(), key=lambda kv: kv[1][0])[0] if kstats else None
+    roofline = None
+    if dominant:
+        ms, cnt = kstats[dominant]
+        avg_ms = ms / max(1, cnt)
+        ab = algo_bytes.get(dominant, 12 * n)
+        achieved = ab / (avg_ms / 1000.0) / 1e9
+        roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": None, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms, "peak_source": peak_src,
+                    "kernel_share_of_step": ms / total_ms,
+                    "all_kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][0])}}
+        for k in ("k_grid_tile", "k_compress_fit"):
+            if k in kstats and kstats[k][1]:
+                a = algo_bytes[k] / (kstats[k][0] / kstats[k][1] / 1000.0) / 1e9
+                roofline[f"{k}_GBps"] = a
+                roofline[f"{k}_frac"] = a / peak
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        cs = cpu_sample_size(n_points, threads, args.cpu_seconds)
+        rate, stages = cpu_port_throughput(cs, n_points, eb_t, args.kind, args.units, threads)
+        cpu_baseline = {"value": rate, "unit": "points/s", "cores": threads, "kind": "port",
+                        "sample": f"{cs} series x {n_points} points, one pass compress+grid+aggregate, series split over {threads} threads "
+                                  f"(the reference itself compresses on 1 thread: configuration.rs:116-129)",
+                        "stages_s": stages}
+
+    med = {k: statistics.median(v) for k, v in stage_ms.items() if v}
+    line = {
+        "metric": "compress+grid+aggregate data points/s", "value": value, "unit": "points/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32 values, f64 fitting, i64 timestamps", "data": "synthetic",
+        "config": workload_config(args, n_series),
+        "stage_ms_median": med,
+        "stage_points_per_s": {k: world * n / (v / 1000.0) for k, v in med.items()},
+        "segments": {"rows_per_slab": n_rows, "segment_bytes_per_point": seg_bytes / n if n else None,
+                     "compression_ratio": 12 * n / seg_bytes if seg_bytes else None},
+        "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _wrap_device_i64(torch, ptr, n, device):
+    """A torch view of a library-owned device array (no copy), via the CUDA array interface."""
+    class _Arr:
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, True), "version": 2}
+    return torch.as_tensor(_Arr(), device=device)
+
+
+if __name__ == "__main__":
+    main()

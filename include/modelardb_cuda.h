@@ -95,6 +95,14 @@ int mdbcu_context_set_stream(mdbcu_context *ctx, void *cuda_stream);
 void *mdbcu_context_stream(mdbcu_context *ctx);
 /* Number of kernels this context has launched since it was created. */
 uint64_t mdbcu_context_launch_count(const mdbcu_context *ctx);
+/* Per-kernel device time: while enabled every launch is bracketed by CUDA events on the context's
+ * stream (enabling also clears the table).  This is the analogue of the EXPLAIN ANALYZE counters
+ * GridExec keeps (crates/modelardb_storage/src/query/grid_exec.rs:441-519). */
+int mdbcu_context_set_profiling(mdbcu_context *ctx, int enabled);
+/* Entry `index` of the table: kernel name, summed device milliseconds, number of launches.
+ * Fails when index is past the end (iterate from 0 until failure). */
+int mdbcu_context_kernel_stat(mdbcu_context *ctx, uint32_t index, const char **name, double *total_ms,
+                              uint64_t *launches);
 
 /* ---- K1: compress -------------------------------------------------------------------------- */
 

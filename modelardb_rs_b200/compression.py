@@ -98,6 +98,22 @@ class Context:
     def launch_count(self) -> int:
         return _native.lib().mdbcu_context_launch_count(self._h)
 
+    def set_profiling(self, enabled: bool):
+        _native.check(_native.lib().mdbcu_context_set_profiling(self._h, 1 if enabled else 0))
+
+    def kernel_stats(self) -> dict:
+        """{kernel name: (total device ms, launches)} since profiling was enabled."""
+        out = {}
+        i = 0
+        L = _native.lib()
+        while True:
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_uint64()
+            if L.mdbcu_context_kernel_stat(self._h, i, C.byref(name), C.byref(ms), C.byref(n)) != 0:
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            i += 1
+        return out
+
 
 _default_contexts = {}
 
@@ -216,6 +232,10 @@ def _space_of(*arrays) -> int:
                 raise ValueError("torch tensors must live on the GPU; pass numpy arrays for host memory")
             if a is not None and not a.is_contiguous():
                 raise ValueError("tensors must be contiguous")
+        # the context launches on its own non-blocking stream: whatever produced these tensors on
+        # torch's current stream must have finished before the library reads them
+        import torch
+        torch.cuda.current_stream().synchronize()
         return DEVICE
     return HOST
 
@@ -300,7 +320,8 @@ def grid_count(segments, ctx: Optional[Context] = None):
         off = np.zeros(v.n_segments + 1, np.uint64)
     else:
         import torch
-        off = torch.zeros(v.n_segments + 1, dtype=torch.int64, device=f"cuda:{ctx.device}")
+        # torch.empty, never torch.zeros: a fill kernel on torch's stream is unordered w.r.t. the context's stream
+        off = torch.empty(v.n_segments + 1, dtype=torch.int64, device=f"cuda:{ctx.device}")
     _native.check(_native.lib().mdbcu_grid_count(ctx._h, space, C.byref(v), _ptr(off), C.byref(total)))
     return off, total.value
 
@@ -355,10 +376,10 @@ def aggregate(segments, group_off=None, ctx: Optional[Context] = None):
     else:
         import torch
         dev = f"cuda:{ctx.device}"
-        count = torch.zeros(g, dtype=torch.int64, device=dev)
-        mn = torch.zeros(g, dtype=torch.float32, device=dev)
-        mx = torch.zeros(g, dtype=torch.float32, device=dev)
-        sm = torch.zeros(g, dtype=torch.float64, device=dev)
+        count = torch.empty(g, dtype=torch.int64, device=dev)
+        mn = torch.empty(g, dtype=torch.float32, device=dev)
+        mx = torch.empty(g, dtype=torch.float32, device=dev)
+        sm = torch.empty(g, dtype=torch.float64, device=dev)
     gp = group_off if isinstance(group_off, int) else _ptr(group_off)
     _native.check(_native.lib().mdbcu_aggregate(ctx._h, space, C.byref(v), gp, g if group_off is not None else 1,
                                                 _ptr(count), _ptr(mn), _ptr(mx), _ptr(sm)))

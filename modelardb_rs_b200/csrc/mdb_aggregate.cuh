@@ -72,10 +72,10 @@ MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &coun
         model_sum = macaque_v_sum(r.values, r.n_values, model_length, false, 0.0f);
     }
     count = length;
-    if (r.n_residuals == 0) { sum = model_sum; return true; }
+    if (r.n_residuals == 0) { sum = canonical_nan(model_sum); return true; }
     // models/mod.rs:173-183: residuals are seeded with the DECODED model last value here (quirk Q1)
     float residuals_sum = macaque_v_sum(r.residuals, r.n_residuals - 1, res_len, true, model_last_value);
-    sum = __fadd_rn(model_sum, residuals_sum);
+    sum = canonical_nan(__fadd_rn(model_sum, residuals_sum));
     return true;
 }
 

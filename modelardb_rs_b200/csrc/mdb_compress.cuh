@@ -63,7 +63,7 @@ struct PMCMean { // pmc_mean.rs:31-93
         }
         return false;
     }
-    MDB_DEV float model() const { return __double2float_rn(__ddiv_rn(sum_of_values, (double)length)); }
+    MDB_DEV float model() const { return canonical_nan(__double2float_rn(__ddiv_rn(sum_of_values, (double)length))); }
 };
 
 struct Swing { // swing.rs:34-259
@@ -133,8 +133,8 @@ struct Swing { // swing.rs:34-259
         double projected = __ddiv_rn(mse_numerator, mse_denominator);
         double slope = rust_maxd(lower_slope, rust_mind(projected, upper_slope));
         double last = __dadd_rn(__dmul_rn(slope, (double)(end_time - start_time)), first_value);
-        first_out = __double2float_rn(first_value);
-        last_out = __double2float_rn(last);
+        first_out = canonical_nan(__double2float_rn(first_value));
+        last_out = canonical_nan(__double2float_rn(last));
     }
 };
 

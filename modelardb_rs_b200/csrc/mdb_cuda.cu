@@ -44,18 +44,72 @@ static int fail(const std::string &msg) {
             return fail(std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
     } while (0)
 
+struct KernelStat {
+    std::string name;
+    double ms = 0.0;
+    uint64_t launches = 0;
+};
+
+struct PendingTiming {
+    size_t stat;
+    cudaEvent_t start, stop;
+};
+
 struct mdbcu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
+    // optional per-kernel CUDA-event timing (mdbcu_context_set_profiling)
+    bool profiling = false;
+    std::vector<KernelStat> stats;
+    std::vector<PendingTiming> pending;
+    std::vector<cudaEvent_t> event_pool;
+
+    size_t stat_index(const char *name) {
+        for (size_t i = 0; i < stats.size(); i++)
+            if (stats[i].name == name) return i;
+        stats.push_back(KernelStat{name});
+        return stats.size() - 1;
+    }
+    cudaEvent_t get_event() {
+        if (!event_pool.empty()) {
+            cudaEvent_t e = event_pool.back();
+            event_pool.pop_back();
+            return e;
+        }
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        return e;
+    }
+    void resolve_timings() { // caller has synchronised the stream
+        for (PendingTiming &p : pending) {
+            float ms = 0.0f;
+            if (cudaEventElapsedTime(&ms, p.start, p.stop) == cudaSuccess) stats[p.stat].ms += ms;
+            event_pool.push_back(p.start);
+            event_pool.push_back(p.stop);
+        }
+        pending.clear();
+    }
 };
 
-#define LAUNCH(ctx, kernel, grid, block, smem, ...)                      \
-    do {                                                                 \
-        kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
-        (ctx)->launches++;                                               \
+#define LAUNCH(ctx, kernel, grid, block, smem, ...)                          \
+    do {                                                                     \
+        if ((ctx)->profiling) {                                              \
+            PendingTiming pt_;                                               \
+            pt_.stat = (ctx)->stat_index(#kernel);                           \
+            pt_.start = (ctx)->get_event();                                  \
+            pt_.stop = (ctx)->get_event();                                   \
+            cudaEventRecord(pt_.start, (ctx)->stream);                       \
+            kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+            cudaEventRecord(pt_.stop, (ctx)->stream);                        \
+            (ctx)->stats[pt_.stat].launches++;                               \
+            (ctx)->pending.push_back(pt_);                                   \
+        } else {                                                             \
+            kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__); \
+        }                                                                    \
+        (ctx)->launches++;                                                   \
     } while (0)
 
 // Stream-ordered device buffer (cudaMallocAsync: after warm-up this is a pool hit, not a driver call).
@@ -643,6 +697,26 @@ int mdbcu_context_set_stream(mdbcu_context *ctx, void *cuda_stream) {
 void *mdbcu_context_stream(mdbcu_context *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 uint64_t mdbcu_context_launch_count(const mdbcu_context *ctx) { return ctx ? ctx->launches : 0; }
+
+int mdbcu_context_set_profiling(mdbcu_context *ctx, int enabled) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->resolve_timings();
+    ctx->profiling = enabled != 0;
+    if (enabled) ctx->stats.clear();
+    return MDBCU_SUCCESS;
+}
+
+int mdbcu_context_kernel_stat(mdbcu_context *ctx, uint32_t index, const char **name, double *total_ms, uint64_t *launches) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    ctx->resolve_timings();
+    if (index >= ctx->stats.size()) return fail("kernel stat index out of range");
+    if (name) *name = ctx->stats[index].name.c_str();
+    if (total_ms) *total_ms = ctx->stats[index].ms;
+    if (launches) *launches = ctx->stats[index].launches;
+    return MDBCU_SUCCESS;
+}
 
 // ---- K2 ------------------------------------------------------------------------------------------
 

@@ -34,6 +34,13 @@ MDB_DEV float rust_maxf(float a, float b) { return (a != a) ? b : (b > a ? b : a
 MDB_DEV double rust_mind(double a, double b) { return (a != a) ? b : (b < a ? b : a); }
 MDB_DEV double rust_maxd(double a, double b) { return (a != a) ? b : (b > a ? b : a); }
 
+// The sign and payload of a NaN PRODUCED BY ARITHMETIC are unspecified in Rust and differ between x86
+// SSE (propagates the quieted operand, 0x7fc00000 for the usual input NaN) and the GPU (0x7fffffff).
+// Model parameters and sums that come out NaN are canonicalised to 0x7fc00000, which is what the
+// reference yields on x86-64 for default-NaN inputs; NaNs that are bit COPIES of input values
+// (MacaqueV-coded values) keep their payload exactly.
+MDB_DEV float canonical_nan(float x) { return (x != x) ? __uint_as_float(0x7fc00000u) : x; }
+
 // models/mod.rs:92-95
 MDB_DEV bool equal_or_nan(double a, double b) { return a == b || (a != a && b != b); }
 MDB_DEV bool equal_or_nanf(float a, float b) { return a == b || (a != a && b != b); }

@@ -58,6 +58,11 @@ def small_cases():
                    1.0, np.nan, 3.0, np.float32(1e-45), np.float32(-1e-45), 3.4e38, -3.4e38] * 20, np.float32)
     for eb in (LOSSLESS, (1, 1.0), (2, 10.0)):
         cases.append((f"specials-eb{eb}", syn.regular_timestamps(len(sp)), sp, np.array([0, len(sp)], np.uint64), [eb]))
+    # runs long enough for a model of NaN / inf / -0.0 to be stored (PMC-Mean and Swing special paths)
+    runs = np.concatenate([np.full(12, np.nan), np.full(9, np.inf), np.full(10, -np.inf), np.full(8, -0.0),
+                           np.full(8, 0.0), [1.0, 2.0, 3.0], np.full(20, np.nan), [5.0], np.full(8, np.inf)]).astype(np.float32)
+    for eb in (LOSSLESS, (1, 1.0), (2, 10.0)):
+        cases.append((f"special-runs-eb{eb}", syn.regular_timestamps(len(runs)), runs, np.array([0, len(runs)], np.uint64), [eb]))
     # a model followed by > 255 incompressible points -> separate MacaqueV row (compression.rs:329-349)
     v = np.concatenate([np.full(50, 7.0, np.float32), rng.uniform(-1e6, 1e6, 700).astype(np.float32),
                         np.full(50, 9.0, np.float32), rng.uniform(-1e6, 1e6, 255).astype(np.float32),
@@ -90,8 +95,14 @@ def assert_segments_equal(a, b, where=""):
         assert np.array_equal(a.unit_seg_off, b.unit_seg_off), f"{where}: unit_seg_off differs"
 
 
-def assert_f32_bits_equal(x, y, where=""):
-    x, y = np.asarray(x, np.float32).view(np.uint32), np.asarray(y, np.float32).view(np.uint32)
+def assert_f32_bits_equal(x, y, where="", nan_payload_matters=True):
+    """Bit-pattern equality.  nan_payload_matters=False is for values PRODUCED BY ARITHMETIC (sums): there
+    the sign/payload of a NaN is unspecified in Rust and hardware-dependent, so NaN == NaN."""
+    x, y = np.asarray(x, np.float32).copy(), np.asarray(y, np.float32).copy()
+    if not nan_payload_matters:
+        x[np.isnan(x)] = np.float32(np.nan)
+        y[np.isnan(y)] = np.float32(np.nan)
+    x, y = x.view(np.uint32), y.view(np.uint32)
     assert len(x) == len(y), f"{where}: length {len(x)} vs {len(y)}"
     if not np.array_equal(x, y):
         bad = np.flatnonzero(x != y)

@@ -26,7 +26,7 @@ def test_compress_grid_aggregate_bodies_match_oracle(oracle, case):
 
     wsum = oracle.segment_sums(want)
     gsum, gcount = emu.segment_sums(want)
-    assert_f32_bits_equal(gsum, wsum, name + " segment sums")
+    assert_f32_bits_equal(gsum, wsum, name + " segment sums", nan_payload_matters=False)
     assert np.array_equal(gcount, np.diff(woff))
 
     wc, wmn, wmx, wsm = oracle.aggregate(want, want.unit_seg_off)
