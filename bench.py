@@ -411,7 +411,7 @@ def main():
         peak, peak_src = 6650.0, "fallback of B200_PROFILING.md (6.65 TB/s)"
     seg_bytes, n_rows = seg_bytes_last
     algo_bytes = {  # per launch
-        "k_compress_fit": 12 * n + 48 * n_rows,       # reads every point once; writes one 48 B record per row
+        "k_spec_chain": 12 * n + 28 * n_rows,         # reads every point once; writes one 28 B model per accepted model
         "k_grid_tile": seg_bytes + 12 * n,            # reads the segments; writes 12 B per point
         "k_grid_sequential": seg_bytes + 12 * n,
         "k_agg_segments": seg_bytes,
@@ -428,7 +428,7 @@ def main():
                     "traffic": None, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms, "peak_source": peak_src,
                     "kernel_share_of_step": ms / total_ms,
                     "all_kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][0])}}
-        for k in ("k_grid_tile", "k_compress_fit"):
+        for k in ("k_grid_tile", "k_spec_chain"):
             if k in kstats and kstats[k][1]:
                 a = algo_bytes[k] / (kstats[k][0] / kstats[k][1] / 1000.0) / 1e9
                 roofline[f"{k}_GBps"] = a
@@ -452,6 +452,7 @@ def main():
         "config": workload_config(args, n_series),
         "stage_ms_median": med,
         "stage_points_per_s": {k: world * n / (v / 1000.0) for k, v in med.items()},
+        "compress_chain_rounds": ctx.last_compress_rounds,
         "segments": {"rows_per_slab": n_rows, "segment_bytes_per_point": seg_bytes / n if n else None,
                      "compression_ratio": 12 * n / seg_bytes if seg_bytes else None},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
@@ -464,7 +465,7 @@ def main():
 def _wrap_device_i64(torch, ptr, n, device):
     """A torch view of a library-owned device array (no copy), via the CUDA array interface."""
     class _Arr:
-        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, True), "version": 2}
+        __cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
     return torch.as_tensor(_Arr(), device=device)
 
 

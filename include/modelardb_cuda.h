@@ -116,6 +116,13 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
                    const float *values, const uint64_t *unit_off, uint64_t n_units,
                    const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out);
 
+/* Tuning / diagnostics of the parallel segmentation.  Every unit is cut into chunks that run their
+ * greedy chains concurrently and are stitched by a fixpoint that reproduces the sequential chain
+ * exactly (csrc/mdb_compress.cuh); results never depend on the chunk length.  0 = automatic. */
+int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len);
+/* Number of chain rounds the last mdbcu_compress on this context needed (1 = no re-run at all). */
+uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
+
 uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
 /* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off
  * (nullable) receives a pointer to n_units + 1 row offsets: unit u produced rows

@@ -98,6 +98,14 @@ class Context:
     def launch_count(self) -> int:
         return _native.lib().mdbcu_context_launch_count(self._h)
 
+    def set_chunk_len(self, chunk_len: int):
+        """Chunk length of the parallel segmentation (0 = automatic); results never depend on it."""
+        _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
+
+    @property
+    def last_compress_rounds(self) -> int:
+        return _native.lib().mdbcu_context_last_compress_rounds(self._h)
+
     def set_profiling(self, enabled: bool):
         _native.check(_native.lib().mdbcu_context_set_profiling(self._h, 1 if enabled else 0))
 

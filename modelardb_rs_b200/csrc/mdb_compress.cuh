@@ -4,9 +4,10 @@
 // segmenter: segment k+1 starts where segment k ended, and a rejected start index is re-fitted from
 // the next index.  One unit (one call of the reference function) is therefore one chain; units are
 // independent.  The work is split in two so that the byte columns can be allocated exactly:
-//   pass 1  compress_fit_unit:   runs the chain, writes one fixed-size SegRecord per segment row
-//                                (model, boundaries, metadata, and the byte LENGTH of each of the
-//                                three binary columns, obtained by running the encoders on a counter);
+//   pass 1  spec_chain ...:      runs the chain (in parallel over chunks, see below) and turns the
+//                                accepted models into one fixed-size SegRecord per segment row (model,
+//                                boundaries, metadata, and the byte LENGTH of each of the three binary
+//                                columns, obtained by running the encoders on a counter);
 //   pass 2  compress_emit_segment: one thread per segment row re-runs the encoders on a writer at the
 //                                offsets given by an exclusive scan of those lengths.
 #pragma once
@@ -151,27 +152,35 @@ struct FittedModel { // CompressedSegmentBuilder, types.rs:148-166
 struct RegularityTracker {
     uint32_t max_seen;   // highest index visited so far
     int64_t ts_max_seen; // its timestamp
-    int64_t delta0;
+    int64_t delta0;      // the unit's first sampling interval, ts[1] - ts[0]
     bool irregular;
-    MDB_DEV void init(const int64_t *ts) { max_seen = 0; ts_max_seen = ts[0]; delta0 = 0; irregular = false; }
+    // A chain that starts at index `first` of a unit of n points.
+    MDB_DEV void init(const int64_t *ts, uint32_t first, uint32_t n) {
+        max_seen = first;
+        ts_max_seen = ts[first];
+        delta0 = n >= 2 ? ts[1] - ts[0] : 0;
+        irregular = first > 0 && (ts_max_seen - ts[first - 1]) != delta0;
+    }
     MDB_DEV void visit(uint32_t i, int64_t t) { // visits are contiguous: i <= max_seen + 1
         if (i <= max_seen) return;
-        int64_t delta = t - ts_max_seen;
-        if (i == 1) delta0 = delta;
-        else if (delta != delta0) irregular = true;
+        if (t - ts_max_seen != delta0) irregular = true;
         max_seen = i;
         ts_max_seen = t;
     }
 };
 
-// fit_next_model (compression.rs:280-301) + ModelBuilder (types.rs:61-144).
+// fit_next_model (compression.rs:280-301) + ModelBuilder (types.rs:61-144).  A fit that is still
+// growing when it reaches `budget_end` (< n) is abandoned (aborted = true): only speculative chains are
+// given a budget, see spec_chain.
 MDB_DEV FittedModel fit_next_model(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t start,
-                                   uint32_t n, RegularityTracker &trk) {
+                                   uint32_t n, RegularityTracker &trk, uint32_t budget_end, bool &aborted) {
     PMCMean pmc; pmc.init();
     Swing swing; swing.init();
     bool pmc_ok = true, swing_ok = true;
     uint32_t i = start;
+    aborted = false;
     while ((pmc_ok || swing_ok) && i < n) {
+        if (i >= budget_end) { aborted = true; break; }
         float value = values[i];
         int64_t t = ts[i];
         trk.visit(i, t);
@@ -181,6 +190,14 @@ MDB_DEV FittedModel fit_next_model(const ErrorBound &eb, const int64_t *ts, cons
     }
     FittedModel m;
     m.start_index = start;
+    if (aborted) { // the caller discards an abandoned fit
+        m.end_index = start;
+        m.min_value = m.max_value = m.model_last_value = 0.0f;
+        m.bytes_per_value = 1e30f;
+        m.model_type_id = PMC_MEAN;
+        m.values_len = 0;
+        return m;
+    }
     float pmc_bpv = __fdiv_rn(29.0f, (float)pmc.length);    // pmc_mean.rs:83-87
     float swing_bpv = __fdiv_rn(30.0f, (float)swing.length); // swing.rs:236-239
     if (swing_bpv < pmc_bpv) { // min_by keeps the first minimum: PMC-Mean wins ties (types.rs:90-94)
@@ -276,8 +293,6 @@ MDB_DEV uint32_t timestamps_encoded_len(const int64_t *ts, uint32_t lo, uint32_t
 // pass 1: the chain
 // ------------------------------------------------------------------------------------------------
 
-struct UnitTotals { uint64_t ts_bytes, val_bytes, res_bytes; };
-
 // CompressedSegmentBuilder::finish (types.rs:197-267) as a record.
 MDB_DEV void record_model_segment(const ErrorBound &eb, const FittedModel &m, uint32_t res_end, const int64_t *ts,
                                   const float *values, bool unit_regular, SegRecord &rec) {
@@ -340,39 +355,203 @@ MDB_DEV uint32_t store_segments(const ErrorBound &eb, bool have_model, const Fit
     return 1;
 }
 
-// try_compress_univariate_time_series (compression.rs:191-275) over one unit. `recs` has room for
-// max_segments_of_unit(n) records. Returns the number of segment rows.
-MDB_DEV uint32_t compress_fit_unit(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t n,
-                                   SegRecord *recs, UnitTotals &totals) {
-    totals.ts_bytes = totals.val_bytes = totals.res_bytes = 0;
-    if (n == 0) return 0;
+// ------------------------------------------------------------------------------------------------
+// The chain of try_compress_univariate_time_series (compression.rs:224-263), made parallel.
+//
+// The reference's loop is a strictly ordered chain over "fit starts": cur -> fit_next_model(cur) ->
+// (accepted ? model.end + 1 : cur + 1).  fit_next_model(cur) is a pure function of cur, so the chain
+// is determined by the set of indices it visits.  A unit is cut into chunks of `chunk_len` points and
+// every chunk runs its own chain, at first SPECULATIVELY from the chunk's first index.  Two chains
+// that ever visit the same index are identical from there on, so:
+//   round 0   every chunk runs a chain from its first index to the chunk end (spec_chain);
+//   propagate the true entry of chunk 0 is index 0; the entry of every later chunk is the exit of the
+//             chunk before it.  A chunk whose chain was not computed from its entry is marked dirty;
+//   round r   a dirty chunk re-runs from its new entry only UNTIL it visits an index its old chain also
+//             visited (not strictly inside an old model), then splices the old chain's tail on.
+// Rounds repeat until no chunk is dirty.  Chunk 0 always runs from the true entry, and a chunk is
+// clean only if its chain started exactly where the previous chunk's chain left, so by induction the
+// concatenated chains are exactly the sequential chain: the result is bit-identical by construction,
+// never "approximately the same segmentation".  On smooth data chains re-synchronise within a few
+// segments, so round 1 touches a small fraction of the points and round 2 is normally empty.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t IDX_NONE = 0xFFFFFFFFu;
+
+struct ChunkState {            // 48 bytes
+    uint32_t entry;            // index (in the unit) this chunk's current chain started from; IDX_NONE: none yet
+    uint32_t exit;             // first fit start >= chunk end reached by the chain; IDX_NONE: chain was cut short
+    uint32_t truncated_at;     // fit start at which a budgeted chain was cut short (valid when exit == IDX_NONE)
+    uint32_t n_models;         // accepted models of the chain, in list buffer `buf`
+    uint32_t new_entry;        // entry the next round must use (valid when dirty)
+    uint32_t next_start;       // finalize: start of the next model after this chunk's last one, or n
+    uint32_t lead_end;         // finalize: last index of a leading MacaqueV row owned by this chunk, or IDX_NONE
+    uint32_t rows;             // finalize: segment rows this chunk emits
+    uint8_t dirty, exact, buf, skipped;
+    uint8_t irregular, pad[3];
+    uint32_t first_start;      // start of the chain's first model (valid when n_models > 0)
+    uint32_t pad2;
+};
+static_assert(sizeof(ChunkState) == 48, "ChunkState layout");
+
+MDB_DEV uint32_t models_per_chunk(uint32_t chunk_len) { return chunk_len / 8 + 2; }
+
+// One chain over one chunk.  lists: two buffers of models_per_chunk(chunk_len) models each.
+// `budget`: a chain that does not start from a known-exact entry abandons a fit that runs more than
+// `budget` points past the chunk end (otherwise constant data would make every chunk fit to the end
+// of the unit); the cut is resumed later from an exact entry.
+MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t n, uint32_t chunk_start,
+                        uint32_t chunk_end, uint32_t budget, ChunkState &st, FittedModel *lists, uint32_t cap) {
+    const FittedModel *old_list = lists + (size_t)st.buf * cap;
+    FittedModel *new_list = lists + (size_t)(st.buf ^ 1) * cap;
+    const uint32_t old_n = st.n_models, old_entry = st.entry, old_exit = st.exit, old_trunc = st.truncated_at;
+    const bool resume = old_entry != IDX_NONE && st.new_entry == old_entry && old_exit == IDX_NONE;
+    const bool can_sync = !resume && old_entry != IDX_NONE;
+    const uint32_t sync_limit = old_exit == IDX_NONE ? old_trunc : chunk_end; // old chain visited [old_entry, sync_limit)
+    const uint32_t budget_end = st.exact ? n : (uint32_t)((uint64_t)chunk_end + budget < n ? chunk_end + budget : n);
+    (void)chunk_start;
+
+    uint32_t n_new = 0, cur, p = 0;
+    if (resume) {
+        for (uint32_t k = 0; k < old_n; k++) new_list[k] = old_list[k];
+        n_new = old_n;
+        cur = old_trunc;
+    } else {
+        cur = st.new_entry;
+    }
     RegularityTracker trk;
-    trk.init(ts);
-    uint32_t n_rows = 0;
-    uint32_t current_start_index = 0;
-    bool have_previous = false;
-    FittedModel previous_model;
-    previous_model.start_index = previous_model.end_index = 0;
-    while (current_start_index < n) {
-        FittedModel model = fit_next_model(eb, ts, values, current_start_index, n, trk);
+    trk.init(ts, cur, n);
+    uint32_t exit = IDX_NONE, truncated_at = 0;
+    bool done = false;
+    while (cur < chunk_end) {
+        if (can_sync && cur >= old_entry && cur < sync_limit) {
+            while (p < old_n && old_list[p].end_index < cur) p++;
+            bool inside = p < old_n && old_list[p].start_index < cur; // strictly inside old model p
+            if (!inside) { // the old chain also started a fit at cur: identical from here on
+                for (uint32_t k = p; k < old_n; k++) new_list[n_new++] = old_list[k];
+                exit = old_exit;
+                truncated_at = old_trunc;
+                done = true;
+                break;
+            }
+        }
+        bool aborted;
+        FittedModel model = fit_next_model(eb, ts, values, cur, n, trk, budget_end, aborted);
+        if (aborted) {
+            truncated_at = cur;
+            done = true;
+            break;
+        }
         if (model.bytes_per_value <= 4.0f) { // compression.rs:238
-            if (current_start_index > 0)
-                n_rows += store_segments(eb, have_previous, previous_model, current_start_index - 1, ts, values,
-                                         !trk.irregular, recs + n_rows);
-            current_start_index = model.end_index + 1;
-            previous_model = model;
-            have_previous = true;
+            new_list[n_new++] = model;
+            cur = model.end_index + 1;
         } else {
-            current_start_index += 1; // this point becomes a residual; refit from the next one
+            cur += 1; // compression.rs:261: this point becomes a residual; refit from the next one
         }
     }
-    n_rows += store_segments(eb, have_previous, previous_model, n - 1, ts, values, !trk.irregular, recs + n_rows);
-    for (uint32_t k = 0; k < n_rows; k++) {
-        totals.ts_bytes += recs[k].ts_len;
-        totals.val_bytes += recs[k].val_len;
-        totals.res_bytes += recs[k].res_len;
+    if (!done) exit = cur;
+    st.entry = st.new_entry;
+    st.exit = exit;
+    st.truncated_at = truncated_at;
+    st.n_models = n_new;
+    st.first_start = n_new ? new_list[0].start_index : IDX_NONE;
+    st.buf ^= 1;
+    st.dirty = 0;
+    if (trk.irregular) st.irregular = 1;
+}
+
+// Walks the chunks of one unit in order and marks the chunks whose chain must be (re)run.
+// Returns the number of chunks marked dirty (0: the unit's chains are final).
+// allow_optimistic: also re-run chunks AFTER the first inconsistent one, betting that the re-run of the
+// chunk before them splices back into its old chain and keeps its exit.  That bet is made once (after
+// round 0); on data whose chains do not re-synchronise (very smooth signal, loose bound, segments of
+// thousands of points) later rounds re-run only the first inconsistent chunk, whose entry is exact, so
+// the total work stays within ~3x the sequential chain instead of growing quadratically.
+MDB_DEV uint32_t spec_propagate_unit(uint32_t n, uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, bool allow_optimistic) {
+    uint32_t e = 0, dirty = 0;
+    bool exact = true; // everything before the first inconsistent chunk is the true sequential chain
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        uint32_t chunk_end = (uint64_t)(c + 1) * chunk_len < n ? (c + 1) * chunk_len : n;
+        if (e >= chunk_end) continue; // no fit starts in this chunk: a model spans it
+        ChunkState &s = st[c];
+        if (s.entry == e) {
+            if (s.exit == IDX_NONE) { // right entry, but the chain was cut short: resume it
+                if (!exact) break;    // (once everything before it is final, so that it runs without a budget)
+                s.new_entry = e;
+                s.exact = exact ? 1 : 0;
+                s.dirty = 1;
+                dirty++;
+                break; // its exit is unknown, nothing after it can be checked yet
+            }
+            e = s.exit;
+        } else {
+            if (!exact && !allow_optimistic) break;
+            s.new_entry = e;
+            s.exact = exact ? 1 : 0;
+            s.dirty = 1;
+            dirty++;
+            exact = false;
+            if (s.exit == IDX_NONE) break;
+            e = s.exit; // optimistic: the re-run will most likely splice into the old chain and keep its exit
+        }
     }
-    return n_rows;
+    return dirty;
+}
+
+// After the fixpoint: marks skipped chunks, links every chunk to the start of the next model in the
+// unit (the end of its last model's residual run) and assigns the leading MacaqueV row.
+MDB_DEV void spec_finalize_unit(uint32_t n, uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, uint8_t &unit_irregular) {
+    uint32_t e = 0;
+    int64_t last_nonempty = -1;
+    uint8_t irregular = 0;
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        ChunkState &s = st[c];
+        uint32_t chunk_end = (uint64_t)(c + 1) * chunk_len < n ? (c + 1) * chunk_len : n;
+        irregular |= s.irregular;
+        s.lead_end = IDX_NONE;
+        s.next_start = n;
+        s.rows = 0;
+        if (e >= chunk_end) { s.skipped = 1; continue; }
+        s.skipped = 0;
+        e = s.exit;
+        if (s.n_models == 0) continue;
+        const uint32_t first_start = s.first_start;
+        if (last_nonempty >= 0) st[last_nonempty].next_start = first_start;
+        else if (first_start > 0) s.lead_end = first_start - 1; // compression.rs:350-361: leading residuals
+        last_nonempty = c;
+    }
+    if (last_nonempty < 0 && n > 0) { // no model anywhere: the whole unit is one MacaqueV row
+        st[0].skipped = 0;
+        st[0].n_models = 0;
+        st[0].lead_end = n - 1;
+    }
+    unit_irregular = irregular;
+}
+
+// Number of segment rows a chunk emits (store_compressed_segments_with_model_and_or_residuals,
+// compression.rs:310-362): one per model, one more when a model is followed by > 255 residuals, plus
+// the leading MacaqueV row if the chunk owns it.
+MDB_DEV uint32_t spec_count_rows(const ChunkState &s, const FittedModel *list) {
+    if (s.skipped) return 0;
+    uint32_t rows = s.lead_end != IDX_NONE ? 1 : 0;
+    for (uint32_t k = 0; k < s.n_models; k++) {
+        uint32_t next_start = k + 1 < s.n_models ? list[k + 1].start_index : s.next_start;
+        uint32_t res_end = next_start - 1;
+        rows += (res_end - list[k].end_index <= RESIDUAL_VALUES_MAX_LENGTH) ? 1 : 2;
+    }
+    return rows;
+}
+
+// Writes the chunk's SegRecords in final row order. Returns the number written (== spec_count_rows).
+MDB_DEV uint32_t spec_records(const ErrorBound &eb, const int64_t *ts, const float *values, const ChunkState &s,
+                              const FittedModel *list, bool unit_regular, SegRecord *recs) {
+    if (s.skipped) return 0;
+    uint32_t r = 0;
+    if (s.lead_end != IDX_NONE) record_macaque_v_segment(eb, 0, s.lead_end, ts, values, unit_regular, recs[r++]);
+    for (uint32_t k = 0; k < s.n_models; k++) {
+        uint32_t next_start = k + 1 < s.n_models ? list[k + 1].start_index : s.next_start;
+        r += store_segments(eb, true, list[k], next_start - 1, ts, values, unit_regular, recs + r);
+    }
+    return r;
 }
 
 // ------------------------------------------------------------------------------------------------

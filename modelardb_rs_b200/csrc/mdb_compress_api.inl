@@ -1,0 +1,380 @@
+// mdb_compress_api.inl -- K1: compress kernels and mdbcu_compress (included at the end of mdb_cuda.cu).
+//
+// Flow (all on the context's stream; the three host syncs each read back a handful of counters):
+//   k_unit_chunks      validate units / error bounds, chunks per unit            -> scan -> chunk_base
+//   k_spec_init        ChunkState of every chunk, chunk -> unit map, list sizes  -> scan -> list_base
+//   repeat { k_spec_chain (one thread per dirty chunk) ; k_spec_propagate (one thread per unit) }
+//                      until no chunk is dirty (mdb_compress.cuh explains why this is exact)
+//   k_spec_finalize    skipped chunks, residual-run ends, leading MacaqueV rows, regularity
+//   k_spec_count_rows  rows per chunk                                            -> scan -> row_base
+//   k_spec_records     SegRecord of every row in final order (byte lengths by running the encoders
+//                      on a counter)
+//   k_compress_gather  row metadata columns + per-row byte lengths               -> 3 scans -> offsets
+//   k_compress_emit    MacaqueTS / MacaqueV byte columns at their final offsets
+
+struct CompressCounters { // device-resident, read back once per round
+    unsigned int dirty;
+    unsigned int pad;
+};
+
+__global__ void __launch_bounds__(256) k_unit_chunks(const uint64_t *unit_off, uint64_t n_units, const uint8_t *eb_kind, const float *eb_value,
+                                                     uint32_t chunk_len, uint32_t *unit_chunks, Status *status) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint64_t a = unit_off[u], b = unit_off[u + 1];
+    bool ok = b >= a && (b - a) < 0xFFFFFF00ull;
+    uint8_t kind = eb_kind[u];
+    float value = eb_value[u];
+    // ErrorBound::try_new_absolute / try_new_relative (modelardb_types/src/types.rs:312-334)
+    if (kind == KIND_ABSOLUTE) ok = ok && value > 0.0f && !isinf(value) && value == value;
+    else if (kind == KIND_RELATIVE) ok = ok && value > 0.0f && value <= 100.0f;
+    else if (kind != KIND_LOSSLESS) ok = false;
+    if (!ok) report_bad(status, u);
+    unit_chunks[u] = ok ? (uint32_t)((b - a + chunk_len - 1) / chunk_len) : 0;
+}
+
+// One thread per unit: initial state of its chunks (round 0 runs every chunk from its first index).
+__global__ void __launch_bounds__(128) k_spec_init(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
+                                                   ChunkState *st, uint32_t *chunk_unit, uint32_t *list_cap) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint64_t n = unit_off[u + 1] - unit_off[u];
+    uint64_t g0 = chunk_base[u], C = chunk_base[u + 1] - g0;
+    for (uint64_t c = 0; c < C; c++) {
+        ChunkState s;
+        s.entry = IDX_NONE;
+        s.exit = IDX_NONE;
+        s.truncated_at = 0;
+        s.n_models = 0;
+        s.new_entry = (uint32_t)(c * chunk_len);
+        s.next_start = 0;
+        s.lead_end = IDX_NONE;
+        s.rows = 0;
+        s.dirty = 1;
+        s.exact = c == 0;
+        s.buf = 0;
+        s.skipped = 0;
+        s.irregular = 0;
+        s.pad[0] = s.pad[1] = s.pad[2] = 0;
+        s.first_start = IDX_NONE;
+        s.pad2 = 0;
+        st[g0 + c] = s;
+        chunk_unit[g0 + c] = (uint32_t)u;
+        uint64_t rest = n - c * chunk_len;
+        uint64_t len = rest < chunk_len ? rest : chunk_len;
+        list_cap[g0 + c] = 2 * models_per_chunk((uint32_t)len); // two buffers
+    }
+}
+
+// One thread per chunk; a block is one warp of which the first `lanes` lanes carry a chain (few chains:
+// one per warp, no divergence and every SM busy; many chains: lanes fill up).
+__global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                   const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks,
+                                                   uint32_t lanes, uint32_t chunk_len, ChunkState *st, FittedModel *lists,
+                                                   const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap) {
+    if (threadIdx.x >= lanes) return;
+    uint64_t g = (uint64_t)blockIdx.x * lanes + threadIdx.x;
+    if (g >= n_chunks) return;
+    ChunkState s = st[g];
+    if (!s.dirty) return;
+    uint32_t u = chunk_unit[g];
+    uint64_t a = unit_off[u];
+    uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+    uint32_t c = (uint32_t)(g - chunk_base[u]);
+    uint32_t chunk_start = c * chunk_len;
+    uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    spec_chain(eb, ts + a, values + a, n, chunk_start, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+    st[g] = s;
+}
+
+__global__ void __launch_bounds__(128) k_spec_propagate(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
+                                                        ChunkState *st, int allow_optimistic, CompressCounters *counters) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint32_t n = (uint32_t)(unit_off[u + 1] - unit_off[u]);
+    uint64_t g0 = chunk_base[u];
+    uint32_t C = (uint32_t)(chunk_base[u + 1] - g0);
+    if (C == 0) return;
+    uint32_t dirty = spec_propagate_unit(n, chunk_len, C, st + g0, allow_optimistic != 0);
+    if (dirty) atomicAdd(&counters->dirty, dirty);
+}
+
+__global__ void __launch_bounds__(128) k_spec_finalize(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
+                                                       ChunkState *st, uint8_t *unit_irregular) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    uint32_t n = (uint32_t)(unit_off[u + 1] - unit_off[u]);
+    uint64_t g0 = chunk_base[u];
+    uint32_t C = (uint32_t)(chunk_base[u + 1] - g0);
+    uint8_t irregular = 0;
+    if (C) spec_finalize_unit(n, chunk_len, C, st + g0, irregular);
+    unit_irregular[u] = irregular;
+}
+
+__global__ void __launch_bounds__(128) k_spec_count_rows(ChunkState *st, uint64_t n_chunks, const FittedModel *lists, const uint64_t *list_base,
+                                                         const uint32_t *list_cap, uint32_t *rows) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    const ChunkState s = st[g];
+    rows[g] = spec_count_rows(s, lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2));
+}
+
+__global__ void __launch_bounds__(256) k_unit_seg_off(const uint64_t *chunk_base, uint64_t n_units, const uint64_t *row_base, uint64_t *unit_seg_off) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u > n_units) return;
+    unit_seg_off[u] = row_base[chunk_base[u]]; // chunk_base[n_units] == n_chunks, row_base[n_chunks] == total rows
+}
+
+// One thread per chunk (same lane geometry as k_spec_chain): the chunk's rows, in order.
+__global__ void __launch_bounds__(32) k_spec_records(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                     const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                     const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, uint32_t lanes, const ChunkState *st,
+                                                     const FittedModel *lists, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                     const uint8_t *__restrict__ unit_irregular, const uint64_t *__restrict__ row_base, SegRecord *recs,
+                                                     uint32_t *row_unit) {
+    if (threadIdx.x >= lanes) return;
+    uint64_t g = (uint64_t)blockIdx.x * lanes + threadIdx.x;
+    if (g >= n_chunks) return;
+    const ChunkState s = st[g];
+    uint64_t r0 = row_base[g], rows = row_base[g + 1] - r0;
+    if (rows == 0) return;
+    uint32_t u = chunk_unit[g];
+    uint64_t a = unit_off[u];
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    spec_records(eb, ts + a, values + a, s, lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2), unit_irregular[u] == 0, recs + r0);
+    for (uint64_t k = 0; k < rows; k++) row_unit[r0 + k] = u;
+}
+
+// One thread per row: metadata columns and the byte lengths of the three binary columns.
+__global__ void __launch_bounds__(256) k_compress_gather(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off,
+                                                         const SegRecord *__restrict__ recs, const uint32_t *__restrict__ row_unit, uint64_t n_rows,
+                                                         int8_t *model_type_id, int64_t *start_time, int64_t *end_time, float *min_value,
+                                                         float *max_value, uint32_t *ts_len, uint32_t *val_len, uint32_t *res_len) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const SegRecord rec = recs[r];
+    const int64_t *uts = ts + unit_off[row_unit[r]];
+    model_type_id[r] = rec.model_type_id;
+    start_time[r] = uts[rec.start_index];
+    end_time[r] = uts[rec.res_end_index];
+    min_value[r] = rec.min_value;
+    max_value[r] = rec.max_value;
+    ts_len[r] = rec.ts_len;
+    val_len[r] = rec.val_len;
+    res_len[r] = rec.res_len;
+}
+
+__global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                      const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                      const SegRecord *__restrict__ recs, const uint32_t *__restrict__ row_unit, uint64_t n_rows,
+                                                      const uint64_t *__restrict__ ts_off, uint8_t *ts_data, const uint64_t *__restrict__ val_off,
+                                                      uint8_t *val_data, const uint64_t *__restrict__ res_off, uint8_t *res_data) {
+    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    uint32_t u = row_unit[r];
+    const SegRecord rec = recs[r];
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    uint64_t a = unit_off[u];
+    compress_emit_segment(eb, rec, ts + a, values + a, ts_data + ts_off[r], val_data + val_off[r], res_data + res_off[r]);
+}
+
+// Chunk length: enough chains to give every SM 32 warps of 32 chains, within [2048, 65536] points.
+static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points) {
+    if (ctx->chunk_len_override) return ctx->chunk_len_override;
+    uint64_t target_chains = (uint64_t)ctx->sm_count * 32 * 32;
+    uint64_t len = n_points / target_chains;
+    uint32_t l = 2048;
+    while (l < len && l < 65536) l <<= 1;
+    return l;
+}
+
+extern "C" {
+
+int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (chunk_len != 0 && chunk_len < 8) return fail("chunk_len must be 0 (automatic) or >= 8");
+    ctx->chunk_len_override = chunk_len;
+    return MDBCU_SUCCESS;
+}
+
+uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return ctx ? ctx->last_rounds : 0; }
+
+int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timestamps, const float *values, const uint64_t *unit_off,
+                   uint64_t n_units, const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (!out) return fail("compress: out is null");
+    *out = nullptr;
+    if (n_units > 0xFFFFFFF0ull) return fail("compress: more than 2^32 units");
+    if (n_units && (!unit_off || !eb_kind || !eb_value)) return fail("compress: unit_off / eb_kind / eb_value is null");
+    cudaStream_t s = ctx->stream;
+
+    // total number of points: unit_off[0] .. unit_off[n_units]
+    uint64_t first = 0, last = 0;
+    if (n_units) {
+        if (space == MDBCU_HOST) {
+            first = unit_off[0];
+            last = unit_off[n_units];
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(&first, unit_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaMemcpyAsync(&last, unit_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+            CUDA_TRY(cudaStreamSynchronize(s));
+        }
+        if (last < first) return fail("compress: unit_off is not monotone");
+    }
+    uint64_t n_points = last; // arrays are indexed by absolute unit_off values
+    if (n_points && (!timestamps || !values)) return fail("compress: timestamps / values is null");
+
+    DBuf<int64_t> ts_buf;
+    DBuf<float> val_buf;
+    DBuf<uint64_t> off_buf;
+    DBuf<uint8_t> kind_buf;
+    DBuf<float> ebv_buf;
+    const int64_t *d_ts = timestamps;
+    const float *d_val = values;
+    const uint64_t *d_off = unit_off;
+    const uint8_t *d_kind = eb_kind;
+    const float *d_ebv = eb_value;
+    if (space == MDBCU_HOST && n_units) {
+        CUDA_TRY(upload(ts_buf, timestamps, n_points, s));
+        CUDA_TRY(upload(val_buf, values, n_points, s));
+        CUDA_TRY(upload(off_buf, unit_off, n_units + 1, s));
+        CUDA_TRY(upload(kind_buf, eb_kind, n_units, s));
+        CUDA_TRY(upload(ebv_buf, eb_value, n_units, s));
+        d_ts = ts_buf.p; d_val = val_buf.p; d_off = off_buf.p; d_kind = kind_buf.p; d_ebv = ebv_buf.p;
+    }
+
+    mdbcu_segments *sg = new mdbcu_segments();
+    sg->ctx = ctx;
+    sg->n_units = n_units;
+    auto bail = [&](int rc) { mdbcu_segments_free(sg); return rc; };
+#define TRY_SG(expr)                                                                                \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            fail(std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
+            return bail(MDBCU_FAILURE);                                                             \
+        }                                                                                           \
+    } while (0)
+
+    TRY_SG(cudaMallocAsync((void **)&sg->unit_seg_off, (n_units + 1) * sizeof(uint64_t), s));
+    uint64_t S = 0;
+    DBuf<SegRecord> recs;
+    DBuf<uint32_t> row_unit;
+    ctx->last_rounds = 0;
+
+    if (n_units) {
+        // ---- chunks
+        const uint32_t chunk_len = choose_chunk_len(ctx, n_points - first);
+        DBuf<Status> status;
+        if (new_status(ctx, status)) return bail(MDBCU_FAILURE);
+        DBuf<uint32_t> unit_chunks;
+        DBuf<uint64_t> chunk_base;
+        TRY_SG(unit_chunks.alloc(n_units, s));
+        TRY_SG(chunk_base.alloc(n_units + 1, s));
+        LAUNCH(ctx, k_unit_chunks, div_up(n_units, 256), 256, 0, d_off, n_units, d_kind, d_ebv, chunk_len, unit_chunks.p, status.p);
+        if (exclusive_scan<uint32_t>(ctx, unit_chunks.p, n_units, chunk_base.p)) return bail(MDBCU_FAILURE);
+        uint64_t G = 0;
+        TRY_SG(cudaMemcpyAsync(&G, chunk_base.p + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        Status h;
+        if (read_status(ctx, status.p, h, "unit (bad unit_off or error bound)")) return bail(MDBCU_FAILURE);
+        if (G > 0xFFFFFFF0ull) return bail(fail("compress: too many chunks"));
+
+        DBuf<ChunkState> st;
+        DBuf<uint32_t> chunk_unit, list_cap, rows;
+        DBuf<uint64_t> list_base, row_base;
+        DBuf<uint8_t> unit_irregular;
+        DBuf<CompressCounters> counters;
+        TRY_SG(st.alloc(G, s));
+        TRY_SG(chunk_unit.alloc(G, s));
+        TRY_SG(list_cap.alloc(G, s));
+        TRY_SG(list_base.alloc(G + 1, s));
+        TRY_SG(rows.alloc(G, s));
+        TRY_SG(row_base.alloc(G + 1, s));
+        TRY_SG(unit_irregular.alloc(n_units, s));
+        TRY_SG(counters.alloc(1, s));
+        LAUNCH(ctx, k_spec_init, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, chunk_unit.p, list_cap.p);
+        if (exclusive_scan<uint32_t>(ctx, list_cap.p, G, list_base.p)) return bail(MDBCU_FAILURE);
+        uint64_t n_models_cap = 0;
+        TRY_SG(cudaMemcpyAsync(&n_models_cap, list_base.p + G, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        TRY_SG(cudaStreamSynchronize(s));
+        DBuf<FittedModel> lists;
+        TRY_SG(lists.alloc(n_models_cap, s));
+
+        // ---- rounds
+        const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
+        uint32_t round = 0;
+        while (G) {
+            LAUNCH(ctx, k_spec_chain, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, G, lanes, chunk_len,
+                   st.p, lists.p, list_base.p, list_cap.p);
+            round++;
+            TRY_SG(cudaMemsetAsync(counters.p, 0, sizeof(CompressCounters), s));
+            LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, round == 1 ? 1 : 0, counters.p);
+            CompressCounters hc;
+            TRY_SG(cudaMemcpyAsync(&hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
+            TRY_SG(cudaStreamSynchronize(s));
+            TRY_SG(cudaGetLastError());
+            if (hc.dirty == 0) break;
+            if (round > 4 * G + 8) return bail(fail("compress: chunk fixpoint did not converge (internal error)"));
+        }
+        ctx->last_rounds = round;
+
+        // ---- rows
+        LAUNCH(ctx, k_spec_finalize, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, unit_irregular.p);
+        if (G) LAUNCH(ctx, k_spec_count_rows, div_up(G, 128), 128, 0, st.p, G, lists.p, list_base.p, list_cap.p, rows.p);
+        if (exclusive_scan<uint32_t>(ctx, rows.p, G, row_base.p)) return bail(MDBCU_FAILURE);
+        LAUNCH(ctx, k_unit_seg_off, div_up(n_units + 1, 256), 256, 0, chunk_base.p, n_units, row_base.p, sg->unit_seg_off);
+        TRY_SG(cudaMemcpyAsync(&S, row_base.p + G, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        TRY_SG(cudaStreamSynchronize(s));
+        TRY_SG(cudaGetLastError());
+        TRY_SG(recs.alloc(S, s));
+        TRY_SG(row_unit.alloc(S, s));
+        if (G && S)
+            LAUNCH(ctx, k_spec_records, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, lanes, st.p, lists.p,
+                   list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p);
+        // the scratch above is released (stream-ordered) when this scope ends
+    } else {
+        TRY_SG(cudaMemsetAsync(sg->unit_seg_off, 0, sizeof(uint64_t), s));
+    }
+    sg->n_segments = S;
+
+    // ---- row metadata in final order + byte offsets of the three binary columns
+    TRY_SG(cudaMallocAsync((void **)&sg->model_type_id, (S ? S : 1) * sizeof(int8_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->start_time, (S ? S : 1) * sizeof(int64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->end_time, (S ? S : 1) * sizeof(int64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->min_value, (S ? S : 1) * sizeof(float), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->max_value, (S ? S : 1) * sizeof(float), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->ts_off, (S + 1) * sizeof(uint64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->val_off, (S + 1) * sizeof(uint64_t), s));
+    TRY_SG(cudaMallocAsync((void **)&sg->res_off, (S + 1) * sizeof(uint64_t), s));
+    DBuf<uint32_t> ts_len, val_len, res_len;
+    TRY_SG(ts_len.alloc(S, s));
+    TRY_SG(val_len.alloc(S, s));
+    TRY_SG(res_len.alloc(S, s));
+    if (S)
+        LAUNCH(ctx, k_compress_gather, div_up(S, 256), 256, 0, d_ts, d_off, recs.p, row_unit.p, S, sg->model_type_id, sg->start_time, sg->end_time,
+               sg->min_value, sg->max_value, ts_len.p, val_len.p, res_len.p);
+    if (exclusive_scan<uint32_t>(ctx, ts_len.p, S, sg->ts_off)) return bail(MDBCU_FAILURE);
+    if (exclusive_scan<uint32_t>(ctx, val_len.p, S, sg->val_off)) return bail(MDBCU_FAILURE);
+    if (exclusive_scan<uint32_t>(ctx, res_len.p, S, sg->res_off)) return bail(MDBCU_FAILURE);
+    TRY_SG(cudaMemcpyAsync(&sg->ts_bytes, sg->ts_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaMemcpyAsync(&sg->val_bytes, sg->val_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaMemcpyAsync(&sg->res_bytes, sg->res_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    TRY_SG(cudaStreamSynchronize(s));
+
+    // ---- byte columns
+    TRY_SG(cudaMallocAsync((void **)&sg->ts_data, sg->ts_bytes ? sg->ts_bytes : 1, s));
+    TRY_SG(cudaMallocAsync((void **)&sg->val_data, sg->val_bytes ? sg->val_bytes : 1, s));
+    TRY_SG(cudaMallocAsync((void **)&sg->res_data, sg->res_bytes ? sg->res_bytes : 1, s));
+    if (S)
+        LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, recs.p, row_unit.p, S, sg->ts_off, sg->ts_data,
+               sg->val_off, sg->val_data, sg->res_off, sg->res_data);
+    TRY_SG(cudaGetLastError());
+    TRY_SG(cudaStreamSynchronize(s));
+#undef TRY_SG
+    *out = sg;
+    return MDBCU_SUCCESS;
+}
+
+} // extern "C"

@@ -8,8 +8,10 @@
 //   k_grid_sequential     irregular timestamps, MacaqueV values, residuals (serial per row)
 //   k_agg_segments        one thread per row: COUNT and SUM of the row from its model
 //   k_agg_partial/final   deterministic in-order tree reduction per group
-//   k_compress_fit        one thread per unit: greedy PMC-Mean/Swing segmentation -> SegRecords
-//   k_compress_gather     row metadata + per-row byte lengths in final row order
+//   k_spec_chain          one thread per chunk of a unit: greedy PMC-Mean/Swing chain (speculative, see
+//                         mdb_compress.cuh); k_spec_propagate / k_spec_finalize stitch chunks per unit
+//   k_spec_records        accepted models -> SegRecords in final row order
+//   k_compress_gather     row metadata + per-row byte lengths
 //   k_compress_emit       one thread per row: MacaqueTS / MacaqueV byte columns
 #include <cuda_runtime.h>
 
@@ -61,6 +63,8 @@ struct mdbcu_context {
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
+    uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
+    uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
     // optional per-kernel CUDA-event timing (mdbcu_context_set_profiling)
     bool profiling = false;
     std::vector<KernelStat> stats;
@@ -441,76 +445,7 @@ __global__ void __launch_bounds__(AGG_THREADS) k_agg_final(const GroupAgg *parti
 // K1: compress
 // ------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) k_unit_caps(const uint64_t *unit_off, uint64_t n_units, const uint8_t *eb_kind, const float *eb_value,
-                                                   uint64_t *caps, Status *status) {
-    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
-    uint64_t a = unit_off[u], b = unit_off[u + 1];
-    bool ok = b >= a && (b - a) < 0xFFFFFFFFull;
-    uint8_t kind = eb_kind[u];
-    float value = eb_value[u];
-    // ErrorBound::try_new_absolute / try_new_relative (modelardb_types/src/types.rs:312-334)
-    if (kind == KIND_ABSOLUTE) ok = ok && value > 0.0f && !isinf(value) && value == value;
-    else if (kind == KIND_RELATIVE) ok = ok && value > 0.0f && value <= 100.0f;
-    else if (kind != KIND_LOSSLESS) ok = false;
-    if (!ok) report_bad(status, u);
-    caps[u] = ok ? max_segments_of_unit(b - a) : 0;
-}
-
-// One thread per unit; 32-thread blocks spread the chains over all SMs.
-__global__ void __launch_bounds__(32) k_compress_fit(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
-                                                     uint64_t n_units, const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
-                                                     const uint64_t *__restrict__ rec_base, SegRecord *recs, uint32_t *unit_rows) {
-    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (u >= n_units) return;
-    uint64_t a = unit_off[u];
-    uint32_t n = (uint32_t)(unit_off[u + 1] - a);
-    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-    UnitTotals totals;
-    unit_rows[u] = compress_fit_unit(eb, ts + a, values + a, n, recs + rec_base[u], totals);
-}
-
-// One warp per unit: row metadata and byte lengths in final row order.
-__global__ void __launch_bounds__(256) k_compress_gather(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off, uint64_t n_units,
-                                                         const uint64_t *__restrict__ rec_base, const SegRecord *__restrict__ recs,
-                                                         const uint64_t *__restrict__ unit_seg_off, int8_t *model_type_id, int64_t *start_time,
-                                                         int64_t *end_time, float *min_value, float *max_value, uint32_t *ts_len,
-                                                         uint32_t *val_len, uint32_t *res_len, uint32_t *row_unit) {
-    uint64_t u = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    if (u >= n_units) return;
-    const int lane = threadIdx.x & 31;
-    uint64_t r0 = unit_seg_off[u], rows = unit_seg_off[u + 1] - r0;
-    const SegRecord *urecs = recs + rec_base[u];
-    const int64_t *uts = ts + unit_off[u];
-    for (uint64_t k = lane; k < rows; k += 32) {
-        SegRecord rec = urecs[k];
-        uint64_t r = r0 + k;
-        model_type_id[r] = rec.model_type_id;
-        start_time[r] = uts[rec.start_index];
-        end_time[r] = uts[rec.res_end_index];
-        min_value[r] = rec.min_value;
-        max_value[r] = rec.max_value;
-        ts_len[r] = rec.ts_len;
-        val_len[r] = rec.val_len;
-        res_len[r] = rec.res_len;
-        row_unit[r] = (uint32_t)u;
-    }
-}
-
-__global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
-                                                      const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
-                                                      const uint64_t *__restrict__ rec_base, const SegRecord *__restrict__ recs,
-                                                      const uint64_t *__restrict__ unit_seg_off, const uint32_t *__restrict__ row_unit, uint64_t n_rows,
-                                                      const uint64_t *__restrict__ ts_off, uint8_t *ts_data, const uint64_t *__restrict__ val_off,
-                                                      uint8_t *val_data, const uint64_t *__restrict__ res_off, uint8_t *res_data) {
-    uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= n_rows) return;
-    uint32_t u = row_unit[r];
-    SegRecord rec = recs[rec_base[u] + (r - unit_seg_off[u])];
-    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-    uint64_t a = unit_off[u];
-    compress_emit_segment(eb, rec, ts + a, values + a, ts_data + ts_off[r], val_data + val_off[r], res_data + res_off[r]);
-}
+// (the compress kernels and mdbcu_compress live in mdb_compress_api.inl, included at the end of this file)
 
 // ------------------------------------------------------------------------------------------------
 // host side
@@ -957,136 +892,6 @@ int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_vie
     return MDBCU_SUCCESS;
 }
 
-int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timestamps, const float *values, const uint64_t *unit_off,
-                   uint64_t n_units, const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out) {
-    if (check_ctx(ctx)) return MDBCU_FAILURE;
-    if (!out) return fail("compress: out is null");
-    *out = nullptr;
-    if (n_units > 0xFFFFFFF0ull) return fail("compress: more than 2^32 units");
-    if (n_units && (!unit_off || !eb_kind || !eb_value)) return fail("compress: unit_off / eb_kind / eb_value is null");
-    cudaStream_t s = ctx->stream;
-
-    // total number of points: unit_off[0] .. unit_off[n_units]
-    uint64_t first = 0, last = 0;
-    if (n_units) {
-        if (space == MDBCU_HOST) {
-            first = unit_off[0];
-            last = unit_off[n_units];
-        } else {
-            CUDA_TRY(cudaMemcpyAsync(&first, unit_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(&last, unit_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
-        }
-        if (last < first) return fail("compress: unit_off is not monotone");
-    }
-    uint64_t n_points = last; // arrays are indexed by absolute unit_off values
-    if (n_points && (!timestamps || !values)) return fail("compress: timestamps / values is null");
-
-    DBuf<int64_t> ts_buf;
-    DBuf<float> val_buf;
-    DBuf<uint64_t> off_buf;
-    DBuf<uint8_t> kind_buf;
-    DBuf<float> ebv_buf;
-    const int64_t *d_ts = timestamps;
-    const float *d_val = values;
-    const uint64_t *d_off = unit_off;
-    const uint8_t *d_kind = eb_kind;
-    const float *d_ebv = eb_value;
-    if (space == MDBCU_HOST && n_units) {
-        CUDA_TRY(upload(ts_buf, timestamps, n_points, s));
-        CUDA_TRY(upload(val_buf, values, n_points, s));
-        CUDA_TRY(upload(off_buf, unit_off, n_units + 1, s));
-        CUDA_TRY(upload(kind_buf, eb_kind, n_units, s));
-        CUDA_TRY(upload(ebv_buf, eb_value, n_units, s));
-        d_ts = ts_buf.p; d_val = val_buf.p; d_off = off_buf.p; d_kind = kind_buf.p; d_ebv = ebv_buf.p;
-    }
-
-    mdbcu_segments *sg = new mdbcu_segments();
-    sg->ctx = ctx;
-    sg->n_units = n_units;
-    auto bail = [&](int rc) { mdbcu_segments_free(sg); return rc; };
-#define TRY_SG(expr)                                                                       \
-    do {                                                                                   \
-        cudaError_t e_ = (expr);                                                           \
-        if (e_ != cudaSuccess) {                                                           \
-            fail(std::string(#expr) + ": " + cudaGetErrorName(e_) + ": " + cudaGetErrorString(e_)); \
-            return bail(MDBCU_FAILURE);                                                    \
-        }                                                                                  \
-    } while (0)
-
-    TRY_SG(cudaMallocAsync((void **)&sg->unit_seg_off, (n_units + 1) * sizeof(uint64_t), s));
-    if (n_units == 0) {
-        TRY_SG(cudaMemsetAsync(sg->unit_seg_off, 0, sizeof(uint64_t), s));
-        TRY_SG(cudaMallocAsync((void **)&sg->ts_off, sizeof(uint64_t), s));
-        TRY_SG(cudaMallocAsync((void **)&sg->val_off, sizeof(uint64_t), s));
-        TRY_SG(cudaMallocAsync((void **)&sg->res_off, sizeof(uint64_t), s));
-        TRY_SG(cudaMemsetAsync(sg->ts_off, 0, sizeof(uint64_t), s));
-        TRY_SG(cudaMemsetAsync(sg->val_off, 0, sizeof(uint64_t), s));
-        TRY_SG(cudaMemsetAsync(sg->res_off, 0, sizeof(uint64_t), s));
-        TRY_SG(cudaStreamSynchronize(s));
-        *out = sg;
-        return MDBCU_SUCCESS;
-    }
-
-    // pass 1: worst-case record table, one chain per unit
-    DBuf<Status> status;
-    if (new_status(ctx, status)) return bail(MDBCU_FAILURE);
-    DBuf<uint64_t> caps, rec_base;
-    TRY_SG(caps.alloc(n_units, s));
-    TRY_SG(rec_base.alloc(n_units + 1, s));
-    LAUNCH(ctx, k_unit_caps, div_up(n_units, 256), 256, 0, d_off, n_units, d_kind, d_ebv, caps.p, status.p);
-    if (exclusive_scan<uint64_t>(ctx, caps.p, n_units, rec_base.p)) return bail(MDBCU_FAILURE);
-    Status h;
-    if (read_status(ctx, status.p, h, "unit (bad unit_off or error bound)")) return bail(MDBCU_FAILURE);
-    uint64_t rec_cap = (n_points - first) / 8 + (n_points - first) / 264 + 2 * n_units;
-    DBuf<SegRecord> recs;
-    DBuf<uint32_t> unit_rows;
-    TRY_SG(recs.alloc(rec_cap, s));
-    TRY_SG(unit_rows.alloc(n_units, s));
-    LAUNCH(ctx, k_compress_fit, div_up(n_units, 32), 32, 0, d_ts, d_val, d_off, n_units, d_kind, d_ebv, rec_base.p, recs.p, unit_rows.p);
-    if (exclusive_scan<uint32_t>(ctx, unit_rows.p, n_units, sg->unit_seg_off)) return bail(MDBCU_FAILURE);
-    uint64_t S = 0;
-    TRY_SG(cudaMemcpyAsync(&S, sg->unit_seg_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaStreamSynchronize(s));
-    TRY_SG(cudaGetLastError());
-    sg->n_segments = S;
-
-    // row metadata in final order + byte offsets of the three binary columns
-    TRY_SG(cudaMallocAsync((void **)&sg->model_type_id, (S ? S : 1) * sizeof(int8_t), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->start_time, (S ? S : 1) * sizeof(int64_t), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->end_time, (S ? S : 1) * sizeof(int64_t), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->min_value, (S ? S : 1) * sizeof(float), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->max_value, (S ? S : 1) * sizeof(float), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->ts_off, (S + 1) * sizeof(uint64_t), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->val_off, (S + 1) * sizeof(uint64_t), s));
-    TRY_SG(cudaMallocAsync((void **)&sg->res_off, (S + 1) * sizeof(uint64_t), s));
-    DBuf<uint32_t> ts_len, val_len, res_len, row_unit;
-    TRY_SG(ts_len.alloc(S, s));
-    TRY_SG(val_len.alloc(S, s));
-    TRY_SG(res_len.alloc(S, s));
-    TRY_SG(row_unit.alloc(S, s));
-    LAUNCH(ctx, k_compress_gather, div_up(n_units * 32, 256), 256, 0, d_ts, d_off, n_units, rec_base.p, recs.p, sg->unit_seg_off,
-           sg->model_type_id, sg->start_time, sg->end_time, sg->min_value, sg->max_value, ts_len.p, val_len.p, res_len.p, row_unit.p);
-    if (exclusive_scan<uint32_t>(ctx, ts_len.p, S, sg->ts_off)) return bail(MDBCU_FAILURE);
-    if (exclusive_scan<uint32_t>(ctx, val_len.p, S, sg->val_off)) return bail(MDBCU_FAILURE);
-    if (exclusive_scan<uint32_t>(ctx, res_len.p, S, sg->res_off)) return bail(MDBCU_FAILURE);
-    TRY_SG(cudaMemcpyAsync(&sg->ts_bytes, sg->ts_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaMemcpyAsync(&sg->val_bytes, sg->val_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaMemcpyAsync(&sg->res_bytes, sg->res_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaStreamSynchronize(s));
-
-    // pass 2: byte columns
-    TRY_SG(cudaMallocAsync((void **)&sg->ts_data, sg->ts_bytes ? sg->ts_bytes : 1, s));
-    TRY_SG(cudaMallocAsync((void **)&sg->val_data, sg->val_bytes ? sg->val_bytes : 1, s));
-    TRY_SG(cudaMallocAsync((void **)&sg->res_data, sg->res_bytes ? sg->res_bytes : 1, s));
-    if (S)
-        LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, rec_base.p, recs.p, sg->unit_seg_off, row_unit.p, S,
-               sg->ts_off, sg->ts_data, sg->val_off, sg->val_data, sg->res_off, sg->res_data);
-    TRY_SG(cudaGetLastError());
-    TRY_SG(cudaStreamSynchronize(s));
-#undef TRY_SG
-    *out = sg;
-    return MDBCU_SUCCESS;
-}
-
 } // extern "C"
+
+#include "mdb_compress_api.inl"

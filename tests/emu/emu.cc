@@ -6,6 +6,7 @@
 // errors in those bodies are caught by `pytest -m "not gpu"` before GPU time is spent.  What it cannot
 // cover -- launch geometry, scans, shared-memory tiling, warp primitives, the C-ABI -- is covered by
 // the `-m gpu` tests.  Nothing under modelardb_rs_b200/ links or loads this.
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -26,48 +27,80 @@ struct EmuSegments {
 
 extern "C" {
 
+// chunk_len == 0: one chunk per unit (the plain sequential chain).
 EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t *unit_off, uint64_t n_units,
-                          const uint8_t *eb_kind, const float *eb_value) {
+                          const uint8_t *eb_kind, const float *eb_value, uint32_t chunk_len, uint32_t *rounds_out) {
     EmuSegments *out = new EmuSegments();
-    std::vector<std::vector<SegRecord>> recs(n_units);
     out->unit_seg_off.assign(n_units + 1, 0);
-    for (uint64_t u = 0; u < n_units; u++) { // pass 1: one "thread" per unit
-        uint64_t n = unit_off[u + 1] - unit_off[u];
-        recs[u].resize(max_segments_of_unit(n));
+    std::vector<SegRecord> recs;
+    std::vector<uint32_t> row_unit;
+    uint32_t max_rounds = 0;
+    for (uint64_t u = 0; u < n_units; u++) {
+        uint32_t n = (uint32_t)(unit_off[u + 1] - unit_off[u]);
+        out->unit_seg_off[u + 1] = out->unit_seg_off[u];
+        if (n == 0) continue;
+        const int64_t *uts = ts + unit_off[u];
+        const float *uval = values + unit_off[u];
         ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-        UnitTotals totals;
-        uint32_t rows = compress_fit_unit(eb, ts + unit_off[u], values + unit_off[u], (uint32_t)n, recs[u].data(), totals);
-        recs[u].resize(rows);
-        out->unit_seg_off[u + 1] = out->unit_seg_off[u] + rows;
+        uint32_t L = chunk_len ? chunk_len : n;
+        uint32_t C = (n + L - 1) / L;
+        uint32_t cap = models_per_chunk(L);
+        std::vector<ChunkState> st(C);
+        std::vector<FittedModel> lists((size_t)C * 2 * cap);
+        for (uint32_t c = 0; c < C; c++) { // k_spec_init
+            std::memset(&st[c], 0, sizeof(ChunkState));
+            st[c].entry = IDX_NONE; st[c].exit = IDX_NONE; st[c].new_entry = c * L; st[c].dirty = 1; st[c].exact = c == 0;
+        }
+        uint32_t rounds = 0;
+        while (true) { // rounds: k_spec_chain over dirty chunks, then k_spec_propagate per unit
+            for (uint32_t c = 0; c < C; c++)
+                if (st[c].dirty) {
+                    uint32_t cs = c * L, ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
+                    spec_chain(eb, uts, uval, n, cs, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
+                }
+            rounds++;
+            if (spec_propagate_unit(n, L, C, st.data(), rounds == 1) == 0) break;
+            if (rounds > 4 * C + 8) return nullptr; // must converge: one chunk becomes final per round at worst
+        }
+        max_rounds = std::max(max_rounds, rounds);
+        uint8_t irregular;
+        spec_finalize_unit(n, L, C, st.data(), irregular);
+        for (uint32_t c = 0; c < C; c++) {
+            const FittedModel *list = lists.data() + ((size_t)c * 2 + st[c].buf) * cap;
+            uint32_t rows = spec_count_rows(st[c], list);
+            size_t base = recs.size();
+            recs.resize(base + rows);
+            uint32_t wrote = spec_records(eb, uts, uval, st[c], list, !irregular, recs.data() + base);
+            if (wrote != rows) return nullptr;
+            row_unit.insert(row_unit.end(), rows, (uint32_t)u);
+            out->unit_seg_off[u + 1] += rows;
+        }
     }
-    uint64_t S = out->unit_seg_off[n_units];
+    if (rounds_out) *rounds_out = max_rounds;
+    uint64_t S = recs.size();
     out->model_type_id.resize(S); out->start_time.resize(S); out->end_time.resize(S);
     out->min_value.resize(S); out->max_value.resize(S);
     out->ts_off.assign(S + 1, 0); out->val_off.assign(S + 1, 0); out->res_off.assign(S + 1, 0);
-    for (uint64_t u = 0; u < n_units; u++) // gather + scans
-        for (size_t k = 0; k < recs[u].size(); k++) {
-            uint64_t r = out->unit_seg_off[u] + k;
-            const SegRecord &rec = recs[u][k];
-            out->model_type_id[r] = rec.model_type_id;
-            out->start_time[r] = ts[unit_off[u] + rec.start_index];
-            out->end_time[r] = ts[unit_off[u] + rec.res_end_index];
-            out->min_value[r] = rec.min_value;
-            out->max_value[r] = rec.max_value;
-            out->ts_off[r + 1] = out->ts_off[r] + rec.ts_len;
-            out->val_off[r + 1] = out->val_off[r] + rec.val_len;
-            out->res_off[r + 1] = out->res_off[r] + rec.res_len;
-        }
+    for (uint64_t r = 0; r < S; r++) { // gather + scans
+        const SegRecord &rec = recs[r];
+        uint64_t a = unit_off[row_unit[r]];
+        out->model_type_id[r] = rec.model_type_id;
+        out->start_time[r] = ts[a + rec.start_index];
+        out->end_time[r] = ts[a + rec.res_end_index];
+        out->min_value[r] = rec.min_value;
+        out->max_value[r] = rec.max_value;
+        out->ts_off[r + 1] = out->ts_off[r] + rec.ts_len;
+        out->val_off[r + 1] = out->val_off[r] + rec.val_len;
+        out->res_off[r + 1] = out->res_off[r] + rec.res_len;
+    }
     out->ts_data.assign(out->ts_off[S] + 1, 0xAA);
     out->val_data.assign(out->val_off[S] + 1, 0xAA);
     out->res_data.assign(out->res_off[S] + 1, 0xAA);
-    for (uint64_t u = 0; u < n_units; u++) { // pass 2: one "thread" per row
+    for (uint64_t r = 0; r < S; r++) { // pass 2: one "thread" per row
+        uint32_t u = row_unit[r];
         ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-        for (size_t k = 0; k < recs[u].size(); k++) {
-            uint64_t r = out->unit_seg_off[u] + k;
-            compress_emit_segment(eb, recs[u][k], ts + unit_off[u], values + unit_off[u],
-                                  out->ts_data.data() + out->ts_off[r], out->val_data.data() + out->val_off[r],
-                                  out->res_data.data() + out->res_off[r]);
-        }
+        compress_emit_segment(eb, recs[r], ts + unit_off[u], values + unit_off[u], out->ts_data.data() + out->ts_off[r],
+                              out->val_data.data() + out->val_off[r], out->res_data.data() + out->res_off[r]);
     }
     return out;
 }

@@ -27,7 +27,7 @@ def lib():
                                "-x", "c++", _SRC, "-o", _SO])
     L = C.CDLL(_SO)
     vp, u64 = C.c_void_p, C.c_uint64
-    L.emu_compress.argtypes = [vp, vp, vp, u64, vp, vp]
+    L.emu_compress.argtypes = [vp, vp, vp, u64, vp, vp, C.c_uint32, vp]
     L.emu_compress.restype = vp
     L.emu_segments_len.argtypes = [vp]
     L.emu_segments_len.restype = u64
@@ -50,7 +50,7 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def compress(ts, values, unit_off=None, eb=(0, 0.0)) -> O.Segments:
+def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None) -> O.Segments:
     ts = np.ascontiguousarray(ts, np.int64)
     vals = np.ascontiguousarray(values, np.float32)
     if unit_off is None:
@@ -62,7 +62,12 @@ def compress(ts, values, unit_off=None, eb=(0, 0.0)) -> O.Segments:
     kinds = np.array([e[0] for e in eb], np.uint8)
     evals = np.array([e[1] for e in eb], np.float32)
     L = lib()
-    h = L.emu_compress(_p(ts), _p(vals), _p(unit_off), n_units, _p(kinds), _p(evals))
+    r = C.c_uint32(0)
+    h = L.emu_compress(_p(ts), _p(vals), _p(unit_off), n_units, _p(kinds), _p(evals), chunk_len, C.byref(r))
+    if not h:
+        raise RuntimeError("emulated chunk-speculative compress did not converge / row count mismatch")
+    if rounds is not None:
+        rounds.append(r.value)
     v = O._View()
     uso = C.c_void_p()
     L.emu_segments_view(h, C.byref(v), C.byref(uso))
