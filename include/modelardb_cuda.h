@@ -122,6 +122,9 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len);
 /* Number of chain rounds the last mdbcu_compress on this context needed (1 = no re-run at all). */
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
+/* Which fit_next_model engine runs the chains: 0 automatic, 1 one thread per chain, 2 one warp per
+ * chain (32 lanes fit 32 points per step, csrc/mdb_fit_warp.cuh).  Results are identical. */
+int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine);
 
 uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
 /* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off

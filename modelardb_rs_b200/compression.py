@@ -102,6 +102,10 @@ class Context:
         """Chunk length of the parallel segmentation (0 = automatic); results never depend on it."""
         _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
 
+    def set_fit_engine(self, engine: int):
+        """0 automatic, 1 one thread per chain, 2 one warp per chain; results are identical."""
+        _native.check(_native.lib().mdbcu_context_set_fit_engine(self._h, engine))
+
     @property
     def last_compress_rounds(self) -> int:
         return _native.lib().mdbcu_context_last_compress_rounds(self._h)

@@ -399,8 +399,26 @@ MDB_DEV uint32_t models_per_chunk(uint32_t chunk_len) { return chunk_len / 8 + 2
 // `budget`: a chain that does not start from a known-exact entry abandons a fit that runs more than
 // `budget` points past the chunk end (otherwise constant data would make every chunk fit to the end
 // of the unit); the cut is resumed later from an exact entry.
-MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t n, uint32_t chunk_start,
-                        uint32_t chunk_end, uint32_t budget, ChunkState &st, FittedModel *lists, uint32_t cap) {
+// Fit: the fit_next_model engine -- ScalarFit (one thread) or WarpFit (32 lanes cooperate on every fit,
+// mdb_fit_warp.cuh); in the warp case every lane runs this control code redundantly on uniform values
+// and only the `writer` lane stores to global memory.
+struct ScalarFit {
+    const ErrorBound &eb;
+    const int64_t *ts;
+    const float *values;
+    uint32_t n;
+    RegularityTracker trk;
+    MDB_DEV ScalarFit(const ErrorBound &e, const int64_t *t, const float *v, uint32_t n_) : eb(e), ts(t), values(v), n(n_) {}
+    MDB_DEV void begin(uint32_t cur) { trk.init(ts, cur, n); }
+    MDB_DEV FittedModel fit(uint32_t cur, uint32_t budget_end, bool &aborted) {
+        return fit_next_model(eb, ts, values, cur, n, trk, budget_end, aborted);
+    }
+    MDB_DEV bool irregular() const { return trk.irregular; }
+};
+
+template <typename Fit>
+MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end, uint32_t budget, ChunkState &st,
+                        FittedModel *lists, uint32_t cap) {
     const FittedModel *old_list = lists + (size_t)st.buf * cap;
     FittedModel *new_list = lists + (size_t)(st.buf ^ 1) * cap;
     const uint32_t old_n = st.n_models, old_entry = st.entry, old_exit = st.exit, old_trunc = st.truncated_at;
@@ -408,18 +426,19 @@ MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *va
     const bool can_sync = !resume && old_entry != IDX_NONE;
     const uint32_t sync_limit = old_exit == IDX_NONE ? old_trunc : chunk_end; // old chain visited [old_entry, sync_limit)
     const uint32_t budget_end = st.exact ? n : (uint32_t)((uint64_t)chunk_end + budget < n ? chunk_end + budget : n);
-    (void)chunk_start;
 
     uint32_t n_new = 0, cur, p = 0;
+    uint32_t first_start = IDX_NONE;
     if (resume) {
-        for (uint32_t k = 0; k < old_n; k++) new_list[k] = old_list[k];
+        if (writer)
+            for (uint32_t k = 0; k < old_n; k++) new_list[k] = old_list[k];
         n_new = old_n;
+        if (old_n) first_start = old_list[0].start_index;
         cur = old_trunc;
     } else {
         cur = st.new_entry;
     }
-    RegularityTracker trk;
-    trk.init(ts, cur, n);
+    fitter.begin(cur);
     uint32_t exit = IDX_NONE, truncated_at = 0;
     bool done = false;
     while (cur < chunk_end) {
@@ -427,7 +446,10 @@ MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *va
             while (p < old_n && old_list[p].end_index < cur) p++;
             bool inside = p < old_n && old_list[p].start_index < cur; // strictly inside old model p
             if (!inside) { // the old chain also started a fit at cur: identical from here on
-                for (uint32_t k = p; k < old_n; k++) new_list[n_new++] = old_list[k];
+                if (n_new == 0 && p < old_n) first_start = old_list[p].start_index;
+                if (writer)
+                    for (uint32_t k = p; k < old_n; k++) new_list[n_new + (k - p)] = old_list[k];
+                n_new += old_n - p;
                 exit = old_exit;
                 truncated_at = old_trunc;
                 done = true;
@@ -435,14 +457,16 @@ MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *va
             }
         }
         bool aborted;
-        FittedModel model = fit_next_model(eb, ts, values, cur, n, trk, budget_end, aborted);
+        FittedModel model = fitter.fit(cur, budget_end, aborted);
         if (aborted) {
             truncated_at = cur;
             done = true;
             break;
         }
         if (model.bytes_per_value <= 4.0f) { // compression.rs:238
-            new_list[n_new++] = model;
+            if (n_new == 0) first_start = model.start_index;
+            if (writer) new_list[n_new] = model;
+            n_new++;
             cur = model.end_index + 1;
         } else {
             cur += 1; // compression.rs:261: this point becomes a residual; refit from the next one
@@ -453,10 +477,10 @@ MDB_DEV void spec_chain(const ErrorBound &eb, const int64_t *ts, const float *va
     st.exit = exit;
     st.truncated_at = truncated_at;
     st.n_models = n_new;
-    st.first_start = n_new ? new_list[0].start_index : IDX_NONE;
+    st.first_start = first_start;
     st.buf ^= 1;
     st.dirty = 0;
-    if (trk.irregular) st.irregular = 1;
+    if (fitter.irregular()) st.irregular = 1;
 }
 
 // Walks the chunks of one unit in order and marks the chunks whose chain must be (re)run.

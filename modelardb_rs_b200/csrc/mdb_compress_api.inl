@@ -85,8 +85,39 @@ __global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ t
     uint32_t chunk_start = c * chunk_len;
     uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
     ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-    spec_chain(eb, ts + a, values + a, n, chunk_start, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+    ScalarFit fitter(eb, ts + a, values + a, n);
+    spec_chain(fitter, true, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
     st[g] = s;
+}
+
+// One WARP per chunk: the chain's control flow is uniform across the lanes and every fit is done by the
+// 32 lanes together (mdb_fit_warp.cuh).  This is the default engine: it does not need tens of
+// thousands of independent chains to fill the GPU, and a warp's loads of 32 consecutive points are
+// fully coalesced (128 B of values, 256 B of timestamps per step).
+constexpr int CHAIN_WARPS = 4;
+__global__ void __launch_bounds__(CHAIN_WARPS * 32) k_spec_chain_warp(const int64_t *__restrict__ ts, const float *__restrict__ values,
+                                                                      const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
+                                                                      const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
+                                                                      const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, uint32_t chunk_len,
+                                                                      ChunkState *st, FittedModel *lists, const uint64_t *__restrict__ list_base,
+                                                                      const uint32_t *__restrict__ list_cap) {
+    __shared__ double smem[CHAIN_WARPS][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t g = (uint64_t)blockIdx.x * CHAIN_WARPS + warp;
+    if (g >= n_chunks) return; // whole warps leave together
+    ChunkState s = st[g];
+    if (!s.dirty) return;
+    uint32_t u = chunk_unit[g];
+    uint64_t a = unit_off[u];
+    uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+    uint32_t c = (uint32_t)(g - chunk_base[u]);
+    uint32_t chunk_start = c * chunk_len;
+    uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
+    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    WarpFit fitter(eb, ts + a, values + a, n, smem[warp]);
+    spec_chain(fitter, lane == 0, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+    __syncwarp();
+    if (lane == 0) st[g] = s;
 }
 
 __global__ void __launch_bounds__(128) k_spec_propagate(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
@@ -201,6 +232,13 @@ int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len) {
 
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return ctx ? ctx->last_rounds : 0; }
 
+int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (engine < 0 || engine > 2) return fail("fit engine must be 0 (automatic), 1 (one thread per chain) or 2 (one warp per chain)");
+    ctx->fit_mode = engine;
+    return MDBCU_SUCCESS;
+}
+
 int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timestamps, const float *values, const uint64_t *unit_off,
                    uint64_t n_units, const uint8_t *eb_kind, const float *eb_value, mdbcu_segments **out) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
@@ -306,8 +344,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
         uint32_t round = 0;
         while (G) {
-            LAUNCH(ctx, k_spec_chain, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, G, lanes, chunk_len,
-                   st.p, lists.p, list_base.p, list_cap.p);
+            if (ctx->fit_mode == 1)
+                LAUNCH(ctx, k_spec_chain, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, G, lanes,
+                       chunk_len, st.p, lists.p, list_base.p, list_cap.p);
+            else
+                LAUNCH(ctx, k_spec_chain_warp, div_up(G, CHAIN_WARPS), CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
+                       chunk_unit.p, G, chunk_len, st.p, lists.p, list_base.p, list_cap.p);
             round++;
             TRY_SG(cudaMemsetAsync(counters.p, 0, sizeof(CompressCounters), s));
             LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, round == 1 ? 1 : 0, counters.p);

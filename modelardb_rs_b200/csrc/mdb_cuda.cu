@@ -24,6 +24,7 @@
 #include "../../include/modelardb_cuda.h"
 #include "mdb_aggregate.cuh"
 #include "mdb_compress.cuh"
+#include "mdb_fit_warp.cuh"
 #include "mdb_grid.cuh"
 
 using namespace mdb;
@@ -65,6 +66,7 @@ struct mdbcu_context {
     int sm_count = 148;
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
+    int fit_mode = 0;                // 0 automatic (warp per chain), 1 thread per chain, 2 warp per chain
     // optional per-kernel CUDA-event timing (mdbcu_context_set_profiling)
     bool profiling = false;
     std::vector<KernelStat> stats;

@@ -56,7 +56,9 @@ EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t
             for (uint32_t c = 0; c < C; c++)
                 if (st[c].dirty) {
                     uint32_t cs = c * L, ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
-                    spec_chain(eb, uts, uval, n, cs, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
+                    (void)cs;
+                    ScalarFit fitter(eb, uts, uval, n);
+                    spec_chain(fitter, true, n, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
                 }
             rounds++;
             if (spec_propagate_unit(n, L, C, st.data(), rounds == 1) == 0) break;

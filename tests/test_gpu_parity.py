@@ -99,12 +99,15 @@ def test_device_space_matches_host_space(oracle, ctx, case):
     seg.free()
 
 
+@pytest.mark.parametrize("engine", [1, 2], ids=["thread-per-chain", "warp-per-chain"])
 @pytest.mark.parametrize("chunk_len", [8, 64, 1000, 4096])
-def test_parallel_segmentation_is_independent_of_chunk_length(oracle, chunk_len):
+def test_parallel_segmentation_is_independent_of_chunk_length(oracle, chunk_len, engine):
     """The chunked, speculative, fixpoint-stitched segmentation (csrc/mdb_compress.cuh) must yield exactly
-    the sequential chain's rows for every chunk length, including chunks far shorter than a segment."""
+    the sequential chain's rows for every chunk length, including chunks far shorter than a segment, and
+    with either fit engine (one thread, or 32 lanes cooperating on each fit: csrc/mdb_fit_warp.cuh)."""
     ctx = mc.Context(0)
     ctx.set_chunk_len(chunk_len)
+    ctx.set_fit_engine(engine)
     for name, ts, vals, off, ebs in CASES:
         if len(ts) > 20_000 and chunk_len < 64:
             continue
