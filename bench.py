@@ -417,22 +417,25 @@ def main():
         "k_agg_segments": seg_bytes,
         "k_compress_emit": seg_bytes,
     }
-    dominant = max(kstats.items(), key=lambda kv: kv[1][0])[0] if kstats else None
+    # The chain kernel runs once per fixpoint round; its unit of work is one SLAB (one step), so every
+    # kernel is accounted per step: algorithmic bytes of one slab / device time the kernel took in one step.
+    algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_chain"]
+    per_step_ms = {k: v[0] / args.steps for k, v in kstats.items()}
+    dominant = max(per_step_ms.items(), key=lambda kv: kv[1])[0] if per_step_ms else None
     roofline = None
     if dominant:
-        ms, cnt = kstats[dominant]
-        avg_ms = ms / max(1, cnt)
         ab = algo_bytes.get(dominant, 12 * n)
-        achieved = ab / (avg_ms / 1000.0) / 1e9
+        achieved = ab / (per_step_ms[dominant] / 1000.0) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms, "peak_source": peak_src,
-                    "kernel_share_of_step": ms / total_ms,
-                    "all_kernels_ms_per_step": {k: v[0] / args.steps for k, v in sorted(kstats.items(), key=lambda kv: -kv[1][0])}}
-        for k in ("k_grid_tile", "k_spec_chain"):
-            if k in kstats and kstats[k][1]:
-                a = algo_bytes[k] / (kstats[k][0] / kstats[k][1] / 1000.0) / 1e9
-                roofline[f"{k}_GBps"] = a
-                roofline[f"{k}_frac"] = a / peak
+                    "traffic": None, "algorithmic_bytes_per_step": ab, "kernel_ms_per_step": per_step_ms[dominant],
+                    "launches_per_step": kstats[dominant][1] / args.steps, "peak_source": peak_src,
+                    "kernel_share_of_step": per_step_ms[dominant] / ms_per_step,
+                    "all_kernels_ms_per_step": dict(sorted(per_step_ms.items(), key=lambda kv: -kv[1]))}
+        for k in ("k_grid_tile", "k_spec_chain", "k_spec_chain_warp", "k_grid_sequential", "k_agg_segments"):
+            if k in per_step_ms and per_step_ms[k] > 0:
+                a_ = algo_bytes[k] / (per_step_ms[k] / 1000.0) / 1e9
+                roofline[f"{k}_GBps"] = a_
+                roofline[f"{k}_frac"] = a_ / peak
 
     cpu_baseline = None
     if not args.no_cpu_baseline:

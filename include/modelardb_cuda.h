@@ -126,6 +126,14 @@ uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
  * chain (32 lanes fit 32 points per step, csrc/mdb_fit_warp.cuh).  Results are identical. */
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine);
 
+/* Diagnostics: fit_next_model (compression.rs:280-301) at each of `starts` with the chosen engine
+ * (1 one thread, 2 one warp); out receives n_starts records of 40 bytes {u32 start, u32 end, f32 min,
+ * f32 max, f32 last, f32 bytes_per_value, i32 model_type_id, i32 values_len, i32 aborted, i32 irregular}.
+ * Host space only.  Used by the tests to compare the two engines model by model. */
+int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timestamps, const float *values, uint32_t n,
+                           int eb_kind, float eb_value, int engine, const uint32_t *starts,
+                           const uint32_t *budget_ends, uint32_t n_starts, void *out);
+
 uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
 /* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off
  * (nullable) receives a pointer to n_units + 1 row offsets: unit u produced rows

@@ -420,3 +420,62 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 }
 
 } // extern "C"
+
+// ---- diagnostics -----------------------------------------------------------------------------------
+// fit_next_model for a list of start indices with either engine, so that tests can compare the
+// warp-cooperative fit against the one-thread fit model by model.
+struct DebugFit {
+    uint32_t start_index, end_index;
+    float min_value, max_value, model_last_value, bytes_per_value;
+    int32_t model_type_id, values_len, aborted, irregular;
+};
+
+__global__ void __launch_bounds__(32) k_debug_fit(const int64_t *ts, const float *values, uint32_t n, int kind, float value, int engine,
+                                                  const uint32_t *starts, const uint32_t *budget_ends, uint32_t n_starts, DebugFit *out) {
+    __shared__ double smem[64];
+    uint32_t k = blockIdx.x;
+    if (k >= n_starts) return;
+    ErrorBound eb = make_error_bound(kind, value);
+    bool aborted = false, irregular = false;
+    FittedModel m;
+    if (engine == 2) {
+        WarpFit f(eb, ts, values, n, smem);
+        f.begin(starts[k]);
+        m = f.fit(starts[k], budget_ends[k], aborted);
+        irregular = f.irregular();
+    } else {
+        ScalarFit f(eb, ts, values, n);
+        f.begin(starts[k]);
+        m = f.fit(starts[k], budget_ends[k], aborted);
+        irregular = f.irregular();
+    }
+    if (threadIdx.x == 0) {
+        DebugFit d;
+        d.start_index = m.start_index; d.end_index = m.end_index;
+        d.min_value = m.min_value; d.max_value = m.max_value; d.model_last_value = m.model_last_value;
+        d.bytes_per_value = m.bytes_per_value;
+        d.model_type_id = m.model_type_id; d.values_len = m.values_len; d.aborted = aborted; d.irregular = irregular;
+        out[k] = d;
+    }
+}
+
+extern "C" int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timestamps, const float *values, uint32_t n, int eb_kind,
+                                      float eb_value, int engine, const uint32_t *starts, const uint32_t *budget_ends, uint32_t n_starts,
+                                      void *out /* n_starts x 40 bytes */) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    cudaStream_t s = ctx->stream;
+    DBuf<int64_t> d_ts;
+    DBuf<float> d_val;
+    DBuf<uint32_t> d_starts, d_budget;
+    DBuf<DebugFit> d_out;
+    CUDA_TRY(upload(d_ts, timestamps, n, s));
+    CUDA_TRY(upload(d_val, values, n, s));
+    CUDA_TRY(upload(d_starts, starts, n_starts, s));
+    CUDA_TRY(upload(d_budget, budget_ends, n_starts, s));
+    CUDA_TRY(d_out.alloc(n_starts, s));
+    if (n_starts) LAUNCH(ctx, k_debug_fit, n_starts, 32, 0, d_ts.p, d_val.p, n, eb_kind, eb_value, engine, d_starts.p, d_budget.p, n_starts, d_out.p);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n_starts * sizeof(DebugFit), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return MDBCU_SUCCESS;
+}
