@@ -50,7 +50,8 @@ def parse_args():
                         "buffers: 65 536-point buffers (server ingestion path)")
     p.add_argument("--kind", default="sine", choices=["sine", "walk"])
     p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
-    p.add_argument("--e2e-steps", type=int, default=3)
+    p.add_argument("--e2e-steps", type=int, default=3, help="slabs per worker in the timed e2e region")
+    p.add_argument("--e2e-workers", type=int, default=3, help="host threads pipelining slabs (one context each)")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -354,49 +355,64 @@ def main():
     # ---- e2e: same path through the C-ABI with HOST (pinned) buffers
     e2e = None
     if not args.no_e2e:
-        es, esteps = min(args.e2e_series, n_series), args.e2e_steps
+        # The user-level pattern for host data: slabs are independent, so a few worker threads -- each with its
+        # own context (stream) and its own pinned buffers -- keep H2D of one slab, kernels of another and D2H
+        # of a third in flight (the calls are blocking but release the GIL; PCIe is full duplex).
+        es, esteps, workers = min(args.e2e_series, n_series), args.e2e_steps, args.e2e_workers
         en = es * n_points
-        h_ts = torch.empty(en, dtype=torch.int64).pin_memory()
-        h_vals = torch.empty(en, dtype=torch.float32).pin_memory()
-        h_ts.copy_(ts[:en])
-        h_vals.copy_(vals[:en])
-        h_ts_out = torch.empty(en, dtype=torch.int64).pin_memory()
-        h_val_out = torch.empty(en, dtype=torch.float32).pin_memory()
         e_off = unit_offsets(es, n_points, args.units)
         e_units = len(e_off) - 1
-        e_group = e_off_group = None
-        if args.units == "series":
-            e_group_sel = None
-        h2d = d2h = 0
+        bufs = []
+        for w in range(workers):
+            b = {"ctx": mc.Context(local_rank),
+                 "ts": torch.empty(en, dtype=torch.int64).pin_memory(), "vals": torch.empty(en, dtype=torch.float32).pin_memory(),
+                 "ts_out": torch.empty(en, dtype=torch.int64).pin_memory(), "val_out": torch.empty(en, dtype=torch.float32).pin_memory()}
+            b["ts"].copy_(ts[:en])
+            b["vals"].copy_(vals[(w * en) % max(1, n - en + 1):][:en] if n > en else vals[:en])
+            bufs.append(b)
+        io = {"h2d": 0, "d2h": 0}
 
-        def e2e_step():
-            nonlocal h2d, d2h
-            seg = mc.compress(h_ts.numpy(), h_vals.numpy(), e_off, [eb] * e_units, ctx)
+        def e2e_slab(b):
+            seg = mc.compress(b["ts"].numpy(), b["vals"].numpy(), e_off, [eb] * e_units, b["ctx"])
             host_seg = seg.to_host()                      # what the Rust caller gets back: the RecordBatch columns
             seg.free()
-            mc.grid(host_seg, h_ts_out.numpy(), h_val_out.numpy(), ctx)
+            mc.grid(host_seg, b["ts_out"].numpy(), b["val_out"].numpy(), b["ctx"])
             uso = host_seg.unit_seg_off
             group = uso if args.units == "series" else uso[:: (e_units // es)]
-            res = mc.aggregate(host_seg, group, ctx)
+            res = mc.aggregate(host_seg, group, b["ctx"])
             seg_b = host_seg.segment_bytes() + 3 * 8 * (len(host_seg) + 1)
-            h2d = 12 * en + 2 * seg_b                      # raw points in; segments in again for grid and aggregate
-            d2h = seg_b + 12 * en + 24 * len(res[0])       # segments out; reconstructed points out; aggregates out
+            io["h2d"] = 12 * en + 2 * seg_b               # raw points in; segments in again for grid and aggregate
+            io["d2h"] = seg_b + 12 * en + 24 * len(res[0])  # segments out; reconstructed points out; aggregates out
             return res
 
-        for _ in range(1):
-            e2e_step()
+        def worker(b, k):
+            for _ in range(k):
+                e2e_slab(b)
+
+        def run_all(k):
+            th = [threading.Thread(target=worker, args=(b, k)) for b in bufs]
+            for t_ in th:
+                t_.start()
+            for t_ in th:
+                t_.join()
+
+        run_all(1)  # warm-up: every worker once
         barrier()
         t0 = time.perf_counter()
-        for _ in range(esteps):
-            e2e_step()
+        run_all(esteps)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=device)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * en * esteps / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(h2d),
-               "d2h_bytes_per_step": int(d2h), "series_per_gpu_per_step": es, "steps": esteps,
-               "note": "numpy views of pinned host tensors passed to the C-ABI in MDBCU_HOST space; wall clock, max over ranks"}
+        slabs = workers * esteps
+        e2e = {"value": world * en * slabs / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(io["h2d"]),
+               "d2h_bytes_per_step": int(io["d2h"]), "series_per_gpu_per_step": es, "steps": slabs, "workers": workers,
+               "note": "a step is one slab through compress -> to_host -> grid -> aggregate with numpy views of pinned host "
+                       "tensors in MDBCU_HOST space; `workers` threads each own a context and pipeline slabs; wall clock, max over ranks"}
+        for b in bufs:
+            b["ctx"].close()
+        del bufs
 
     if rank != 0:
         if world > 1:

@@ -134,6 +134,11 @@ int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timestamps, const 
                            int eb_kind, float eb_value, int engine, const uint32_t *starts,
                            const uint32_t *budget_ends, uint32_t n_starts, void *out);
 
+/* Diagnostics: reads and clears eight event counters of the warp fit engine (fits, fits handed to the
+ * one-thread code, steps, quiet steps, speculation passes, mismatches, in-order PMC sums, unused).
+ * They only count in a library built with -DMDB_FIT_COUNTERS. */
+int mdbcu_debug_counters(mdbcu_context *ctx, uint64_t *out8);
+
 uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
 /* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off
  * (nullable) receives a pointer to n_units + 1 row offsets: unit u produced rows

@@ -17,7 +17,7 @@ SYMBOLS = (
     "mdbcu_last_error", "mdbcu_device_count", "mdbcu_version",
     "mdbcu_context_create", "mdbcu_context_destroy", "mdbcu_context_set_stream", "mdbcu_context_stream",
     "mdbcu_context_launch_count", "mdbcu_context_set_profiling", "mdbcu_context_kernel_stat",
-    "mdbcu_context_set_chunk_len", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models",
+    "mdbcu_context_set_chunk_len", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models", "mdbcu_debug_counters",
     "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
     "mdbcu_grid_count", "mdbcu_grid", "mdbcu_segment_sums", "mdbcu_aggregate",
 )
@@ -82,6 +82,8 @@ def lib():
     L.mdbcu_context_set_fit_engine.restype = i32
     L.mdbcu_debug_fit_models.argtypes = [vp, vp, vp, C.c_uint32, i32, C.c_float, i32, vp, vp, C.c_uint32, vp]
     L.mdbcu_debug_fit_models.restype = i32
+    L.mdbcu_debug_counters.argtypes = [vp, vp]
+    L.mdbcu_debug_counters.restype = i32
     L.mdbcu_compress.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, C.POINTER(vp)]
     L.mdbcu_compress.restype = i32
     L.mdbcu_segments_len.argtypes = [vp]

@@ -144,7 +144,57 @@ struct FittedModel { // CompressedSegmentBuilder, types.rs:148-166
     float min_value, max_value, model_last_value, bytes_per_value;
     int8_t model_type_id;
     uint8_t values_len; // Swing: 0 -> [] (first < last), 1 -> [0]
+    // A Swing model fitted by the warp engine is left `pending`: its boundaries (all the chain needs) are
+    // final, but min/max/last still need the two MSE sums of swing.rs:212-228, which are order dependent.
+    // They are accumulated afterwards, strictly in order, by one thread per ACCEPTED model
+    // (swing_finish), instead of on the latency-critical path of the chain.
+    uint8_t pending;
+    uint8_t pad;
+    double lower_slope, upper_slope; // Swing bounds when the fit ended (valid when pending)
 };
+
+// Completes a pending Swing model: the MSE sums over its points in order (swing.rs:180-193, 212-228),
+// then Swing::model (swing.rs:246-259) and select_swing (types.rs:122-144).
+// The MSE terms of one point (swing.rs:212-228): (0, 0) when the value equals the first value.
+MDB_DEV void swing_mse_terms(int64_t t0, double v0, int64_t t, double v, double &x, double &y) {
+    x = 0.0;
+    y = 0.0;
+    if (!equal_or_nan(v0, v)) {
+        const double dt = (double)(t - t0);
+        x = __dmul_rn(__dsub_rn(v, v0), dt);
+        y = __dmul_rn(dt, dt);
+    }
+}
+
+MDB_DEV void swing_finish_from_sums(FittedModel &m, double num, double den, const int64_t *ts, const float *values);
+
+MDB_DEV void swing_finish(FittedModel &m, const int64_t *ts, const float *values) {
+    const int64_t t0 = ts[m.start_index];
+    const double v0 = (double)values[m.start_index];
+    double num = 0.0, den = 0.0;
+    for (uint32_t i = m.start_index + 2; i <= m.end_index; i++) { // the first two points add no term
+        double x, y;
+        swing_mse_terms(t0, v0, ts[i], (double)values[i], x, y);
+        num = __dadd_rn(num, x);
+        den = __dadd_rn(den, y);
+    }
+    swing_finish_from_sums(m, num, den, ts, values);
+}
+
+MDB_DEV void swing_finish_from_sums(FittedModel &m, double num, double den, const int64_t *ts, const float *values) {
+    const int64_t t0 = ts[m.start_index];
+    const double v0 = (double)values[m.start_index];
+    const double projected = __ddiv_rn(num, den);
+    const double slope = rust_maxd(m.lower_slope, rust_mind(projected, m.upper_slope));
+    const double last_d = __dadd_rn(__dmul_rn(slope, (double)(ts[m.end_index] - t0)), v0);
+    const float first = canonical_nan(__double2float_rn(v0));
+    const float last = canonical_nan(__double2float_rn(last_d));
+    m.min_value = rust_minf(first, last);
+    m.max_value = rust_maxf(first, last);
+    m.values_len = (first < last) ? 0 : 1;
+    m.model_last_value = last;
+    m.pending = 0;
+}
 
 // Tracks, as the chain first touches each point of the unit, whether any sampling-interval change has
 // been seen so far.  While none has, every row is regular (a sub-range of a regular range is regular)
@@ -190,6 +240,9 @@ MDB_DEV FittedModel fit_next_model(const ErrorBound &eb, const int64_t *ts, cons
     }
     FittedModel m;
     m.start_index = start;
+    m.pending = 0;
+    m.pad = 0;
+    m.lower_slope = m.upper_slope = 0.0;
     if (aborted) { // the caller discards an abandoned fit
         m.end_index = start;
         m.min_value = m.max_value = m.model_last_value = 0.0f;
@@ -401,7 +454,7 @@ MDB_DEV uint32_t models_per_chunk(uint32_t chunk_len) { return chunk_len / 8 + 2
 // of the unit); the cut is resumed later from an exact entry.
 // Fit: the fit_next_model engine -- ScalarFit (one thread) or WarpFit (32 lanes cooperate on every fit,
 // mdb_fit_warp.cuh); in the warp case every lane runs this control code redundantly on uniform values
-// and only the `writer` lane stores to global memory.
+// and stores to global memory are made by lane 0 (list copies are spread over the n_lanes lanes).
 struct ScalarFit {
     const ErrorBound &eb;
     const int64_t *ts;
@@ -417,7 +470,7 @@ struct ScalarFit {
 };
 
 template <typename Fit>
-MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end, uint32_t budget, ChunkState &st,
+MDB_DEV void spec_chain(Fit &fitter, uint32_t lane, uint32_t n_lanes, uint32_t n, uint32_t chunk_end, uint32_t budget, ChunkState &st,
                         FittedModel *lists, uint32_t cap) {
     const FittedModel *old_list = lists + (size_t)st.buf * cap;
     FittedModel *new_list = lists + (size_t)(st.buf ^ 1) * cap;
@@ -430,8 +483,7 @@ MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end
     uint32_t n_new = 0, cur, p = 0;
     uint32_t first_start = IDX_NONE;
     if (resume) {
-        if (writer)
-            for (uint32_t k = 0; k < old_n; k++) new_list[k] = old_list[k];
+        for (uint32_t k = lane; k < old_n; k += n_lanes) new_list[k] = old_list[k]; // copies are spread over the lanes
         n_new = old_n;
         if (old_n) first_start = old_list[0].start_index;
         cur = old_trunc;
@@ -447,8 +499,7 @@ MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end
             bool inside = p < old_n && old_list[p].start_index < cur; // strictly inside old model p
             if (!inside) { // the old chain also started a fit at cur: identical from here on
                 if (n_new == 0 && p < old_n) first_start = old_list[p].start_index;
-                if (writer)
-                    for (uint32_t k = p; k < old_n; k++) new_list[n_new + (k - p)] = old_list[k];
+                for (uint32_t k = p + lane; k < old_n; k += n_lanes) new_list[n_new + (k - p)] = old_list[k];
                 n_new += old_n - p;
                 exit = old_exit;
                 truncated_at = old_trunc;
@@ -465,7 +516,7 @@ MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end
         }
         if (model.bytes_per_value <= 4.0f) { // compression.rs:238
             if (n_new == 0) first_start = model.start_index;
-            if (writer) new_list[n_new] = model;
+            if (lane == 0) new_list[n_new] = model;
             n_new++;
             cur = model.end_index + 1;
         } else {
@@ -490,19 +541,27 @@ MDB_DEV void spec_chain(Fit &fitter, bool writer, uint32_t n, uint32_t chunk_end
 // round 0); on data whose chains do not re-synchronise (very smooth signal, loose bound, segments of
 // thousands of points) later rounds re-run only the first inconsistent chunk, whose entry is exact, so
 // the total work stays within ~3x the sequential chain instead of growing quadratically.
-MDB_DEV uint32_t spec_propagate_unit(uint32_t n, uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, bool allow_optimistic) {
-    uint32_t e = 0, dirty = 0;
+// resume_c / resume_e: the walk's position (chunk, entry) up to which the unit's chains are already known
+// to be final; kept between rounds so that a round does not re-walk the finished prefix of the unit.
+// on_dirty(c) is called for every chunk marked dirty (the kernels use it to build the next round's worklist).
+template <typename OnDirty>
+MDB_DEV uint32_t spec_propagate_unit(uint32_t n, uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, bool allow_optimistic,
+                                     uint32_t &resume_c, uint32_t &resume_e, OnDirty &&on_dirty) {
+    uint32_t e = resume_e, dirty = 0;
     bool exact = true; // everything before the first inconsistent chunk is the true sequential chain
-    for (uint32_t c = 0; c < n_chunks; c++) {
+    uint32_t c = resume_c;
+    for (; c < n_chunks; c++) {
         uint32_t chunk_end = (uint64_t)(c + 1) * chunk_len < n ? (c + 1) * chunk_len : n;
         if (e >= chunk_end) continue; // no fit starts in this chunk: a model spans it
         ChunkState &s = st[c];
+        if (exact) { resume_c = c; resume_e = e; } // chunk c is the first one not yet known to be final
         if (s.entry == e) {
             if (s.exit == IDX_NONE) { // right entry, but the chain was cut short: resume it
                 if (!exact) break;    // (once everything before it is final, so that it runs without a budget)
                 s.new_entry = e;
-                s.exact = exact ? 1 : 0;
+                s.exact = 1;
                 s.dirty = 1;
+                on_dirty(c);
                 dirty++;
                 break; // its exit is unknown, nothing after it can be checked yet
             }
@@ -512,12 +571,14 @@ MDB_DEV uint32_t spec_propagate_unit(uint32_t n, uint32_t chunk_len, uint32_t n_
             s.new_entry = e;
             s.exact = exact ? 1 : 0;
             s.dirty = 1;
+            on_dirty(c);
             dirty++;
             exact = false;
             if (s.exit == IDX_NONE) break;
             e = s.exit; // optimistic: the re-run will most likely splice into the old chain and keep its exit
         }
     }
+    if (exact && c >= n_chunks) { resume_c = n_chunks; resume_e = e; } // the whole unit is final
     return dirty;
 }
 

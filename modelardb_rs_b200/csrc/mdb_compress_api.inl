@@ -70,12 +70,14 @@ __global__ void __launch_bounds__(128) k_spec_init(const uint64_t *unit_off, uin
 // one per warp, no divergence and every SM busy; many chains: lanes fill up).
 __global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
                                                    const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
-                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks,
-                                                   uint32_t lanes, uint32_t chunk_len, ChunkState *st, FittedModel *lists,
-                                                   const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap) {
+                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
+                                                   const uint32_t *__restrict__ worklist, uint64_t n_work, uint32_t lanes, uint32_t chunk_len,
+                                                   ChunkState *st, FittedModel *lists, const uint64_t *__restrict__ list_base,
+                                                   const uint32_t *__restrict__ list_cap) {
     if (threadIdx.x >= lanes) return;
-    uint64_t g = (uint64_t)blockIdx.x * lanes + threadIdx.x;
-    if (g >= n_chunks) return;
+    uint64_t w = (uint64_t)blockIdx.x * lanes + threadIdx.x;
+    if (w >= n_work) return;
+    uint64_t g = worklist ? worklist[w] : w; // round 0: every chunk
     ChunkState s = st[g];
     if (!s.dirty) return;
     uint32_t u = chunk_unit[g];
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ t
     uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
     ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
     ScalarFit fitter(eb, ts + a, values + a, n);
-    spec_chain(fitter, true, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+    spec_chain(fitter, 0u, 1u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
     st[g] = s;
 }
 
@@ -98,13 +100,14 @@ constexpr int CHAIN_WARPS = 4;
 __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_spec_chain_warp(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                       const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
                                                                       const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
-                                                                      const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, uint32_t chunk_len,
-                                                                      ChunkState *st, FittedModel *lists, const uint64_t *__restrict__ list_base,
-                                                                      const uint32_t *__restrict__ list_cap) {
-    __shared__ double smem[CHAIN_WARPS][64];
+                                                                      const uint32_t *__restrict__ chunk_unit, const uint32_t *__restrict__ worklist,
+                                                                      uint64_t n_work, uint32_t chunk_len, ChunkState *st, FittedModel *lists,
+                                                                      const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap) {
+    __shared__ double smem[CHAIN_WARPS][WarpFit::SMEM_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    uint64_t g = (uint64_t)blockIdx.x * CHAIN_WARPS + warp;
-    if (g >= n_chunks) return; // whole warps leave together
+    uint64_t w = (uint64_t)blockIdx.x * CHAIN_WARPS + warp;
+    if (w >= n_work) return; // whole warps leave together
+    uint64_t g = worklist ? worklist[w] : w; // round 0: every chunk
     ChunkState s = st[g];
     if (!s.dirty) return;
     uint32_t u = chunk_unit[g];
@@ -115,21 +118,85 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32) k_spec_chain_warp(const int6
     uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
     ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
     WarpFit fitter(eb, ts + a, values + a, n, smem[warp]);
-    spec_chain(fitter, lane == 0, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+    spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
     __syncwarp();
     if (lane == 0) st[g] = s;
 }
 
+// After the fixpoint: one warp per chunk, one lane per accepted model -- completes the pending Swing
+// models (their order-dependent MSE sums, see swing_finish).  Only models of the FINAL chains are
+// finished; speculative models that were spliced away never cost this pass.
+__global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict__ ts, const float *__restrict__ values,
+                                                      const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ chunk_unit,
+                                                      uint64_t n_chunks, const ChunkState *st, FittedModel *lists,
+                                                      const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap) {
+    __shared__ double smem[4][64];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint64_t g = (uint64_t)blockIdx.x * 4 + warp;
+    if (g >= n_chunks) return;
+    const ChunkState s = st[g];
+    if (s.skipped || s.n_models == 0) return;
+    uint64_t a = unit_off[chunk_unit[g]];
+    const int64_t *uts = ts + a;
+    const float *uval = values + a;
+    FittedModel *list = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2);
+    double *sx = smem[warp], *sy = smem[warp] + 32;
+    // The warp walks the chunk's models one after the other: 32 points per step are loaded coalesced
+    // and their terms computed in parallel; only the two running sums are chained, in point order.
+    for (uint32_t k = 0; k < s.n_models; k++) {
+        FittedModel m = list[k];
+        if (!m.pending) continue;
+        const int64_t t0 = uts[m.start_index];
+        const double v0 = (double)uval[m.start_index];
+        double num = 0.0, den = 0.0;
+        // the loads of the next two steps are in flight while this step's add chain runs
+        const uint32_t first = m.start_index + 2 + lane;
+        int64_t ta = first <= m.end_index ? uts[first] : 0, tb = first + 32 <= m.end_index ? uts[first + 32] : 0;
+        float va = first <= m.end_index ? uval[first] : 0.0f, vb = first + 32 <= m.end_index ? uval[first + 32] : 0.0f;
+        for (uint32_t base = m.start_index + 2; base <= m.end_index; base += 32) {
+            const uint32_t i = base + lane;
+            const int64_t tc = ta;
+            const float vc = va;
+            ta = tb;
+            va = vb;
+            tb = i + 64 <= m.end_index ? uts[i + 64] : 0;
+            vb = i + 64 <= m.end_index ? uval[i + 64] : 0.0f;
+            double x = 0.0, y = 0.0;
+            if (i <= m.end_index) swing_mse_terms(t0, v0, tc, (double)vc, x, y);
+            sx[lane] = x;
+            sy[lane] = y;
+            __syncwarp();
+            const int cnt = (int)min(32u, m.end_index - base + 1);
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+                const double xj = sx[j], yj = sy[j];
+                if (j < cnt) {
+                    num = __dadd_rn(num, xj);
+                    den = __dadd_rn(den, yj);
+                }
+            }
+            __syncwarp();
+        }
+        swing_finish_from_sums(m, num, den, uts, uval);
+        if (lane == 0) list[k] = m;
+    }
+}
+
 __global__ void __launch_bounds__(128) k_spec_propagate(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
-                                                        ChunkState *st, int allow_optimistic, CompressCounters *counters) {
+                                                        ChunkState *st, int allow_optimistic, uint2 *unit_resume, uint32_t *worklist,
+                                                        CompressCounters *counters) {
     uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u >= n_units) return;
     uint32_t n = (uint32_t)(unit_off[u + 1] - unit_off[u]);
     uint64_t g0 = chunk_base[u];
     uint32_t C = (uint32_t)(chunk_base[u + 1] - g0);
     if (C == 0) return;
-    uint32_t dirty = spec_propagate_unit(n, chunk_len, C, st + g0, allow_optimistic != 0);
-    if (dirty) atomicAdd(&counters->dirty, dirty);
+    uint2 r = unit_resume[u]; // (chunk, entry) up to which this unit is final
+    if (r.x >= C) return;
+    spec_propagate_unit(n, chunk_len, C, st + g0, allow_optimistic != 0, r.x, r.y, [&](uint32_t c) {
+        worklist[atomicAdd(&counters->dirty, 1u)] = (uint32_t)(g0 + c); // the next round runs exactly these chunks
+    });
+    unit_resume[u] = r;
 }
 
 __global__ void __launch_bounds__(128) k_spec_finalize(const uint64_t *unit_off, uint64_t n_units, const uint64_t *chunk_base, uint32_t chunk_len,
@@ -211,12 +278,15 @@ __global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict_
     compress_emit_segment(eb, rec, ts + a, values + a, ts_data + ts_off[r], val_data + val_off[r], res_data + res_off[r]);
 }
 
-// Chunk length: enough chains to give every SM 32 warps of 32 chains, within [2048, 65536] points.
+// Chunk length.  With one warp per chain, ~128 chains per SM already saturate the machine in round 0;
+// longer chunks mean fewer fixpoint rounds for units whose chains do not re-synchronise (measured on
+// 4e8 points: 4096 -> 140 ms, 16384 -> 74 ms, 65536 -> 81 ms).  The one-thread engine wants 32x more
+// chains (one per lane).  Within [4096, 65536] points.
 static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points) {
     if (ctx->chunk_len_override) return ctx->chunk_len_override;
-    uint64_t target_chains = (uint64_t)ctx->sm_count * 32 * 32;
+    uint64_t target_chains = (uint64_t)ctx->sm_count * 128 * (ctx->fit_mode == 1 ? 32 : 1);
     uint64_t len = n_points / target_chains;
-    uint32_t l = 2048;
+    uint32_t l = 4096;
     while (l < len && l < 65536) l <<= 1;
     return l;
 }
@@ -340,30 +410,41 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         DBuf<FittedModel> lists;
         TRY_SG(lists.alloc(n_models_cap, s));
 
-        // ---- rounds
-        const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
+        // ---- rounds: the chains of the chunks in the worklist, then the per-unit walk that builds the next worklist
+        DBuf<uint32_t> worklist;
+        DBuf<uint2> unit_resume;
+        TRY_SG(worklist.alloc(G, s));
+        TRY_SG(unit_resume.alloc(n_units, s));
+        TRY_SG(cudaMemsetAsync(unit_resume.p, 0, n_units * sizeof(uint2), s));
         uint32_t round = 0;
-        while (G) {
+        uint64_t n_work = G;
+        const uint32_t *d_work = nullptr; // round 0 runs every chunk
+        while (n_work) {
+            const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(n_work, (uint64_t)ctx->sm_count * 32)));
             if (ctx->fit_mode == 1)
-                LAUNCH(ctx, k_spec_chain, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, G, lanes,
-                       chunk_len, st.p, lists.p, list_base.p, list_cap.p);
+                LAUNCH(ctx, k_spec_chain, div_up(n_work, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, d_work,
+                       n_work, lanes, chunk_len, st.p, lists.p, list_base.p, list_cap.p);
             else
-                LAUNCH(ctx, k_spec_chain_warp, div_up(G, CHAIN_WARPS), CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
-                       chunk_unit.p, G, chunk_len, st.p, lists.p, list_base.p, list_cap.p);
+                LAUNCH(ctx, k_spec_chain_warp, div_up(n_work, CHAIN_WARPS), CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
+                       chunk_unit.p, d_work, n_work, chunk_len, st.p, lists.p, list_base.p, list_cap.p);
             round++;
             TRY_SG(cudaMemsetAsync(counters.p, 0, sizeof(CompressCounters), s));
-            LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, round == 1 ? 1 : 0, counters.p);
+            LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, round == 1 ? 1 : 0,
+                   unit_resume.p, worklist.p, counters.p);
             CompressCounters hc;
             TRY_SG(cudaMemcpyAsync(&hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
             TRY_SG(cudaStreamSynchronize(s));
             TRY_SG(cudaGetLastError());
-            if (hc.dirty == 0) break;
+            n_work = hc.dirty;
+            d_work = worklist.p;
             if (round > 4 * G + 8) return bail(fail("compress: chunk fixpoint did not converge (internal error)"));
         }
         ctx->last_rounds = round;
 
         // ---- rows
         LAUNCH(ctx, k_spec_finalize, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, unit_irregular.p);
+        if (G && ctx->fit_mode != 1)
+            LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p);
         if (G) LAUNCH(ctx, k_spec_count_rows, div_up(G, 128), 128, 0, st.p, G, lists.p, list_base.p, list_cap.p, rows.p);
         if (exclusive_scan<uint32_t>(ctx, rows.p, G, row_base.p)) return bail(MDBCU_FAILURE);
         LAUNCH(ctx, k_unit_seg_off, div_up(n_units + 1, 256), 256, 0, chunk_base.p, n_units, row_base.p, sg->unit_seg_off);
@@ -372,6 +453,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(cudaGetLastError());
         TRY_SG(recs.alloc(S, s));
         TRY_SG(row_unit.alloc(S, s));
+        const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
         if (G && S)
             LAUNCH(ctx, k_spec_records, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, lanes, st.p, lists.p,
                    list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p);
@@ -432,7 +514,7 @@ struct DebugFit {
 
 __global__ void __launch_bounds__(32) k_debug_fit(const int64_t *ts, const float *values, uint32_t n, int kind, float value, int engine,
                                                   const uint32_t *starts, const uint32_t *budget_ends, uint32_t n_starts, DebugFit *out) {
-    __shared__ double smem[64];
+    __shared__ double smem[WarpFit::SMEM_DOUBLES];
     uint32_t k = blockIdx.x;
     if (k >= n_starts) return;
     ErrorBound eb = make_error_bound(kind, value);
@@ -443,6 +525,7 @@ __global__ void __launch_bounds__(32) k_debug_fit(const int64_t *ts, const float
         f.begin(starts[k]);
         m = f.fit(starts[k], budget_ends[k], aborted);
         irregular = f.irregular();
+        if (!aborted && m.pending) swing_finish(m, ts, values); // every lane, redundantly
     } else {
         ScalarFit f(eb, ts, values, n);
         f.begin(starts[k]);
@@ -477,5 +560,16 @@ extern "C" int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timesta
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n_starts * sizeof(DebugFit), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
+    return MDBCU_SUCCESS;
+}
+
+// Diagnostics: reads (and clears) the fit event counters; all zero unless built with -DMDB_FIT_COUNTERS.
+extern "C" int mdbcu_debug_counters(mdbcu_context *ctx, uint64_t *out8 /* 16 entries */) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    unsigned long long h[16], z[16] = {0};
+    CUDA_TRY(cudaMemcpyFromSymbol(h, g_fit_counters, sizeof(h)));
+    CUDA_TRY(cudaMemcpyToSymbol(g_fit_counters, z, sizeof(z)));
+    for (int i = 0; i < 16; i++) out8[i] = h[i];
     return MDBCU_SUCCESS;
 }

@@ -51,17 +51,17 @@ EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t
             std::memset(&st[c], 0, sizeof(ChunkState));
             st[c].entry = IDX_NONE; st[c].exit = IDX_NONE; st[c].new_entry = c * L; st[c].dirty = 1; st[c].exact = c == 0;
         }
-        uint32_t rounds = 0;
+        uint32_t rounds = 0, resume_c = 0, resume_e = 0;
         while (true) { // rounds: k_spec_chain over dirty chunks, then k_spec_propagate per unit
             for (uint32_t c = 0; c < C; c++)
                 if (st[c].dirty) {
                     uint32_t cs = c * L, ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
                     (void)cs;
                     ScalarFit fitter(eb, uts, uval, n);
-                    spec_chain(fitter, true, n, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
+                    spec_chain(fitter, 0u, 1u, n, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
                 }
             rounds++;
-            if (spec_propagate_unit(n, L, C, st.data(), rounds == 1) == 0) break;
+            if (spec_propagate_unit(n, L, C, st.data(), rounds == 1, resume_c, resume_e, [](uint32_t) {}) == 0) break;
             if (rounds > 4 * C + 8) return nullptr; // must converge: one chunk becomes final per round at worst
         }
         max_rounds = std::max(max_rounds, rounds);
