@@ -51,7 +51,7 @@ def parse_args():
     p.add_argument("--kind", default="sine", choices=["sine", "walk"])
     p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
     p.add_argument("--e2e-steps", type=int, default=3, help="slabs per worker in the timed e2e region")
-    p.add_argument("--e2e-workers", type=int, default=3, help="host threads pipelining slabs (one context each)")
+    p.add_argument("--e2e-workers", type=int, default=4, help="host threads pipelining slabs (one context each)")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -372,17 +372,27 @@ def main():
             bufs.append(b)
         io = {"h2d": 0, "d2h": 0}
 
+        phase_s = {"compress": 0.0, "to_host": 0.0, "grid": 0.0, "aggregate": 0.0}
+
         def e2e_slab(b):
+            p0 = time.perf_counter()
             seg = mc.compress(b["ts"].numpy(), b["vals"].numpy(), e_off, [eb] * e_units, b["ctx"])
-            host_seg = seg.to_host()                      # what the Rust caller gets back: the RecordBatch columns
-            seg.free()
+            p1 = time.perf_counter()
+            host_seg = seg.to_host(copy=False)            # what the Rust caller gets back: the RecordBatch columns (host memory)
+            p2 = time.perf_counter()
             mc.grid(host_seg, b["ts_out"].numpy(), b["val_out"].numpy(), b["ctx"])
+            p3 = time.perf_counter()
             uso = host_seg.unit_seg_off
             group = uso if args.units == "series" else uso[:: (e_units // es)]
             res = mc.aggregate(host_seg, group, b["ctx"])
+            p4 = time.perf_counter()
+            for key, d in (("compress", p1 - p0), ("to_host", p2 - p1), ("grid", p3 - p2), ("aggregate", p4 - p3)):
+                phase_s[key] += d  # under the GIL; per-call wall time inside a worker, not exclusive time
             seg_b = host_seg.segment_bytes() + 3 * 8 * (len(host_seg) + 1)
             io["h2d"] = 12 * en + 2 * seg_b               # raw points in; segments in again for grid and aggregate
             io["d2h"] = seg_b + 12 * en + 24 * len(res[0])  # segments out; reconstructed points out; aggregates out
+            del host_seg
+            seg.free()
             return res
 
         def worker(b, k):
@@ -397,6 +407,8 @@ def main():
                 t_.join()
 
         run_all(1)  # warm-up: every worker once
+        for key in phase_s:
+            phase_s[key] = 0.0
         barrier()
         t0 = time.perf_counter()
         run_all(esteps)
@@ -408,6 +420,7 @@ def main():
         slabs = workers * esteps
         e2e = {"value": world * en * slabs / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(io["h2d"]),
                "d2h_bytes_per_step": int(io["d2h"]), "series_per_gpu_per_step": es, "steps": slabs, "workers": workers,
+               "call_ms_mean": {k: 1e3 * v / slabs for k, v in phase_s.items()},
                "note": "a step is one slab through compress -> to_host -> grid -> aggregate with numpy views of pinned host "
                        "tensors in MDBCU_HOST space; `workers` threads each own a context and pipeline slabs; wall clock, max over ranks"}
         for b in bufs:

@@ -215,14 +215,18 @@ class CompressedSegments:
     def unit_seg_off_device_ptr(self) -> int:
         return self._get(DEVICE)[1] or 0
 
-    def to_host(self) -> HostSegments:
+    def to_host(self, copy: bool = True) -> HostSegments:
+        """The columns in host memory.  copy=False returns views of the library's own (pinned) host copy: they
+        stay valid only while this object is alive and un-freed, and passing them back to grid / aggregate
+        skips the bounce through the staging ring."""
         v, uso = self._get(HOST)
         n = v.n_segments
 
         def arr(ptr, count, dt):
             if count == 0 or not ptr:
                 return np.zeros(0, dt)
-            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,)).copy()
+            a = np.ctypeslib.as_array(C.cast(ptr, C.POINTER(np.ctypeslib.as_ctypes_type(dt))), shape=(count,))
+            return a.copy() if copy else a
 
         cols = {}
         for c in ("model_type_id", "start_time", "end_time", "min_value", "max_value"):
@@ -231,7 +235,10 @@ class CompressedSegments:
             off = arr(getattr(v, name + "_off"), n + 1, np.uint64)
             cols[name + "_off"] = off
             cols[name + "_data"] = arr(getattr(v, name + "_data"), int(off[-1]) if len(off) else 0, np.uint8)
-        return HostSegments(unit_seg_off=arr(uso, self.n_units + 1, np.uint64), **cols)
+        host = HostSegments(unit_seg_off=arr(uso, self.n_units + 1, np.uint64), **cols)
+        if not copy:
+            host._owner = self
+        return host
 
 
 def _space_of(*arrays) -> int:

@@ -325,9 +325,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             first = unit_off[0];
             last = unit_off[n_units];
         } else {
-            CUDA_TRY(cudaMemcpyAsync(&first, unit_off, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaMemcpyAsync(&last, unit_off + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-            CUDA_TRY(cudaStreamSynchronize(s));
+            CUDA_TRY(post(ctx, 0, unit_off, 1));
+            CUDA_TRY(post(ctx, 1, unit_off + n_units, 1));
+            CUDA_TRY(sync_stream(ctx));
+            first = ctx->mailbox[0];
+            last = ctx->mailbox[1];
         }
         if (last < first) return fail("compress: unit_off is not monotone");
     }
@@ -345,11 +347,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     const uint8_t *d_kind = eb_kind;
     const float *d_ebv = eb_value;
     if (space == MDBCU_HOST && n_units) {
-        CUDA_TRY(upload(ts_buf, timestamps, n_points, s));
-        CUDA_TRY(upload(val_buf, values, n_points, s));
-        CUDA_TRY(upload(off_buf, unit_off, n_units + 1, s));
-        CUDA_TRY(upload(kind_buf, eb_kind, n_units, s));
-        CUDA_TRY(upload(ebv_buf, eb_value, n_units, s));
+        CUDA_TRY(upload(ctx, off_buf, unit_off, n_units + 1));
+        CUDA_TRY(upload(ctx, kind_buf, eb_kind, n_units));
+        CUDA_TRY(upload(ctx, ebv_buf, eb_value, n_units));
+        CUDA_TRY(upload(ctx, ts_buf, timestamps, n_points));
+        CUDA_TRY(upload(ctx, val_buf, values, n_points));
         d_ts = ts_buf.p; d_val = val_buf.p; d_off = off_buf.p; d_kind = kind_buf.p; d_ebv = ebv_buf.p;
     }
 
@@ -383,10 +385,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(chunk_base.alloc(n_units + 1, s));
         LAUNCH(ctx, k_unit_chunks, div_up(n_units, 256), 256, 0, d_off, n_units, d_kind, d_ebv, chunk_len, unit_chunks.p, status.p);
         if (exclusive_scan<uint32_t>(ctx, unit_chunks.p, n_units, chunk_base.p)) return bail(MDBCU_FAILURE);
-        uint64_t G = 0;
-        TRY_SG(cudaMemcpyAsync(&G, chunk_base.p + n_units, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+        TRY_SG(post(ctx, 0, chunk_base.p + n_units, 1));
         Status h;
         if (read_status(ctx, status.p, h, "unit (bad unit_off or error bound)")) return bail(MDBCU_FAILURE);
+        const uint64_t G = ctx->mailbox[0];
         if (G > 0xFFFFFFF0ull) return bail(fail("compress: too many chunks"));
 
         DBuf<ChunkState> st;
@@ -404,9 +406,9 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(counters.alloc(1, s));
         LAUNCH(ctx, k_spec_init, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, chunk_unit.p, list_cap.p);
         if (exclusive_scan<uint32_t>(ctx, list_cap.p, G, list_base.p)) return bail(MDBCU_FAILURE);
-        uint64_t n_models_cap = 0;
-        TRY_SG(cudaMemcpyAsync(&n_models_cap, list_base.p + G, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        TRY_SG(cudaStreamSynchronize(s));
+        TRY_SG(post(ctx, 0, list_base.p + G, 1));
+        TRY_SG(sync_stream(ctx));
+        const uint64_t n_models_cap = ctx->mailbox[0];
         DBuf<FittedModel> lists;
         TRY_SG(lists.alloc(n_models_cap, s));
 
@@ -431,10 +433,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             TRY_SG(cudaMemsetAsync(counters.p, 0, sizeof(CompressCounters), s));
             LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, round == 1 ? 1 : 0,
                    unit_resume.p, worklist.p, counters.p);
-            CompressCounters hc;
-            TRY_SG(cudaMemcpyAsync(&hc, counters.p, sizeof(hc), cudaMemcpyDeviceToHost, s));
-            TRY_SG(cudaStreamSynchronize(s));
+            static_assert(sizeof(CompressCounters) == 8, "CompressCounters is posted as one word");
+            TRY_SG(post(ctx, 0, counters.p, 1));
+            TRY_SG(sync_stream(ctx));
             TRY_SG(cudaGetLastError());
+            CompressCounters hc;
+            std::memcpy(&hc, ctx->mailbox, sizeof(hc));
             n_work = hc.dirty;
             d_work = worklist.p;
             if (round > 4 * G + 8) return bail(fail("compress: chunk fixpoint did not converge (internal error)"));
@@ -448,9 +452,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         if (G) LAUNCH(ctx, k_spec_count_rows, div_up(G, 128), 128, 0, st.p, G, lists.p, list_base.p, list_cap.p, rows.p);
         if (exclusive_scan<uint32_t>(ctx, rows.p, G, row_base.p)) return bail(MDBCU_FAILURE);
         LAUNCH(ctx, k_unit_seg_off, div_up(n_units + 1, 256), 256, 0, chunk_base.p, n_units, row_base.p, sg->unit_seg_off);
-        TRY_SG(cudaMemcpyAsync(&S, row_base.p + G, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-        TRY_SG(cudaStreamSynchronize(s));
+        TRY_SG(post(ctx, 0, row_base.p + G, 1));
+        TRY_SG(sync_stream(ctx));
         TRY_SG(cudaGetLastError());
+        S = ctx->mailbox[0];
         TRY_SG(recs.alloc(S, s));
         TRY_SG(row_unit.alloc(S, s));
         const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
@@ -482,10 +487,13 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     if (exclusive_scan<uint32_t>(ctx, ts_len.p, S, sg->ts_off)) return bail(MDBCU_FAILURE);
     if (exclusive_scan<uint32_t>(ctx, val_len.p, S, sg->val_off)) return bail(MDBCU_FAILURE);
     if (exclusive_scan<uint32_t>(ctx, res_len.p, S, sg->res_off)) return bail(MDBCU_FAILURE);
-    TRY_SG(cudaMemcpyAsync(&sg->ts_bytes, sg->ts_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaMemcpyAsync(&sg->val_bytes, sg->val_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaMemcpyAsync(&sg->res_bytes, sg->res_off + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
-    TRY_SG(cudaStreamSynchronize(s));
+    TRY_SG(post(ctx, 0, sg->ts_off + S, 1));
+    TRY_SG(post(ctx, 1, sg->val_off + S, 1));
+    TRY_SG(post(ctx, 2, sg->res_off + S, 1));
+    TRY_SG(sync_stream(ctx));
+    sg->ts_bytes = ctx->mailbox[0];
+    sg->val_bytes = ctx->mailbox[1];
+    sg->res_bytes = ctx->mailbox[2];
 
     // ---- byte columns
     TRY_SG(cudaMallocAsync((void **)&sg->ts_data, sg->ts_bytes ? sg->ts_bytes : 1, s));
@@ -495,7 +503,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, recs.p, row_unit.p, S, sg->ts_off, sg->ts_data,
                sg->val_off, sg->val_data, sg->res_off, sg->res_data);
     TRY_SG(cudaGetLastError());
-    TRY_SG(cudaStreamSynchronize(s));
+    TRY_SG(sync_stream(ctx));
 #undef TRY_SG
     *out = sg;
     return MDBCU_SUCCESS;
@@ -551,15 +559,15 @@ extern "C" int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timesta
     DBuf<float> d_val;
     DBuf<uint32_t> d_starts, d_budget;
     DBuf<DebugFit> d_out;
-    CUDA_TRY(upload(d_ts, timestamps, n, s));
-    CUDA_TRY(upload(d_val, values, n, s));
-    CUDA_TRY(upload(d_starts, starts, n_starts, s));
-    CUDA_TRY(upload(d_budget, budget_ends, n_starts, s));
+    CUDA_TRY(upload(ctx, d_ts, timestamps, n));
+    CUDA_TRY(upload(ctx, d_val, values, n));
+    CUDA_TRY(upload(ctx, d_starts, starts, n_starts));
+    CUDA_TRY(upload(ctx, d_budget, budget_ends, n_starts));
     CUDA_TRY(d_out.alloc(n_starts, s));
     if (n_starts) LAUNCH(ctx, k_debug_fit, n_starts, 32, 0, d_ts.p, d_val.p, n, eb_kind, eb_value, engine, d_starts.p, d_budget.p, n_starts, d_out.p);
     CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaMemcpyAsync(out, d_out.p, n_starts * sizeof(DebugFit), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(d2h_bytes(ctx, out, d_out.p, n_starts * sizeof(DebugFit)));
+    CUDA_TRY(sync_stream(ctx));
     return MDBCU_SUCCESS;
 }
 

@@ -58,6 +58,29 @@ struct PendingTiming {
     cudaEvent_t start, stop;
 };
 
+struct PinnedBlock {
+    uint8_t *p = nullptr;
+    size_t cap = 0;
+};
+
+// Deferred copy out of the bounce ring into pageable caller memory.
+struct PendingOut {
+    void *dst;
+    const uint8_t *src;
+    size_t bytes;
+};
+
+// Two pinned halves used in turn: the DMA of one half overlaps the host memcpy into / out of the other.
+struct Stager {
+    static constexpr size_t HALF = 32u << 20;
+    uint8_t *base = nullptr;
+    int cur = 0;
+    size_t head = 0;
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    bool in_flight[2] = {false, false};
+    std::vector<PendingOut> out[2];
+};
+
 struct mdbcu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -72,6 +95,10 @@ struct mdbcu_context {
     std::vector<KernelStat> stats;
     std::vector<PendingTiming> pending;
     std::vector<cudaEvent_t> event_pool;
+    // host <-> device plumbing (see "host transfers" below)
+    uint64_t *mailbox = nullptr, *mailbox_dev = nullptr; // mapped pinned words that kernels post scalars into
+    Stager stager;                                       // pinned bounce ring for pageable caller memory
+    std::vector<PinnedBlock> pinned_cache;               // reusable pinned blocks for library-owned host copies
 
     size_t stat_index(const char *name) {
         for (size_t i = 0; i < stats.size(); i++)
@@ -145,6 +172,152 @@ struct Status {            // zeroed before each call
 };
 
 static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
+
+// ------------------------------------------------------------------------------------------------
+// host transfers
+//  * Scalars the host needs between launches (scan totals, the dirty count of a round, the status
+//    word) are posted by a one-warp kernel into mapped pinned memory.  A cudaMemcpy of 8 bytes would
+//    queue on the device-to-host copy engine behind whatever bulk copy another context has in flight,
+//    which serialises contexts that are meant to pipeline.
+//  * Bulk copies go straight to / from caller memory when it is pinned.  Pageable memory (Arrow
+//    buffers are) is bounced through the context's pinned ring, 32 MiB halves used in turn so that the
+//    DMA of one half overlaps the host memcpy of the other.
+//  * sync_ctx() is the only way an entry point waits for the stream: it also completes the bounced
+//    device-to-host copies.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t MAILBOX_WORDS = 64;
+constexpr uint32_t SLOT_STATUS = 60; // Status is two words; entry points use slots below this one freely
+
+__global__ void k_post(uint64_t *mailbox, const uint64_t *src, uint32_t n_words) {
+    if (threadIdx.x < n_words) mailbox[threadIdx.x] = src[threadIdx.x];
+    __threadfence_system();
+}
+
+static cudaError_t post(mdbcu_context *ctx, uint32_t slot, const void *d_src, uint32_t n_words) {
+    LAUNCH(ctx, k_post, 1, 32, 0, ctx->mailbox_dev + slot, (const uint64_t *)d_src, n_words);
+    return cudaGetLastError();
+}
+
+static bool is_pinned(const void *p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+static cudaError_t stager_retire(mdbcu_context *ctx, int h) {
+    Stager &g = ctx->stager;
+    if (g.in_flight[h]) {
+        cudaError_t e = cudaEventSynchronize(g.done[h]);
+        if (e != cudaSuccess) return e;
+        g.in_flight[h] = false;
+    }
+    for (const PendingOut &o : g.out[h]) std::memcpy(o.dst, o.src, o.bytes);
+    g.out[h].clear();
+    return cudaSuccess;
+}
+
+// `bytes` (<= Stager::HALF) of bounce space that stays untouched until the stream has passed this point.
+static cudaError_t stager_reserve(mdbcu_context *ctx, size_t bytes, uint8_t **out) {
+    Stager &g = ctx->stager;
+    if (!g.base) {
+        cudaError_t e = cudaHostAlloc((void **)&g.base, 2 * Stager::HALF, cudaHostAllocPortable);
+        if (e != cudaSuccess) return e;
+        for (int h = 0; h < 2; h++)
+            if ((e = cudaEventCreateWithFlags(&g.done[h], cudaEventDisableTiming)) != cudaSuccess) return e;
+    }
+    if (g.head + bytes > Stager::HALF) {
+        cudaError_t e = cudaEventRecord(g.done[g.cur], ctx->stream);
+        if (e != cudaSuccess) return e;
+        g.in_flight[g.cur] = true;
+        g.cur ^= 1;
+        g.head = 0;
+        if ((e = stager_retire(ctx, g.cur)) != cudaSuccess) return e;
+    }
+    *out = g.base + (size_t)g.cur * Stager::HALF + g.head;
+    g.head += (bytes + 255) & ~(size_t)255;
+    return cudaSuccess;
+}
+
+static size_t stager_piece(const mdbcu_context *ctx, size_t bytes) {
+    size_t room = Stager::HALF - ctx->stager.head;
+    return std::min(bytes, room >= (1u << 20) ? room : Stager::HALF);
+}
+
+static cudaError_t h2d_bytes(mdbcu_context *ctx, void *d_dst, const void *h_src, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    if (is_pinned(h_src)) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    while (bytes) {
+        size_t n = stager_piece(ctx, bytes);
+        uint8_t *b;
+        cudaError_t e = stager_reserve(ctx, n, &b);
+        if (e != cudaSuccess) return e;
+        std::memcpy(b, h_src, n);
+        if ((e = cudaMemcpyAsync(d_dst, b, n, cudaMemcpyHostToDevice, ctx->stream)) != cudaSuccess) return e;
+        d_dst = (uint8_t *)d_dst + n;
+        h_src = (const uint8_t *)h_src + n;
+        bytes -= n;
+    }
+    return cudaSuccess;
+}
+
+// The bytes are in `h_dst` after the next sync_ctx().
+static cudaError_t d2h_bytes(mdbcu_context *ctx, void *h_dst, const void *d_src, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    if (is_pinned(h_dst)) return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    while (bytes) {
+        size_t n = stager_piece(ctx, bytes);
+        uint8_t *b;
+        cudaError_t e = stager_reserve(ctx, n, &b);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaMemcpyAsync(b, d_src, n, cudaMemcpyDeviceToHost, ctx->stream)) != cudaSuccess) return e;
+        ctx->stager.out[ctx->stager.cur].push_back(PendingOut{h_dst, b, n});
+        h_dst = (uint8_t *)h_dst + n;
+        d_src = (const uint8_t *)d_src + n;
+        bytes -= n;
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t sync_stream(mdbcu_context *ctx) {
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    Stager &g = ctx->stager;
+    g.in_flight[0] = g.in_flight[1] = false;
+    if (e != cudaSuccess) { // the caller's buffers may be gone by the next call: drop, never replay
+        g.out[0].clear();
+        g.out[1].clear();
+    }
+    stager_retire(ctx, g.cur ^ 1); // older half first: a copy may continue from it into the current one
+    stager_retire(ctx, g.cur);
+    g.head = 0;
+    return e;
+}
+
+static cudaError_t pinned_acquire(mdbcu_context *ctx, size_t bytes, PinnedBlock &b) {
+    std::vector<PinnedBlock> &cache = ctx->pinned_cache;
+    int best = -1;
+    for (size_t i = 0; i < cache.size(); i++)
+        if (cache[i].cap >= bytes && (best < 0 || cache[i].cap < cache[best].cap)) best = (int)i;
+    if (best >= 0 && cache[best].cap <= 2 * bytes + (1u << 20)) {
+        b = cache[best];
+        cache.erase(cache.begin() + best);
+        return cudaSuccess;
+    }
+    b.cap = ((bytes + bytes / 4) | ((1u << 20) - 1)) + 1;
+    return cudaHostAlloc((void **)&b.p, b.cap, cudaHostAllocPortable);
+}
+
+static void pinned_release(mdbcu_context *ctx, PinnedBlock b) {
+    if (!b.p) return;
+    if (ctx->pinned_cache.size() >= 8) {
+        cudaFreeHost(b.p);
+        return;
+    }
+    ctx->pinned_cache.push_back(b);
+}
 
 // ------------------------------------------------------------------------------------------------
 // exclusive scan: out[i] = sum(in[0..i)), out[n] = total.  Three small kernels; the inputs here are
@@ -463,13 +636,12 @@ struct mdbcu_segments {
     uint64_t *ts_off = nullptr, *val_off = nullptr, *res_off = nullptr, *unit_seg_off = nullptr;
     uint8_t *ts_data = nullptr, *val_data = nullptr, *res_data = nullptr;
     uint64_t ts_bytes = 0, val_bytes = 0, res_bytes = 0;
-    // lazily made host copy
+    // lazily made host copy: every column in one pinned block, so the copy runs at link speed and the
+    // views can be handed back to grid / aggregate without being bounced
     bool have_host = false;
-    std::vector<int8_t> h_model_type_id;
-    std::vector<int64_t> h_start_time, h_end_time;
-    std::vector<float> h_min_value, h_max_value;
-    std::vector<uint64_t> h_ts_off, h_val_off, h_res_off, h_unit_seg_off;
-    std::vector<uint8_t> h_ts_data, h_val_data, h_res_data;
+    PinnedBlock host_block;
+    mdbcu_segments_view host_view{};
+    const uint64_t *h_unit_seg_off = nullptr;
 };
 
 static SegmentsView to_device_view(const mdbcu_segments_view *v) {
@@ -499,17 +671,10 @@ struct StagedSegments {
     SegmentsView view;
 };
 
-template <typename T> static cudaError_t upload(DBuf<T> &dst, const T *src, size_t n, cudaStream_t s) {
-    cudaError_t e = dst.alloc(n, s);
+template <typename T> static cudaError_t upload(mdbcu_context *ctx, DBuf<T> &dst, const T *src, size_t n) {
+    cudaError_t e = dst.alloc(n, ctx->stream);
     if (e != cudaSuccess) return e;
-    if (n == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst.p, src, n * sizeof(T), cudaMemcpyHostToDevice, s);
-}
-
-template <typename T> static cudaError_t download(std::vector<T> &dst, const T *src, size_t n, cudaStream_t s) {
-    dst.resize(n);
-    if (n == 0) return cudaSuccess;
-    return cudaMemcpyAsync(dst.data(), src, n * sizeof(T), cudaMemcpyDeviceToHost, s);
+    return h2d_bytes(ctx, dst.p, src, n * sizeof(T));
 }
 
 static int stage_segments(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *v, StagedSegments &st) {
@@ -520,20 +685,19 @@ static int stage_segments(mdbcu_context *ctx, mdbcu_space space, const mdbcu_seg
         st.view = to_device_view(v);
         return MDBCU_SUCCESS;
     }
-    cudaStream_t s = ctx->stream;
     if (S && (!v->timestamps_off || !v->values_off || !v->residuals_off)) return fail("offset column is null");
     uint64_t tb = S ? v->timestamps_off[S] : 0, vb = S ? v->values_off[S] : 0, rb = S ? v->residuals_off[S] : 0;
-    CUDA_TRY(upload(st.model_type_id, v->model_type_id, S, s));
-    CUDA_TRY(upload(st.start_time, v->start_time, S, s));
-    CUDA_TRY(upload(st.end_time, v->end_time, S, s));
-    CUDA_TRY(upload(st.min_value, v->min_value, S, s));
-    CUDA_TRY(upload(st.max_value, v->max_value, S, s));
-    CUDA_TRY(upload(st.ts_off, v->timestamps_off, S ? S + 1 : 0, s));
-    CUDA_TRY(upload(st.val_off, v->values_off, S ? S + 1 : 0, s));
-    CUDA_TRY(upload(st.res_off, v->residuals_off, S ? S + 1 : 0, s));
-    CUDA_TRY(upload(st.ts_data, v->timestamps_data, tb, s));
-    CUDA_TRY(upload(st.val_data, v->values_data, vb, s));
-    CUDA_TRY(upload(st.res_data, v->residuals_data, rb, s));
+    CUDA_TRY(upload(ctx, st.model_type_id, v->model_type_id, S));
+    CUDA_TRY(upload(ctx, st.start_time, v->start_time, S));
+    CUDA_TRY(upload(ctx, st.end_time, v->end_time, S));
+    CUDA_TRY(upload(ctx, st.min_value, v->min_value, S));
+    CUDA_TRY(upload(ctx, st.max_value, v->max_value, S));
+    CUDA_TRY(upload(ctx, st.ts_off, v->timestamps_off, S ? S + 1 : 0));
+    CUDA_TRY(upload(ctx, st.val_off, v->values_off, S ? S + 1 : 0));
+    CUDA_TRY(upload(ctx, st.res_off, v->residuals_off, S ? S + 1 : 0));
+    CUDA_TRY(upload(ctx, st.ts_data, v->timestamps_data, tb));
+    CUDA_TRY(upload(ctx, st.val_data, v->values_data, vb));
+    CUDA_TRY(upload(ctx, st.res_data, v->residuals_data, rb));
     st.view.n_segments = S;
     st.view.model_type_id = st.model_type_id.p;
     st.view.start_time = st.start_time.p;
@@ -552,24 +716,33 @@ static int stage_segments(mdbcu_context *ctx, mdbcu_space space, const mdbcu_seg
 static int check_ctx(mdbcu_context *ctx) {
     if (!ctx) return fail("context is null");
     CUDA_TRY(cudaSetDevice(ctx->device));
+    Stager &g = ctx->stager;
+    if (g.head || g.in_flight[0] || g.in_flight[1] || !g.out[0].empty() || !g.out[1].empty()) {
+        // an earlier call failed midway: none of its bounced copies may land in memory the caller has since reused
+        cudaStreamSynchronize(ctx->stream);
+        g.out[0].clear();
+        g.out[1].clear();
+        g.in_flight[0] = g.in_flight[1] = false;
+        g.head = 0;
+    }
     return MDBCU_SUCCESS;
 }
 
+// Waits for the stream (and with it for every transfer queued so far).
 static int read_status(mdbcu_context *ctx, const Status *d_status, Status &h, const char *what) {
-    CUDA_TRY(cudaMemcpyAsync(&h, d_status, sizeof(Status), cudaMemcpyDeviceToHost, ctx->stream));
-    CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+    static_assert(sizeof(Status) == 16, "Status is posted as two words");
+    CUDA_TRY(post(ctx, SLOT_STATUS, d_status, 2));
+    CUDA_TRY(sync_stream(ctx));
+    std::memcpy(&h, ctx->mailbox + SLOT_STATUS, sizeof(Status));
     if (h.bad) return fail(std::string("malformed ") + what + " " + std::to_string(h.first_bad));
     return MDBCU_SUCCESS;
 }
 
 static int new_status(mdbcu_context *ctx, DBuf<Status> &st) {
     CUDA_TRY(st.alloc(1, ctx->stream));
-    Status init;
-    init.bad = 0;
-    init.n_seq = 0;
-    init.first_bad = ~0ull;
-    // tiny H2D of a stack value: cudaMemcpyAsync from pageable memory returns after staging the copy
-    CUDA_TRY(cudaMemcpyAsync(st.p, &init, sizeof(Status), cudaMemcpyHostToDevice, ctx->stream));
+    // bad = n_seq = 0, first_bad = ~0: two memsets, no copy engine involved
+    CUDA_TRY(cudaMemsetAsync(st.p, 0, 8, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)st.p + 8, 0xFF, 8, ctx->stream));
     return MDBCU_SUCCESS;
 }
 
@@ -603,6 +776,12 @@ int mdbcu_context_create(int device, mdbcu_context **out) {
         return fail(std::string("cudaStreamCreate: ") + cudaGetErrorString(e));
     }
     ctx->own_stream = true;
+    e = cudaHostAlloc((void **)&ctx->mailbox, MAILBOX_WORDS * sizeof(uint64_t), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void **)&ctx->mailbox_dev, ctx->mailbox, 0);
+    if (e != cudaSuccess) {
+        mdbcu_context_destroy(ctx);
+        return fail(std::string("mailbox allocation: ") + cudaGetErrorString(e));
+    }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
     // keep freed blocks in the pool: steady-state calls then never reach the driver allocator
     cudaMemPool_t pool;
@@ -619,6 +798,12 @@ void mdbcu_context_destroy(mdbcu_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
+    if (ctx->stager.base) cudaFreeHost(ctx->stager.base);
+    for (cudaEvent_t ev : ctx->stager.done)
+        if (ev) cudaEventDestroy(ev);
+    for (PinnedBlock &b : ctx->pinned_cache) cudaFreeHost(b.p);
+    for (cudaEvent_t ev : ctx->event_pool) cudaEventDestroy(ev);
     delete ctx;
 }
 
@@ -677,8 +862,9 @@ static int grid_plan(mdbcu_context *ctx, const SegmentsView &v, GridPlan &pl) {
     if (new_status(ctx, pl.status)) return MDBCU_FAILURE;
     if (S) LAUNCH(ctx, k_grid_prepare, div_up(S, 256), 256, 0, v, pl.desc.p, pl.len.p, pl.worklist.p, pl.status.p);
     if (exclusive_scan<uint32_t>(ctx, pl.len.p, S, pl.point_off.p)) return MDBCU_FAILURE;
-    CUDA_TRY(cudaMemcpyAsync(&pl.total, pl.point_off.p + S, sizeof(uint64_t), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(post(ctx, 0, pl.point_off.p + S, 1));
     if (read_status(ctx, pl.status.p, pl.h_status, "segment row")) return MDBCU_FAILURE;
+    pl.total = ctx->mailbox[0];
     return MDBCU_SUCCESS;
 }
 
@@ -689,9 +875,12 @@ int mdbcu_grid_count(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments
     GridPlan pl;
     if (grid_plan(ctx, st.view, pl)) return MDBCU_FAILURE;
     if (point_off) {
-        CUDA_TRY(cudaMemcpyAsync(point_off, pl.point_off.p, (st.view.n_segments + 1) * sizeof(uint64_t),
-                                 space == MDBCU_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
-        CUDA_TRY(cudaStreamSynchronize(ctx->stream));
+        const size_t bytes = (st.view.n_segments + 1) * sizeof(uint64_t);
+        if (space == MDBCU_HOST)
+            CUDA_TRY(d2h_bytes(ctx, point_off, pl.point_off.p, bytes));
+        else
+            CUDA_TRY(cudaMemcpyAsync(point_off, pl.point_off.p, bytes, cudaMemcpyDeviceToDevice, ctx->stream));
+        CUDA_TRY(sync_stream(ctx));
     }
     if (total) *total = pl.total;
     return MDBCU_SUCCESS;
@@ -731,10 +920,10 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
                (uint32_t)pl.h_status.n_seq, d_ts, d_val);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
-        CUDA_TRY(cudaMemcpyAsync(timestamps_out, d_ts, pl.total * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(values_out, d_val, pl.total * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(d2h_bytes(ctx, timestamps_out, d_ts, pl.total * sizeof(int64_t)));
+        CUDA_TRY(d2h_bytes(ctx, values_out, d_val, pl.total * sizeof(float)));
     }
-    CUDA_TRY(cudaStreamSynchronize(s));
+    CUDA_TRY(sync_stream(ctx));
     return MDBCU_SUCCESS;
 }
 
@@ -758,7 +947,7 @@ int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segmen
     }
     LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, status.p);
     CUDA_TRY(cudaGetLastError());
-    if (space == MDBCU_HOST) CUDA_TRY(cudaMemcpyAsync(sums_out, d_sum, S * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (space == MDBCU_HOST) CUDA_TRY(d2h_bytes(ctx, sums_out, d_sum, S * sizeof(float)));
     Status h;
     return read_status(ctx, status.p, h, "segment row");
 }
@@ -778,7 +967,7 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     const uint64_t *d_group_off = group_off;
     if (group_off && space == MDBCU_HOST) {
         if (group_off[n_groups] > S) return fail("aggregate: group_off exceeds the number of rows");
-        CUDA_TRY(upload(group_off_buf, group_off, n_groups + 1, s));
+        CUDA_TRY(upload(ctx, group_off_buf, group_off, n_groups + 1));
         d_group_off = group_off_buf.p;
     }
     DBuf<Status> status;
@@ -815,10 +1004,10 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     LAUNCH(ctx, k_agg_final, div_up(n_groups, AGG_THREADS), AGG_THREADS, 0, partial.p, n_groups, parts, d_count, d_min, d_max, d_sum);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
-        CUDA_TRY(cudaMemcpyAsync(count, d_count, n_groups * sizeof(int64_t), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(min, d_min, n_groups * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(max, d_max, n_groups * sizeof(float), cudaMemcpyDeviceToHost, s));
-        CUDA_TRY(cudaMemcpyAsync(sum, d_sum, n_groups * sizeof(double), cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(d2h_bytes(ctx, count, d_count, n_groups * sizeof(int64_t)));
+        CUDA_TRY(d2h_bytes(ctx, min, d_min, n_groups * sizeof(float)));
+        CUDA_TRY(d2h_bytes(ctx, max, d_max, n_groups * sizeof(float)));
+        CUDA_TRY(d2h_bytes(ctx, sum, d_sum, n_groups * sizeof(double)));
     }
     Status h;
     return read_status(ctx, status.p, h, "segment row");
@@ -837,6 +1026,7 @@ void mdbcu_segments_free(mdbcu_segments *sg) {
                         sg->res_off, sg->unit_seg_off, sg->ts_data, sg->val_data, sg->res_data};
         for (void *p : ptrs)
             if (p) cudaFreeAsync(p, s);
+        pinned_release(sg->ctx, sg->host_block);
     }
     delete sg;
 }
@@ -862,35 +1052,40 @@ int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_vie
         return MDBCU_SUCCESS;
     }
     if (!sg->have_host) {
-        cudaStream_t s = sg->ctx->stream;
-        CUDA_TRY(download(sg->h_model_type_id, sg->model_type_id, S, s));
-        CUDA_TRY(download(sg->h_start_time, sg->start_time, S, s));
-        CUDA_TRY(download(sg->h_end_time, sg->end_time, S, s));
-        CUDA_TRY(download(sg->h_min_value, sg->min_value, S, s));
-        CUDA_TRY(download(sg->h_max_value, sg->max_value, S, s));
-        CUDA_TRY(download(sg->h_ts_off, sg->ts_off, S + 1, s));
-        CUDA_TRY(download(sg->h_val_off, sg->val_off, S + 1, s));
-        CUDA_TRY(download(sg->h_res_off, sg->res_off, S + 1, s));
-        CUDA_TRY(download(sg->h_unit_seg_off, sg->unit_seg_off, sg->n_units + 1, s));
-        CUDA_TRY(download(sg->h_ts_data, sg->ts_data, sg->ts_bytes, s));
-        CUDA_TRY(download(sg->h_val_data, sg->val_data, sg->val_bytes, s));
-        CUDA_TRY(download(sg->h_res_data, sg->res_data, sg->res_bytes, s));
-        CUDA_TRY(cudaStreamSynchronize(s));
+        mdbcu_context *ctx = sg->ctx;
+        // one pinned block, columns at 64-byte aligned offsets
+        const void *src[12] = {sg->model_type_id, sg->start_time, sg->end_time, sg->min_value, sg->max_value, sg->ts_off,
+                               sg->val_off, sg->res_off, sg->unit_seg_off, sg->ts_data, sg->val_data, sg->res_data};
+        const size_t bytes[12] = {S, S * 8, S * 8, S * 4, S * 4, (S + 1) * 8, (S + 1) * 8, (S + 1) * 8, (sg->n_units + 1) * 8,
+                                  sg->ts_bytes, sg->val_bytes, sg->res_bytes};
+        size_t at[12], total = 0;
+        for (int c = 0; c < 12; c++) {
+            at[c] = total;
+            total += (bytes[c] + 63) & ~(size_t)63;
+        }
+        CUDA_TRY(pinned_acquire(ctx, total + 64, sg->host_block));
+        uint8_t *base = sg->host_block.p;
+        for (int c = 0; c < 12; c++)
+            if (bytes[c]) CUDA_TRY(cudaMemcpyAsync(base + at[c], src[c], bytes[c], cudaMemcpyDeviceToHost, ctx->stream));
+        CUDA_TRY(sync_stream(ctx));
+        mdbcu_segments_view &h = sg->host_view;
+        h.n_segments = S;
+        h.model_type_id = (const int8_t *)(base + at[0]);
+        h.start_time = (const int64_t *)(base + at[1]);
+        h.end_time = (const int64_t *)(base + at[2]);
+        h.min_value = (const float *)(base + at[3]);
+        h.max_value = (const float *)(base + at[4]);
+        h.timestamps_off = (const uint64_t *)(base + at[5]);
+        h.values_off = (const uint64_t *)(base + at[6]);
+        h.residuals_off = (const uint64_t *)(base + at[7]);
+        sg->h_unit_seg_off = (const uint64_t *)(base + at[8]);
+        h.timestamps_data = base + at[9];
+        h.values_data = base + at[10];
+        h.residuals_data = base + at[11];
         sg->have_host = true;
     }
-    view->n_segments = S;
-    view->model_type_id = sg->h_model_type_id.data();
-    view->start_time = sg->h_start_time.data();
-    view->end_time = sg->h_end_time.data();
-    view->min_value = sg->h_min_value.data();
-    view->max_value = sg->h_max_value.data();
-    view->timestamps_off = sg->h_ts_off.data();
-    view->timestamps_data = sg->h_ts_data.data();
-    view->values_off = sg->h_val_off.data();
-    view->values_data = sg->h_val_data.data();
-    view->residuals_off = sg->h_res_off.data();
-    view->residuals_data = sg->h_res_data.data();
-    if (unit_seg_off) *unit_seg_off = sg->h_unit_seg_off.data();
+    *view = sg->host_view;
+    if (unit_seg_off) *unit_seg_off = sg->h_unit_seg_off;
     return MDBCU_SUCCESS;
 }
 

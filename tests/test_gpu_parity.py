@@ -232,6 +232,76 @@ def test_medium_sizes_match_oracle(oracle, ctx, kind, eb):
     seg.free()
 
 
+def test_pageable_and_pinned_host_memory_give_the_same_bytes(oracle, ctx):
+    """Host-space calls bounce pageable caller memory through a 2 x 32 MiB pinned ring and copy pinned memory
+    directly: 9 M points (72 MB of timestamps in, 72 MB out) cross the ring halves several times each way."""
+    import torch
+    n_series, n = 9, 1_000_000
+    ts, vals, off = syn.multi_series(n_series, n, 5, "sine")
+    eb = (2, 1.0)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+    wts, wval, _ = oracle.grid(want, n_threads=8)
+    # pageable in, pageable out
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    got = seg.to_host()
+    assert_segments_equal(got, want, "pageable")
+    gts = np.full(len(ts), -1, np.int64)
+    gval = np.full(len(ts), np.nan, np.float32)
+    mc.grid(got, gts, gval, ctx)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, "pageable grid")
+    # pinned in, pinned out, and the zero-copy view of the library's host copy
+    pts, pvals = torch.from_numpy(ts).pin_memory(), torch.from_numpy(vals).pin_memory()
+    seg2 = mc.compress(pts.numpy(), pvals.numpy(), off, mc.ErrorBound(*eb), ctx)
+    view = seg2.to_host(copy=False)
+    assert_segments_equal(view, want, "pinned")
+    pts_out = torch.empty(len(ts), dtype=torch.int64).pin_memory()
+    pval_out = torch.empty(len(ts), dtype=torch.float32).pin_memory()
+    mc.grid(view, pts_out.numpy(), pval_out.numpy(), ctx)
+    assert np.array_equal(pts_out.numpy(), wts)
+    assert_f32_bits_equal(pval_out.numpy(), wval, "pinned grid")
+    gc, _, _, gsm = mc.aggregate(view, want.unit_seg_off, ctx)
+    wc, _, _, wsm = oracle.aggregate(want, want.unit_seg_off, n_threads=8)
+    assert np.array_equal(gc, wc)
+    _check_sum(gsm, wsm, "pinned aggregate")
+    del view
+    seg.free()
+    seg2.free()
+
+
+def test_contexts_on_threads_pipeline_independent_slabs(oracle):
+    """One context per host thread (the e2e pattern of bench.py): results do not depend on what the others do."""
+    import threading
+    ts, vals, off = syn.multi_series(8, 200_000, 9, "walk")
+    eb = (2, 1.0)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+    wts, wval, _ = oracle.grid(want, n_threads=8)
+    errors = []
+
+    def work():
+        try:
+            c = mc.Context(0)
+            for _ in range(3):
+                seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), c)
+                host = seg.to_host(copy=False)
+                assert_segments_equal(host, want, "threaded")
+                gts, gval = mc.grid(host, ctx=c)
+                assert np.array_equal(gts, wts)
+                assert_f32_bits_equal(gval, wval, "threaded grid")
+                del host
+                seg.free()
+            c.close()
+        except Exception as e:  # noqa: BLE001 -- reported by the main thread
+            errors.append(e)
+
+    threads = [threading.Thread(target=work) for _ in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors
+
+
 def test_full_size_properties_device(ctx):
     """Size-independent properties at a bench-sized slab (no oracle run): lossless round trip is exact,
     timestamps round-trip exactly, COUNT equals the number of points, grouped aggregates add up to the

@@ -42,6 +42,26 @@ def both():
     d2h()
 
 
+def small_d2h_latency(busy):
+    """Wall time of an 8-byte D2H + stream sync on s1 while s2 is idle / busy with a bulk D2H."""
+    small_d = torch.zeros(1, dtype=torch.int64, device="cuda")
+    small_h = torch.zeros(1, dtype=torch.int64).pin_memory()
+    torch.cuda.synchronize()
+    if busy:
+        d2h()
+    t0 = time.perf_counter()
+    with torch.cuda.stream(s1):
+        small_h.copy_(small_d, non_blocking=True)
+    s1.synchronize()
+    dt = time.perf_counter() - t0
+    torch.cuda.synchronize()
+    return dt
+
+
+small_d2h_latency(False)
+print(f"8-byte D2H + sync, other stream idle:          {small_d2h_latency(False) * 1e3:8.3f} ms")
+print(f"8-byte D2H + sync, other stream in a bulk D2H: {small_d2h_latency(True) * 1e3:8.3f} ms")
+
 t = timed(h2d)
 print(f"H2D  {n / t / 1e9:7.1f} GB/s")
 t = timed(d2h)
