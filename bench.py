@@ -280,7 +280,7 @@ def main():
     stage_ms = {"compress": [], "grid": [], "aggregate": []}
     seg_bytes_last = [0, 0]
 
-    def step(record):
+    def step(record, measure_segments=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         ev[0].record(stream)
         seg = mc.compress(ts, vals, off, (kinds, ebv), ctx)
@@ -303,10 +303,11 @@ def main():
             stage_ms["compress"].append(ev[0].elapsed_time(ev[1]))
             stage_ms["grid"].append(ev[1].elapsed_time(ev[2]))
             stage_ms["aggregate"].append(ev[2].elapsed_time(ev[3]))
-            h = seg.to_host() if not seg_bytes_last[0] else None
-            if h is not None:
-                seg_bytes_last[0] = h.segment_bytes()
-                seg_bytes_last[1] = len(h)
+        if measure_segments:  # (untimed steps only: a host copy of the segments is not part of the device-resident path)
+            h = seg.to_host(copy=False)
+            seg_bytes_last[0] = h.segment_bytes()
+            seg_bytes_last[1] = len(h)
+            del h
         seg.free()
         return count
 
@@ -324,6 +325,7 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    step(False, measure_segments=True)  # sizes of the compressed output, outside every timed region
     for _ in range(args.warmup):
         step(False)
     barrier()

@@ -97,7 +97,10 @@ __global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ t
 // thousands of independent chains to fill the GPU, and a warp's loads of 32 consecutive points are
 // fully coalesced (128 B of values, 256 B of timestamps per step).
 constexpr int CHAIN_WARPS = 4;
-__global__ void __launch_bounds__(CHAIN_WARPS * 32) k_spec_chain_warp(const int64_t *__restrict__ ts, const float *__restrict__ values,
+#ifndef MDB_CHAIN_MIN_BLOCKS
+#define MDB_CHAIN_MIN_BLOCKS 2
+#endif
+__global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_chain_warp(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                       const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
                                                                       const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
                                                                       const uint32_t *__restrict__ chunk_unit, const uint32_t *__restrict__ worklist,
@@ -421,7 +424,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         uint32_t round = 0;
         uint64_t n_work = G;
         const uint32_t *d_work = nullptr; // round 0 runs every chunk
+        const bool trace = std::getenv("MDBCU_TRACE_ROUNDS") != nullptr; // diagnostics: chunks and wall time per round
         while (n_work) {
+            const auto t_round = std::chrono::steady_clock::now();
+            const uint64_t n_this = n_work;
             const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(n_work, (uint64_t)ctx->sm_count * 32)));
             if (ctx->fit_mode == 1)
                 LAUNCH(ctx, k_spec_chain, div_up(n_work, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p, d_work,
@@ -441,6 +447,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             std::memcpy(&hc, ctx->mailbox, sizeof(hc));
             n_work = hc.dirty;
             d_work = worklist.p;
+            if (trace)
+                fprintf(stderr, "[mdbcu] round %u: %llu of %llu chunks (chunk_len %u), %.3f ms\n", round, (unsigned long long)n_this,
+                        (unsigned long long)G, chunk_len,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_round).count());
             if (round > 4 * G + 8) return bail(fail("compress: chunk fixpoint did not converge (internal error)"));
         }
         ctx->last_rounds = round;

@@ -44,3 +44,86 @@ def test_warp_fit_equals_thread_fit_at_every_start(case):
         for f in ("start", "end", "min", "max", "last", "bpv", "type", "vlen"):
             bad = np.flatnonzero(ok & (a[f] != b[f]))
             assert len(bad) == 0, f"{name} budget={budget}: field {f} differs at starts {bad[:5]}: {a[bad[:3]]} vs {b[bad[:3]]}"
+
+
+# ---- long models: the wide steps of the warp engine (mdb_fit_warp.cuh) --------------------------------------------
+
+def _long_cases():
+    n = 20_000
+    i = np.arange(n)
+    rng = np.random.default_rng(42)
+    ts = (1_600_000_000_000_000 + 1000 * i).astype(np.int64)
+    noise = rng.standard_normal(n)
+    cases = []
+
+    def add(name, vals, ebs, t=ts):
+        for eb in ebs:
+            cases.append((f"{name}-eb{eb[0]}:{eb[1]}", t, np.asarray(vals, np.float32), eb))
+
+    add("constant", np.full(n, 100.0), [(0, 0.0), (1, 0.5), (2, 1.0)])
+    add("constant-noise", 100.0 + 0.1 * noise, [(1, 1.0), (2, 1.0), (2, 0.2)])
+    add("slow-ramp", 100.0 + 0.001 * i + 0.01 * noise, [(1, 0.1), (2, 0.05), (2, 1.0)])
+    add("steps", np.where(i < 9_000, 100.0, 150.0) + 0.05 * noise, [(1, 1.0), (2, 1.0)])
+    add("zeros", np.zeros(n), [(0, 0.0), (1, 0.5), (2, 1.0)])
+    add("signed-zeros", np.where(i % 3 == 0, -0.0, 0.0), [(0, 0.0), (1, 0.5), (2, 1.0)])
+    add("zero-touching", np.maximum(0.0, 0.5 * np.sin(i / 900.0)), [(1, 1.0), (2, 10.0)])
+    add("sign-change", -5.0 + 10.0 * i / n, [(1, 10.0), (1, 0.01), (2, 5.0)])
+    t_irr = ts.copy()
+    t_irr[7_000:] += 137
+    add("late-irregular", 100.0 + 0.05 * noise, [(1, 1.0), (2, 1.0)], t_irr)
+    v = 100.0 + 0.05 * noise
+    v_nan = v.copy(); v_nan[9_000] = np.nan
+    v_inf = v.copy(); v_inf[9_001] = np.inf
+    add("nan-inside", v_nan, [(1, 1.0), (2, 1.0)])
+    add("inf-inside", v_inf, [(1, 1.0), (2, 1.0)])
+    add("huge", np.full(n, 1e30) * (1.0 + 1e-4 * noise), [(2, 1.0), (1, 1e28)])
+    add("tiny", np.full(n, 1e-35) * (1.0 + 1e-3 * noise), [(2, 1.0), (1, 1e-36)])
+    add("subnormal", np.full(n, 1e-41) * (1.0 + 1e-2 * noise), [(2, 5.0), (1, 1e-42)])
+    add("wide-exponents", np.where(i % 2 == 0, 1e10, 1e-10), [(1, 1e11)])
+    for hi in (101.9, 102.0, 102.02, 102.05, 102.5):  # PMC-Mean close to a 1 % relative bound from either side
+        add(f"alternating-{hi}", np.where(i % 2 == 0, 100.0, hi), [(2, 1.0)])
+    for amp in (0.45, 0.5, 0.55):  # Swing close to an absolute bound of 0.5 around a line
+        add(f"sawtooth-{amp}", 10.0 + 0.002 * i + amp * np.where(i % 2 == 0, 1.0, -1.0), [(1, 0.5)])
+    add("plateau-then-noise", np.where(i < 12_345, 42.0, 42.0 + 5.0 * noise), [(0, 0.0), (2, 1.0)])
+    return cases
+
+
+LONG_CASES = _long_cases()
+
+
+@pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])
+def test_warp_fit_equals_thread_fit_on_long_models(case):
+    name, ts, vals, eb = case
+    ctx = mc.default_context()
+    n = len(ts)
+    rng = np.random.default_rng(7)
+    starts = np.unique(np.concatenate([np.arange(0, 40), rng.integers(0, n, 40), np.arange(6_990, 7_003), np.arange(8_995, 9_005),
+                                       np.arange(12_340, 12_350), np.arange(n - 600, n, 37)])).astype(np.uint32)
+    for budget in (None, 700, 3_000):
+        be = np.full(len(starts), n, np.uint32) if budget is None else np.minimum(starts + budget, n).astype(np.uint32)
+        a = fit_models(ctx, ts, vals, eb, 1, starts, be)
+        b = fit_models(ctx, ts, vals, eb, 2, starts, be)
+        assert np.array_equal(a["aborted"], b["aborted"]), (name, budget, starts[np.flatnonzero(a["aborted"] != b["aborted"])[:5]])
+        ok = a["aborted"] == 0
+        for f in ("start", "end", "min", "max", "last", "bpv", "type", "vlen", "irregular"):
+            bad = np.flatnonzero(ok & (a[f] != b[f]))
+            assert len(bad) == 0, f"{name} budget={budget}: field {f} differs at starts {starts[bad[:5]]}: {a[bad[:3]]} vs {b[bad[:3]]}"
+
+
+@pytest.mark.parametrize("chunk_len", [0, 512, 4096])
+def test_long_model_series_match_oracle(oracle, chunk_len):
+    """The same series through the whole compress path (chunk speculation with budgets) against the oracle."""
+    from tests.parity_cases import assert_segments_equal
+    ctx = mc.Context(0)
+    ctx.set_chunk_len(chunk_len)
+    by_eb = {}
+    for name, ts, vals, eb in LONG_CASES:
+        by_eb.setdefault(eb, []).append((name, ts, vals))
+    for eb, group in by_eb.items():
+        ts = np.concatenate([g[1] for g in group])
+        vals = np.concatenate([g[2] for g in group])
+        off = np.arange(len(group) + 1, dtype=np.uint64) * np.uint64(len(group[0][1]))
+        want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+        got = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx).to_host()
+        assert_segments_equal(got, want, f"long models eb={eb} chunk_len={chunk_len}: {[g[0] for g in group]}")
+    ctx.close()

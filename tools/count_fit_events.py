@@ -15,7 +15,7 @@ for ebs in ("rel:1.0","rel:5.0"):
     _native.lib().mdbcu_debug_counters(ctx._h, out)
     import time; torch.cuda.synchronize(); t0=time.time(); seg = mc.compress(ts, vals, off, eb, ctx); print("compress s", time.time()-t0)
     _native.lib().mdbcu_debug_counters(ctx._h, out)
-    print(ebs, "rounds", ctx.last_compress_rounds, dict(zip(["fits","scalar","steps","quiet","spec","mismatch","pmc_inorder","-","cyc_load","cyc_pmc","cyc_quiet","cyc_cand","cyc_scan"], list(out))))
+    print(ebs, "rounds", ctx.last_compress_rounds, dict(zip(["fits","scalar","steps","quiet","spec","mismatch","pmc_inorder","wide","cyc_load","cyc_pmc","cyc_quiet","cyc_cand","cyc_scan","wide_fail"], list(out))))
     o=list(out); steps=max(1,o[2])
     print("  cycles per step:", {k: round(v/steps) for k,v in zip(["load","pmc","quiet","cand","scan"], o[8:13])})
     seg.free()
