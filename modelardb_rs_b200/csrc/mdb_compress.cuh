@@ -442,7 +442,7 @@ struct ChunkState {            // 48 bytes
     uint8_t dirty, exact, buf, skipped;
     uint8_t irregular, pad[3];
     uint32_t first_start;      // start of the chain's first model (valid when n_models > 0)
-    uint32_t pad2;
+    uint32_t phase;            // scheduler: PH_QUEUED / PH_RUNNING / PH_DONE / PH_LOCKED (asynchronous scheduling only)
 };
 static_assert(sizeof(ChunkState) == 48, "ChunkState layout");
 
@@ -483,9 +483,9 @@ MDB_DEV void spec_chain(Fit &fitter, uint32_t lane, uint32_t n_lanes, uint32_t n
     uint32_t n_new = 0, cur, p = 0;
     uint32_t first_start = IDX_NONE;
     if (resume) {
-        for (uint32_t k = lane; k < old_n; k += n_lanes) new_list[k] = old_list[k]; // copies are spread over the lanes
+        for (uint32_t k = lane; k < old_n; k += n_lanes) new_list[k] = load_shared_record(old_list + k); // copies are spread over the lanes
         n_new = old_n;
-        if (old_n) first_start = old_list[0].start_index;
+        if (old_n) first_start = sync_load(&old_list[0].start_index);
         cur = old_trunc;
     } else {
         cur = st.new_entry;
@@ -495,11 +495,11 @@ MDB_DEV void spec_chain(Fit &fitter, uint32_t lane, uint32_t n_lanes, uint32_t n
     bool done = false;
     while (cur < chunk_end) {
         if (can_sync && cur >= old_entry && cur < sync_limit) {
-            while (p < old_n && old_list[p].end_index < cur) p++;
-            bool inside = p < old_n && old_list[p].start_index < cur; // strictly inside old model p
+            while (p < old_n && sync_load(&old_list[p].end_index) < cur) p++;
+            bool inside = p < old_n && sync_load(&old_list[p].start_index) < cur; // strictly inside old model p
             if (!inside) { // the old chain also started a fit at cur: identical from here on
-                if (n_new == 0 && p < old_n) first_start = old_list[p].start_index;
-                for (uint32_t k = p + lane; k < old_n; k += n_lanes) new_list[n_new + (k - p)] = old_list[k];
+                if (n_new == 0 && p < old_n) first_start = sync_load(&old_list[p].start_index);
+                for (uint32_t k = p + lane; k < old_n; k += n_lanes) new_list[n_new + (k - p)] = load_shared_record(old_list + k);
                 n_new += old_n - p;
                 exit = old_exit;
                 truncated_at = old_trunc;
@@ -580,6 +580,92 @@ MDB_DEV uint32_t spec_propagate_unit(uint32_t n, uint32_t chunk_len, uint32_t n_
     }
     if (exact && c >= n_chunks) { resume_c = n_chunks; resume_e = e; } // the whole unit is final
     return dirty;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Asynchronous scheduling: the same chains without the global rounds.
+//
+// Rounds make every unit wait for the slowest chain of the round, and a unit whose chains do not
+// re-synchronise (its segmentation depends on where the chain started) needs one round per chunk, each
+// as long as a whole chunk's chain, while the rest of the GPU idles.  Here every chunk is a work item in a
+// device-side queue served by persistent warps, and each unit keeps its own FRONTIER: the first chunk
+// whose chain is not yet known to be final, and the exact entry of that chunk.  Whenever a chain of the unit
+// completes, sched_advance moves the frontier over every finished chunk whose chain started from the
+// right entry, and at the first chunk that did not it either
+//   * re-aims the chunk at the exact entry if no worker has started it yet (so a unit whose turn comes late
+//     never runs a speculative chain at all: with at least as many units as warps the whole scheme
+//     degenerates into one exact, sequential chain per unit, with no wasted work), or
+//   * queues a re-run from the exact entry (which splices into the old chain as in the round scheme), or
+//   * returns, if that chunk is running right now: its completion calls sched_advance again.
+// A unit's sequential dependency is thereby followed as fast as its own chains complete, concurrently with
+// everything else.  Exactness is unchanged: a chunk is final only if its chain started at the exit of the
+// final chain before it, and chunk 0 starts at index 0.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t PH_QUEUED = 0, PH_RUNNING = 1, PH_DONE = 2, PH_LOCKED = 3;
+
+struct UnitSched {        // 16 bytes, one per unit
+    uint32_t lock;        // sched_advance is serialised per unit
+    uint32_t next_c;      // frontier: first chunk not yet known to be final
+    uint32_t entry;       // exact entry of that chunk
+    uint32_t finished;    // the whole unit is final
+};
+
+// Called by ONE thread after a chain of the unit has been published (state stored, fence, phase = PH_DONE).
+// st: the unit's chunks.  push(c) appends chunk c of this unit to the work queue (after a fence).
+// Returns true if this call made the unit final.
+template <typename Push>
+MDB_DEV bool sched_advance(UnitSched &us, uint32_t n, uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, Push &&push) {
+    while (sync_cas(&us.lock, 0u, 1u) != 0u) sync_pause();
+    sync_fence();
+    bool became_final = false;
+    if (!sync_load(&us.finished)) {
+        uint32_t c = sync_load(&us.next_c), e = sync_load(&us.entry);
+        while (true) {
+            if (c >= n_chunks) {
+                sync_store(&us.finished, 1u);
+                became_final = true;
+                break;
+            }
+            const uint32_t chunk_end = (uint64_t)(c + 1) * chunk_len < n ? (c + 1) * chunk_len : n;
+            if (e >= chunk_end) { // no fit starts in this chunk: a model spans it
+                c++;
+                continue;
+            }
+            ChunkState &s = st[c];
+            const uint32_t phase = sync_load(&s.phase);
+            if (phase == PH_RUNNING || phase == PH_LOCKED) break; // its completion continues from here
+            if (phase == PH_QUEUED) {
+                // not started yet: aim it at the exact entry instead of a speculative one
+                if (sync_cas(&s.phase, PH_QUEUED, PH_LOCKED) == PH_QUEUED) {
+                    sync_store(&s.new_entry, e);
+                    sync_store8(&s.exact, 1);
+                    sync_fence();
+                    sync_exch(&s.phase, PH_QUEUED);
+                }
+                break; // (a lost CAS means a worker has just claimed it)
+            }
+            sync_fence(); // PH_DONE: the chain's results are visible
+            if (sync_load(&s.entry) == e && sync_load(&s.exit) != IDX_NONE) {
+                e = sync_load(&s.exit);
+                c++;
+                continue;
+            }
+            // wrong entry, or the right one but cut short by the budget of a speculative chain: run it from the exact entry
+            sync_store(&s.new_entry, e);
+            sync_store8(&s.exact, 1);
+            sync_store8(&s.dirty, 1);
+            sync_fence();
+            sync_exch(&s.phase, PH_QUEUED);
+            push(c);
+            break;
+        }
+        sync_store(&us.next_c, c);
+        sync_store(&us.entry, e);
+    }
+    sync_fence();
+    sync_exch(&us.lock, 0u);
+    return became_final;
 }
 
 // After the fixpoint: marks skipped chunks, links every chunk to the start of the next model in the

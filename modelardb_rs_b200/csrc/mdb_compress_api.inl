@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(128) k_spec_init(const uint64_t *unit_off, uin
         s.irregular = 0;
         s.pad[0] = s.pad[1] = s.pad[2] = 0;
         s.first_start = IDX_NONE;
-        s.pad2 = 0;
+        s.phase = PH_QUEUED;
         st[g0 + c] = s;
         chunk_unit[g0 + c] = (uint32_t)u;
         uint64_t rest = n - c * chunk_len;
@@ -126,62 +126,258 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
     if (lane == 0) st[g] = s;
 }
 
-// After the fixpoint: one warp per chunk, one lane per accepted model -- completes the pending Swing
-// models (their order-dependent MSE sums, see swing_finish).  Only models of the FINAL chains are
-// finished; speculative models that were spliced away never cost this pass.
+// ---- asynchronous scheduling (mdb_compress.cuh: sched_advance) ------------------------------------------
+struct SchedQueue {
+    uint32_t head;       // next ticket
+    uint32_t tail;       // next free slot of `items`
+    uint32_t finished;   // every live unit is final
+    uint32_t units_done;
+    uint32_t live_units; // units with at least one chunk
+    uint32_t capacity;   // slots in `items` (a zero slot has not been written yet; chunk g is stored as g + 1)
+    uint32_t pad[2];
+};
+
+// Initial queue order: chunk 0 of every unit, then chunk 1 of every unit, ...: the exact frontiers (chunk 0 is
+// exact by definition) start moving in the first wave, and later chunks are still unstarted -- and can be
+// re-aimed at their exact entry -- when the frontier reaches them.
+__global__ void __launch_bounds__(256) k_sched_count(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, uint32_t *per_index) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    atomicAdd(&per_index[(uint32_t)(g - chunk_base[chunk_unit[g]])], 1u);
+}
+__global__ void __launch_bounds__(256) k_sched_fill(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, const uint64_t *index_base,
+                                                    uint32_t *cursor, uint32_t *items) {
+    uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_chunks) return;
+    const uint32_t c = (uint32_t)(g - chunk_base[chunk_unit[g]]);
+    items[index_base[c] + atomicAdd(&cursor[c], 1u)] = (uint32_t)g + 1u;
+}
+__global__ void __launch_bounds__(128) k_sched_units(const uint64_t *chunk_base, uint64_t n_units, uint64_t n_chunks, uint32_t capacity, UnitSched *units,
+                                                     SchedQueue *q) {
+    uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u == 0) {
+        q->head = 0;
+        q->tail = (uint32_t)n_chunks;
+        q->units_done = 0;
+        q->capacity = capacity;
+    }
+    if (u >= n_units) return;
+    UnitSched s;
+    s.lock = 0;
+    s.next_c = 0;
+    s.entry = 0;
+    s.finished = 0;
+    units[u] = s;
+    if (chunk_base[u + 1] > chunk_base[u]) atomicAdd(&q->live_units, 1u);
+}
+
+// Persistent workers: one warp = one worker; each takes a ticket, waits for that queue slot to be filled,
+// claims the chunk, runs its chain (the same spec_chain as the round scheme) and advances the unit.
+__global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_async(const int64_t *__restrict__ ts, const float *__restrict__ values,
+                                                                 const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
+                                                                 const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
+                                                                 const uint32_t *__restrict__ chunk_unit, uint32_t chunk_len, ChunkState *st,
+                                                                 FittedModel *lists, const uint64_t *__restrict__ list_base,
+                                                                 const uint32_t *__restrict__ list_cap, UnitSched *units, SchedQueue *q, uint32_t *items,
+                                                                 unsigned long long stall_ns) {
+    __shared__ double smem[CHAIN_WARPS][WarpFit::SMEM_DOUBLES];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    while (true) {
+        uint32_t item = 0;
+        if (lane == 0) {
+            const uint32_t ticket = atomicAdd(&q->head, 1u);
+            if (ticket < sync_load(&q->capacity)) {
+                unsigned long long waited_since = 0;
+                while ((item = sync_load(&items[ticket])) == 0) {
+                    if (sync_load(&q->finished)) break;
+                    __nanosleep(200);
+                    if (stall_ns) { // diagnostics (MDBCU_STALL_MS): give up instead of hanging if the queue never fills
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (!waited_since) waited_since = now;
+                        else if (now - waited_since > stall_ns) atomicCAS(&q->finished, 0u, 3u);
+                    }
+                }
+            }
+        }
+        item = __shfl_sync(FULL_MASK, item, 0);
+        if (item == 0) return; // every unit is final (or the queue is exhausted, which the host reports)
+        const uint64_t g = item - 1;
+        const uint32_t u = chunk_unit[g];
+        const uint64_t g0 = chunk_base[u];
+        const uint32_t c = (uint32_t)(g - g0), C = (uint32_t)(chunk_base[u + 1] - g0);
+        int run = 1;
+        if (lane == 0) {
+            while (true) { // claim: PH_QUEUED -> PH_RUNNING (PH_LOCKED: sched_advance is re-aiming it right now)
+                const uint32_t old = atomicCAS(&st[g].phase, PH_QUEUED, PH_RUNNING);
+                if (old == PH_QUEUED) break;
+                if (old != PH_LOCKED) { run = 0; break; }
+                __nanosleep(50);
+            }
+            if (run && c < sync_load(&units[u].next_c)) { // the frontier is already past it: a model spans this chunk
+                atomicExch(&st[g].phase, PH_DONE);
+                run = 0;
+            }
+            __threadfence();
+        }
+        run = __shfl_sync(FULL_MASK, run, 0);
+        if (!run) continue;
+        const uint64_t a = unit_off[u];
+        const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+        const uint32_t chunk_start = c * chunk_len;
+        const uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
+        ChunkState s = load_shared_record(st + g);
+        ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        WarpFit fitter(eb, ts + a, values + a, n, smem[warp]);
+        spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+        __threadfence(); // this lane's list writes, before lane 0 publishes the chunk
+        __syncwarp();
+        if (lane == 0) {
+            s.phase = PH_RUNNING;
+            st[g] = s;
+            __threadfence();
+            atomicExch(&st[g].phase, PH_DONE);
+            const bool unit_final = sched_advance(units[u], n, chunk_len, C, st + g0, [&](uint32_t cc) {
+                __threadfence();
+                const uint32_t slot = atomicAdd(&q->tail, 1u);
+                if (slot < sync_load(&q->capacity)) sync_store(&items[slot], (uint32_t)(g0 + cc) + 1u);
+                else sync_store(&q->finished, 2u); // cannot happen (a chunk is queued at most three times); stops the workers
+            });
+            if (unit_final && atomicAdd(&q->units_done, 1u) + 1u == sync_load(&q->live_units)) {
+                __threadfence();
+                atomicCAS(&q->finished, 0u, 1u);
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// ---- completing the pending Swing models (swing_finish) ---------------------------------------------------
+// The two MSE sums of swing.rs:212-228 must be accumulated in point order, one rounding per point, so a model
+// is a serial chain of additions -- but the models are independent of each other.  One LANE therefore sums one
+// model (32 chains advance per instruction), reading its points with 16-byte loads; on a regular unit the time
+// differences are k * interval and the timestamps are not read at all.  Models longer than
+// SWING_FINISH_LONG points would leave the other 31 lanes waiting: those are summed by the whole warp instead
+// (coalesced loads, terms in parallel, the additions chained through shared memory).
+#ifndef MDB_SWING_FINISH_LONG
+#define MDB_SWING_FINISH_LONG 4096
+#endif
+constexpr uint32_t SWING_FINISH_LONG = MDB_SWING_FINISH_LONG;
+
+__device__ __forceinline__ void swing_sums_one_lane(const int64_t *__restrict__ uts, const float *__restrict__ uval, bool regular, double delta_d,
+                                                    uint32_t start, uint32_t end, double &num, double &den) {
+    const double v0 = (double)uval[start];
+    num = 0.0;
+    den = 0.0;
+    uint32_t i = start + 2; // the first two points add no term
+    if (regular) {
+        // t[i] - t[start] = k * interval exactly; k and the interval are exact doubles, so the rounded product is
+        // the same double as the conversion of the integer difference
+        double kd = 2.0;
+        auto term = [&](float vf) {
+            const double v = (double)vf;
+            const double dt = __dmul_rn(kd, delta_d);
+            const bool eq = equal_or_nan(v0, v);
+            const double x = __dmul_rn(__dsub_rn(v, v0), dt), y = __dmul_rn(dt, dt);
+            num = __dadd_rn(num, eq ? 0.0 : x);
+            den = __dadd_rn(den, eq ? 0.0 : y);
+            kd = __dadd_rn(kd, 1.0);
+        };
+        for (; i <= end && (reinterpret_cast<uintptr_t>(uval + i) & 15); i++) term(uval[i]);
+        for (; i + 3 <= end; i += 4) {
+            const float4 q = __ldg(reinterpret_cast<const float4 *>(uval + i));
+            term(q.x);
+            term(q.y);
+            term(q.z);
+            term(q.w);
+        }
+        for (; i <= end; i++) term(uval[i]);
+    } else {
+        const int64_t t0 = uts[start];
+        for (; i <= end; i++) {
+            double x, y;
+            swing_mse_terms(t0, v0, uts[i], (double)uval[i], x, y);
+            num = __dadd_rn(num, x);
+            den = __dadd_rn(den, y);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                       const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ chunk_unit,
                                                       uint64_t n_chunks, const ChunkState *st, FittedModel *lists,
-                                                      const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap) {
+                                                      const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                      const uint8_t *__restrict__ unit_irregular) {
     __shared__ double smem[4][64];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t g = (uint64_t)blockIdx.x * 4 + warp;
     if (g >= n_chunks) return;
     const ChunkState s = st[g];
     if (s.skipped || s.n_models == 0) return;
-    uint64_t a = unit_off[chunk_unit[g]];
+    const uint32_t u = chunk_unit[g];
+    const uint64_t a = unit_off[u];
+    const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
     const int64_t *uts = ts + a;
     const float *uval = values + a;
+    const int64_t delta0 = n >= 2 ? uts[1] - uts[0] : 0;
+    const bool regular = !unit_irregular[u] && delta0 >= 0 && delta0 < (1ll << 31);
+    const double delta_d = (double)delta0;
     FittedModel *list = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2);
     double *sx = smem[warp], *sy = smem[warp] + 32;
-    // The warp walks the chunk's models one after the other: 32 points per step are loaded coalesced
-    // and their terms computed in parallel; only the two running sums are chained, in point order.
-    for (uint32_t k = 0; k < s.n_models; k++) {
-        FittedModel m = list[k];
-        if (!m.pending) continue;
-        const int64_t t0 = uts[m.start_index];
-        const double v0 = (double)uval[m.start_index];
-        double num = 0.0, den = 0.0;
-        // the loads of the next two steps are in flight while this step's add chain runs
-        const uint32_t first = m.start_index + 2 + lane;
-        int64_t ta = first <= m.end_index ? uts[first] : 0, tb = first + 32 <= m.end_index ? uts[first + 32] : 0;
-        float va = first <= m.end_index ? uval[first] : 0.0f, vb = first + 32 <= m.end_index ? uval[first + 32] : 0.0f;
-        for (uint32_t base = m.start_index + 2; base <= m.end_index; base += 32) {
-            const uint32_t i = base + lane;
-            const int64_t tc = ta;
-            const float vc = va;
-            ta = tb;
-            va = vb;
-            tb = i + 64 <= m.end_index ? uts[i + 64] : 0;
-            vb = i + 64 <= m.end_index ? uval[i + 64] : 0.0f;
-            double x = 0.0, y = 0.0;
-            if (i <= m.end_index) swing_mse_terms(t0, v0, tc, (double)vc, x, y);
-            sx[lane] = x;
-            sy[lane] = y;
-            __syncwarp();
-            const int cnt = (int)min(32u, m.end_index - base + 1);
-#pragma unroll
-            for (int j = 0; j < 32; j++) {
-                const double xj = sx[j], yj = sy[j];
-                if (j < cnt) {
-                    num = __dadd_rn(num, xj);
-                    den = __dadd_rn(den, yj);
-                }
-            }
-            __syncwarp();
+    for (uint32_t k0 = 0; k0 < s.n_models; k0 += 32) {
+        const uint32_t k = k0 + (uint32_t)lane;
+        FittedModel m;
+        bool mine = false;
+        if (k < s.n_models) {
+            m = list[k];
+            mine = m.pending != 0;
         }
-        swing_finish_from_sums(m, num, den, uts, uval);
-        if (lane == 0) list[k] = m;
+        const bool is_long = mine && (m.end_index - m.start_index) >= SWING_FINISH_LONG;
+        if (mine && !is_long) {
+            double num, den;
+            swing_sums_one_lane(uts, uval, regular, delta_d, m.start_index, m.end_index, num, den);
+            swing_finish_from_sums(m, num, den, uts, uval);
+            list[k] = m;
+        }
+        unsigned long_mask = __ballot_sync(FULL_MASK, is_long);
+        while (long_mask) { // the whole warp on one long model: 32 points per step, only the two running sums are chained
+            const int src = __ffs(long_mask) - 1;
+            long_mask &= long_mask - 1;
+            FittedModel lm = list[k0 + (uint32_t)src];
+            const int64_t t0 = uts[lm.start_index];
+            const double v0 = (double)uval[lm.start_index];
+            double num = 0.0, den = 0.0;
+            // the loads of the next two steps are in flight while this step's add chain runs
+            const uint32_t first = lm.start_index + 2 + lane;
+            int64_t ta = first <= lm.end_index ? uts[first] : 0, tb = first + 32 <= lm.end_index ? uts[first + 32] : 0;
+            float va = first <= lm.end_index ? uval[first] : 0.0f, vb = first + 32 <= lm.end_index ? uval[first + 32] : 0.0f;
+            for (uint32_t base = lm.start_index + 2; base <= lm.end_index; base += 32) {
+                const uint32_t i = base + lane;
+                const int64_t tc = ta;
+                const float vc = va;
+                ta = tb;
+                va = vb;
+                tb = i + 64 <= lm.end_index ? uts[i + 64] : 0;
+                vb = i + 64 <= lm.end_index ? uval[i + 64] : 0.0f;
+                double x = 0.0, y = 0.0;
+                if (i <= lm.end_index) swing_mse_terms(t0, v0, tc, (double)vc, x, y);
+                sx[lane] = x;
+                sy[lane] = y;
+                __syncwarp();
+                const int cnt = (int)min(32u, lm.end_index - base + 1);
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    const double xj = sx[j], yj = sy[j];
+                    if (j < cnt) {
+                        num = __dadd_rn(num, xj);
+                        den = __dadd_rn(den, yj);
+                    }
+                }
+                __syncwarp();
+            }
+            swing_finish_from_sums(lm, num, den, uts, uval);
+            if (lane == 0) list[k0 + (uint32_t)src] = lm;
+        }
     }
 }
 
@@ -307,7 +503,9 @@ uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return c
 
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
-    if (engine < 0 || engine > 2) return fail("fit engine must be 0 (automatic), 1 (one thread per chain) or 2 (one warp per chain)");
+    if (engine < 0 || engine > 3)
+        return fail("fit engine must be 0 (automatic), 1 (one thread per chain, rounds), 2 (one warp per chain, rounds) or 3 (one warp per chain, "
+                    "asynchronous scheduling)");
     ctx->fit_mode = engine;
     return MDBCU_SUCCESS;
 }
@@ -415,6 +613,48 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         DBuf<FittedModel> lists;
         TRY_SG(lists.alloc(n_models_cap, s));
 
+        const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3;
+        if (async_sched && G) {
+            // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
+            const char *stall_env = std::getenv("MDBCU_STALL_MS"); // diagnostics: abort a scheduler that makes no progress
+            const unsigned long long stall_ns = stall_env ? std::strtoull(stall_env, nullptr, 10) * 1000000ull : 0ull;
+            int blocks_per_sm = 0;
+            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_spec_async, CHAIN_WARPS * 32, 0));
+            if (blocks_per_sm < 1) return bail(fail("compress: the chain kernel does not fit on this device"));
+            const uint64_t n_blocks = std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, CHAIN_WARPS));
+            const uint64_t capacity = 3 * G + n_blocks * CHAIN_WARPS + 8;
+            if (capacity > 0xFFFFFFF0ull) return bail(fail("compress: too many chunks"));
+            DBuf<UnitSched> units;
+            DBuf<SchedQueue> queue;
+            DBuf<uint32_t> items, per_index, cursor;
+            DBuf<uint64_t> index_base;
+            TRY_SG(units.alloc(n_units, s));
+            TRY_SG(queue.alloc(1, s));
+            TRY_SG(items.alloc(capacity, s));
+            TRY_SG(per_index.alloc(G, s));
+            TRY_SG(cursor.alloc(G, s));
+            TRY_SG(index_base.alloc(G + 1, s));
+            TRY_SG(cudaMemsetAsync(queue.p, 0, sizeof(SchedQueue), s));
+            TRY_SG(cudaMemsetAsync(items.p, 0, capacity * sizeof(uint32_t), s));
+            TRY_SG(cudaMemsetAsync(per_index.p, 0, G * sizeof(uint32_t), s));
+            TRY_SG(cudaMemsetAsync(cursor.p, 0, G * sizeof(uint32_t), s));
+            LAUNCH(ctx, k_sched_count, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, per_index.p);
+            if (exclusive_scan<uint32_t>(ctx, per_index.p, G, index_base.p)) return bail(MDBCU_FAILURE);
+            LAUNCH(ctx, k_sched_fill, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, index_base.p, cursor.p, items.p);
+            LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, units.p, queue.p);
+            LAUNCH(ctx, k_spec_async, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p,
+                   chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, stall_ns);
+            static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");
+            TRY_SG(post(ctx, 0, queue.p, 4));
+            TRY_SG(sync_stream(ctx));
+            TRY_SG(cudaGetLastError());
+            SchedQueue hq;
+            std::memcpy(&hq, ctx->mailbox, sizeof(hq));
+            if (hq.finished != 1 || hq.units_done != hq.live_units)
+                return bail(fail("compress: chain scheduler stopped early (internal error)"));
+            ctx->last_rounds = 1;
+        }
+
         // ---- rounds: the chains of the chunks in the worklist, then the per-unit walk that builds the next worklist
         DBuf<uint32_t> worklist;
         DBuf<uint2> unit_resume;
@@ -422,7 +662,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(unit_resume.alloc(n_units, s));
         TRY_SG(cudaMemsetAsync(unit_resume.p, 0, n_units * sizeof(uint2), s));
         uint32_t round = 0;
-        uint64_t n_work = G;
+        uint64_t n_work = async_sched ? 0 : G;
         const uint32_t *d_work = nullptr; // round 0 runs every chunk
         const bool trace = std::getenv("MDBCU_TRACE_ROUNDS") != nullptr; // diagnostics: chunks and wall time per round
         while (n_work) {
@@ -453,12 +693,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_round).count());
             if (round > 4 * G + 8) return bail(fail("compress: chunk fixpoint did not converge (internal error)"));
         }
-        ctx->last_rounds = round;
+        if (!async_sched) ctx->last_rounds = round;
 
         // ---- rows
         LAUNCH(ctx, k_spec_finalize, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, unit_irregular.p);
         if (G && ctx->fit_mode != 1)
-            LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p);
+            LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p, unit_irregular.p);
         if (G) LAUNCH(ctx, k_spec_count_rows, div_up(G, 128), 128, 0, st.p, G, lists.p, list_base.p, list_cap.p, rows.p);
         if (exclusive_scan<uint32_t>(ctx, rows.p, G, row_base.p)) return bail(MDBCU_FAILURE);
         LAUNCH(ctx, k_unit_seg_off, div_up(n_units + 1, 256), 256, 0, chunk_base.p, n_units, row_base.p, sg->unit_seg_off);

@@ -20,6 +20,34 @@
 
 namespace mdb {
 
+// ---------------------------------------------------------------------------------------------
+// Words shared between warps that run at the same time (the chain scheduler, mdb_compress.cuh):
+// device-scope atomics, L1-bypassing loads / stores and a device-scope fence.  The host versions in
+// mdb_host_shim.h are the single-threaded equivalents.
+// ---------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+MDB_DEV uint32_t sync_cas(uint32_t *p, uint32_t expect, uint32_t val) { return atomicCAS(p, expect, val); }
+MDB_DEV uint32_t sync_exch(uint32_t *p, uint32_t val) { return atomicExch(p, val); }
+MDB_DEV uint32_t sync_add(uint32_t *p, uint32_t val) { return atomicAdd(p, val); }
+MDB_DEV uint32_t sync_load(const uint32_t *p) { return *(const volatile uint32_t *)p; }
+MDB_DEV void sync_store(uint32_t *p, uint32_t v) { *(volatile uint32_t *)p = v; }
+MDB_DEV void sync_store8(uint8_t *p, uint8_t v) { *(volatile uint8_t *)p = v; }
+MDB_DEV void sync_fence() { __threadfence(); }
+MDB_DEV void sync_pause() { __nanosleep(100); }
+// 16-byte aligned records written by another SM earlier in the same kernel: read around L1
+template <typename T> MDB_DEV T load_shared_record(const T *p) {
+    static_assert(sizeof(T) % 16 == 0, "record size");
+    union alignas(16) {
+        T value;
+        uint4 q[sizeof(T) / 16];
+    } u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (unsigned i = 0; i < sizeof(T) / 16; i++) u.q[i] = __ldcg(src + i);
+    return u.value;
+}
+#endif
+
 constexpr int KIND_LOSSLESS = 0, KIND_ABSOLUTE = 1, KIND_RELATIVE = 2;
 constexpr int PMC_MEAN = 0, SWING = 1, MACAQUE_V = 2;
 

@@ -24,4 +24,17 @@ static inline int __clz(int x) { return x == 0 ? 32 : __builtin_clz((unsigned)x)
 static inline int __clzll(long long x) { return x == 0 ? 64 : __builtin_clzll((unsigned long long)x); }
 static inline int __ffs(int x) { return __builtin_ffs(x); }
 using std::isinf;
+
+// single-threaded equivalents of the inter-warp synchronisation words (mdb_device.cuh)
+namespace mdb {
+static inline uint32_t sync_cas(uint32_t *p, uint32_t expect, uint32_t val) { uint32_t old = *p; if (old == expect) *p = val; return old; }
+static inline uint32_t sync_exch(uint32_t *p, uint32_t val) { uint32_t old = *p; *p = val; return old; }
+static inline uint32_t sync_add(uint32_t *p, uint32_t val) { uint32_t old = *p; *p += val; return old; }
+static inline uint32_t sync_load(const uint32_t *p) { return *p; }
+static inline void sync_store(uint32_t *p, uint32_t v) { *p = v; }
+static inline void sync_store8(uint8_t *p, uint8_t v) { *p = v; }
+static inline void sync_fence() {}
+static inline void sync_pause() {}
+template <typename T> static inline T load_shared_record(const T *p) { return *p; }
+} // namespace mdb
 #endif

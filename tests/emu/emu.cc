@@ -25,11 +25,69 @@ struct EmuSegments {
     std::vector<uint8_t> ts_data, val_data, res_data;
 };
 
+// The asynchronous scheduler (k_spec_async + sched_advance) for one unit, single-threaded: up to `in_flight`
+// "workers" hold a claimed chunk at a time, and a seeded generator decides whether the next event is a worker
+// claiming the next queue item or one of the claimed chains completing (publish + sched_advance).  Returns
+// false if the schedule stalls or the queue overflows.
+static bool emu_unit_async(const ErrorBound &eb, const int64_t *uts, const float *uval, uint32_t n, uint32_t L, uint32_t C, uint32_t cap,
+                           std::vector<ChunkState> &st, std::vector<FittedModel> &lists, uint32_t seed, uint32_t in_flight, uint32_t *runs_out) {
+    uint64_t rng = 0x9E3779B97F4A7C15ull * (seed + 1);
+    auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
+    std::vector<uint32_t> queue;
+    for (uint32_t c = 0; c < C; c++) queue.push_back(c);
+    size_t head = 0;
+    UnitSched us;
+    us.lock = 0; us.next_c = 0; us.entry = 0; us.finished = 0;
+    struct Claimed { uint32_t c; ChunkState s; };
+    std::vector<Claimed> claimed;
+    uint32_t runs = 0;
+    while (!us.finished) {
+        const bool can_claim = head < queue.size() && claimed.size() < in_flight;
+        if (!can_claim && claimed.empty()) return false; // stalled: nothing queued, nothing running, unit not final
+        if (can_claim && (claimed.empty() || (next() & 1))) {
+            uint32_t c = queue[head++];
+            if (sync_cas(&st[c].phase, PH_QUEUED, PH_RUNNING) != PH_QUEUED) return false; // one queue entry per PH_QUEUED state
+            if (c < us.next_c) { st[c].phase = PH_DONE; continue; } // the frontier is past it
+            Claimed w;
+            w.c = c;
+            w.s = st[c];
+            uint32_t ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
+            ScalarFit fitter(eb, uts, uval, n);
+            spec_chain(fitter, 0u, 1u, n, ce, L, w.s, lists.data() + (size_t)c * 2 * cap, cap); // (new list is unread until published)
+            runs++;
+            claimed.push_back(w);
+        } else {
+            size_t k = next() % claimed.size();
+            Claimed w = claimed[k];
+            claimed.erase(claimed.begin() + k);
+            w.s.phase = PH_RUNNING;
+            st[w.c] = w.s;
+            st[w.c].phase = PH_DONE;
+            sched_advance(us, n, L, C, st.data(), [&](uint32_t cc) { queue.push_back(cc); });
+            if (queue.size() > 3 * (size_t)C + 8) return false;
+        }
+    }
+    if (runs_out) *runs_out = runs;
+    return true;
+}
+
 extern "C" {
 
 // chunk_len == 0: one chunk per unit (the plain sequential chain).
+// sched_seed == 0: rounds (k_spec_chain + k_spec_propagate); otherwise the asynchronous scheduler with that seed and
+// `in_flight` concurrent workers; rounds_out then receives the largest number of chain runs of any unit.
+EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const uint64_t *unit_off, uint64_t n_units,
+                                const uint8_t *eb_kind, const float *eb_value, uint32_t chunk_len, uint32_t *rounds_out,
+                                uint32_t sched_seed, uint32_t in_flight);
+
 EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t *unit_off, uint64_t n_units,
                           const uint8_t *eb_kind, const float *eb_value, uint32_t chunk_len, uint32_t *rounds_out) {
+    return emu_compress_sched(ts, values, unit_off, n_units, eb_kind, eb_value, chunk_len, rounds_out, 0, 0);
+}
+
+EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const uint64_t *unit_off, uint64_t n_units,
+                                const uint8_t *eb_kind, const float *eb_value, uint32_t chunk_len, uint32_t *rounds_out,
+                                uint32_t sched_seed, uint32_t in_flight) {
     EmuSegments *out = new EmuSegments();
     out->unit_seg_off.assign(n_units + 1, 0);
     std::vector<SegRecord> recs;
@@ -52,7 +110,11 @@ EmuSegments *emu_compress(const int64_t *ts, const float *values, const uint64_t
             st[c].entry = IDX_NONE; st[c].exit = IDX_NONE; st[c].new_entry = c * L; st[c].dirty = 1; st[c].exact = c == 0;
         }
         uint32_t rounds = 0, resume_c = 0, resume_e = 0;
-        while (true) { // rounds: k_spec_chain over dirty chunks, then k_spec_propagate per unit
+        if (sched_seed) {
+            for (uint32_t c = 0; c < C; c++) st[c].phase = PH_QUEUED;
+            if (!emu_unit_async(eb, uts, uval, n, L, C, cap, st, lists, sched_seed + (uint32_t)u, in_flight ? in_flight : 1, &rounds)) return nullptr;
+        }
+        while (!sched_seed) { // rounds: k_spec_chain over dirty chunks, then k_spec_propagate per unit
             for (uint32_t c = 0; c < C; c++)
                 if (st[c].dirty) {
                     uint32_t cs = c * L, ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);

@@ -29,6 +29,8 @@ def lib():
     vp, u64 = C.c_void_p, C.c_uint64
     L.emu_compress.argtypes = [vp, vp, vp, u64, vp, vp, C.c_uint32, vp]
     L.emu_compress.restype = vp
+    L.emu_compress_sched.argtypes = [vp, vp, vp, u64, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
+    L.emu_compress_sched.restype = vp
     L.emu_segments_len.argtypes = [vp]
     L.emu_segments_len.restype = u64
     L.emu_segments_view.argtypes = [vp, C.POINTER(O._View), C.POINTER(vp)]
@@ -50,7 +52,9 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None) -> O.Segments:
+def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0) -> O.Segments:
+    """sched_seed == 0: the round scheme; otherwise the asynchronous scheduler stepped in a seeded random order with
+    `in_flight` concurrent workers (rounds then receives the largest number of chain runs of any unit)."""
     ts = np.ascontiguousarray(ts, np.int64)
     vals = np.ascontiguousarray(values, np.float32)
     if unit_off is None:
@@ -63,9 +67,9 @@ def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None) -
     evals = np.array([e[1] for e in eb], np.float32)
     L = lib()
     r = C.c_uint32(0)
-    h = L.emu_compress(_p(ts), _p(vals), _p(unit_off), n_units, _p(kinds), _p(evals), chunk_len, C.byref(r))
+    h = L.emu_compress_sched(_p(ts), _p(vals), _p(unit_off), n_units, _p(kinds), _p(evals), chunk_len, C.byref(r), sched_seed, in_flight)
     if not h:
-        raise RuntimeError("emulated chunk-speculative compress did not converge / row count mismatch")
+        raise RuntimeError("emulated chunk-speculative compress did not converge / stalled / row count mismatch")
     if rounds is not None:
         rounds.append(r.value)
     v = O._View()

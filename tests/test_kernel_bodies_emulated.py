@@ -77,3 +77,43 @@ def test_chunk_speculation_converges_quickly_on_benchmark_like_data(oracle):
         got = emu.compress(ts, vals, off, eb=eb, chunk_len=8192, rounds=rounds)
         assert_segments_equal(got, want, f"sine eb={eb}")
         assert rounds[0] <= max_rounds, (eb, rounds)
+
+
+# ---- the asynchronous scheduler (sched_advance + the worker loop of k_spec_async), stepped in random orders ----------
+
+@pytest.mark.parametrize("in_flight", [1, 3, 16])
+@pytest.mark.parametrize("chunk_len", [8, 64, 1000])
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_async_scheduler_gives_the_sequential_chain(oracle, case, chunk_len, in_flight):
+    """Whatever the order in which workers claim chunks and chains complete, the per-unit frontier must end on
+    exactly the sequential chain (and never stall or overflow the queue)."""
+    name, ts, vals, off, ebs = case
+    want = oracle.compress(ts, vals, off, eb=ebs)
+    for seed in (1, 2, 3):
+        got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=seed, in_flight=in_flight)
+        assert_segments_equal(got, want, f"{name} chunk_len={chunk_len} in_flight={in_flight} seed={seed}")
+
+
+@pytest.mark.parametrize("chunk_len", [16, 128, 1024])
+def test_async_scheduler_with_models_longer_than_chunks(oracle, chunk_len):
+    rng = np.random.default_rng(3)
+    parts = [np.full(5000, 3.25, np.float32), rng.uniform(0, 1, 37).astype(np.float32), np.full(3000, -7.5, np.float32),
+             (0.5 * np.arange(4000)).astype(np.float32), rng.uniform(0, 1, 300).astype(np.float32), np.full(2500, 1.0, np.float32)]
+    vals = np.concatenate(parts)
+    ts = syn.regular_timestamps(len(vals))
+    for eb in ((0, 0.0), (2, 1.0), (1, 0.1)):
+        want = oracle.compress(ts, vals, eb=eb)
+        for seed, in_flight in ((1, 1), (2, 4), (3, 64), (4, 1000)):
+            got = emu.compress(ts, vals, eb=eb, chunk_len=chunk_len, sched_seed=seed, in_flight=in_flight)
+            assert_segments_equal(got, want, f"long models eb={eb} chunk_len={chunk_len} seed={seed}")
+
+
+def test_async_scheduler_runs_each_chunk_once_when_workers_are_scarce(oracle):
+    """One worker: every later chunk is still unstarted when the frontier reaches it and is re-aimed at its exact
+    entry, so no chain is ever run speculatively and discarded (chain runs == chunks with a fit start)."""
+    ts, vals, off = syn.multi_series(2, 40_000, 5, "sine")
+    runs = []
+    want = oracle.compress(ts, vals, off, eb=(2, 1.0))
+    got = emu.compress(ts, vals, off, eb=(2, 1.0), chunk_len=4096, rounds=runs, sched_seed=9, in_flight=1)
+    assert_segments_equal(got, want, "one worker")
+    assert runs[0] <= 10, runs  # 40 000 / 4096 -> 10 chunks per unit
