@@ -128,13 +128,14 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
 
 // ---- asynchronous scheduling (mdb_compress.cuh: sched_advance) ------------------------------------------
 struct SchedQueue {
-    uint32_t head;       // next ticket
+    uint32_t head;       // oldest queued slot
     uint32_t tail;       // next free slot of `items`
     uint32_t finished;   // every live unit is final
     uint32_t units_done;
     uint32_t live_units; // units with at least one chunk
     uint32_t capacity;   // slots in `items` (a zero slot has not been written yet; chunk g is stored as g + 1)
-    uint32_t pad[2];
+    uint32_t init_head;  // next slot of the pre-filled part [0, n_chunks); `head` serves the pushed part behind it
+    uint32_t pad;
 };
 
 // Initial queue order: chunk 0 of every unit, then chunk 1 of every unit, ...: the exact frontiers (chunk 0 is
@@ -152,11 +153,12 @@ __global__ void __launch_bounds__(256) k_sched_fill(const uint64_t *chunk_base, 
     const uint32_t c = (uint32_t)(g - chunk_base[chunk_unit[g]]);
     items[index_base[c] + atomicAdd(&cursor[c], 1u)] = (uint32_t)g + 1u;
 }
-__global__ void __launch_bounds__(128) k_sched_units(const uint64_t *chunk_base, uint64_t n_units, uint64_t n_chunks, uint32_t capacity, UnitSched *units,
-                                                     SchedQueue *q) {
+__global__ void __launch_bounds__(128) k_sched_units(const uint64_t *chunk_base, uint64_t n_units, uint64_t n_chunks, uint32_t capacity, uint32_t n_initial,
+                                                     UnitSched *units, SchedQueue *q) {
     uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (u == 0) {
-        q->head = 0;
+        q->init_head = n_initial;
+        q->head = (uint32_t)n_chunks;
         q->tail = (uint32_t)n_chunks;
         q->units_done = 0;
         q->capacity = capacity;
@@ -171,37 +173,49 @@ __global__ void __launch_bounds__(128) k_sched_units(const uint64_t *chunk_base,
     if (chunk_base[u + 1] > chunk_base[u]) atomicAdd(&q->live_units, 1u);
 }
 
-// Persistent workers: one warp = one worker; each takes a ticket, waits for that queue slot to be filled,
-// claims the chunk, runs its chain (the same spec_chain as the round scheme) and advances the unit.
+// Workers: one warp = one worker.  Worker w starts with queue slot w; afterwards it pops the oldest queued chunk,
+// claims it, runs its chain (the same spec_chain as the round scheme) and advances the unit.  A worker that finds
+// the queue empty EXITS: every later push is made by a worker that is still alive and pops right afterwards, so
+// nothing is ever stranded, and the SM slots of a draining kernel become free for other streams.
 __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_async(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                  const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
                                                                  const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
                                                                  const uint32_t *__restrict__ chunk_unit, uint32_t chunk_len, ChunkState *st,
                                                                  FittedModel *lists, const uint64_t *__restrict__ list_base,
                                                                  const uint32_t *__restrict__ list_cap, UnitSched *units, SchedQueue *q, uint32_t *items,
-                                                                 unsigned long long stall_ns) {
+                                                                 uint32_t n_initial, uint32_t n_chunks) {
     __shared__ double smem[CHAIN_WARPS][WarpFit::SMEM_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    bool first = true, initial_phase = true;
     while (true) {
         uint32_t item = 0;
         if (lane == 0) {
-            const uint32_t ticket = atomicAdd(&q->head, 1u);
-            if (ticket < sync_load(&q->capacity)) {
-                unsigned long long waited_since = 0;
-                while ((item = sync_load(&items[ticket])) == 0) {
-                    if (sync_load(&q->finished)) break;
-                    __nanosleep(200);
-                    if (stall_ns) { // diagnostics (MDBCU_STALL_MS): give up instead of hanging if the queue never fills
-                        unsigned long long now;
-                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-                        if (!waited_since) waited_since = now;
-                        else if (now - waited_since > stall_ns) atomicCAS(&q->finished, 0u, 3u);
+            const uint32_t w = blockIdx.x * CHAIN_WARPS + warp;
+            if (first && w < n_initial) { // (init_head starts at n_initial)
+                item = sync_load(&items[w]);
+            } else {
+                // the pushed part first: those are frontier chunks, the critical path of their unit.  Popped exactly
+                // (a worker must never hold a ticket for a slot that nobody may ever fill).
+                while (true) {
+                    const uint32_t h = sync_load(&q->head), t = min(sync_load(&q->tail), sync_load(&q->capacity));
+                    if (h >= t) break;
+                    if (atomicCAS(&q->head, h, h + 1u) == h) {
+                        while ((item = sync_load(&items[h])) == 0) __nanosleep(20); // its pusher has the slot and is writing it
+                        break;
                     }
                 }
+                // then the pre-filled part: a plain ticket counter (overshooting it is harmless)
+                if (item == 0 && initial_phase) {
+                    const uint32_t h = atomicAdd(&q->init_head, 1u);
+                    if (h < n_chunks) item = sync_load(&items[h]);
+                    else initial_phase = false;
+                }
+                // (both empty: this worker is surplus and leaves)
             }
         }
+        first = false;
         item = __shfl_sync(FULL_MASK, item, 0);
-        if (item == 0) return; // every unit is final (or the queue is exhausted, which the host reports)
+        if (item == 0) return;
         const uint64_t g = item - 1;
         const uint32_t u = chunk_unit[g];
         const uint64_t g0 = chunk_base[u];
@@ -616,8 +630,6 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3;
         if (async_sched && G) {
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
-            const char *stall_env = std::getenv("MDBCU_STALL_MS"); // diagnostics: abort a scheduler that makes no progress
-            const unsigned long long stall_ns = stall_env ? std::strtoull(stall_env, nullptr, 10) * 1000000ull : 0ull;
             int blocks_per_sm = 0;
             TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_spec_async, CHAIN_WARPS * 32, 0));
             if (blocks_per_sm < 1) return bail(fail("compress: the chain kernel does not fit on this device"));
@@ -641,9 +653,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             LAUNCH(ctx, k_sched_count, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, per_index.p);
             if (exclusive_scan<uint32_t>(ctx, per_index.p, G, index_base.p)) return bail(MDBCU_FAILURE);
             LAUNCH(ctx, k_sched_fill, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, index_base.p, cursor.p, items.p);
-            LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, units.p, queue.p);
+            const uint32_t n_initial = (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G); // slots handed out without the queue
+            LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, n_initial, units.p, queue.p);
             LAUNCH(ctx, k_spec_async, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p,
-                   chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, stall_ns);
+                   chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
             static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");
             TRY_SG(post(ctx, 0, queue.p, 4));
             TRY_SG(sync_stream(ctx));
