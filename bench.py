@@ -52,6 +52,9 @@ def parse_args():
     p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
     p.add_argument("--e2e-steps", type=int, default=3, help="slabs per worker in the timed e2e region")
     p.add_argument("--e2e-workers", type=int, default=4, help="host threads pipelining slabs (one context each)")
+    p.add_argument("--e2e-stages", default="all", choices=["all", "compress", "grid"], help="diagnostics: time one half of the e2e slab alone")
+    p.add_argument("--e2e-up-gate", type=int, default=2, help="workers allowed at once in the upload-heavy call (compress)")
+    p.add_argument("--e2e-down-gate", type=int, default=1, help="workers allowed at once in the download-heavy call (grid)")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -376,13 +379,30 @@ def main():
 
         phase_s = {"compress": 0.0, "to_host": 0.0, "grid": 0.0, "aggregate": 0.0}
 
+        # A bounded number of workers at a time inside the upload-heavy call and inside the download-heavy call: bulk
+        # copies in one direction only share that link (and concurrent bulk downloads were measured to slow each other
+        # down: 4.3 -> 2.8 G points/s with four at once), while the other direction sits idle.
+        up_gate = threading.Semaphore(args.e2e_up_gate)
+        down_gate = threading.Semaphore(args.e2e_down_gate)
+
         def e2e_slab(b):
             p0 = time.perf_counter()
-            seg = mc.compress(b["ts"].numpy(), b["vals"].numpy(), e_off, [eb] * e_units, b["ctx"])
+            if args.e2e_stages == "grid" and "seg" in b:  # diagnostics: the download-heavy half alone, on kept segments
+                seg = b["seg"]
+            else:
+                with up_gate:
+                    seg = mc.compress(b["ts"].numpy(), b["vals"].numpy(), e_off, [eb] * e_units, b["ctx"])
             p1 = time.perf_counter()
             host_seg = seg.to_host(copy=False)            # what the Rust caller gets back: the RecordBatch columns (host memory)
             p2 = time.perf_counter()
-            mc.grid(host_seg, b["ts_out"].numpy(), b["val_out"].numpy(), b["ctx"])
+            if args.e2e_stages == "compress":             # diagnostics: the upload-heavy half alone
+                del host_seg
+                seg.free()
+                phase_s["compress"] += p1 - p0
+                phase_s["to_host"] += p2 - p1
+                return None
+            with down_gate:
+                mc.grid(host_seg, b["ts_out"].numpy(), b["val_out"].numpy(), b["ctx"])
             p3 = time.perf_counter()
             uso = host_seg.unit_seg_off
             group = uso if args.units == "series" else uso[:: (e_units // es)]
@@ -394,7 +414,10 @@ def main():
             io["h2d"] = 12 * en + 2 * seg_b               # raw points in; segments in again for grid and aggregate
             io["d2h"] = seg_b + 12 * en + 24 * len(res[0])  # segments out; reconstructed points out; aggregates out
             del host_seg
-            seg.free()
+            if args.e2e_stages == "grid":
+                b["seg"] = seg
+            else:
+                seg.free()
             return res
 
         def worker(b, k):
@@ -421,11 +444,13 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         slabs = workers * esteps
         e2e = {"value": world * en * slabs / float(tt.item()), "unit": "points/s", "h2d_bytes_per_step": int(io["h2d"]),
-               "d2h_bytes_per_step": int(io["d2h"]), "series_per_gpu_per_step": es, "steps": slabs, "workers": workers,
+               "d2h_bytes_per_step": int(io["d2h"]), "series_per_gpu_per_step": es, "steps": slabs, "workers": workers, "gate": [args.e2e_up_gate, args.e2e_down_gate],
                "call_ms_mean": {k: 1e3 * v / slabs for k, v in phase_s.items()},
                "note": "a step is one slab through compress -> to_host -> grid -> aggregate with numpy views of pinned host "
                        "tensors in MDBCU_HOST space; `workers` threads each own a context and pipeline slabs; wall clock, max over ranks"}
         for b in bufs:
+            if "seg" in b:
+                b.pop("seg").free()
             b["ctx"].close()
         del bufs
 

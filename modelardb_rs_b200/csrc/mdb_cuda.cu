@@ -201,13 +201,39 @@ static cudaError_t post(mdbcu_context *ctx, uint32_t slot, const void *d_src, ui
     return cudaGetLastError();
 }
 
-static bool is_pinned(const void *p) {
+// Pinned (page-locked) host memory is also mapped into the device's address space (unified addressing);
+// *device_alias receives the pointer kernels can use for it, or nullptr.
+static bool is_pinned(const void *p, void **device_alias = nullptr) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
         return false;
     }
+    if (device_alias) *device_alias = a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
     return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+// Copies of up to SMALL_COPY bytes between device memory and PINNED host memory are done by a kernel through the
+// mapping instead of by a copy engine: a copy engine serves its queue in order, so a 30 MB column would wait behind
+// any multi-gigabyte copy another context has queued in the same direction (tens of milliseconds), while loads and
+// stores issued by SMs share the link with it.
+constexpr size_t SMALL_COPY = 64u << 20;
+
+__global__ void __launch_bounds__(256) k_copy_bytes(uint8_t *dst, const uint8_t *src, size_t n) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x, stride = (size_t)gridDim.x * blockDim.x;
+    if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0) {
+        const size_t n16 = n / 16;
+        for (size_t k = i; k < n16; k += stride) reinterpret_cast<uint4 *>(dst)[k] = reinterpret_cast<const uint4 *>(src)[k];
+        for (size_t k = n16 * 16 + i; k < n; k += stride) dst[k] = src[k];
+    } else {
+        for (size_t k = i; k < n; k += stride) dst[k] = src[k];
+    }
+}
+
+static cudaError_t copy_by_kernel(mdbcu_context *ctx, void *dst, const void *src, size_t bytes) {
+    const unsigned int blocks = (unsigned int)std::min<size_t>((size_t)ctx->sm_count * 4, (bytes / 16 + 255) / 256 + 1);
+    LAUNCH(ctx, k_copy_bytes, blocks, 256, 0, (uint8_t *)dst, (const uint8_t *)src, bytes);
+    return cudaGetLastError();
 }
 
 static cudaError_t stager_retire(mdbcu_context *ctx, int h) {
@@ -251,7 +277,11 @@ static size_t stager_piece(const mdbcu_context *ctx, size_t bytes) {
 
 static cudaError_t h2d_bytes(mdbcu_context *ctx, void *d_dst, const void *h_src, size_t bytes) {
     if (!bytes) return cudaSuccess;
-    if (is_pinned(h_src)) return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    void *alias = nullptr;
+    if (is_pinned(h_src, &alias)) {
+        if (alias && bytes <= SMALL_COPY) return copy_by_kernel(ctx, d_dst, alias, bytes);
+        return cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
     while (bytes) {
         size_t n = stager_piece(ctx, bytes);
         uint8_t *b;
@@ -269,7 +299,11 @@ static cudaError_t h2d_bytes(mdbcu_context *ctx, void *d_dst, const void *h_src,
 // The bytes are in `h_dst` after the next sync_ctx().
 static cudaError_t d2h_bytes(mdbcu_context *ctx, void *h_dst, const void *d_src, size_t bytes) {
     if (!bytes) return cudaSuccess;
-    if (is_pinned(h_dst)) return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    void *alias = nullptr;
+    if (is_pinned(h_dst, &alias)) {
+        if (alias && bytes <= SMALL_COPY) return copy_by_kernel(ctx, alias, d_src, bytes);
+        return cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream);
+    }
     while (bytes) {
         size_t n = stager_piece(ctx, bytes);
         uint8_t *b;
@@ -1067,8 +1101,7 @@ int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_vie
         }
         CUDA_TRY(pinned_acquire(ctx, total + 64, sg->host_block));
         uint8_t *base = sg->host_block.p;
-        for (int c = 0; c < 12; c++)
-            if (bytes[c]) CUDA_TRY(cudaMemcpyAsync(base + at[c], src[c], bytes[c], cudaMemcpyDeviceToHost, ctx->stream));
+        for (int c = 0; c < 12; c++) CUDA_TRY(d2h_bytes(ctx, base + at[c], src[c], bytes[c]));
         CUDA_TRY(sync_stream(ctx));
         mdbcu_segments_view &h = sg->host_view;
         h.n_segments = S;
