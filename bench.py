@@ -475,7 +475,14 @@ def main():
     }
     # The chain kernel runs once per fixpoint round; its unit of work is one SLAB (one step), so every
     # kernel is accounted per step: algorithmic bytes of one slab / device time the kernel took in one step.
-    algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_chain"]
+    algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_async"] = algo_bytes["k_spec_chain"]
+    # dram bytes per launch from the committed ncu --set full captures (default workload only), scaled by points
+    traffic_of = {}
+    traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(traffic_path) and args.kind == "sine" and args.eb == "rel:1.0" and args.units == "series":
+        for k, v in json.load(open(traffic_path)).items():
+            if isinstance(v, dict):
+                traffic_of[k] = (v["dram_bytes"] * n / v["points"], v["source"])
     per_step_ms = {k: v[0] / args.steps for k, v in kstats.items()}
     dominant = max(per_step_ms.items(), key=lambda kv: kv[1])[0] if per_step_ms else None
     roofline = None
@@ -483,11 +490,12 @@ def main():
         ab = algo_bytes.get(dominant, 12 * n)
         achieved = ab / (per_step_ms[dominant] / 1000.0) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": None, "algorithmic_bytes_per_step": ab, "kernel_ms_per_step": per_step_ms[dominant],
+                    "traffic": traffic_of.get(dominant, (None, None))[0], "traffic_source": traffic_of.get(dominant, (None, None))[1],
+                    "algorithmic_bytes_per_step": ab, "kernel_ms_per_step": per_step_ms[dominant],
                     "launches_per_step": kstats[dominant][1] / args.steps, "peak_source": peak_src,
                     "kernel_share_of_step": per_step_ms[dominant] / ms_per_step,
                     "all_kernels_ms_per_step": dict(sorted(per_step_ms.items(), key=lambda kv: -kv[1]))}
-        for k in ("k_grid_tile", "k_spec_chain", "k_spec_chain_warp", "k_grid_sequential", "k_agg_segments"):
+        for k in ("k_grid_tile", "k_spec_async", "k_spec_chain", "k_spec_chain_warp", "k_agg_segments"):
             if k in per_step_ms and per_step_ms[k] > 0:
                 a_ = algo_bytes[k] / (per_step_ms[k] / 1000.0) / 1e9
                 roofline[f"{k}_GBps"] = a_
