@@ -264,6 +264,7 @@ def main():
     n_series, n_points = args.series, args.points
     n = n_series * n_points
 
+    from modelardb_rs_b200.sharding import gather_group_aggregates
     ctx = mc.Context(local_rank)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
@@ -296,10 +297,8 @@ def main():
             group = series_group_off_of(seg)
         count, mn, mx, sm = mc.aggregate(seg, group, ctx)
         if world > 1:  # only the per-series aggregate partials travel (disjoint groups -> all-gather)
-            with torch.cuda.stream(stream):
-                for t in (count, mn, mx, sm):
-                    g = torch.empty(world * t.numel(), dtype=t.dtype, device=device)
-                    dist.all_gather_into_tensor(g, t)
+            with torch.cuda.stream(stream):  # weak scaling: every rank owns n_series series of the world * n_series table
+                count, mn, mx, sm = gather_group_aggregates(count, mn, mx, sm, world * n_series)
         ev[3].record(stream)
         if record:
             ev[3].synchronize()
