@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(32) k_spec_chain(const int64_t *__restrict__ t
 // thousands of independent chains to fill the GPU, and a warp's loads of 32 consecutive points are
 // fully coalesced (128 B of values, 256 B of timestamps per step).
 constexpr int CHAIN_WARPS = 4;
+// three blocks of four warps per SM (168 registers per thread; measured best of 2 / 3 / 4 on B200)
 #ifndef MDB_CHAIN_MIN_BLOCKS
-#define MDB_CHAIN_MIN_BLOCKS 2
+#define MDB_CHAIN_MIN_BLOCKS 3
 #endif
 __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_chain_warp(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                       const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
