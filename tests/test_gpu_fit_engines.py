@@ -62,6 +62,10 @@ def _long_cases():
 
     add("constant", np.full(n, 100.0), [(0, 0.0), (1, 0.5), (2, 1.0)])
     add("constant-noise", 100.0 + 0.1 * noise, [(1, 1.0), (2, 1.0), (2, 0.2)])
+    # PMC-Mean's relative test at assorted bounds, values scattered right around each bound
+    for pct in (1e-4, 0.37, 3.0, 33.3, 100.0):
+        add(f"around-{pct}pct", 250.0 * (1.0 + (pct / 100.0) * 0.9 * np.clip(noise, -1.3, 1.3)), [(2, pct)])
+        add(f"negative-around-{pct}pct", -0.004 * (1.0 + (pct / 100.0) * 0.9 * np.clip(noise, -1.3, 1.3)), [(2, pct)])
     add("slow-ramp", 100.0 + 0.001 * i + 0.01 * noise, [(1, 0.1), (2, 0.05), (2, 1.0)])
     add("steps", np.where(i < 9_000, 100.0, 150.0) + 0.05 * noise, [(1, 1.0), (2, 1.0)])
     add("zeros", np.zeros(n), [(0, 0.0), (1, 0.5), (2, 1.0)])
