@@ -48,7 +48,10 @@ MDB_DEV float macaque_v_sum(const uint8_t *bytes, uint64_t n_bytes, uint64_t len
 }
 
 // COUNT (len) and SUM (sum) of row s. Returns false for a row the reference would panic on.
-MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &count, float &sum) {
+// defer_min / deferred: a MacaqueV row of at least defer_min (> 0) model values only gets its COUNT here and is
+// reported through *deferred; its SUM is left to the kernel that decodes long streams with a whole warp.
+MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &count, float &sum, uint32_t defer_min = 0,
+                               bool *deferred = nullptr) {
     Row r = load_row(v, s);
     count = 0;
     sum = 0.0f;
@@ -68,6 +71,11 @@ MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &coun
         model_last_value = last;
         model_sum = swing_sum(r, first, last, length, res_len);
     } else {
+        if (defer_min && model_length >= defer_min) {
+            count = length;
+            *deferred = true;
+            return true;
+        }
         model_last_value = __uint_as_float(0x7fc00000u);
         model_sum = macaque_v_sum(r.values, r.n_values, model_length, false, 0.0f);
     }

@@ -167,10 +167,11 @@ template <typename T> struct DBuf {
     T *take() { T *q = p; p = nullptr; return q; }
 };
 
-struct Status {            // zeroed before each call
-    unsigned int bad;      // some row / unit was malformed
-    unsigned int n_seq;    // rows in the serial worklist
-    unsigned long long first_bad;
+struct Status {              // reset before each call (new_status)
+    unsigned int bad;        // some row / unit was malformed
+    unsigned int n_seq;      // rows in the serial worklist (filled from the front of the worklist array)
+    unsigned int first_bad;  // smallest malformed row / unit index
+    unsigned int n_wide;     // long MacaqueV rows decoded by a whole warp (filled from the back of the worklist array)
 };
 
 static inline unsigned int div_up(uint64_t a, uint64_t b) { return (unsigned int)((a + b - 1) / b); }
@@ -465,12 +466,159 @@ constexpr int TILE = TILE_THREADS * TILE_POINTS_PER_THREAD; // 2048 output point
 
 __device__ __forceinline__ void report_bad(Status *status, uint64_t index) {
     atomicExch(&status->bad, 1u);
-    atomicMin(&status->first_bad, (unsigned long long)index);
+    atomicMin(&status->first_bad, (unsigned int)index); // (row and unit counts are below 2^32)
+}
+
+// ------------------------------------------------------------------------------------------------
+// MacaqueV streams decoded by a whole warp
+//
+// A MacaqueV stream (macaque_v.rs:272-323) is a serial state machine: where a value's code starts and how long it
+// is depend on every code before it, so one stream cannot be split.  What a single thread per row loses on a GPU is
+// (1) a memory round trip for every few bytes of the stream, (2) divergence between the lanes' three-way code
+// branches, and (3) scattered 4-byte stores.  Here one WARP owns one long row: the lanes stage the row's bytes
+// into shared memory with coalesced loads, all of them run the same decoder on the same bits (uniform control
+// flow, no divergence; the 64-bit window lives in registers), lane l keeps every value whose index is l mod 32,
+// and 32 values are stored by one coalesced instruction.  Parallelism comes from the rows: thousands of
+// warps are resident at once.  Rows shorter than WIDE_ROW_MIN values stay with the one-thread-per-row kernels.
+// ------------------------------------------------------------------------------------------------
+
+constexpr uint32_t WIDE_ROW_MIN = 64;
+constexpr int WIDE_WARPS = 4;      // warps (rows in flight) per block
+constexpr int STAGE_WORDS = 128;   // 512 B of the stream per refill
+
+struct WarpBitStream {
+    const uint32_t *words; // 4-byte aligned address at or before the first byte of the stream
+    uint64_t n_words, next_word;
+    uint32_t last_mask;    // keeps the stream's bytes of the last word (big-endian), zeroes what follows it
+    uint32_t *stage;       // STAGE_WORDS words of shared memory owned by this warp
+    uint32_t rd, avail;
+    uint64_t buf;          // valid bits are the top `nbits`
+    int nbits;
+
+    __device__ __forceinline__ void restage(int lane) {
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < STAGE_WORDS / 32; i++) {
+            const uint64_t w = next_word + (uint64_t)(i * 32 + lane);
+            uint32_t x = 0;
+            if (w < n_words) {
+                x = __byte_perm(__ldg(words + w), 0, 0x0123); // the stream is big-endian bit order
+                if (w == n_words - 1) x &= last_mask;
+            }
+            stage[i * 32 + lane] = x;
+        }
+        next_word += STAGE_WORDS;
+        rd = 0;
+        avail = STAGE_WORDS;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void refill(int lane) { // nbits <= 32
+        if (rd == avail) restage(lane);
+        buf |= (uint64_t)stage[rd++] << (32 - nbits);
+        nbits += 32;
+    }
+    __device__ __forceinline__ void init(const uint8_t *bytes, uint64_t n_bytes, uint32_t *stage_, int lane) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(bytes);
+        const uint32_t skip = (uint32_t)(a & 3);
+        words = reinterpret_cast<const uint32_t *>(a - skip);
+        n_words = (skip + n_bytes + 3) / 4;
+        const uint32_t used = (uint32_t)((skip + n_bytes) & 3); // bytes of the last word that belong to the stream (0: all)
+        last_mask = used ? 0xFFFFFFFFu << (8 * (4 - used)) : 0xFFFFFFFFu;
+        next_word = 0;
+        stage = stage_;
+        rd = avail = 0;
+        buf = 0;
+        nbits = 0;
+        if (skip && n_bytes) { // drop the bytes in front of the stream
+            refill(lane);
+            buf <<= 8 * skip;
+            nbits -= 8 * (int)skip;
+        }
+    }
+    // n in [0, 32]; bits past the end of the stream read as zero
+    __device__ __forceinline__ uint32_t read(int n, int lane) {
+        if (n == 0) return 0;
+        if (nbits < n) refill(lane);
+        const uint32_t v = (uint32_t)(buf >> (64 - n));
+        buf <<= n;
+        nbits -= n;
+        return v;
+    }
+};
+
+// MacaqueVDecoder (mdb_device.cuh) on a WarpBitStream; emit(k, value) is called for k = first .. first + count - 1.
+template <typename Emit>
+__device__ __forceinline__ float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, bool has_seed, float seed,
+                                                       uint32_t *stage, int lane, Emit &&emit) {
+    WarpBitStream bits;
+    bits.init(bytes, n_bytes, stage, lane);
+    uint32_t leading_zeros = 255, trailing_zeros = 0;
+    uint32_t last_value;
+    uint32_t k = 0;
+    if (has_seed) {
+        last_value = __float_as_uint(seed);
+    } else {
+        last_value = bits.read(32, lane);
+        if (count) emit(k++, __uint_as_float(last_value));
+    }
+    for (; k < count; k++) {
+        if (bits.read(1, lane)) {
+            if (bits.read(1, lane)) {
+                leading_zeros = bits.read(5, lane);
+                uint32_t meaningful_bits = bits.read(6, lane);
+                trailing_zeros = (32u - meaningful_bits - leading_zeros) & 0xffu;
+                meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
+                uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits, lane);
+                value = trailing_zeros < 32 ? value << trailing_zeros : 0;
+                last_value ^= value;
+            }
+        } else {
+            const uint32_t meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
+            uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits, lane);
+            value = trailing_zeros < 32 ? value << trailing_zeros : 0;
+            last_value ^= value;
+        }
+        emit(k, __uint_as_float(last_value));
+    }
+    return __uint_as_float(last_value);
+}
+
+// One warp per wide row (the worklist's back part): the row's MacaqueV values, then its residuals if it has any.
+// Timestamps of these rows are regular and were written by the tile kernel.
+__global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsView v, const SegDesc *desc, const uint64_t *point_off,
+                                                                        const uint32_t *worklist_back, uint32_t n_wide, float *val_out) {
+    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t w = blockIdx.x * WIDE_WARPS + warp;
+    if (w >= n_wide) return;
+    const uint64_t s = *(worklist_back - w);
+    const SegDesc d = desc[s];
+    const Row r = load_row(v, s);
+    const uint64_t base = point_off[s];
+    const uint32_t len = (uint32_t)(point_off[s + 1] - base);
+    float mine = 0.0f;
+    auto emit_to = [&](uint64_t out_base) {
+        return [&, out_base](uint32_t k, float value) {
+            if ((k & 31u) == (uint32_t)lane) mine = value;
+            if ((k & 31u) == 31u) val_out[out_base + (k - 31u) + lane] = mine; // 32 consecutive values, one store
+        };
+    };
+    const float last = warp_macaque_v_decode(r.values, r.n_values, d.model_len, false, 0.0f, stage[warp], lane, emit_to(base));
+    if (d.model_len & 31u) { // the tail that did not fill a whole store
+        const uint32_t k0 = d.model_len & ~31u;
+        if (k0 + lane < d.model_len) val_out[base + k0 + lane] = mine;
+    }
+    if (d.flags & F_HAS_RESIDUALS) { // models/mod.rs:241-249: seeded with the last gridded model value
+        const uint32_t n_res = len - d.model_len;
+        warp_macaque_v_decode(r.residuals, r.n_residuals - 1, n_res, true, last, stage[warp], lane, emit_to(base + d.model_len));
+        const uint32_t k0 = n_res & ~31u;
+        if ((n_res & 31u) && k0 + lane < n_res) val_out[base + d.model_len + k0 + lane] = mine;
+    }
 }
 
 __global__ void __launch_bounds__(256) k_grid_prepare(SegmentsView v, SegDesc *desc, uint32_t *len, uint32_t *worklist, Status *status) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    bool serial = false;
+    bool serial = false, wide = false;
     if (s < v.n_segments) {
         SegDesc d;
         uint32_t n = grid_prepare_segment(v, s, d);
@@ -478,16 +626,27 @@ __global__ void __launch_bounds__(256) k_grid_prepare(SegmentsView v, SegDesc *d
         len[s] = n;
         if (d.flags & F_MALFORMED) report_bad(status, s);
         serial = (d.flags & F_SEQUENTIAL) != 0;
+        // a long MacaqueV value stream on regular timestamps: decoded by a whole warp (k_grid_macaque_warp)
+        wide = serial && (d.flags & F_REGULAR) && (d.flags & F_TYPE_MASK) == MACAQUE_V && d.model_len >= WIDE_ROW_MIN;
+        serial = serial && !wide;
     }
-    // warp-aggregated append to the worklist of rows that need the serial kernel
+    // warp-aggregated appends: serial rows from the front of the worklist array, wide rows from its back
+    const int lane = threadIdx.x & 31;
     unsigned int mask = __ballot_sync(0xffffffffu, serial);
     if (mask) {
-        int lane = threadIdx.x & 31;
         int leader = __ffs(mask) - 1;
         unsigned int base = 0;
         if (lane == leader) base = atomicAdd(&status->n_seq, (unsigned int)__popc(mask));
         base = __shfl_sync(0xffffffffu, base, leader);
         if (serial) worklist[base + __popc(mask & ((1u << lane) - 1))] = (uint32_t)s;
+    }
+    mask = __ballot_sync(0xffffffffu, wide);
+    if (mask) {
+        int leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&status->n_wide, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (wide) worklist[v.n_segments - 1 - (base + __popc(mask & ((1u << lane) - 1)))] = (uint32_t)s;
     }
 }
 
@@ -578,14 +737,53 @@ __global__ void __launch_bounds__(128) k_grid_sequential(SegmentsView v, const S
 // K3: aggregates
 // ------------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *seg_count, float *seg_sum, Status *status) {
+__global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *seg_count, float *seg_sum, uint32_t *wide_list, Status *status) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= v.n_segments) return;
-    uint64_t c;
-    float sum;
-    if (!aggregate_segment(v, s, c, sum)) report_bad(status, s);
-    if (seg_count) seg_count[s] = c;
-    seg_sum[s] = sum;
+    bool wide = false;
+    if (s < v.n_segments) {
+        uint64_t c;
+        float sum;
+        if (!aggregate_segment(v, s, c, sum, WIDE_ROW_MIN, &wide)) report_bad(status, s);
+        if (seg_count) seg_count[s] = c;
+        if (!wide) seg_sum[s] = sum;
+    }
+    // long MacaqueV rows: their SUM is computed by k_agg_macaque_warp
+    const unsigned int mask = __ballot_sync(0xffffffffu, wide);
+    if (mask) {
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&status->n_wide, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (wide) wide_list[base + __popc(mask & ((1u << lane) - 1))] = (uint32_t)s;
+    }
+}
+
+// One warp per long MacaqueV row: the f32 sum in stream order (macaque_v.rs:220-265), as aggregate_segment computes it.
+__global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsView v, const uint32_t *wide_list, const unsigned int *n_wide_ptr,
+                                                                       float *seg_sum) {
+    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_wide = *n_wide_ptr;
+    for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
+        const uint64_t s = wide_list[w];
+        const Row r = load_row(v, s);
+        const uint64_t res_len = r.n_residuals ? r.residuals[r.n_residuals - 1] : 0;
+        const uint64_t length = segment_len(r.start_time, r.end_time, r.timestamps, r.n_timestamps);
+        const uint32_t model_length = (uint32_t)(length - res_len);
+        float sum = 0.0f;
+        bool first = true;
+        warp_macaque_v_decode(r.values, r.n_values, model_length, false, 0.0f, stage[warp], lane, [&](uint32_t, float value) {
+            sum = first ? value : __fadd_rn(sum, value); // the first value starts the sum (macaque_v.rs:228-233)
+            first = false;
+        });
+        if (r.n_residuals) { // models/mod.rs:173-183: seeded with the "last value" a MacaqueV model reports there, NaN
+            float res_sum = 0.0f;
+            warp_macaque_v_decode(r.residuals, r.n_residuals - 1, (uint32_t)res_len, true, __uint_as_float(0x7fc00000u), stage[warp], lane,
+                                  [&](uint32_t, float value) { res_sum = __fadd_rn(res_sum, value); });
+            sum = __fadd_rn(sum, res_sum);
+        }
+        if (lane == 0) seg_sum[s] = canonical_nan(sum);
+    }
 }
 
 constexpr int AGG_THREADS = 256;
@@ -776,9 +974,9 @@ static int read_status(mdbcu_context *ctx, const Status *d_status, Status &h, co
 
 static int new_status(mdbcu_context *ctx, DBuf<Status> &st) {
     CUDA_TRY(st.alloc(1, ctx->stream));
-    // bad = n_seq = 0, first_bad = ~0: two memsets, no copy engine involved
-    CUDA_TRY(cudaMemsetAsync(st.p, 0, 8, ctx->stream));
-    CUDA_TRY(cudaMemsetAsync((uint8_t *)st.p + 8, 0xFF, 8, ctx->stream));
+    // bad = n_seq = n_wide = 0, first_bad = ~0: two memsets, no copy engine involved
+    CUDA_TRY(cudaMemsetAsync(st.p, 0, 16, ctx->stream));
+    CUDA_TRY(cudaMemsetAsync((uint8_t *)st.p + 8, 0xFF, 4, ctx->stream));
     return MDBCU_SUCCESS;
 }
 
@@ -954,6 +1152,9 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     if (pl.h_status.n_seq)
         LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p,
                (uint32_t)pl.h_status.n_seq, d_ts, d_val);
+    if (pl.h_status.n_wide)
+        LAUNCH(ctx, k_grid_macaque_warp, div_up(pl.h_status.n_wide, WIDE_WARPS), WIDE_WARPS * 32, 0, st.view, pl.desc.p, pl.point_off.p,
+               pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, d_val);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
         CUDA_TRY(d2h_bytes(ctx, timestamps_out, d_ts, pl.total * sizeof(int64_t)));
@@ -981,7 +1182,11 @@ int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segmen
         CUDA_TRY(sum_buf.alloc(S, s));
         d_sum = sum_buf.p;
     }
-    LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, status.p);
+    DBuf<uint32_t> wide_list;
+    CUDA_TRY(wide_list.alloc(S, s));
+    LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, wide_list.p, status.p);
+    LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0, st.view,
+           wide_list.p, &status.p->n_wide, d_sum);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) CUDA_TRY(d2h_bytes(ctx, sums_out, d_sum, S * sizeof(float)));
     Status h;
@@ -1012,7 +1217,13 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     DBuf<float> seg_sum;
     CUDA_TRY(seg_count.alloc(S, s));
     CUDA_TRY(seg_sum.alloc(S, s));
-    if (S) LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, seg_count.p, seg_sum.p, status.p);
+    DBuf<uint32_t> wide_list;
+    CUDA_TRY(wide_list.alloc(S, s));
+    if (S) {
+        LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, seg_count.p, seg_sum.p, wide_list.p, status.p);
+        LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
+               st.view, wide_list.p, &status.p->n_wide, seg_sum.p);
+    }
 
     // parts per group: enough blocks to fill the GPU when there are few large groups
     uint64_t avg_rows = S / n_groups + 1;
