@@ -35,8 +35,13 @@ struct SegRecord {           // 48 bytes
     uint8_t values[8];       // `values` of PMC-Mean / Swing rows (types.rs:283-370)
     int8_t model_type_id;
     uint8_t regular;         // timestamps of the row are regular
-    uint8_t pad[2];
+    uint8_t wide;            // long MacaqueV row: val_len / min / max and the value bytes come from the warp kernels
+    uint8_t pad;
 };
+
+// MacaqueV rows of at least this many values are encoded by a whole warp (k_records_macaque_warp,
+// k_emit_macaque_warp) when the caller passes it as defer_min; 0 never defers (host emulation, tests).
+constexpr uint32_t WIDE_ENCODE_MIN = 256;
 static_assert(sizeof(SegRecord) == 48, "SegRecord layout");
 
 // ------------------------------------------------------------------------------------------------
@@ -356,7 +361,8 @@ MDB_DEV void record_model_segment(const ErrorBound &eb, const FittedModel &m, ui
     rec.model_last_value = m.model_last_value;
     rec.min_value = m.min_value;
     rec.max_value = m.max_value;
-    rec.pad[0] = rec.pad[1] = 0;
+    rec.wide = 0;
+    rec.pad = 0;
     for (int k = 0; k < 8; k++) rec.values[k] = 0;
     rec.val_len = m.values_len; // Swing [0] or []
     rec.res_len = 0;
@@ -377,16 +383,23 @@ MDB_DEV void record_model_segment(const ErrorBound &eb, const FittedModel &m, ui
 
 // compress_and_store_residuals_in_a_separate_segment (compression.rs:367-400) as a record.
 MDB_DEV void record_macaque_v_segment(const ErrorBound &eb, uint32_t lo, uint32_t hi, const int64_t *ts,
-                                      const float *values, bool unit_regular, SegRecord &rec) {
+                                      const float *values, bool unit_regular, SegRecord &rec, uint32_t defer_min = 0) {
     rec.start_index = lo;
     rec.model_end_index = hi;
     rec.res_end_index = hi;
     rec.model_type_id = MACAQUE_V;
     rec.model_last_value = 0.0f;
-    rec.pad[0] = rec.pad[1] = 0;
+    rec.wide = 0;
+    rec.pad = 0;
     for (int k = 0; k < 8; k++) rec.values[k] = 0;
     rec.res_len = 0;
     rec.ts_len = timestamps_encoded_len(ts, lo, hi, unit_regular, rec.regular);
+    if (defer_min && hi - lo + 1 >= defer_min) { // sized (and later written) by a whole warp
+        rec.wide = 1;
+        rec.val_len = 0;
+        rec.min_value = rec.max_value = 0.0f;
+        return;
+    }
     BitCounter c;
     macaque_v_encode(eb, values, lo, hi, false, 0.0f, c, rec.min_value, rec.max_value);
     rec.val_len = (uint32_t)c.bytes();
@@ -394,17 +407,17 @@ MDB_DEV void record_macaque_v_segment(const ErrorBound &eb, uint32_t lo, uint32_
 
 // store_compressed_segments_with_model_and_or_residuals (compression.rs:310-362). Returns rows written.
 MDB_DEV uint32_t store_segments(const ErrorBound &eb, bool have_model, const FittedModel &m, uint32_t res_end,
-                                const int64_t *ts, const float *values, bool unit_regular, SegRecord *recs) {
+                                const int64_t *ts, const float *values, bool unit_regular, SegRecord *recs, uint32_t defer_min = 0) {
     if (have_model) {
         if (res_end - m.end_index <= RESIDUAL_VALUES_MAX_LENGTH) {
             record_model_segment(eb, m, res_end, ts, values, unit_regular, recs[0]);
             return 1;
         }
         record_model_segment(eb, m, m.end_index, ts, values, unit_regular, recs[0]);
-        record_macaque_v_segment(eb, m.end_index + 1, res_end, ts, values, unit_regular, recs[1]);
+        record_macaque_v_segment(eb, m.end_index + 1, res_end, ts, values, unit_regular, recs[1], defer_min);
         return 2;
     }
-    record_macaque_v_segment(eb, 0, res_end, ts, values, unit_regular, recs[0]);
+    record_macaque_v_segment(eb, 0, res_end, ts, values, unit_regular, recs[0], defer_min);
     return 1;
 }
 
@@ -714,13 +727,13 @@ MDB_DEV uint32_t spec_count_rows(const ChunkState &s, const FittedModel *list) {
 
 // Writes the chunk's SegRecords in final row order. Returns the number written (== spec_count_rows).
 MDB_DEV uint32_t spec_records(const ErrorBound &eb, const int64_t *ts, const float *values, const ChunkState &s,
-                              const FittedModel *list, bool unit_regular, SegRecord *recs) {
+                              const FittedModel *list, bool unit_regular, SegRecord *recs, uint32_t defer_min = 0) {
     if (s.skipped) return 0;
     uint32_t r = 0;
-    if (s.lead_end != IDX_NONE) record_macaque_v_segment(eb, 0, s.lead_end, ts, values, unit_regular, recs[r++]);
+    if (s.lead_end != IDX_NONE) record_macaque_v_segment(eb, 0, s.lead_end, ts, values, unit_regular, recs[r++], defer_min);
     for (uint32_t k = 0; k < s.n_models; k++) {
         uint32_t next_start = k + 1 < s.n_models ? list[k + 1].start_index : s.next_start;
-        r += store_segments(eb, true, list[k], next_start - 1, ts, values, unit_regular, recs + r);
+        r += store_segments(eb, true, list[k], next_start - 1, ts, values, unit_regular, recs + r, defer_min);
     }
     return r;
 }
@@ -743,7 +756,9 @@ MDB_DEV void compress_emit_segment(const ErrorBound &eb, const SegRecord &rec, c
         }
     }
     // values
-    if (rec.model_type_id == MACAQUE_V) {
+    if (rec.model_type_id == MACAQUE_V && rec.wide) {
+        // written by k_emit_macaque_warp
+    } else if (rec.model_type_id == MACAQUE_V) {
         BitWriter w(val_out);
         float mn, mx;
         macaque_v_encode(eb, values, rec.start_index, rec.res_end_index, false, 0.0f, w, mn, mx);

@@ -445,7 +445,7 @@ __global__ void __launch_bounds__(32) k_spec_records(const int64_t *__restrict__
                                                      const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, uint32_t lanes, const ChunkState *st,
                                                      const FittedModel *lists, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
                                                      const uint8_t *__restrict__ unit_irregular, const uint64_t *__restrict__ row_base, SegRecord *recs,
-                                                     uint32_t *row_unit) {
+                                                     uint32_t *row_unit, uint32_t *wide_rows, unsigned int *n_wide) {
     if (threadIdx.x >= lanes) return;
     uint64_t g = (uint64_t)blockIdx.x * lanes + threadIdx.x;
     if (g >= n_chunks) return;
@@ -455,8 +455,112 @@ __global__ void __launch_bounds__(32) k_spec_records(const int64_t *__restrict__
     uint32_t u = chunk_unit[g];
     uint64_t a = unit_off[u];
     ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-    spec_records(eb, ts + a, values + a, s, lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2), unit_irregular[u] == 0, recs + r0);
-    for (uint64_t k = 0; k < rows; k++) row_unit[r0 + k] = u;
+    spec_records(eb, ts + a, values + a, s, lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2), unit_irregular[u] == 0, recs + r0,
+                 WIDE_ENCODE_MIN);
+    for (uint64_t k = 0; k < rows; k++) {
+        row_unit[r0 + k] = u;
+        if (recs[r0 + k].wide) wide_rows[atomicAdd(n_wide, 1u)] = (uint32_t)(r0 + k); // long MacaqueV rows: the warp kernels below
+    }
+}
+
+// ---- long MacaqueV rows encoded by a whole warp ---------------------------------------------------------
+// The encoder (macaque_v.rs:39-164) is a serial state machine like the decoder; one warp owns one long row: 32
+// values per coalesced load, every lane runs the same MacaqueVEncoder on them (uniform control flow), and the
+// bytes leave through shared memory in coalesced stores.  k_records_macaque_warp runs it on a bit counter to
+// size the row (and to get its min / max), k_emit_macaque_warp on a writer at the row's final offset.
+template <typename Sink>
+__device__ __forceinline__ void warp_macaque_v_encode(const ErrorBound &eb, const float *__restrict__ values, uint32_t lo, uint32_t hi, Sink &sink,
+                                                      int lane, float &min_out, float &max_out) {
+    MacaqueVEncoder enc;
+    enc.init();
+    for (uint32_t k0 = lo; k0 <= hi; k0 += 32) {
+        const uint32_t idx = k0 + (uint32_t)lane;
+        const float mine = idx <= hi ? values[idx] : 0.0f;
+        const int cnt = (int)min(32u, hi - k0 + 1);
+        for (int j = 0; j < cnt; j++) {
+            const float value = __shfl_sync(FULL_MASK, mine, j);
+            if (k0 == lo && j == 0) enc.first_raw(value, sink);
+            else enc.compress_value_xor_last_value(eb, value, sink);
+        }
+    }
+    min_out = enc.min_value;
+    max_out = enc.max_value;
+}
+
+struct WarpBitSink { // BitWriter through a shared-memory stage; every lane holds the same state
+    uint8_t *out;
+    uint32_t *stage;
+    uint32_t wr;
+    uint64_t acc; // pending bits in the low `n` bits, n < 32 between appends
+    int n, lane;
+    __device__ __forceinline__ void init(uint8_t *o, uint32_t *stage_, int lane_) { out = o; stage = stage_; wr = 0; acc = 0; n = 0; lane = lane_; }
+    __device__ __forceinline__ void flush(uint32_t n_bytes) { // the first n_bytes of the stage, big-endian words
+        __syncwarp();
+        for (uint32_t i = (uint32_t)lane; i < n_bytes; i += 32) out[i] = (uint8_t)(stage[i >> 2] >> (24 - 8 * (i & 3)));
+        out += n_bytes;
+        wr = 0;
+        __syncwarp();
+    }
+    __device__ __forceinline__ void append(uint64_t value, int nb) { // nb in [0, 32]
+        if (nb == 0) return;
+        acc = (acc << nb) | (value & ((1ull << nb) - 1));
+        n += nb;
+        if (n >= 32) {
+            stage[wr++] = (uint32_t)(acc >> (n - 32)); // (all lanes store the same word)
+            n -= 32;
+            if (wr == STAGE_WORDS) flush(STAGE_WORDS * 4);
+        }
+    }
+    __device__ __forceinline__ void finish() { // zero padding to a whole byte (macaque_v.rs:160-164)
+        uint32_t n_bytes = wr * 4;
+        if (n > 0) {
+            stage[wr] = (uint32_t)(acc << (32 - n));
+            n_bytes += (uint32_t)(n + 7) / 8;
+        }
+        flush(n_bytes);
+    }
+};
+
+__global__ void __launch_bounds__(WIDE_WARPS * 32) k_records_macaque_warp(const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                                           const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                                           const uint32_t *__restrict__ row_unit, const uint32_t *__restrict__ wide_rows,
+                                                                           const unsigned int *n_wide_ptr, SegRecord *recs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_wide = *n_wide_ptr;
+    for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
+        const uint32_t r = wide_rows[w];
+        const uint32_t u = row_unit[r];
+        const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        const uint32_t lo = recs[r].start_index, hi = recs[r].res_end_index;
+        BitCounter c;
+        float mn, mx;
+        warp_macaque_v_encode(eb, values + unit_off[u], lo, hi, c, lane, mn, mx);
+        if (lane == 0) {
+            recs[r].val_len = (uint32_t)c.bytes();
+            recs[r].min_value = mn;
+            recs[r].max_value = mx;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(WIDE_WARPS * 32) k_emit_macaque_warp(const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                                        const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                                        const uint32_t *__restrict__ row_unit, const uint32_t *__restrict__ wide_rows,
+                                                                        const unsigned int *n_wide_ptr, const SegRecord *__restrict__ recs,
+                                                                        const uint64_t *__restrict__ val_off, uint8_t *val_data) {
+    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_wide = *n_wide_ptr;
+    for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
+        const uint32_t r = wide_rows[w];
+        const uint32_t u = row_unit[r];
+        const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        WarpBitSink sink;
+        sink.init(val_data + val_off[r], stage[warp], lane);
+        float mn, mx;
+        warp_macaque_v_encode(eb, values + unit_off[u], recs[r].start_index, recs[r].res_end_index, sink, lane, mn, mx);
+        sink.finish();
+    }
 }
 
 // One thread per row: metadata columns and the byte lengths of the three binary columns.
@@ -587,7 +691,10 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     TRY_SG(cudaMallocAsync((void **)&sg->unit_seg_off, (n_units + 1) * sizeof(uint64_t), s));
     uint64_t S = 0;
     DBuf<SegRecord> recs;
-    DBuf<uint32_t> row_unit;
+    DBuf<uint32_t> row_unit, wide_rows; // wide_rows: long MacaqueV rows, sized and written by a whole warp
+    DBuf<unsigned int> n_wide;
+    TRY_SG(n_wide.alloc(1, s));
+    TRY_SG(cudaMemsetAsync(n_wide.p, 0, sizeof(unsigned int), s));
     ctx->last_rounds = 0;
 
     if (n_units) {
@@ -723,9 +830,14 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(recs.alloc(S, s));
         TRY_SG(row_unit.alloc(S, s));
         const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
-        if (G && S)
+        TRY_SG(wide_rows.alloc(S, s));
+        TRY_SG(cudaMemsetAsync(n_wide.p, 0, sizeof(unsigned int), s));
+        if (G && S) {
             LAUNCH(ctx, k_spec_records, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, lanes, st.p, lists.p,
-                   list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p);
+                   list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p, wide_rows.p, n_wide.p);
+            LAUNCH(ctx, k_records_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
+                   d_val, d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p);
+        }
         // the scratch above is released (stream-ordered) when this scope ends
     } else {
         TRY_SG(cudaMemsetAsync(sg->unit_seg_off, 0, sizeof(uint64_t), s));
@@ -763,9 +875,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     TRY_SG(cudaMallocAsync((void **)&sg->ts_data, sg->ts_bytes ? sg->ts_bytes : 1, s));
     TRY_SG(cudaMallocAsync((void **)&sg->val_data, sg->val_bytes ? sg->val_bytes : 1, s));
     TRY_SG(cudaMallocAsync((void **)&sg->res_data, sg->res_bytes ? sg->res_bytes : 1, s));
-    if (S)
+    if (S) {
         LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, recs.p, row_unit.p, S, sg->ts_off, sg->ts_data,
                sg->val_off, sg->val_data, sg->res_off, sg->res_data);
+        LAUNCH(ctx, k_emit_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0, d_val,
+               d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p, sg->val_off, sg->val_data);
+    }
     TRY_SG(cudaGetLastError());
     TRY_SG(sync_stream(ctx));
 #undef TRY_SG
