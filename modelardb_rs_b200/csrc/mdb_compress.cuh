@@ -468,6 +468,24 @@ MDB_DEV uint32_t models_per_chunk(uint32_t chunk_len) { return chunk_len / 8 + 2
 // Fit: the fit_next_model engine -- ScalarFit (one thread) or WarpFit (32 lanes cooperate on every fit,
 // mdb_fit_warp.cuh); in the warp case every lane runs this control code redundantly on uniform values
 // and stores to global memory are made by lane 0 (list copies are spread over the n_lanes lanes).
+// Can fit_next_model(start) return a model that gets stored (bytes_per_value <= 4, compression.rs:238)?  Below 8
+// points both models cost more than that (29 / len and 30 / len), and each model is fed the points in order until
+// it rejects one (types.rs:88-118), so it is enough to feed each of them the first 8 points.  The points
+// [start, limit) exist; with fewer than 8 of them no model can be stored.
+MDB_DEV bool fit_reaches_eight_points(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t start, uint32_t limit) {
+    if (limit < start || limit - start < 8) return false;
+    PMCMean pmc;
+    pmc.init();
+    bool all = true;
+    for (uint32_t k = 0; k < 8 && all; k++) all = pmc.fit_value(eb, values[start + k]);
+    if (all) return true;
+    Swing swing;
+    swing.init();
+    all = true;
+    for (uint32_t k = 0; k < 8 && all; k++) all = swing.fit_data_point(eb, ts[start + k], values[start + k]);
+    return all;
+}
+
 struct ScalarFit {
     const ErrorBound &eb;
     const int64_t *ts;
@@ -480,6 +498,8 @@ struct ScalarFit {
         return fit_next_model(eb, ts, values, cur, n, trk, budget_end, aborted);
     }
     MDB_DEV bool irregular() const { return trk.irregular; }
+    // After a rejected fit: the next index worth fitting (the one-thread engine simply tries the next one).
+    MDB_DEV uint32_t skip_rejected(uint32_t from, uint32_t, uint32_t) { return from; }
 };
 
 template <typename Fit>
@@ -533,7 +553,10 @@ MDB_DEV void spec_chain(Fit &fitter, uint32_t lane, uint32_t n_lanes, uint32_t n
             n_new++;
             cur = model.end_index + 1;
         } else {
-            cur += 1; // compression.rs:261: this point becomes a residual; refit from the next one
+            // compression.rs:261: this point becomes a residual; refit from the next one -- or, with the warp engine,
+            // from the next index at which a fit can yield a stored model at all (every index in between is rejected
+            // just the same, one residual point each; see WarpFitT::skip_rejected)
+            cur = fitter.skip_rejected(cur + 1, chunk_end, budget_end);
         }
     }
     if (!done) exit = cur;

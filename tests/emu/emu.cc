@@ -169,6 +169,22 @@ EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const ui
     return out;
 }
 
+// For every start index: does fit_reaches_eight_points agree with "fit_next_model returns a stored model"?
+// Returns the number of disagreements (the warp engine's skip_rejected relies on there being none).
+uint64_t emu_check_eight_points(const int64_t *ts, const float *values, uint32_t n, uint8_t eb_kind, float eb_value) {
+    ErrorBound eb = make_error_bound(eb_kind, eb_value);
+    uint64_t bad = 0;
+    for (uint32_t s = 0; s < n; s++) {
+        RegularityTracker trk;
+        trk.init(ts, s, n);
+        bool aborted;
+        FittedModel m = fit_next_model(eb, ts, values, s, n, trk, n, aborted);
+        bool stored = m.bytes_per_value <= 4.0f;
+        if (stored != fit_reaches_eight_points(eb, ts, values, s, n)) bad++;
+    }
+    return bad;
+}
+
 uint64_t emu_segments_len(const EmuSegments *s) { return s->model_type_id.size(); }
 void emu_segments_view(const EmuSegments *s, SegmentsView *v, const uint64_t **unit_seg_off) {
     v->n_segments = s->model_type_id.size();

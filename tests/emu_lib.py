@@ -31,6 +31,8 @@ def lib():
     L.emu_compress.restype = vp
     L.emu_compress_sched.argtypes = [vp, vp, vp, u64, vp, vp, C.c_uint32, vp, C.c_uint32, C.c_uint32]
     L.emu_compress_sched.restype = vp
+    L.emu_check_eight_points.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_float]
+    L.emu_check_eight_points.restype = u64
     L.emu_segments_len.argtypes = [vp]
     L.emu_segments_len.restype = u64
     L.emu_segments_view.argtypes = [vp, C.POINTER(O._View), C.POINTER(vp)]
@@ -126,3 +128,10 @@ def aggregate(seg: O.Segments, group_off=None):
     if lib().emu_aggregate(C.byref(v), None if go is None else _p(go), g, _p(count), _p(mn), _p(mx), _p(sm)) != 0:
         raise ValueError("malformed segment")
     return count, mn, mx, sm
+
+
+def check_eight_points(ts, values, eb) -> int:
+    """Number of start indices at which fit_reaches_eight_points disagrees with fit_next_model's outcome."""
+    ts = np.ascontiguousarray(ts, np.int64)
+    vals = np.ascontiguousarray(values, np.float32)
+    return int(lib().emu_check_eight_points(_p(ts), _p(vals), len(ts), eb[0], eb[1]))

@@ -117,3 +117,15 @@ def test_async_scheduler_runs_each_chunk_once_when_workers_are_scarce(oracle):
     got = emu.compress(ts, vals, off, eb=(2, 1.0), chunk_len=4096, rounds=runs, sched_seed=9, in_flight=1)
     assert_segments_equal(got, want, "one worker")
     assert runs[0] <= 10, runs  # 40 000 / 4096 -> 10 chunks per unit
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_eight_point_screen_agrees_with_fit_next_model(case):
+    """skip_rejected (warp engine) skips a start iff neither model can take its first 8 points; that must be exactly
+    the set of starts whose fit the reference rejects (bytes per value > 4)."""
+    name, ts, vals, off, ebs = case
+    for u in range(len(off) - 1):
+        a, b = int(off[u]), int(off[u + 1])
+        if b - a == 0:
+            continue
+        assert emu.check_eight_points(ts[a:b], vals[a:b], ebs[u]) == 0, (name, u)
