@@ -486,99 +486,113 @@ constexpr uint32_t WIDE_ROW_MIN = 64;
 constexpr int WIDE_WARPS = 4;      // warps (rows in flight) per block
 constexpr int STAGE_WORDS = 128;   // 512 B of the stream per refill
 
-struct WarpBitStream {
+// The row's bytes, staged: STAGE_WORDS big-endian words of the stream starting at word `first_word`.  Bits are
+// addressed by their absolute position in the (4-byte aligned) word sequence that contains the stream.
+struct WarpBitStage {
     const uint32_t *words; // 4-byte aligned address at or before the first byte of the stream
-    uint64_t n_words, next_word;
-    uint32_t last_mask;    // keeps the stream's bytes of the last word (big-endian), zeroes what follows it
+    uint64_t n_words;
+    uint32_t last_mask;    // keeps the stream's bytes of the last word, zeroes what follows it
     uint32_t *stage;       // STAGE_WORDS words of shared memory owned by this warp
-    uint32_t rd, avail;
-    uint64_t buf;          // valid bits are the top `nbits`
-    int nbits;
+    uint64_t first_word;   // stream word held in stage[0]
+    uint64_t start_bit;    // position of the stream's first bit
 
-    __device__ __forceinline__ void restage(int lane) {
-        __syncwarp();
-#pragma unroll
-        for (int i = 0; i < STAGE_WORDS / 32; i++) {
-            const uint64_t w = next_word + (uint64_t)(i * 32 + lane);
-            uint32_t x = 0;
-            if (w < n_words) {
-                x = __byte_perm(__ldg(words + w), 0, 0x0123); // the stream is big-endian bit order
-                if (w == n_words - 1) x &= last_mask;
-            }
-            stage[i * 32 + lane] = x;
-        }
-        next_word += STAGE_WORDS;
-        rd = 0;
-        avail = STAGE_WORDS;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void refill(int lane) { // nbits <= 32
-        if (rd == avail) restage(lane);
-        buf |= (uint64_t)stage[rd++] << (32 - nbits);
-        nbits += 32;
-    }
-    __device__ __forceinline__ void init(const uint8_t *bytes, uint64_t n_bytes, uint32_t *stage_, int lane) {
+    __device__ __forceinline__ void init(const uint8_t *bytes, uint64_t n_bytes, uint32_t *stage_) {
         const uintptr_t a = reinterpret_cast<uintptr_t>(bytes);
         const uint32_t skip = (uint32_t)(a & 3);
         words = reinterpret_cast<const uint32_t *>(a - skip);
         n_words = (skip + n_bytes + 3) / 4;
-        const uint32_t used = (uint32_t)((skip + n_bytes) & 3); // bytes of the last word that belong to the stream (0: all)
+        const uint32_t used = (uint32_t)((skip + n_bytes) & 3);
         last_mask = used ? 0xFFFFFFFFu << (8 * (4 - used)) : 0xFFFFFFFFu;
-        next_word = 0;
         stage = stage_;
-        rd = avail = 0;
-        buf = 0;
-        nbits = 0;
-        if (skip && n_bytes) { // drop the bytes in front of the stream
-            refill(lane);
-            buf <<= 8 * skip;
-            nbits -= 8 * (int)skip;
-        }
+        first_word = ~0ull;
+        start_bit = 8ull * skip;
     }
-    // n in [0, 32]; bits past the end of the stream read as zero
-    __device__ __forceinline__ uint32_t read(int n, int lane) {
-        if (n == 0) return 0;
-        if (nbits < n) refill(lane);
-        const uint32_t v = (uint32_t)(buf >> (64 - n));
-        buf <<= n;
-        nbits -= n;
-        return v;
+    // makes bits [p, p + span) addressable (span <= (STAGE_WORDS - 1) * 32); bits past the stream read as zero
+    __device__ __forceinline__ void cover(uint64_t p, uint32_t span, int lane) {
+        const uint64_t w0 = p >> 5;
+        if (first_word != ~0ull && w0 >= first_word && ((p + span + 31) >> 5) < first_word + STAGE_WORDS) return;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < STAGE_WORDS / 32; i++) {
+            const uint64_t w = w0 + (uint64_t)(i * 32 + lane);
+            uint32_t x = 0;
+            if (w < n_words) {
+                x = __byte_perm(__ldg(words + w), 0, 0x0123);
+                if (w == n_words - 1) x &= last_mask;
+            }
+            stage[i * 32 + lane] = x;
+        }
+        first_word = w0;
+        __syncwarp();
+    }
+    // the 32 bits starting at bit p (covered)
+    __device__ __forceinline__ uint32_t peek32(uint64_t p) const {
+        const uint32_t i = (uint32_t)((p >> 5) - first_word);
+        return __funnelshift_l(stage[i + 1], stage[i], (uint32_t)(p & 31));
     }
 };
 
-// MacaqueVDecoder (mdb_device.cuh) on a WarpBitStream; emit(k, value) is called for k = first .. first + count - 1.
-template <typename Emit>
+// MacaqueVDecoder (mdb_device.cuh, macaque_v.rs:272-323) for one long stream, 32 values per batch.  Where a code
+// starts depends on every code before it, so the warp first WALKS the batch's codes serially -- every lane runs the same
+// few instructions per code (flag bits, a new window's 11 header bits, the payload's position), nothing else -- and
+// lane k keeps the position, width and shift of the k-th payload.  The payloads are then extracted by the 32 lanes at
+// once, and the values are an exclusive-or prefix scan over them (value k = value k - 1 XOR payload k).
+// on_batch(k0, value, valid): this lane's value k0 + lane of the stream.
+template <typename OnBatch>
 __device__ __forceinline__ float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, bool has_seed, float seed,
-                                                       uint32_t *stage, int lane, Emit &&emit) {
-    WarpBitStream bits;
-    bits.init(bytes, n_bytes, stage, lane);
+                                                       uint32_t *stage_words, int lane, OnBatch &&on_batch) {
+    WarpBitStage bits;
+    bits.init(bytes, n_bytes, stage_words);
+    uint64_t p = bits.start_bit;
     uint32_t leading_zeros = 255, trailing_zeros = 0;
-    uint32_t last_value;
-    uint32_t k = 0;
-    if (has_seed) {
-        last_value = __float_as_uint(seed);
-    } else {
-        last_value = bits.read(32, lane);
-        if (count) emit(k++, __uint_as_float(last_value));
-    }
-    for (; k < count; k++) {
-        if (bits.read(1, lane)) {
-            if (bits.read(1, lane)) {
-                leading_zeros = bits.read(5, lane);
-                uint32_t meaningful_bits = bits.read(6, lane);
-                trailing_zeros = (32u - meaningful_bits - leading_zeros) & 0xffu;
-                meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
-                uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits, lane);
-                value = trailing_zeros < 32 ? value << trailing_zeros : 0;
-                last_value ^= value;
+    uint32_t last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
+    for (uint32_t k0 = 0; k0 < count; k0 += 32) {
+        const int cnt = (int)min(32u, count - k0);
+        bits.cover(p, 32u * 45u + 64u, lane);
+        uint64_t my_pos = 0;
+        uint32_t my_width = 0, my_shift = 0;
+        for (int k = 0; k < cnt; k++) {
+            uint64_t pos;
+            uint32_t width, shift;
+            if (!has_seed && k0 == 0 && k == 0) { // macaque_v.rs:282-285: the first value is stored raw
+                pos = p; width = 32; shift = 0;
+                p += 32;
+            } else {
+                const uint32_t head = bits.peek32(p);
+                if (!(head & 0x80000000u)) {        // `0`: the XOR's meaningful bits in the window in force
+                    const uint32_t meaningful = (32u - leading_zeros - trailing_zeros) & 0xffu;
+                    width = meaningful > 32u ? 32u : meaningful;
+                    shift = trailing_zeros;
+                    pos = p + 1;
+                } else if (!(head & 0x40000000u)) { // `10`: the same value again
+                    width = 0; shift = 0;
+                    pos = p + 2;
+                } else {                            // `11`, 5 bits of leading zeros, 6 bits of length, the bits
+                    leading_zeros = (head >> 25) & 31u;
+                    uint32_t meaningful = (head >> 19) & 63u;
+                    trailing_zeros = (32u - meaningful - leading_zeros) & 0xffu; // u8 wrapping as in release builds
+                    meaningful = (32u - leading_zeros - trailing_zeros) & 0xffu;
+                    width = meaningful > 32u ? 32u : meaningful;
+                    shift = trailing_zeros;
+                    pos = p + 13;
+                }
+                p = pos + width;
             }
-        } else {
-            const uint32_t meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
-            uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits, lane);
-            value = trailing_zeros < 32 ? value << trailing_zeros : 0;
-            last_value ^= value;
+            if (k == lane) { my_pos = pos; my_width = width; my_shift = shift; }
         }
-        emit(k, __uint_as_float(last_value));
+        uint32_t x = 0;
+        if (lane < cnt && my_width) {
+            x = bits.peek32(my_pos) >> (32u - my_width);
+            x = my_shift < 32u ? x << my_shift : 0u;
+        }
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { // inclusive XOR scan
+            const uint32_t o = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x ^= o;
+        }
+        const uint32_t value = last_value ^ x;
+        on_batch(k0, __uint_as_float(value), lane < cnt);
+        last_value = __shfl_sync(0xffffffffu, value, cnt - 1);
     }
     return __uint_as_float(last_value);
 }
@@ -587,7 +601,7 @@ __device__ __forceinline__ float warp_macaque_v_decode(const uint8_t *bytes, uin
 // Timestamps of these rows are regular and were written by the tile kernel.
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsView v, const SegDesc *desc, const uint64_t *point_off,
                                                                         const uint32_t *worklist_back, uint32_t n_wide, float *val_out) {
-    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS];
+    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * WIDE_WARPS + warp;
     if (w >= n_wide) return;
@@ -596,23 +610,16 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsV
     const Row r = load_row(v, s);
     const uint64_t base = point_off[s];
     const uint32_t len = (uint32_t)(point_off[s + 1] - base);
-    float mine = 0.0f;
-    auto emit_to = [&](uint64_t out_base) {
-        return [&, out_base](uint32_t k, float value) {
-            if ((k & 31u) == (uint32_t)lane) mine = value;
-            if ((k & 31u) == 31u) val_out[out_base + (k - 31u) + lane] = mine; // 32 consecutive values, one store
-        };
-    };
-    const float last = warp_macaque_v_decode(r.values, r.n_values, d.model_len, false, 0.0f, stage[warp], lane, emit_to(base));
-    if (d.model_len & 31u) { // the tail that did not fill a whole store
-        const uint32_t k0 = d.model_len & ~31u;
-        if (k0 + lane < d.model_len) val_out[base + k0 + lane] = mine;
-    }
+    const float last = warp_macaque_v_decode(r.values, r.n_values, d.model_len, false, 0.0f, stage[warp], lane,
+                                             [&](uint32_t k0, float value, bool valid) {
+                                                 if (valid) val_out[base + k0 + lane] = value; // 32 consecutive values, one store
+                                             });
     if (d.flags & F_HAS_RESIDUALS) { // models/mod.rs:241-249: seeded with the last gridded model value
-        const uint32_t n_res = len - d.model_len;
-        warp_macaque_v_decode(r.residuals, r.n_residuals - 1, n_res, true, last, stage[warp], lane, emit_to(base + d.model_len));
-        const uint32_t k0 = n_res & ~31u;
-        if ((n_res & 31u) && k0 + lane < n_res) val_out[base + d.model_len + k0 + lane] = mine;
+        const uint64_t res_base = base + d.model_len;
+        warp_macaque_v_decode(r.residuals, r.n_residuals - 1, len - d.model_len, true, last, stage[warp], lane,
+                              [&](uint32_t k0, float value, bool valid) {
+                                  if (valid) val_out[res_base + k0 + lane] = value;
+                              });
     }
 }
 
@@ -759,9 +766,11 @@ __global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *
 }
 
 // One warp per long MacaqueV row: the f32 sum in stream order (macaque_v.rs:220-265), as aggregate_segment computes it.
+// The 32 values of a batch are decoded in parallel; their additions stay a serial chain (one rounding per value).
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsView v, const uint32_t *wide_list, const unsigned int *n_wide_ptr,
                                                                        float *seg_sum) {
-    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS];
+    __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
+    __shared__ float batch[WIDE_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_wide = *n_wide_ptr;
     for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
@@ -771,16 +780,27 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsVi
         const uint64_t length = segment_len(r.start_time, r.end_time, r.timestamps, r.n_timestamps);
         const uint32_t model_length = (uint32_t)(length - res_len);
         float sum = 0.0f;
-        bool first = true;
-        warp_macaque_v_decode(r.values, r.n_values, model_length, false, 0.0f, stage[warp], lane, [&](uint32_t, float value) {
-            sum = first ? value : __fadd_rn(sum, value); // the first value starts the sum (macaque_v.rs:228-233)
-            first = false;
-        });
+        bool first = true; // the first value STARTS the model's sum (macaque_v.rs:228-233); a seeded stream starts from 0
+        auto add_in_order = [&](uint32_t k0, float value, bool, uint32_t total) {
+            __syncwarp();
+            batch[warp][lane] = value;
+            __syncwarp();
+            const int cnt = (int)min(32u, total - k0);
+            for (int j = 0; j < cnt; j++) {
+                const float x = batch[warp][j];
+                sum = first ? x : __fadd_rn(sum, x);
+                first = false;
+            }
+        };
+        warp_macaque_v_decode(r.values, r.n_values, model_length, false, 0.0f, stage[warp], lane,
+                              [&](uint32_t k0, float value, bool valid) { add_in_order(k0, value, valid, model_length); });
         if (r.n_residuals) { // models/mod.rs:173-183: seeded with the "last value" a MacaqueV model reports there, NaN
-            float res_sum = 0.0f;
+            const float model_sum = sum;
+            sum = 0.0f;
+            first = false;
             warp_macaque_v_decode(r.residuals, r.n_residuals - 1, (uint32_t)res_len, true, __uint_as_float(0x7fc00000u), stage[warp], lane,
-                                  [&](uint32_t, float value) { res_sum = __fadd_rn(res_sum, value); });
-            sum = __fadd_rn(sum, res_sum);
+                                  [&](uint32_t k0, float value, bool valid) { add_in_order(k0, value, valid, (uint32_t)res_len); });
+            sum = __fadd_rn(model_sum, sum);
         }
         if (lane == 0) seg_sum[s] = canonical_nan(sum);
     }
