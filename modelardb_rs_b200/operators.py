@@ -1,0 +1,202 @@
+"""Host-side mirrors of the two query operators that sit on the hot path in the reference, driving the CUDA
+kernels through the C-ABI (modelardb_rs_b200.compression):
+
+  * GridStream            crates/modelardb_storage/src/query/grid_exec.rs:197-430   
+  * Model*Accumulator     crates/modelardb_storage/src/optimizer/model_simple_aggregates.rs:336-618   (row a23)
+
+Same names, same state machines and the same results as the Rust operators; the per-row loops of the reference
+(`modelardb_compression::grid` / `sum` / `len` once per segment) are replaced by ONE batched call per segment batch.
+The reference's toolchain is not in this image, so these are Python where the reference is Rust; INTEGRATION.md
+shows the Rust call sites that would bind the same C-ABI entry points.
+"""
+from __future__ import annotations
+
+from typing import Callable, Iterable, Iterator, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import compression as mc
+
+F32_MAX = np.float32(3.4028234663852886e38)
+F32_MIN = np.float32(-3.4028234663852886e38)
+
+
+class GridStreamMetrics:
+    """grid_exec.rs:433-520: rows created in total and per model type, with residuals, with regular timestamps."""
+
+    def __init__(self):
+        self.rows_created = 0
+        self.rows_by_model_type = {mc.PMC_MEAN_ID: 0, mc.SWING_ID: 0, mc.MACAQUE_V_ID: 0}
+        self.segments_with_residuals = 0
+        self.segments_with_regular_timestamps = 0
+
+    def add_batch(self, segments: mc.HostSegments, point_off: np.ndarray):
+        lens = np.diff(point_off).astype(np.int64)
+        self.rows_created += int(lens.sum())
+        for type_id in self.rows_by_model_type:
+            self.rows_by_model_type[type_id] += int(lens[segments.model_type_id == type_id].sum())
+        self.segments_with_residuals += int(np.count_nonzero(np.diff(segments.residuals_off)))
+        ts_len = np.diff(segments.timestamps_off)
+        first_byte = segments.timestamps_data[np.minimum(segments.timestamps_off[:-1], max(len(segments.timestamps_data) - 1, 0)).astype(np.int64)] \
+            if len(segments.timestamps_data) else np.zeros(len(segments), np.uint8)
+        regular = (ts_len == 0) | ((first_byte & 128) == 0)  # are_compressed_timestamps_regular, timestamps.rs:199-202
+        self.segments_with_regular_timestamps += int(np.count_nonzero(regular))
+
+
+class GridStream:
+    """Reconstructs data points from batches of segments and hands them out in batches of `batch_size` rows:
+    (timestamps int64[], values float32[], tag columns...), sorted as the input is (grid_exec.rs:187-195).
+
+    input: an iterable of (segments, tags) where `segments` is a HostSegments / CompressedSegments batch and `tags` a
+    sequence of per-row tag arrays (one array per tag column, possibly none).
+    predicate: optional function (timestamps, values) -> bool mask applied to every reconstructed batch, the
+    reference's `maybe_predicate` (all points are reconstructed, then pruned: grid_exec.rs:368-386).
+    """
+
+    def __init__(self, input: Iterable[Tuple[object, Sequence[np.ndarray]]], batch_size: int, n_tag_columns: int = 0,
+                 predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None):
+        if batch_size <= 0:
+            raise ValueError("batch_size must be positive")
+        self._input: Iterator = iter(input)
+        self._input_done = False
+        self.batch_size = batch_size
+        self.predicate = predicate
+        self.ctx = ctx
+        self.metrics = GridStreamMetrics()
+        self._timestamps = np.zeros(0, np.int64)
+        self._values = np.zeros(0, np.float32)
+        self._tags: List[np.ndarray] = [np.zeros(0, object) for _ in range(n_tag_columns)]
+        self._offset = 0  # current_batch_offset
+
+    def __iter__(self):
+        return self
+
+    def _remaining(self) -> int:
+        return len(self._timestamps) - self._offset
+
+    def _grid_and_append_to_leftovers_in_current_batch(self, segments, tags: Sequence[np.ndarray]):
+        # grid_exec.rs:261-391 -- one batched kernel call instead of one grid() per row
+        host = segments.to_host() if isinstance(segments, mc.CompressedSegments) else segments
+        point_off, _ = mc.grid_count(host, self.ctx)
+        ts, vals = mc.grid(host, ctx=self.ctx)
+        self.metrics.add_batch(host, point_off)
+        lens = np.diff(point_off).astype(np.int64)
+        new_tags = [np.repeat(np.asarray(t, object), lens) for t in tags]  # each tag value once per created row
+        if len(new_tags) != len(self._tags):
+            raise ValueError("every batch must carry the same tag columns")
+        if self.predicate is not None:
+            # (the leftovers were filtered when they were created; filtering them again is idempotent)
+            pass
+        ts = np.concatenate([self._timestamps[self._offset:], ts])
+        vals = np.concatenate([self._values[self._offset:], vals])
+        new_tags = [np.concatenate([old[self._offset:], new]) for old, new in zip(self._tags, new_tags)]
+        if self.predicate is not None:
+            keep = np.asarray(self.predicate(ts, vals), bool)
+            ts, vals = ts[keep], vals[keep]
+            new_tags = [t[keep] for t in new_tags]
+        self._timestamps, self._values, self._tags = ts, vals, new_tags
+        self._offset = 0
+
+    def __next__(self):
+        # grid_exec.rs:394-430
+        if self._remaining() < self.batch_size and not self._input_done:
+            try:
+                segments, tags = next(self._input)
+                self._grid_and_append_to_leftovers_in_current_batch(segments, tags)
+            except StopIteration:
+                self._input_done = True
+        if self._input_done and self._remaining() == 0:
+            raise StopIteration
+        length = min(self.batch_size, self._remaining())
+        lo, hi = self._offset, self._offset + length
+        self._offset = hi
+        return (self._timestamps[lo:hi], self._values[lo:hi], *[t[lo:hi] for t in self._tags])
+
+
+class _ModelAccumulator:
+    """Accumulator protocol of the reference: update_batch folds a batch of segments into the state, state() returns
+    it and resets; merge_batch / evaluate are never called on the model accumulators (`unreachable!()`)."""
+
+    def __init__(self, ctx: Optional[mc.Context] = None):
+        self.ctx = ctx
+
+    def merge_batch(self, _states):
+        raise RuntimeError("unreachable: model accumulators are only used in Partial aggregates")
+
+    def evaluate(self):
+        raise RuntimeError("unreachable: model accumulators are only used in Partial aggregates")
+
+    def _aggregate(self, segments):
+        count, mn, mx, sm = mc.aggregate(segments, None, self.ctx)
+        return int(count[0]), np.float32(mn[0]), np.float32(mx[0]), float(sm[0])
+
+
+class ModelCountAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:337-388
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self.count = 0
+
+    def update_batch(self, segments):
+        self.count += self._aggregate(segments)[0]
+
+    def state(self):
+        state, self.count = [self.count], 0
+        return state
+
+
+class ModelMinAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:391-431 (starts at f32::MAX, NaN ignored)
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self.min = F32_MAX
+
+    def update_batch(self, segments):
+        batch_min = self._aggregate(segments)[1]
+        self.min = batch_min if np.isnan(self.min) else (batch_min if batch_min < self.min else self.min)
+
+    def state(self):
+        state, self.min = [self.min], F32_MAX
+        return state
+
+
+class ModelMaxAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:434-470 (starts at f32::MIN)
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self.max = F32_MIN
+
+    def update_batch(self, segments):
+        batch_max = self._aggregate(segments)[2]
+        self.max = batch_max if np.isnan(self.max) else (batch_max if batch_max > self.max else self.max)
+
+    def state(self):
+        state, self.max = [self.max], F32_MIN
+        return state
+
+
+class ModelSumAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:473-527 (per-row f32 sums added in f64)
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self.sum = 0.0
+
+    def update_batch(self, segments):
+        self.sum += self._aggregate(segments)[3]
+
+    def state(self):
+        state, self.sum = [self.sum], 0.0
+        return state
+
+
+class ModelAvgAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:530-618: state is (count u64, sum f64)
+    def __init__(self, ctx=None):
+        super().__init__(ctx)
+        self.sum = 0.0
+        self.count = 0
+
+    def update_batch(self, segments):
+        count, _, _, sm = self._aggregate(segments)
+        self.sum += sm
+        self.count += count
+
+    def state(self):
+        state = [self.count, self.sum]
+        self.sum, self.count = 0.0, 0
+        return state

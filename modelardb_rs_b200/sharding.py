@@ -40,3 +40,29 @@ def gather_group_aggregates(count, mn, mx, sm, n_units: int, group=None):
             parts.append(gathered[r * widest: r * widest + (hi - lo)])
         out.append(torch.cat(parts))
     return tuple(out)
+
+
+def combine_global_aggregates(count, mn, mx, sm, group=None):
+    """Ungrouped aggregates over rows sharded across ranks: COUNT and SUM add, MIN and MAX reduce with the
+    NaN-ignoring fold of the accumulators, whose identities are f32::MAX / f32::MIN (model_simple_aggregates.rs:97, 117).
+    Inputs are this rank's one-element tensors (as returned by aggregate(segments, None)); every rank gets the result.
+    The f64 sums are gathered and added in rank order, so the result does not depend on the reduction tree."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group)
+
+    def gather(t):
+        out = torch.empty(world * t.numel(), dtype=t.dtype, device=t.device)
+        dist.all_gather_into_tensor(out, t.contiguous(), group=group)
+        return out
+
+    counts, mins, maxs, sums = gather(count), gather(mn), gather(mx), gather(sm)
+    total_count = counts.sum().reshape(1)
+    not_nan_min, not_nan_max = mins[~torch.isnan(mins)], maxs[~torch.isnan(maxs)]
+    total_min = not_nan_min.min().reshape(1) if not_nan_min.numel() else mins[-1:].clone()
+    total_max = not_nan_max.max().reshape(1) if not_nan_max.numel() else maxs[-1:].clone()
+    total_sum = torch.zeros(1, dtype=sm.dtype, device=sm.device)
+    for r in range(world):  # rank order = row order
+        total_sum = total_sum + sums[r:r + 1]
+    return total_count, total_min, total_max, total_sum

@@ -44,7 +44,11 @@ def _worker(rank, world, port, n_series, n_points, out_dir):
         seg = O.compress(ts[a:b], vals[a:b], off[lo:hi + 1] - off[lo], eb=(2, 1.0))
         count, mn, mx, sm = O.aggregate(seg, seg.unit_seg_off)
         g = gather_group_aggregates(torch.from_numpy(count), torch.from_numpy(mn), torch.from_numpy(mx), torch.from_numpy(sm), n_series)
-        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), count=g[0].numpy(), mn=g[1].numpy(), mx=g[2].numpy(), sm=g[3].numpy())
+        from modelardb_rs_b200.sharding import combine_global_aggregates
+        c1, mn1, mx1, sm1 = O.aggregate(seg, None)
+        t = combine_global_aggregates(torch.from_numpy(c1), torch.from_numpy(mn1), torch.from_numpy(mx1), torch.from_numpy(sm1))
+        np.savez(os.path.join(out_dir, f"rank{rank}.npz"), count=g[0].numpy(), mn=g[1].numpy(), mx=g[2].numpy(), sm=g[3].numpy(),
+                 tcount=t[0].numpy(), tmn=t[1].numpy(), tmx=t[2].numpy(), tsm=t[3].numpy())
     finally:
         dist.destroy_process_group()
 
@@ -65,3 +69,9 @@ def test_two_ranks_over_gloo_give_the_single_process_aggregates(oracle, tmp_path
         assert np.array_equal(got["mn"].view(np.uint32), mn.view(np.uint32))
         assert np.array_equal(got["mx"].view(np.uint32), mx.view(np.uint32))
         assert np.array_equal(got["sm"].view(np.uint64), sm.view(np.uint64))
+        # ungrouped: the whole table as one group
+        wc, wmn, wmx, wsm = oracle.aggregate(seg, None)
+        assert np.array_equal(got["tcount"], wc)
+        assert np.array_equal(got["tmn"].view(np.uint32), wmn.view(np.uint32))
+        assert np.array_equal(got["tmx"].view(np.uint32), wmx.view(np.uint32))
+        assert abs(got["tsm"][0] - wsm[0]) <= 1e-12 * abs(wsm[0])  # per-rank partial sums added in rank order
