@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
                                                       uint64_t n_chunks, const ChunkState *st, FittedModel *lists,
                                                       const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
                                                       const uint8_t *__restrict__ unit_irregular) {
-    __shared__ double smem[4][64];
+    __shared__ __align__(16) double smem[4][128]; // per warp: two halves of (32 x terms, 32 y terms)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t g = (uint64_t)blockIdx.x * 4 + warp;
     if (g >= n_chunks) return;
@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
     const bool regular = !unit_irregular[u] && delta0 >= 0 && delta0 < (1ll << 31);
     const double delta_d = (double)delta0;
     FittedModel *list = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2);
-    double *sx = smem[warp], *sy = smem[warp] + 32;
+    double *sx = smem[warp];
     for (uint32_t k0 = 0; k0 < s.n_models; k0 += 32) {
         const uint32_t k = k0 + (uint32_t)lane;
         FittedModel m;
@@ -362,32 +362,47 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
             const int64_t t0 = uts[lm.start_index];
             const double v0 = (double)uval[lm.start_index];
             double num = 0.0, den = 0.0;
-            // the loads of the next two steps are in flight while this step's add chain runs
-            const uint32_t first = lm.start_index + 2 + lane;
-            int64_t ta = first <= lm.end_index ? uts[first] : 0, tb = first + 32 <= lm.end_index ? uts[first + 32] : 0;
-            float va = first <= lm.end_index ? uval[first] : 0.0f, vb = first + 32 <= lm.end_index ? uval[first + 32] : 0.0f;
-            for (uint32_t base = lm.start_index + 2; base <= lm.end_index; base += 32) {
-                const uint32_t i = base + lane;
-                const int64_t tc = ta;
-                const float vc = va;
-                ta = tb;
-                va = vb;
-                tb = i + 64 <= lm.end_index ? uts[i + 64] : 0;
-                vb = i + 64 <= lm.end_index ? uval[i + 64] : 0.0f;
+            // Software pipeline over blocks of 32 points: while the two addition chains run over block b (their terms
+            // sit in one half of the shared buffer), the terms of block b + 1 are computed into the other half and the
+            // loads of blocks b + 2 and b + 3 are in flight.  Only the chains are serial: one rounding per point each.
+            const uint32_t p_first = lm.start_index + 2, p_last = lm.end_index;
+            auto load_t = [&](uint32_t i) { return i <= p_last ? uts[i] : (int64_t)0; };
+            auto load_v = [&](uint32_t i) { return i <= p_last ? uval[i] : 0.0f; };
+            auto put_terms = [&](int half, uint32_t i, int64_t t, float vf) {
                 double x = 0.0, y = 0.0;
-                if (i <= lm.end_index) swing_mse_terms(t0, v0, tc, (double)vc, x, y);
-                sx[lane] = x;
-                sy[lane] = y;
-                __syncwarp();
-                const int cnt = (int)min(32u, lm.end_index - base + 1);
+                if (i <= p_last) swing_mse_terms(t0, v0, t, (double)vf, x, y);
+                sx[half * 64 + lane] = x;
+                sx[half * 64 + 32 + lane] = y;
+            };
+            int64_t ta = load_t(p_first + lane), tb = load_t(p_first + 32 + lane), tc = load_t(p_first + 64 + lane);
+            float va = load_v(p_first + lane), vb = load_v(p_first + 32 + lane), vc = load_v(p_first + 64 + lane);
+            put_terms(0, p_first + lane, ta, va);
+            __syncwarp();
+            int half = 0;
+            for (uint32_t base = p_first; base <= p_last; base += 32) {
+                // next block's terms, and the loads three blocks ahead
+                put_terms(half ^ 1, base + 32 + lane, tb, vb);
+                tb = tc;
+                vb = vc;
+                tc = load_t(base + 96 + lane);
+                vc = load_v(base + 96 + lane);
+                const double *bx = sx + half * 64, *by = bx + 32;
+                if (p_last - base >= 31) {
+                    const double2 *bx2 = reinterpret_cast<const double2 *>(bx), *by2 = reinterpret_cast<const double2 *>(by);
 #pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    const double xj = sx[j], yj = sy[j];
-                    if (j < cnt) {
-                        num = __dadd_rn(num, xj);
-                        den = __dadd_rn(den, yj);
+                    for (int j = 0; j < 16; j++) { // 16-byte shared loads: two terms each
+                        const double2 xx = bx2[j], yy = by2[j];
+                        num = __dadd_rn(__dadd_rn(num, xx.x), xx.y);
+                        den = __dadd_rn(__dadd_rn(den, yy.x), yy.y);
+                    }
+                } else { // the last, partial block (adding a padding zero could flip the sign of a zero sum)
+                    const int cnt = (int)(p_last - base + 1);
+                    for (int j = 0; j < cnt; j++) {
+                        num = __dadd_rn(num, bx[j]);
+                        den = __dadd_rn(den, by[j]);
                     }
                 }
+                half ^= 1;
                 __syncwarp();
             }
             swing_finish_from_sums(lm, num, den, uts, uval);
