@@ -491,7 +491,7 @@ constexpr int STAGE_WORDS = 128;   // 512 B of the stream per refill
 struct WarpBitStage {
     const uint32_t *words; // 4-byte aligned address at or before the first byte of the stream
     uint64_t n_words;
-    uint32_t last_mask;    // keeps the stream's bytes of the last word, zeroes what follows it
+    uint64_t lo_byte, hi_byte; // the stream is bytes [lo_byte, hi_byte) of that word sequence
     uint32_t *stage;       // STAGE_WORDS words of shared memory owned by this warp
     uint64_t first_word;   // stream word held in stage[0]
     uint64_t start_bit;    // position of the stream's first bit
@@ -501,8 +501,8 @@ struct WarpBitStage {
         const uint32_t skip = (uint32_t)(a & 3);
         words = reinterpret_cast<const uint32_t *>(a - skip);
         n_words = (skip + n_bytes + 3) / 4;
-        const uint32_t used = (uint32_t)((skip + n_bytes) & 3);
-        last_mask = used ? 0xFFFFFFFFu << (8 * (4 - used)) : 0xFFFFFFFFu;
+        lo_byte = skip;
+        hi_byte = skip + n_bytes;
         stage = stage_;
         first_word = ~0ull;
         start_bit = 8ull * skip;
@@ -517,8 +517,14 @@ struct WarpBitStage {
             const uint64_t w = w0 + (uint64_t)(i * 32 + lane);
             uint32_t x = 0;
             if (w < n_words) {
-                x = __byte_perm(__ldg(words + w), 0, 0x0123);
-                if (w == n_words - 1) x &= last_mask;
+                const uint64_t b0 = 4 * w;
+                if (b0 >= lo_byte && b0 + 4 <= hi_byte) {
+                    x = __byte_perm(__ldg(words + w), 0, 0x0123); // big-endian bit order
+                } else { // the first / last word: only the bytes that belong to the stream are touched
+                    const uint8_t *bytes = reinterpret_cast<const uint8_t *>(words);
+                    for (uint32_t b = 0; b < 4; b++)
+                        if (b0 + b >= lo_byte && b0 + b < hi_byte) x |= (uint32_t)__ldg(bytes + b0 + b) << (24 - 8 * b);
+                }
             }
             stage[i * 32 + lane] = x;
         }
