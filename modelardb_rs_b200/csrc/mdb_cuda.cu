@@ -484,7 +484,7 @@ __device__ __forceinline__ void report_bad(Status *status, uint64_t index) {
 
 constexpr uint32_t WIDE_ROW_MIN = 64;
 constexpr int WIDE_WARPS = 4;      // warps (rows in flight) per block
-constexpr int STAGE_WORDS = 128;   // 512 B of the stream per refill
+constexpr int STAGE_WORDS = 512;   // 2 KiB of the stream per refill (a refill is a synchronous global round trip)
 
 // The row's bytes, staged: STAGE_WORDS big-endian words of the stream starting at word `first_word`.  Bits are
 // addressed by their absolute position in the (4-byte aligned) word sequence that contains the stream.
@@ -531,64 +531,70 @@ struct WarpBitStage {
         first_word = w0;
         __syncwarp();
     }
-    // the 32 bits starting at bit p (covered)
-    __device__ __forceinline__ uint32_t peek32(uint64_t p) const {
-        const uint32_t i = (uint32_t)((p >> 5) - first_word);
-        return __funnelshift_l(stage[i + 1], stage[i], (uint32_t)(p & 31));
+    // the 32 bits starting at bit `rel` of the stage (rel = absolute position - 32 * first_word; covered)
+    __device__ __forceinline__ uint32_t peek32(uint32_t rel) const {
+        const uint32_t i = rel >> 5;
+        return __funnelshift_l(stage[i + 1], stage[i], rel & 31u);
     }
 };
 
 // MacaqueVDecoder (mdb_device.cuh, macaque_v.rs:272-323) for one long stream, 32 values per batch.  Where a code
 // starts depends on every code before it, so the warp first WALKS the batch's codes serially -- every lane runs the same
 // few instructions per code (flag bits, a new window's 11 header bits, the payload's position), nothing else -- and
-// lane k keeps the position, width and shift of the k-th payload.  The payloads are then extracted by the 32 lanes at
-// once, and the values are an exclusive-or prefix scan over them (value k = value k - 1 XOR payload k).
-// on_batch(k0, value, valid): this lane's value k0 + lane of the stream.
+// lane k keeps the position, width and shift of the k-th payload (packed into one register).  The payloads are then
+// extracted by the 32 lanes at once, and the values are an exclusive-or prefix scan over them
+// (value k = value k - 1 XOR payload k).  on_batch(k0, value, valid): this lane's value k0 + lane of the stream.
 template <typename OnBatch>
 __device__ __forceinline__ float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, bool has_seed, float seed,
                                                        uint32_t *stage_words, int lane, OnBatch &&on_batch) {
     WarpBitStage bits;
     bits.init(bytes, n_bytes, stage_words);
     uint64_t p = bits.start_bit;
-    uint32_t leading_zeros = 255, trailing_zeros = 0;
+    uint32_t trailing_zeros = 0;
+    uint32_t width_in_force = 32; // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = 255 at first
     uint32_t last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
     for (uint32_t k0 = 0; k0 < count; k0 += 32) {
         const int cnt = (int)min(32u, count - k0);
         bits.cover(p, 32u * 45u + 64u, lane);
-        uint64_t my_pos = 0;
-        uint32_t my_width = 0, my_shift = 0;
-        for (int k = 0; k < cnt; k++) {
-            uint64_t pos;
-            uint32_t width, shift;
-            if (!has_seed && k0 == 0 && k == 0) { // macaque_v.rs:282-285: the first value is stored raw
-                pos = p; width = 32; shift = 0;
-                p += 32;
-            } else {
-                const uint32_t head = bits.peek32(p);
-                if (!(head & 0x80000000u)) {        // `0`: the XOR's meaningful bits in the window in force
-                    const uint32_t meaningful = (32u - leading_zeros - trailing_zeros) & 0xffu;
-                    width = meaningful > 32u ? 32u : meaningful;
-                    shift = trailing_zeros;
-                    pos = p + 1;
-                } else if (!(head & 0x40000000u)) { // `10`: the same value again
-                    width = 0; shift = 0;
-                    pos = p + 2;
-                } else {                            // `11`, 5 bits of leading zeros, 6 bits of length, the bits
-                    leading_zeros = (head >> 25) & 31u;
-                    uint32_t meaningful = (head >> 19) & 63u;
-                    trailing_zeros = (32u - meaningful - leading_zeros) & 0xffu; // u8 wrapping as in release builds
-                    meaningful = (32u - leading_zeros - trailing_zeros) & 0xffu;
-                    width = meaningful > 32u ? 32u : meaningful;
-                    shift = trailing_zeros;
-                    pos = p + 13;
-                }
-                p = pos + width;
-            }
-            if (k == lane) { my_pos = pos; my_width = width; my_shift = shift; }
+        const uint32_t rel0 = (uint32_t)(p - 32u * bits.first_word); // positions inside the batch are relative to the stage
+        uint32_t rel = rel0;
+        uint32_t mine = 0; // payload position (15 bits) | width (6 bits) << 15 | shift (8 bits) << 21
+        // Branch-free: the three kinds of code are all evaluated and selected between, so the serial dependency from one
+        // code to the next is a shared-memory load, a funnel shift and a handful of dependent integer operations.
+        auto walk_one = [&](int k) {
+            const uint32_t head = bits.peek32(rel);
+            const bool reuse = !(head & 0x80000000u);                  // `0`: the XOR's meaningful bits in the window in force
+            const bool fresh = (head & 0xC0000000u) == 0xC0000000u;    // `11`, 5 bits of leading zeros, 6 bits of length, the bits
+            const uint32_t leading_zeros = (head >> 25) & 31u;         // (`10`: the same value again, no payload)
+            const uint32_t stored_len = (head >> 19) & 63u;
+            const uint32_t new_trailing = (32u - stored_len - leading_zeros) & 0xffu; // u8 wrapping as in release builds
+            const uint32_t new_meaningful = (32u - leading_zeros - new_trailing) & 0xffu;
+            const uint32_t new_width = new_meaningful > 32u ? 32u : new_meaningful;
+            trailing_zeros = fresh ? new_trailing : trailing_zeros;
+            width_in_force = fresh ? new_width : width_in_force;
+            const uint32_t header = reuse ? 1u : (fresh ? 13u : 2u);
+            const uint32_t width = (reuse | fresh) ? width_in_force : 0u;
+            const uint32_t packed = (reuse | fresh) ? ((rel + header) | (width << 15) | (trailing_zeros << 21)) : 0u;
+            rel += header + width;
+            if (k == lane) mine = packed;
+        };
+        int k_begin = 0;
+        if (!has_seed && k0 == 0) { // macaque_v.rs:282-285: the first value is stored raw
+            if (lane == 0) mine = rel | (32u << 15);
+            rel += 32;
+            k_begin = 1;
         }
+        if (cnt == 32 && k_begin == 0) {
+#pragma unroll
+            for (int k = 0; k < 32; k++) walk_one(k);
+        } else {
+            for (int k = k_begin; k < cnt; k++) walk_one(k);
+        }
+        p += rel - rel0;
         uint32_t x = 0;
+        const uint32_t my_width = (mine >> 15) & 63u, my_shift = mine >> 21;
         if (lane < cnt && my_width) {
-            x = bits.peek32(my_pos) >> (32u - my_width);
+            x = bits.peek32(mine & 0x7fffu) >> (32u - my_width);
             x = my_shift < 32u ? x << my_shift : 0u;
         }
 #pragma unroll
@@ -990,6 +996,7 @@ static int check_ctx(mdbcu_context *ctx) {
 
 // Waits for the stream (and with it for every transfer queued so far).
 static int read_status(mdbcu_context *ctx, const Status *d_status, Status &h, const char *what) {
+    static_assert(STAGE_WORDS * 32 <= 0x8000, "payload positions are packed into 15 bits");
     static_assert(sizeof(Status) == 16, "Status is posted as two words");
     CUDA_TRY(post(ctx, SLOT_STATUS, d_status, 2));
     CUDA_TRY(sync_stream(ctx));
