@@ -222,7 +222,7 @@ def run_reference_arm(args):
         "e2e": {"value": value, "unit": "points/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, per_gpu_series):
@@ -257,7 +257,6 @@ def main():
     device = f"cuda:{local_rank}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line and nothing else
         dist.init_process_group("nccl", device_id=torch.device(device))
 
     eb_t = parse_eb(args.eb)
@@ -524,7 +523,7 @@ def main():
                      "compression_ratio": 12 * n / seg_bytes if seg_bytes else None},
         "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": launches, "clocks": clock_info,
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -536,5 +535,23 @@ def _wrap_device_i64(torch, ptr, n, device):
     return torch.as_tensor(_Arr(), device=device)
 
 
+def _emit(line: dict):
+    """The one JSON line, written to the process's ORIGINAL stdout (see _quarantine_stdout)."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+def _quarantine_stdout() -> int:
+    """Native libraries print banners to file descriptor 1 (NCCL: "NCCL version ..." on communicator creation).  The
+    contract is ONE JSON line on stdout, so fd 1 is pointed at stderr for the whole run and the line goes to a
+    duplicate of the original descriptor."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    return real
+
+
+_REAL_STDOUT = 1
+
 if __name__ == "__main__":
+    _REAL_STDOUT = _quarantine_stdout()
     main()
