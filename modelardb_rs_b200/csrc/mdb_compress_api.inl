@@ -1,16 +1,22 @@
 // mdb_compress_api.inl -- K1: compress kernels and mdbcu_compress (included at the end of mdb_cuda.cu).
 //
-// Flow (all on the context's stream; the three host syncs each read back a handful of counters):
+// Flow (all on the context's stream; the host syncs each read back a handful of scalars through the mailbox):
 //   k_unit_chunks      validate units / error bounds, chunks per unit            -> scan -> chunk_base
 //   k_spec_init        ChunkState of every chunk, chunk -> unit map, list sizes  -> scan -> list_base
-//   repeat { k_spec_chain (one thread per dirty chunk) ; k_spec_propagate (one thread per unit) }
-//                      until no chunk is dirty (mdb_compress.cuh explains why this is exact)
+//   chains, either     k_sched_count / k_sched_fill / k_sched_units + k_spec_async: a device-side work queue of
+//                      chunks served by persistent warps, every unit advancing its own exact frontier
+//                      (sched_advance in mdb_compress.cuh; the default)
+//              or      repeat { k_spec_chain[_warp] over the dirty chunks ; k_spec_propagate per unit } in global
+//                      rounds until no chunk is dirty (fit engines 1 and 2)
 //   k_spec_finalize    skipped chunks, residual-run ends, leading MacaqueV rows, regularity
+//   k_swing_finish     the order-dependent MSE sums of the accepted Swing models (one lane per model)
 //   k_spec_count_rows  rows per chunk                                            -> scan -> row_base
-//   k_spec_records     SegRecord of every row in final order (byte lengths by running the encoders
-//                      on a counter)
+//   k_spec_records     SegRecord of every row in final order (byte lengths by running the encoders on a counter);
+//                      long MacaqueV rows are only listed ...
+//   k_records_macaque_warp   ... and sized by a whole warp, 32 values at a time (warp_macaque_v_encode)
 //   k_compress_gather  row metadata columns + per-row byte lengths               -> 3 scans -> offsets
-//   k_compress_emit    MacaqueTS / MacaqueV byte columns at their final offsets
+//   k_compress_emit    MacaqueTS / MacaqueV byte columns at their final offsets (short rows, one thread each)
+//   k_emit_macaque_warp      the value bytes of the long MacaqueV rows
 
 struct CompressCounters { // device-resident, read back once per round
     unsigned int dirty;
