@@ -269,6 +269,32 @@ def test_pageable_and_pinned_host_memory_give_the_same_bytes(oracle, ctx):
     seg2.free()
 
 
+@pytest.mark.parametrize("eb", [(0, 0.0), (1, 1e-3), (2, 1e-4), (2, 3.0)], ids=["lossless", "abs1e-3", "rel1e-4", "rel3"])
+def test_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
+    """Rows of tens of thousands of MacaqueV values: the warp encoder (ballot loops for stored-value and window
+    resets, scanned bit offsets, several drains of the shared stage) and the warp decoder (several refills of the
+    stream stage), lossless and lossy, against the oracle's serial coder."""
+    rng = np.random.default_rng(17)
+    units = [rng.uniform(-1e3, 1e3, 50_000).astype(np.float32),                       # no model ever fits
+             (100.0 + np.cumsum(rng.standard_normal(70_001))).astype(np.float32),     # random walk
+             np.repeat(rng.uniform(-5, 5, 4_000).astype(np.float32), 9)[:33_333]]     # runs of 9 equal values: `10` codes, models between
+    vals = np.concatenate(units)
+    ts = np.concatenate([syn.regular_timestamps(len(u)) for u in units])
+    off = np.concatenate([[0], np.cumsum([len(u) for u in units])]).astype(np.uint64)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=4)
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    got = seg.to_host()
+    assert_segments_equal(got, want, f"long MacaqueV rows eb={eb}")
+    wts, wval, _ = oracle.grid(want, n_threads=4)
+    gts, gval = mc.grid(got, ctx=ctx)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, f"long MacaqueV rows eb={eb} grid")
+    wsum = oracle.segment_sums(want)
+    gsum = mc.segment_sums(got, ctx)
+    assert_f32_bits_equal(gsum, wsum, f"long MacaqueV rows eb={eb} sums", nan_payload_matters=False)
+    seg.free()
+
+
 def test_contexts_on_threads_pipeline_independent_slabs(oracle):
     """One context per host thread (the e2e pattern of bench.py): results do not depend on what the others do."""
     import threading
