@@ -166,13 +166,17 @@ class ClockSampler:
 
 # ----------------------------------------------------------------------------------------------- CPU arm
 
-def cpu_port_throughput(n_series, n_points, eb, kind, units, threads, seed=4242):
+def cpu_port_inputs(n_series, n_points, kind, units, seed=4242):
+    vals = gen_values_host(n_series, n_points, seed, kind)
+    ts = np.tile(EPOCH_US + STEP_US * np.arange(n_points, dtype=np.int64), n_series)
+    return ts, vals, unit_offsets(n_series, n_points, units)
+
+
+def cpu_port_throughput(n_series, n_points, eb, kind, units, threads, seed=4242, inputs=None):
     """Times the CPU port of the reference (the oracle) on `n_series` series: compress -> grid -> aggregate,
     series partitioned statically over `threads` threads.  Returns (points/s, per-stage seconds)."""
     from oracle import mdb_oracle as oracle
-    vals = gen_values_host(n_series, n_points, seed, kind)
-    ts = np.tile(EPOCH_US + STEP_US * np.arange(n_points, dtype=np.int64), n_series)
-    off = unit_offsets(n_series, n_points, units)
+    ts, vals, off = inputs if inputs is not None else cpu_port_inputs(n_series, n_points, kind, units, seed)
     t0 = time.perf_counter()
     seg = oracle.compress(ts, vals, off, eb=eb, n_threads=threads)
     t1 = time.perf_counter()
@@ -199,13 +203,15 @@ def run_reference_arm(args):
         return
     eb = parse_eb(args.eb)
     threads = os.cpu_count() or 1
-    n_series = cpu_sample_size(args.points, threads, min(args.cpu_seconds, 15.0))
-    # bounded: each step is ~15 s of CPU work, so cap the number of steps to keep the run to a few minutes
-    warm, steps = min(args.warmup, 1), min(args.steps, 5)
+    # W warm-up steps and exactly K timed steps, each a bounded sample of the workload: the sample is sized so that the
+    # whole run is about two minutes of CPU work (the inputs, larger than every cache, are generated once)
+    warm, steps = max(0, args.warmup), max(1, args.steps)
+    n_series = cpu_sample_size(args.points, threads, max(1.0, min(args.cpu_seconds, 120.0 / (warm + steps))))
+    inputs = cpu_port_inputs(n_series, args.points, args.kind, args.units)
     times = []
     stages = None
     for step in range(warm + steps):
-        rate, stages = cpu_port_throughput(n_series, args.points, eb, args.kind, args.units, threads, seed=4242 + step)
+        rate, stages = cpu_port_throughput(n_series, args.points, eb, args.kind, args.units, threads, inputs=inputs)
         if step >= warm:
             times.append(n_series * args.points / rate)
     ms = 1000.0 * sum(times) / len(times)
