@@ -731,14 +731,50 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__res
     for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) seg_of[tid * TILE_POINTS_PER_THREAD + k] = (uint16_t)max(prev, loc[k]);
     __syncthreads();
 
+    // Four consecutive points per thread: they nearly always lie in one row, so the row is looked up once and the
+    // points leave in 16-byte stores (a warp store covers 512 contiguous bytes).  Quads that straddle rows, touch
+    // the end of the output, reach into a row's residual part or belong to rows the serial kernels write fall back
+    // to the point-wise code, as do outputs that are not 16-byte aligned.
+    const bool vector_ok = ((reinterpret_cast<uintptr_t>(val_out) | reinterpret_cast<uintptr_t>(ts_out)) & 15) == 0;
 #pragma unroll
-    for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) {
-        int p = tid + k * TILE_THREADS;
-        uint64_t gp = tile_start + p;
-        if (gp < tile_end) {
-            uint32_t i = seg_of[p];
+    for (int k = 0; k < TILE_POINTS_PER_THREAD / 4; k++) {
+        const int p = 4 * (tid + k * TILE_THREADS);
+        const uint64_t gp = tile_start + p;
+        if (gp >= tile_end) continue;
+        const uint32_t i = seg_of[p];
+        if (vector_ok && gp + 3 < tile_end && seg_of[p + 3] == i) {
             const SegDesc d = desc[s0 + i];
-            grid_point(d, (uint32_t)(gp - po_s[i]), ts_out, val_out, gp);
+            if (!(d.flags & F_REGULAR)) continue; // timestamps and values of this row come from k_grid_sequential
+            const uint32_t j = (uint32_t)(gp - po_s[i]);
+            const int64_t t0 = d.start + (int64_t)j * d.interval;
+            const int64_t t1 = t0 + d.interval, t2 = t1 + d.interval, t3 = t2 + d.interval;
+            reinterpret_cast<longlong2 *>(ts_out + gp)[0] = make_longlong2(t0, t1);
+            reinterpret_cast<longlong2 *>(ts_out + gp)[1] = make_longlong2(t2, t3);
+            if (d.flags & F_TILE_VALUES) {
+                if (j + 3 < d.model_len) {
+                    float4 v;
+                    if ((d.flags & F_TYPE_MASK) == PMC_MEAN) {
+                        v.x = v.y = v.z = v.w = (float)d.a;                                  // pmc_mean.rs:104-108
+                    } else {
+                        v.x = swing_value(d.a, d.b, t0);                                     // swing.rs:304-319
+                        v.y = swing_value(d.a, d.b, t1);
+                        v.z = swing_value(d.a, d.b, t2);
+                        v.w = swing_value(d.a, d.b, t3);
+                    }
+                    *reinterpret_cast<float4 *>(val_out + gp) = v;
+                } else { // the model part ends inside the quad: the rest are residual values (k_grid_sequential)
+                    for (int q = 0; q < 4; q++)
+                        if (j + q < d.model_len)
+                            val_out[gp + q] = (d.flags & F_TYPE_MASK) == PMC_MEAN ? (float)d.a : swing_value(d.a, d.b, t0 + q * d.interval);
+                }
+            }
+            continue;
+        }
+        for (int q = 0; q < 4; q++) {
+            if (gp + q < tile_end) {
+                const uint32_t iq = seg_of[p + q];
+                grid_point(desc[s0 + iq], (uint32_t)(gp + q - po_s[iq]), ts_out, val_out, gp + q);
+            }
         }
     }
 }
