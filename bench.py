@@ -55,6 +55,7 @@ def parse_args():
     p.add_argument("--e2e-stages", default="all", choices=["all", "compress", "grid"], help="diagnostics: time one half of the e2e slab alone")
     p.add_argument("--e2e-up-gate", type=int, default=2, help="workers allowed at once in the upload-heavy call (compress)")
     p.add_argument("--e2e-down-gate", type=int, default=1, help="workers allowed at once in the download-heavy call (grid)")
+    p.add_argument("--chunk-len", type=int, default=0, help="chunk length of the parallel segmentation (0 = automatic); tuning only")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
@@ -272,6 +273,8 @@ def main():
 
     from modelardb_rs_b200.sharding import gather_group_aggregates
     ctx = mc.Context(local_rank)
+    if args.chunk_len:
+        ctx.set_chunk_len(args.chunk_len)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
     # ---- inputs resident in HBM
