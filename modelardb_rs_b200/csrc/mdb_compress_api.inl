@@ -460,27 +460,64 @@ __global__ void __launch_bounds__(256) k_unit_seg_off(const uint64_t *chunk_base
     unit_seg_off[u] = row_base[chunk_base[u]]; // chunk_base[n_units] == n_chunks, row_base[n_chunks] == total rows
 }
 
-// One thread per chunk (same lane geometry as k_spec_chain): the chunk's rows, in order.
-__global__ void __launch_bounds__(32) k_spec_records(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
-                                                     const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
-                                                     const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, uint32_t lanes, const ChunkState *st,
-                                                     const FittedModel *lists, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
-                                                     const uint8_t *__restrict__ unit_irregular, const uint64_t *__restrict__ row_base, SegRecord *recs,
-                                                     uint32_t *row_unit, uint32_t *wide_rows, unsigned int *n_wide) {
-    if (threadIdx.x >= lanes) return;
-    uint64_t g = (uint64_t)blockIdx.x * lanes + threadIdx.x;
+// One warp per chunk, one lane per accepted model (spec_records in mdb_compress.cuh is the one-thread form).  A model
+// yields one row, or two when more than 255 residual points follow it (compression.rs:310-362); an exclusive scan over
+// the lanes gives every model its row position, so the rows come out in the chain's order.
+__global__ void __launch_bounds__(128) k_spec_records(const int64_t *__restrict__ ts, const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
+                                                      const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
+                                                      const uint32_t *__restrict__ chunk_unit, uint64_t n_chunks, const ChunkState *st,
+                                                      const FittedModel *lists, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                      const uint8_t *__restrict__ unit_irregular, const uint64_t *__restrict__ row_base, SegRecord *recs,
+                                                      uint32_t *row_unit, uint32_t *wide_rows, unsigned int *n_wide) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t g = (uint64_t)blockIdx.x * 4 + warp;
     if (g >= n_chunks) return;
     const ChunkState s = st[g];
-    uint64_t r0 = row_base[g], rows = row_base[g + 1] - r0;
-    if (rows == 0) return;
-    uint32_t u = chunk_unit[g];
-    uint64_t a = unit_off[u];
-    ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-    spec_records(eb, ts + a, values + a, s, lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2), unit_irregular[u] == 0, recs + r0,
-                 WIDE_ENCODE_MIN);
-    for (uint64_t k = 0; k < rows; k++) {
-        row_unit[r0 + k] = u;
-        if (recs[r0 + k].wide) wide_rows[atomicAdd(n_wide, 1u)] = (uint32_t)(r0 + k); // long MacaqueV rows: the warp kernels below
+    const uint64_t r0 = row_base[g];
+    if (row_base[g + 1] == r0) return; // (skipped chunks have no rows)
+    const uint32_t u = chunk_unit[g];
+    const uint64_t a = unit_off[u];
+    const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    const int64_t *uts = ts + a;
+    const float *uval = values + a;
+    const bool regular = unit_irregular[u] == 0;
+    const FittedModel *list = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2);
+    auto publish = [&](uint64_t row) { // long MacaqueV rows go on to the warp kernels below
+        row_unit[row] = u;
+        if (recs[row].wide) wide_rows[atomicAdd(n_wide, 1u)] = (uint32_t)row;
+    };
+    uint32_t r = 0; // rows written so far (uniform)
+    if (s.lead_end != IDX_NONE) { // compression.rs:350-361: leading residuals of the unit
+        if (lane == 0) {
+            record_macaque_v_segment(eb, 0, s.lead_end, uts, uval, regular, recs[r0], WIDE_ENCODE_MIN);
+            publish(r0);
+        }
+        r = 1;
+    }
+    for (uint32_t k0 = 0; k0 < s.n_models; k0 += 32) {
+        const uint32_t k = k0 + (uint32_t)lane;
+        const bool have = k < s.n_models;
+        FittedModel m;
+        uint32_t res_end = 0, n_rows = 0;
+        if (have) {
+            m = list[k];
+            const uint32_t next_start = k + 1 < s.n_models ? list[k + 1].start_index : s.next_start;
+            res_end = next_start - 1;
+            n_rows = (res_end - m.end_index <= RESIDUAL_VALUES_MAX_LENGTH) ? 1u : 2u;
+        }
+        uint32_t incl = n_rows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t o = __shfl_up_sync(FULL_MASK, incl, d);
+            if (lane >= d) incl += o;
+        }
+        if (have) {
+            const uint64_t row = r0 + r + (incl - n_rows);
+            store_segments(eb, true, m, res_end, uts, uval, regular, recs + row, WIDE_ENCODE_MIN);
+            row_unit[row] = u;
+            if (n_rows == 2) publish(row + 1);
+        }
+        r += __shfl_sync(FULL_MASK, incl, 31);
     }
 }
 
@@ -962,7 +999,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(wide_rows.alloc(S, s));
         TRY_SG(cudaMemsetAsync(n_wide.p, 0, sizeof(unsigned int), s));
         if (G && S) {
-            LAUNCH(ctx, k_spec_records, div_up(G, lanes), 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, lanes, st.p, lists.p,
+            LAUNCH(ctx, k_spec_records, div_up(G, 4), 128, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, st.p, lists.p,
                    list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p, wide_rows.p, n_wide.p);
             LAUNCH(ctx, k_records_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
                    d_val, d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p);
