@@ -372,6 +372,8 @@ def main():
         # own context (stream) and its own pinned buffers -- keep H2D of one slab, kernels of another and D2H
         # of a third in flight (the calls are blocking but release the GIL; PCIe is full duplex).
         es, esteps, workers = min(args.e2e_series, n_series), args.e2e_steps, args.e2e_workers
+        if world > 2:  # every rank pins 24 B/point x workers of host memory: keep the box's total near the 2-rank figure
+            es = max(8, es * 2 // world)
         en = es * n_points
         e_off = unit_offsets(es, n_points, args.units)
         e_units = len(e_off) - 1
