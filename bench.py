@@ -512,7 +512,7 @@ def main():
                 roofline[f"{k}_frac"] = a_ / peak
 
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only: the other ranks' processes would wait on it)
         threads = os.cpu_count() or 1
         cs = cpu_sample_size(n_points, threads, args.cpu_seconds)
         rate, stages = cpu_port_throughput(cs, n_points, eb_t, args.kind, args.units, threads)
