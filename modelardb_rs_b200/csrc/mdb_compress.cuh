@@ -107,8 +107,13 @@ struct Swing { // swing.rs:34-259
             end_time = timestamp;
             compute_slope_and_intercept(start_time, first_value, timestamp, __dadd_rn(value, maximum_deviation),
                                         upper_slope, upper_intercept);
-            compute_slope_and_intercept(start_time, first_value, timestamp, __dsub_rn(value, maximum_deviation),
-                                        lower_slope, lower_intercept);
+            if (maximum_deviation == 0.0) { // value + 0 and value - 0 are the same operand: the same line, one division
+                lower_slope = upper_slope;
+                lower_intercept = upper_intercept;
+            } else {
+                compute_slope_and_intercept(start_time, first_value, timestamp, __dsub_rn(value, maximum_deviation),
+                                            lower_slope, lower_intercept);
+            }
             length = 2;
             return true;
         }
@@ -474,11 +479,32 @@ MDB_DEV uint32_t models_per_chunk(uint32_t chunk_len) { return chunk_len / 8 + 2
 // [start, limit) exist; with fewer than 8 of them no model can be stored.
 MDB_DEV bool fit_reaches_eight_points(const ErrorBound &eb, const int64_t *ts, const float *values, uint32_t start, uint32_t limit) {
     if (limit < start || limit - start < 8) return false;
-    PMCMean pmc;
-    pmc.init();
     bool all = true;
-    for (uint32_t k = 0; k < 8 && all; k++) all = pmc.fit_value(eb, values[start + k]);
-    if (all) return true;
+    if (eb.kind == KIND_LOSSLESS) {
+        // Lossless PMC-Mean on finite values accepts a point iff it equals the first one: min, max and the average of k
+        // equal f32 values (k * v is exact in f64 for k <= 8) are that value, and two different finite values can not both
+        // equal their average.  No division needed; non-finite values take the general path below.
+        const float first = values[start];
+        bool finite = fabsf(first) <= 3.402823466e+38f;
+        for (uint32_t k = 1; k < 8; k++) {
+            const float v = values[start + k];
+            finite = finite && fabsf(v) <= 3.402823466e+38f;
+            all = all && v == first;
+        }
+        if (finite && all) return true;
+        if (!finite) {
+            PMCMean pmc;
+            pmc.init();
+            all = true;
+            for (uint32_t k = 0; k < 8 && all; k++) all = pmc.fit_value(eb, values[start + k]);
+            if (all) return true;
+        }
+    } else {
+        PMCMean pmc;
+        pmc.init();
+        for (uint32_t k = 0; k < 8 && all; k++) all = pmc.fit_value(eb, values[start + k]);
+        if (all) return true;
+    }
     Swing swing;
     swing.init();
     all = true;
