@@ -103,7 +103,8 @@ class Context:
         _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
 
     def set_fit_engine(self, engine: int):
-        """0 automatic, 1 one thread per chain, 2 one warp per chain; results are identical."""
+        """0 automatic (= 3), 1 one thread per chain in rounds, 2 one warp per chain in rounds, 3 one warp per chain with
+        the asynchronous scheduler; results are identical."""
         _native.check(_native.lib().mdbcu_context_set_fit_engine(self._h, engine))
 
     @property
@@ -176,6 +177,22 @@ class HostSegments:
             a, b = int(off[lo]), int(off[hi])
             cols[name + "_off"] = off[lo:hi + 1] - off[lo]
             cols[name + "_data"] = getattr(self, name + "_data")[a:b]
+        return HostSegments(**cols)
+
+    def take(self, rows) -> "HostSegments":
+        """The given rows (a boolean mask or increasing indices) as an independent batch, in their original order."""
+        rows = np.asarray(rows)
+        idx = np.flatnonzero(rows) if rows.dtype == bool else rows.astype(np.int64)
+        cols = {c: getattr(self, c)[idx] for c in ("model_type_id", "start_time", "end_time", "min_value", "max_value")}
+        for name in ("timestamps", "values", "residuals"):
+            off = getattr(self, name + "_off").astype(np.int64)
+            data = getattr(self, name + "_data")
+            lens = off[idx + 1] - off[idx]
+            new_off = np.concatenate([[0], np.cumsum(lens)])
+            # byte k of the output comes from off[row] + (k - new_off[row]) of the input
+            src = np.repeat(off[idx] - new_off[:-1], lens) + np.arange(int(new_off[-1]))
+            cols[name + "_off"] = new_off.astype(np.uint64)
+            cols[name + "_data"] = data[src] if len(src) else np.zeros(0, np.uint8)
         return HostSegments(**cols)
 
 
@@ -310,6 +327,71 @@ def try_compress_univariate_time_series(uncompressed_timestamps, uncompressed_va
         return seg.to_host()
     finally:
         seg.free()
+
+
+def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_columns: Sequence[np.ndarray]):
+    """The host part of try_compress_multivariate_time_series (compression.rs:42-141): sort the rows by all tags and then
+    time (`sort_time_series_by_tags_and_time`, :110-141), split them into time series where any tag changes (:64-93),
+    and lay the (series, field) pairs out as the units of ONE compress call, series-major and field-minor -- the
+    order in which the reference appends its RecordBatches (:147-179).
+
+    Returns (unit_timestamps, unit_values, unit_off, unit_series, unit_field, series_tags): unit u is
+    unit_*[unit_off[u]:unit_off[u+1]], belongs to series unit_series[u] (tags series_tags[unit_series[u]]) and to field
+    column unit_field[u]."""
+    ts = np.ascontiguousarray(timestamps, np.int64)
+    n = len(ts)
+    fields = [np.ascontiguousarray(f, np.float32) for f in field_columns]
+    if any(len(f) != n for f in fields) or any(len(t) != n for t in tag_columns):
+        raise ValueError("all columns must have the same number of rows")
+    n_fields = len(fields)
+    if n == 0 or n_fields == 0:
+        return ts[:0], np.zeros(0, np.float32), np.zeros(1, np.uint64), np.zeros(0, np.int64), np.zeros(0, np.int64), []
+    # lexsort by (tag_0, tag_1, ..., timestamp), ascending; tags compare as UTF-8 strings like Arrow's StringView sort
+    tag_codes, tag_values = [], []
+    for t in tag_columns:
+        values, codes = np.unique(np.asarray(t, dtype=str), return_inverse=True)
+        tag_codes.append(codes)
+        tag_values.append(values)
+    order = np.lexsort([ts] + tag_codes[::-1])  # np.lexsort: the LAST key is the primary one
+    ts = ts[order]
+    tag_codes = [c[order] for c in tag_codes]
+    new_series = np.zeros(n, bool)
+    new_series[0] = True
+    for c in tag_codes:
+        new_series[1:] |= c[1:] != c[:-1]
+    starts = np.flatnonzero(new_series)
+    lens = np.diff(np.append(starts, n))
+    n_series = len(starts)
+    series_tags = [tuple(str(v[c[a]]) for v, c in zip(tag_values, tag_codes)) for a in starts]
+    # units: series-major, field-minor
+    unit_len = np.repeat(lens, n_fields)
+    unit_off = np.concatenate([[0], np.cumsum(unit_len)]).astype(np.uint64)
+    unit_series = np.repeat(np.arange(n_series), n_fields)
+    unit_field = np.tile(np.arange(n_fields), n_series)
+    total = int(unit_off[-1])
+    row = np.repeat(np.repeat(starts, n_fields) - unit_off[:-1].astype(np.int64), unit_len) + np.arange(total)
+    field_of_row = np.repeat(unit_field, unit_len)
+    field_matrix = np.stack([f[order] for f in fields])
+    return ts[row], field_matrix[field_of_row, row], unit_off, unit_series, unit_field, series_tags
+
+
+def try_compress_multivariate_time_series(timestamps, tag_columns: Sequence[Sequence[str]], field_columns: Sequence[np.ndarray],
+                                          error_bounds: Sequence[ErrorBound], ctx: Optional[Context] = None):
+    """compression.rs:42-107 with the per-series loop replaced by one batched kernel call: returns, in the reference's
+    order, one (tag_values, field_column_index, HostSegments) triple per (time series, field column)."""
+    if len(error_bounds) != len(field_columns):
+        raise ValueError("one error bound per field column")
+    u_ts, u_val, unit_off, unit_series, unit_field, series_tags = plan_multivariate(timestamps, tag_columns, field_columns)
+    n_units = len(unit_series)
+    if n_units == 0:
+        return []
+    seg = compress(u_ts, u_val, unit_off, [error_bounds[f] for f in unit_field], ctx)
+    try:
+        host = seg.to_host()
+    finally:
+        seg.free()
+    uso = host.unit_seg_off
+    return [(series_tags[unit_series[u]], int(unit_field[u]), host.slice(int(uso[u]), int(uso[u + 1]))) for u in range(n_units)]
 
 
 def split_into_buffers(n_points_per_series: Sequence[int], capacity: int = UNCOMPRESSED_DATA_BUFFER_CAPACITY) -> np.ndarray:

@@ -54,13 +54,19 @@ class GridStream:
     """
 
     def __init__(self, input: Iterable[Tuple[object, Sequence[np.ndarray]]], batch_size: int, n_tag_columns: int = 0,
-                 predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None):
+                 predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None,
+                 time_range: Optional[Tuple[Optional[int], Optional[int]]] = None):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
         self._input: Iterator = iter(input)
         self._input_done = False
         self.batch_size = batch_size
         self.predicate = predicate
+        # (lo, hi), either may be None: segments that end before lo or start after hi are not reconstructed at all --
+        # the push-down the reference applies to its Parquet scan (time_series_table.rs:290-373), SURVEY 8(f2).  The
+        # caller's predicate must imply the range; points of the surviving segments are still pruned by it.
+        self.time_range = time_range
+        self.segments_skipped = 0
         self.ctx = ctx
         self.metrics = GridStreamMetrics()
         self._timestamps = np.zeros(0, np.int64)
@@ -77,16 +83,29 @@ class GridStream:
     def _grid_and_append_to_leftovers_in_current_batch(self, segments, tags: Sequence[np.ndarray]):
         # grid_exec.rs:261-391 -- one batched kernel call instead of one grid() per row
         host = segments.to_host() if isinstance(segments, mc.CompressedSegments) else segments
-        point_off, _ = mc.grid_count(host, self.ctx)
-        ts, vals = mc.grid(host, ctx=self.ctx)
+        if self.time_range is not None:
+            lo, hi = self.time_range
+            keep = np.ones(len(host), bool)
+            if lo is not None:
+                keep &= host.end_time >= lo
+            if hi is not None:
+                keep &= host.start_time <= hi
+            if not keep.all():
+                self.segments_skipped += int(len(host) - keep.sum())
+                host = host.take(keep)
+                tags = [np.asarray(t, object)[keep] for t in tags]
+        if len(host) == 0:
+            point_off, ts, vals = np.zeros(1, np.uint64), np.zeros(0, np.int64), np.zeros(0, np.float32)
+        else:
+            point_off, _ = mc.grid_count(host, self.ctx)
+            ts, vals = mc.grid(host, ctx=self.ctx)
         self.metrics.add_batch(host, point_off)
         lens = np.diff(point_off).astype(np.int64)
         new_tags = [np.repeat(np.asarray(t, object), lens) for t in tags]  # each tag value once per created row
         if len(new_tags) != len(self._tags):
             raise ValueError("every batch must carry the same tag columns")
-        if self.predicate is not None:
-            # (the leftovers were filtered when they were created; filtering them again is idempotent)
-            pass
+        # (the leftovers were filtered when they were created; the predicate is a per-row test, so filtering them again
+        # together with the new points changes nothing)
         ts = np.concatenate([self._timestamps[self._offset:], ts])
         vals = np.concatenate([self._values[self._offset:], vals])
         new_tags = [np.concatenate([old[self._offset:], new]) for old, new in zip(self._tags, new_tags)]

@@ -56,6 +56,24 @@ def test_grid_stream_prunes_by_time_after_reconstruction(oracle):
     assert_f32_bits_equal(np.concatenate([b[1] for b in out]), want_val[keep], "filtered values")
 
 
+def test_grid_stream_skips_segments_outside_the_time_range(oracle):
+    """Push-down of the time predicate to whole segments: same output as pruning after reconstruction,
+    but segments that cannot contain a matching point are never reconstructed."""
+    batches, want_ts, want_val, want_tag, _ = _segment_batches(oracle)
+    lo, hi = np.quantile(want_ts, [0.45, 0.55]).astype(np.int64)
+    pred = lambda t, v: (t >= lo) & (t <= hi)  # noqa: E731
+    pruned = ops.GridStream(batches, 4096, n_tag_columns=1, predicate=pred)
+    pushed = ops.GridStream(batches, 4096, n_tag_columns=1, predicate=pred, time_range=(int(lo), int(hi)))
+    a, b = list(pruned), list(pushed)
+    for col in range(3):
+        assert np.array_equal(np.concatenate([x[col] for x in a]), np.concatenate([x[col] for x in b]))
+    assert pushed.segments_skipped > 0
+    assert pushed.metrics.rows_created < pruned.metrics.rows_created
+    # a range that matches nothing: every segment is skipped and the stream is empty
+    nothing = ops.GridStream(batches, 4096, n_tag_columns=1, predicate=lambda t, v: t < 0, time_range=(None, -1))
+    assert list(nothing) == [] or all(len(x[0]) == 0 for x in nothing)
+
+
 def test_model_accumulators_equal_folds_over_rows(oracle):
     batches, want_ts, _, _, segs = _segment_batches(oracle)
     accs = [ops.ModelCountAccumulator(), ops.ModelMinAccumulator(), ops.ModelMaxAccumulator(), ops.ModelSumAccumulator(), ops.ModelAvgAccumulator()]
