@@ -87,6 +87,11 @@ int mdbcu_device_count(void);
 /* Library version as "major.minor.patch". */
 const char *mdbcu_version(void);
 
+/* A context is one GPU and one CUDA stream plus the library's staging memory for it (a pinned bounce ring
+ * for pageable caller memory, cached pinned blocks for host copies of segments, a mapped mailbox for
+ * scalar read-backs).  Calls on one context are blocking and must not overlap: use one context per
+ * host thread; contexts on different threads run concurrently on the device.  Free every
+ * mdbcu_segments created on a context before destroying it. */
 int mdbcu_context_create(int device, mdbcu_context **out);
 void mdbcu_context_destroy(mdbcu_context *ctx);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
