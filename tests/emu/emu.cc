@@ -15,6 +15,11 @@
 #include "../../modelardb_rs_b200/csrc/mdb_compress.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_grid.cuh"
 
+// The warp-cooperative fit (mdb_fit_warp.cuh) on the host: 32 fibers per warp, see warp_emu.h.
+#define MDB_WARP_EMU
+#include "warp_emu.h"
+#include "../../modelardb_rs_b200/csrc/mdb_fit_warp.cuh"
+
 using namespace mdb;
 
 struct EmuSegments {
@@ -24,6 +29,28 @@ struct EmuSegments {
     std::vector<uint64_t> ts_off, val_off, res_off, unit_seg_off;
     std::vector<uint8_t> ts_data, val_data, res_data;
 };
+
+// One chain of one chunk with the chosen engine: 1 = the one-thread fit, 2 = the warp-cooperative fit (every lane runs
+// spec_chain on its own copy of the chunk state, as the lanes of k_spec_chain_warp / k_spec_async do; lane 0's copy is kept).
+static void emu_run_chain(int engine, const ErrorBound &eb, const int64_t *uts, const float *uval, uint32_t n, uint32_t chunk_end,
+                          uint32_t budget, ChunkState &st, FittedModel *lists, uint32_t cap) {
+    if (engine != 2) {
+        ScalarFit fitter(eb, uts, uval, n);
+        spec_chain(fitter, 0u, 1u, n, chunk_end, budget, st, lists, cap);
+        return;
+    }
+    std::vector<double> smem(WarpFit::SMEM_DOUBLES);
+    const ChunkState before = st;
+    ChunkState after = st;
+    warp_emu::run([&](int lane) {
+        ChunkState mine = before;
+        WarpFit fitter(eb, uts, uval, n, smem.data());
+        spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, budget, mine, lists, cap);
+        if (lane == 0) after = mine;
+    });
+    st = after;
+}
+static int g_emu_engine = 1;
 
 // The asynchronous scheduler (k_spec_async + sched_advance) for one unit, single-threaded: up to `in_flight`
 // "workers" hold a claimed chunk at a time, and a seeded generator decides whether the next event is a worker
@@ -52,8 +79,7 @@ static bool emu_unit_async(const ErrorBound &eb, const int64_t *uts, const float
             w.c = c;
             w.s = st[c];
             uint32_t ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
-            ScalarFit fitter(eb, uts, uval, n);
-            spec_chain(fitter, 0u, 1u, n, ce, L, w.s, lists.data() + (size_t)c * 2 * cap, cap); // (new list is unread until published)
+            emu_run_chain(g_emu_engine, eb, uts, uval, n, ce, L, w.s, lists.data() + (size_t)c * 2 * cap, cap); // (new list is unread until published)
             runs++;
             claimed.push_back(w);
         } else {
@@ -119,8 +145,7 @@ EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const ui
                 if (st[c].dirty) {
                     uint32_t cs = c * L, ce = std::min<uint64_t>((uint64_t)(c + 1) * L, n);
                     (void)cs;
-                    ScalarFit fitter(eb, uts, uval, n);
-                    spec_chain(fitter, 0u, 1u, n, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
+                    emu_run_chain(g_emu_engine, eb, uts, uval, n, ce, L, st[c], lists.data() + (size_t)c * 2 * cap, cap);
                 }
             rounds++;
             if (spec_propagate_unit(n, L, C, st.data(), rounds == 1, resume_c, resume_e, [](uint32_t) {}) == 0) break;
@@ -130,7 +155,10 @@ EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const ui
         uint8_t irregular;
         spec_finalize_unit(n, L, C, st.data(), irregular);
         for (uint32_t c = 0; c < C; c++) {
-            const FittedModel *list = lists.data() + ((size_t)c * 2 + st[c].buf) * cap;
+            FittedModel *list = lists.data() + ((size_t)c * 2 + st[c].buf) * cap;
+            if (!st[c].skipped)
+                for (uint32_t k = 0; k < st[c].n_models; k++) // k_swing_finish: the warp engine leaves Swing models pending
+                    if (list[k].pending) swing_finish(list[k], uts, uval);
             uint32_t rows = spec_count_rows(st[c], list);
             size_t base = recs.size();
             recs.resize(base + rows);
@@ -183,6 +211,47 @@ uint64_t emu_check_eight_points(const int64_t *ts, const float *values, uint32_t
         if (stored != fit_reaches_eight_points(eb, ts, values, s, n)) bad++;
     }
     return bad;
+}
+
+// Engine of the chains in emu_compress*: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers.
+void emu_set_engine(int engine) { g_emu_engine = engine; }
+uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
+
+// mdbcu_debug_fit_models on the host: fit_next_model at each start with either engine (records of 40 bytes).
+struct EmuDebugFit {
+    uint32_t start_index, end_index;
+    float min_value, max_value, model_last_value, bytes_per_value;
+    int32_t model_type_id, values_len, aborted, irregular;
+};
+void emu_fit_models(const int64_t *ts, const float *values, uint32_t n, uint8_t eb_kind, float eb_value, int engine, const uint32_t *starts,
+                    const uint32_t *budget_ends, uint32_t n_starts, EmuDebugFit *out) {
+    ErrorBound eb = make_error_bound(eb_kind, eb_value);
+    std::vector<double> smem(WarpFit::SMEM_DOUBLES);
+    for (uint32_t k = 0; k < n_starts; k++) {
+        FittedModel m;
+        bool aborted = false, irregular = false;
+        if (engine == 2) {
+            warp_emu::run([&](int lane) {
+                WarpFit f(eb, ts, values, n, smem.data());
+                f.begin(starts[k]);
+                bool ab = false;
+                FittedModel mm = f.fit(starts[k], budget_ends[k], ab);
+                if (!ab && mm.pending) swing_finish(mm, ts, values);
+                if (lane == 0) { m = mm; aborted = ab; irregular = f.irregular(); }
+            });
+        } else {
+            ScalarFit f(eb, ts, values, n);
+            f.begin(starts[k]);
+            m = f.fit(starts[k], budget_ends[k], aborted);
+            irregular = f.irregular();
+        }
+        EmuDebugFit d;
+        d.start_index = m.start_index; d.end_index = m.end_index;
+        d.min_value = m.min_value; d.max_value = m.max_value; d.model_last_value = m.model_last_value;
+        d.bytes_per_value = m.bytes_per_value;
+        d.model_type_id = m.model_type_id; d.values_len = m.values_len; d.aborted = aborted; d.irregular = irregular;
+        out[k] = d;
+    }
 }
 
 uint64_t emu_segments_len(const EmuSegments *s) { return s->model_type_id.size(); }

@@ -21,7 +21,7 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    deps = [_SRC] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
                                "-x", "c++", _SRC, "-o", _SO])
@@ -33,6 +33,11 @@ def lib():
     L.emu_compress_sched.restype = vp
     L.emu_check_eight_points.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_float]
     L.emu_check_eight_points.restype = u64
+    L.emu_set_engine.argtypes = [C.c_int]
+    L.emu_set_engine.restype = None
+    L.emu_division_mismatches.restype = u64
+    L.emu_fit_models.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_float, C.c_int, vp, vp, C.c_uint32, vp]
+    L.emu_fit_models.restype = None
     L.emu_segments_len.argtypes = [vp]
     L.emu_segments_len.restype = u64
     L.emu_segments_view.argtypes = [vp, C.POINTER(O._View), C.POINTER(vp)]
@@ -54,9 +59,32 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
-def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0) -> O.Segments:
+FIT_RECORD = np.dtype([("start", np.uint32), ("end", np.uint32), ("min", np.uint32), ("max", np.uint32), ("last", np.uint32),
+                       ("bpv", np.uint32), ("type", np.int32), ("vlen", np.int32), ("aborted", np.int32), ("irregular", np.int32)])
+
+
+def fit_models(ts, values, eb, engine, starts, budget_ends):
+    """fit_next_model at each start on the host: engine 1 = the one-thread code, 2 = the warp-cooperative code of
+    mdb_fit_warp.cuh run on 32 fibers (tests/emu/warp_emu.h).  Same records as mdbcu_debug_fit_models."""
+    ts = np.ascontiguousarray(ts, np.int64)
+    vals = np.ascontiguousarray(values, np.float32)
+    starts = np.ascontiguousarray(starts, np.uint32)
+    budget_ends = np.ascontiguousarray(budget_ends, np.uint32)
+    out = np.zeros(len(starts), FIT_RECORD)
+    lib().emu_fit_models(_p(ts), _p(vals), len(ts), eb[0], eb[1], engine, _p(starts), _p(budget_ends), len(starts), _p(out))
+    return out
+
+
+def division_mismatches() -> int:
+    """Emulated fast-path quotients (ddiv_fast*) that differed from the host's a / b so far."""
+    return int(lib().emu_division_mismatches())
+
+
+def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0, engine=1) -> O.Segments:
     """sched_seed == 0: the round scheme; otherwise the asynchronous scheduler stepped in a seeded random order with
-    `in_flight` concurrent workers (rounds then receives the largest number of chain runs of any unit)."""
+    `in_flight` concurrent workers (rounds then receives the largest number of chain runs of any unit).
+    engine: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers."""
+    lib().emu_set_engine(engine)
     ts = np.ascontiguousarray(ts, np.int64)
     vals = np.ascontiguousarray(values, np.float32)
     if unit_off is None:

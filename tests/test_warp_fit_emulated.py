@@ -1,0 +1,40 @@
+"""The warp-cooperative fit engine (modelardb_rs_b200/csrc/mdb_fit_warp.cuh) run on the HOST: the 32 lanes of a warp are
+32 cooperative fibers and every warp primitive is a rendezvous (tests/emu/warp_emu.h).  A debugging harness for the
+GPU-less build container -- the same comparisons run on the device in tests/test_gpu_fit_engines.py -- that lets changes to
+the engine be checked here before GPU time is spent: model by model against the one-thread fit, and through the whole
+chunked compress (rounds and asynchronous scheduler, skip_rejected included) against the oracle."""
+import numpy as np
+import pytest
+
+from tests import emu_lib as emu
+from tests.parity_cases import assert_segments_equal, small_cases
+
+CASES = [c for c in small_cases() if len(c[3]) == 2]  # single-unit cases
+FIELDS = ("start", "end", "min", "max", "last", "bpv", "type", "vlen", "irregular")
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_emulated_warp_fit_equals_thread_fit(case):
+    name, ts, vals, off, ebs = case
+    n = len(ts)
+    rng = np.random.default_rng(3)
+    starts = np.unique(np.concatenate([np.arange(0, min(n, 48)), rng.integers(0, n, 60), np.arange(max(0, n - 20), n)])).astype(np.uint32)
+    for budget in (None, 40, 300):
+        be = np.full(len(starts), n, np.uint32) if budget is None else np.minimum(starts + budget, n).astype(np.uint32)
+        a = emu.fit_models(ts, vals, ebs[0], 1, starts, be)
+        b = emu.fit_models(ts, vals, ebs[0], 2, starts, be)
+        assert np.array_equal(a["aborted"], b["aborted"]), (name, budget)
+        ok = a["aborted"] == 0
+        for f in FIELDS:
+            bad = np.flatnonzero(ok & (a[f] != b[f]))
+            assert len(bad) == 0, f"{name} budget={budget}: {f} differs at starts {starts[bad[:5]]}: {a[bad[:3]]} vs {b[bad[:3]]}"
+    assert emu.division_mismatches() == 0  # the branch-free division sequence returned a / b every time
+
+
+@pytest.mark.parametrize("chunk_len,sched", [(64, (0, 0)), (1000, (5, 3))], ids=["rounds-64", "async-1000"])
+@pytest.mark.parametrize("case", [c for c in small_cases() if len(c[1]) <= 8000], ids=lambda c: c[0])
+def test_emulated_warp_engine_compress_matches_oracle(oracle, case, chunk_len, sched):
+    name, ts, vals, off, ebs = case
+    want = oracle.compress(ts, vals, off, eb=ebs)
+    got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2)
+    assert_segments_equal(got, want, f"{name} chunk_len={chunk_len} sched={sched}")
