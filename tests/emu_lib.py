@@ -59,11 +59,32 @@ def _p(a):
     return a.ctypes.data_as(C.c_void_p)
 
 
+_variants = {}
+
+
+def variant(*defines):
+    """A separate build of emu.cc with extra -D flags (e.g. "MDB_FIT_WIDE_ENABLED=1"); only emu_fit_models is bound."""
+    key = tuple(defines)
+    if key not in _variants:
+        lib()  # (builds the default library first, so compile errors show up there)
+        so = os.path.join(_HERE, "emu", "libmdb_emu_" + "_".join(d.replace("=", "-") for d in defines) + ".so")
+        deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+        if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math"] +
+                                  ["-D" + d for d in defines] + ["-x", "c++", _SRC, "-o", so])
+        L = C.CDLL(so)
+        L.emu_fit_models.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
+        L.emu_fit_models.restype = None
+        L.emu_division_mismatches.restype = C.c_uint64
+        _variants[key] = L
+    return _variants[key]
+
+
 FIT_RECORD = np.dtype([("start", np.uint32), ("end", np.uint32), ("min", np.uint32), ("max", np.uint32), ("last", np.uint32),
                        ("bpv", np.uint32), ("type", np.int32), ("vlen", np.int32), ("aborted", np.int32), ("irregular", np.int32)])
 
 
-def fit_models(ts, values, eb, engine, starts, budget_ends):
+def fit_models(ts, values, eb, engine, starts, budget_ends, library=None):
     """fit_next_model at each start on the host: engine 1 = the one-thread code, 2 = the warp-cooperative code of
     mdb_fit_warp.cuh run on 32 fibers (tests/emu/warp_emu.h).  Same records as mdbcu_debug_fit_models."""
     ts = np.ascontiguousarray(ts, np.int64)
@@ -71,7 +92,7 @@ def fit_models(ts, values, eb, engine, starts, budget_ends):
     starts = np.ascontiguousarray(starts, np.uint32)
     budget_ends = np.ascontiguousarray(budget_ends, np.uint32)
     out = np.zeros(len(starts), FIT_RECORD)
-    lib().emu_fit_models(_p(ts), _p(vals), len(ts), eb[0], eb[1], engine, _p(starts), _p(budget_ends), len(starts), _p(out))
+    (library or lib()).emu_fit_models(_p(ts), _p(vals), len(ts), eb[0], eb[1], engine, _p(starts), _p(budget_ends), len(starts), _p(out))
     return out
 
 

@@ -7,7 +7,7 @@ import pytest
 
 from modelardb_rs_b200 import _native
 from modelardb_rs_b200 import compression as mc
-from tests.parity_cases import small_cases
+from tests.parity_cases import long_model_cases, small_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -48,51 +48,7 @@ def test_warp_fit_equals_thread_fit_at_every_start(case):
 
 # ---- long models: the wide steps of the warp engine (mdb_fit_warp.cuh) --------------------------------------------
 
-def _long_cases():
-    n = 20_000
-    i = np.arange(n)
-    rng = np.random.default_rng(42)
-    ts = (1_600_000_000_000_000 + 1000 * i).astype(np.int64)
-    noise = rng.standard_normal(n)
-    cases = []
-
-    def add(name, vals, ebs, t=ts):
-        for eb in ebs:
-            cases.append((f"{name}-eb{eb[0]}:{eb[1]}", t, np.asarray(vals, np.float32), eb))
-
-    add("constant", np.full(n, 100.0), [(0, 0.0), (1, 0.5), (2, 1.0)])
-    add("constant-noise", 100.0 + 0.1 * noise, [(1, 1.0), (2, 1.0), (2, 0.2)])
-    # PMC-Mean's relative test at assorted bounds, values scattered right around each bound
-    for pct in (1e-4, 0.37, 3.0, 33.3, 100.0):
-        add(f"around-{pct}pct", 250.0 * (1.0 + (pct / 100.0) * 0.9 * np.clip(noise, -1.3, 1.3)), [(2, pct)])
-        add(f"negative-around-{pct}pct", -0.004 * (1.0 + (pct / 100.0) * 0.9 * np.clip(noise, -1.3, 1.3)), [(2, pct)])
-    add("slow-ramp", 100.0 + 0.001 * i + 0.01 * noise, [(1, 0.1), (2, 0.05), (2, 1.0)])
-    add("steps", np.where(i < 9_000, 100.0, 150.0) + 0.05 * noise, [(1, 1.0), (2, 1.0)])
-    add("zeros", np.zeros(n), [(0, 0.0), (1, 0.5), (2, 1.0)])
-    add("signed-zeros", np.where(i % 3 == 0, -0.0, 0.0), [(0, 0.0), (1, 0.5), (2, 1.0)])
-    add("zero-touching", np.maximum(0.0, 0.5 * np.sin(i / 900.0)), [(1, 1.0), (2, 10.0)])
-    add("sign-change", -5.0 + 10.0 * i / n, [(1, 10.0), (1, 0.01), (2, 5.0)])
-    t_irr = ts.copy()
-    t_irr[7_000:] += 137
-    add("late-irregular", 100.0 + 0.05 * noise, [(1, 1.0), (2, 1.0)], t_irr)
-    v = 100.0 + 0.05 * noise
-    v_nan = v.copy(); v_nan[9_000] = np.nan
-    v_inf = v.copy(); v_inf[9_001] = np.inf
-    add("nan-inside", v_nan, [(1, 1.0), (2, 1.0)])
-    add("inf-inside", v_inf, [(1, 1.0), (2, 1.0)])
-    add("huge", np.full(n, 1e30) * (1.0 + 1e-4 * noise), [(2, 1.0), (1, 1e28)])
-    add("tiny", np.full(n, 1e-35) * (1.0 + 1e-3 * noise), [(2, 1.0), (1, 1e-36)])
-    add("subnormal", np.full(n, 1e-41) * (1.0 + 1e-2 * noise), [(2, 5.0), (1, 1e-42)])
-    add("wide-exponents", np.where(i % 2 == 0, 1e10, 1e-10), [(1, 1e11)])
-    for hi in (101.9, 102.0, 102.02, 102.05, 102.5):  # PMC-Mean close to a 1 % relative bound from either side
-        add(f"alternating-{hi}", np.where(i % 2 == 0, 100.0, hi), [(2, 1.0)])
-    for amp in (0.45, 0.5, 0.55):  # Swing close to an absolute bound of 0.5 around a line
-        add(f"sawtooth-{amp}", 10.0 + 0.002 * i + amp * np.where(i % 2 == 0, 1.0, -1.0), [(1, 0.5)])
-    add("plateau-then-noise", np.where(i < 12_345, 42.0, 42.0 + 5.0 * noise), [(0, 0.0), (2, 1.0)])
-    return cases
-
-
-LONG_CASES = _long_cases()
+LONG_CASES = long_model_cases()
 
 
 @pytest.mark.parametrize("case", LONG_CASES, ids=[c[0] for c in LONG_CASES])

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from tests import emu_lib as emu
-from tests.parity_cases import assert_segments_equal, small_cases
+from tests.parity_cases import assert_segments_equal, long_model_cases, small_cases
 
 CASES = [c for c in small_cases() if len(c[3]) == 2]  # single-unit cases
 FIELDS = ("start", "end", "min", "max", "last", "bpv", "type", "vlen", "irregular")
@@ -38,3 +38,22 @@ def test_emulated_warp_engine_compress_matches_oracle(oracle, case, chunk_len, s
     want = oracle.compress(ts, vals, off, eb=ebs)
     got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2)
     assert_segments_equal(got, want, f"{name} chunk_len={chunk_len} sched={sched}")
+
+
+def test_emulated_wide_steps_equal_thread_fit():
+    """The optional wide steps (512 points at once inside long models, compiled out of the product by default:
+    MDB_FIT_WIDE_ENABLED) stay exact: a build with them enabled against the one-thread fit on the long-model series."""
+    wide = emu.variant("MDB_FIT_WIDE_ENABLED=1")
+    for name, ts, vals, eb in long_model_cases():
+        ts, vals = np.ascontiguousarray(ts[:6000]), np.ascontiguousarray(vals[:6000])
+        n = len(ts)
+        starts = np.array([0, 1, 5, 100, 2999, 3000, 4000, 5000, 5990], np.uint32)
+        for budget in (None, 700):
+            be = np.full(len(starts), n, np.uint32) if budget is None else np.minimum(starts + budget, n).astype(np.uint32)
+            a = emu.fit_models(ts, vals, eb, 1, starts, be, library=wide)
+            b = emu.fit_models(ts, vals, eb, 2, starts, be, library=wide)
+            assert np.array_equal(a["aborted"], b["aborted"]), (name, budget)
+            ok = a["aborted"] == 0
+            for f in FIELDS:
+                assert np.array_equal(a[f][ok], b[f][ok]), (name, budget, f)
+    assert wide.emu_division_mismatches() == 0
