@@ -57,3 +57,42 @@ def test_emulated_wide_steps_equal_thread_fit():
             for f in FIELDS:
                 assert np.array_equal(a[f][ok], b[f][ok]), (name, budget, f)
     assert wide.emu_division_mismatches() == 0
+
+
+def _fuzz_series(rng):
+    """A short series stitched from constants, ramps, noise, repeats of one value, signed zeros and special values."""
+    parts = []
+    for _ in range(int(rng.integers(2, 7))):
+        kind = int(rng.integers(0, 7))
+        m = int(rng.integers(1, 400))
+        scale = float(10.0 ** rng.integers(-3, 6))
+        if kind == 0:
+            parts.append(np.full(m, rng.normal() * scale))
+        elif kind == 1:
+            parts.append(rng.normal() * scale + rng.normal() * scale * 1e-3 * np.arange(m))
+        elif kind == 2:
+            parts.append(rng.normal() * scale + rng.standard_normal(m) * scale * 10.0 ** rng.integers(-4, 0))
+        elif kind == 3:
+            parts.append(np.repeat(rng.standard_normal(max(1, m // 9)) * scale, 9)[:m])
+        elif kind == 4:
+            parts.append(np.where(rng.random(m) < 0.5, 0.0, -0.0))
+        elif kind == 5:
+            parts.append(rng.choice([np.nan, np.inf, -np.inf, 1.0, 3.4e38, -3.4e38, 1e-45], m))
+        else:
+            parts.append(np.cumsum(rng.standard_normal(m)) * scale)
+    return np.concatenate(parts).astype(np.float32)
+
+
+@pytest.mark.parametrize("seed", range(64))
+def test_emulated_warp_engine_fuzz(oracle, seed):
+    """Random stitched series, random bounds, regular or irregular timestamps: the warp engine's compress (asynchronous
+    scheduler, random interleaving) is the oracle's, column for column."""
+    rng = np.random.default_rng(1000 + seed)
+    vals = _fuzz_series(rng)
+    n = len(vals)
+    step = rng.integers(1, 2000, n) if seed % 3 == 0 else np.full(n, int(rng.integers(1, 5000)))
+    ts = (int(rng.integers(0, 2_000_000_000_000_000)) + np.cumsum(step)).astype(np.int64)
+    eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 3))), (2, float(rng.choice([0.01, 0.5, 1.0, 5.0, 30.0, 100.0])))][seed % 3 if seed % 5 else 0]
+    want = oracle.compress(ts, vals, eb=eb)
+    got = emu.compress(ts, vals, eb=eb, chunk_len=int(rng.choice([8, 100, 700])), sched_seed=seed + 1, in_flight=int(rng.choice([1, 2, 9])), engine=2)
+    assert_segments_equal(got, want, f"fuzz seed={seed} eb={eb} n={n}")
