@@ -1,0 +1,344 @@
+// modelardb_cuda.hpp -- C++ host side above the C-ABI (modelardb_cuda.h), mirroring the reference's own interfaces
+// for the hot path: same names, argument meaning and error behaviour as the Rust functions they stand in for.
+//
+//   modelardb_compression (crates/modelardb_compression/src/lib.rs:26-34)
+//     ErrorBound                                    crates/modelardb_types/src/types.rs:299-335
+//     try_compress_univariate_time_series           compression.rs:191-275
+//     try_split_and_compress_univariate_time_series compression.rs:147-179   (batch form: many units, one call)
+//     len / sum / grid                              models/mod.rs:98-124 / 129-184 / 190-251
+//   query operators
+//     GridStream                                    crates/modelardb_storage/src/query/grid_exec.rs:197-430
+//     Model{Count,Min,Max,Sum,Avg}Accumulator       crates/modelardb_storage/src/optimizer/model_simple_aggregates.rs:336-618
+//
+// The reference is Rust and its toolchain is not in this image, so the host side is C++ (the Python package under
+// modelardb_rs_b200/ is the same mirror for the tests and the benchmark).  Header only; link libmodelardb_cuda.so.
+// Every function forwards to the CUDA library: there is no CPU implementation here either.
+#pragma once
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "modelardb_cuda.h"
+
+namespace modelardb_cuda {
+
+// ModelarDbCompressionError::InvalidArgument and friends (crates/modelardb_compression/src/error.rs): one exception type,
+// carrying the library's last error message.
+class Error : public std::runtime_error {
+public:
+    using std::runtime_error::runtime_error;
+};
+
+inline void check(int rc) {
+    if (rc != MDBCU_SUCCESS) throw Error(mdbcu_last_error());
+}
+
+// crates/modelardb_types/src/types.rs:299-335
+class ErrorBound {
+public:
+    static ErrorBound lossless() { return ErrorBound(MDBCU_LOSSLESS, 0.0f); }
+    static ErrorBound try_new_absolute(float value) {
+        if (!(value > 0.0f) || !std::isfinite(value)) throw Error("An absolute error bound must be a positive finite value.");
+        return ErrorBound(MDBCU_ABSOLUTE, value);
+    }
+    static ErrorBound try_new_relative(float percentage) {
+        if (!(percentage > 0.0f && percentage <= 100.0f)) throw Error("A relative error bound must be a positive value that is at most 100.0%.");
+        return ErrorBound(MDBCU_RELATIVE, percentage);
+    }
+    uint8_t kind() const { return kind_; }
+    float value() const { return value_; }
+
+private:
+    ErrorBound(uint8_t kind, float value) : kind_(kind), value_(value) {}
+    uint8_t kind_;
+    float value_;
+};
+
+// One GPU, one stream.  Calls on a context are blocking; use one context per host thread.
+class Context {
+public:
+    explicit Context(int device = 0) { check(mdbcu_context_create(device, &ctx_)); }
+    ~Context() { mdbcu_context_destroy(ctx_); }
+    Context(const Context &) = delete;
+    Context &operator=(const Context &) = delete;
+    mdbcu_context *get() const { return ctx_; }
+
+private:
+    mdbcu_context *ctx_ = nullptr;
+};
+
+// The columns of QUERY_COMPRESSED_SCHEMA (crates/modelardb_types/src/schemas.rs:40-52) for a batch of segments; the
+// three binary columns as offsets + bytes.  `error` is constant NaN and field_column / tags are per-batch constants
+// (types.rs:492-516), so they are not materialised.
+struct CompressedSegmentBatch {
+    std::vector<int8_t> model_type_ids;
+    std::vector<int64_t> start_times, end_times;
+    std::vector<float> min_values, max_values;
+    std::vector<uint64_t> timestamps_off{0}, values_off{0}, residuals_off{0};
+    std::vector<uint8_t> timestamps, values, residuals;
+
+    size_t num_rows() const { return model_type_ids.size(); }
+    mdbcu_segments_view view() const {
+        mdbcu_segments_view v;
+        v.n_segments = num_rows();
+        v.model_type_id = model_type_ids.data();
+        v.start_time = start_times.data();
+        v.end_time = end_times.data();
+        v.min_value = min_values.data();
+        v.max_value = max_values.data();
+        v.timestamps_off = timestamps_off.data();
+        v.timestamps_data = timestamps.data();
+        v.values_off = values_off.data();
+        v.values_data = values.data();
+        v.residuals_off = residuals_off.data();
+        v.residuals_data = residuals.data();
+        return v;
+    }
+    // Rows [lo, hi) as an independent batch.
+    CompressedSegmentBatch slice(size_t lo, size_t hi) const {
+        CompressedSegmentBatch out;
+        out.model_type_ids.assign(model_type_ids.begin() + lo, model_type_ids.begin() + hi);
+        out.start_times.assign(start_times.begin() + lo, start_times.begin() + hi);
+        out.end_times.assign(end_times.begin() + lo, end_times.begin() + hi);
+        out.min_values.assign(min_values.begin() + lo, min_values.begin() + hi);
+        out.max_values.assign(max_values.begin() + lo, max_values.begin() + hi);
+        auto cut = [&](const std::vector<uint64_t> &off, const std::vector<uint8_t> &data, std::vector<uint64_t> &o, std::vector<uint8_t> &d) {
+            o.clear();
+            for (size_t r = lo; r <= hi; r++) o.push_back(off[r] - off[lo]);
+            d.assign(data.begin() + off[lo], data.begin() + off[hi]);
+        };
+        cut(timestamps_off, timestamps, out.timestamps_off, out.timestamps);
+        cut(values_off, values, out.values_off, out.values);
+        cut(residuals_off, residuals, out.residuals_off, out.residuals);
+        return out;
+    }
+};
+
+namespace detail {
+inline CompressedSegmentBatch copy_out(mdbcu_segments *segments, uint64_t n_units, std::vector<uint64_t> *unit_seg_off) {
+    mdbcu_segments_view v;
+    const uint64_t *uso = nullptr;
+    int rc = mdbcu_segments_get(segments, MDBCU_HOST, &v, &uso);
+    CompressedSegmentBatch out;
+    if (rc == MDBCU_SUCCESS) {
+        const uint64_t s = v.n_segments;
+        out.model_type_ids.assign(v.model_type_id, v.model_type_id + s);
+        out.start_times.assign(v.start_time, v.start_time + s);
+        out.end_times.assign(v.end_time, v.end_time + s);
+        out.min_values.assign(v.min_value, v.min_value + s);
+        out.max_values.assign(v.max_value, v.max_value + s);
+        out.timestamps_off.assign(v.timestamps_off, v.timestamps_off + s + 1);
+        out.values_off.assign(v.values_off, v.values_off + s + 1);
+        out.residuals_off.assign(v.residuals_off, v.residuals_off + s + 1);
+        out.timestamps.assign(v.timestamps_data, v.timestamps_data + out.timestamps_off[s]);
+        out.values.assign(v.values_data, v.values_data + out.values_off[s]);
+        out.residuals.assign(v.residuals_data, v.residuals_data + out.residuals_off[s]);
+        if (unit_seg_off) unit_seg_off->assign(uso, uso + n_units + 1);
+    }
+    mdbcu_segments_free(segments);
+    check(rc);
+    return out;
+}
+} // namespace detail
+
+// compression.rs:191-275.  Different lengths -> InvalidArgument (:202-206); empty input -> empty batch (:208-211).
+inline CompressedSegmentBatch try_compress_univariate_time_series(Context &ctx, const std::vector<int64_t> &uncompressed_timestamps,
+                                                                  const std::vector<float> &uncompressed_values, ErrorBound error_bound) {
+    if (uncompressed_timestamps.size() != uncompressed_values.size())
+        throw Error("Uncompressed timestamps and uncompressed values have different lengths.");
+    const uint64_t unit_off[2] = {0, uncompressed_timestamps.size()};
+    const uint8_t kind = error_bound.kind();
+    const float value = error_bound.value();
+    mdbcu_segments *segments = nullptr;
+    check(mdbcu_compress(ctx.get(), MDBCU_HOST, uncompressed_timestamps.data(), uncompressed_values.data(), unit_off, 1, &kind, &value, &segments));
+    return detail::copy_out(segments, 1, nullptr);
+}
+
+// The batch form behind try_split_and_compress_univariate_time_series (compression.rs:147-179) and the server's
+// compressor (uncompressed_data_manager.rs:563-581): unit u is [unit_off[u], unit_off[u+1]) of the two arrays, with
+// its own bound; rows come back ordered by unit, unit_seg_off (optional) gives the rows of each unit.
+inline CompressedSegmentBatch try_compress_time_series_batch(Context &ctx, const std::vector<int64_t> &timestamps, const std::vector<float> &values,
+                                                             const std::vector<uint64_t> &unit_off, const std::vector<ErrorBound> &error_bounds,
+                                                             std::vector<uint64_t> *unit_seg_off = nullptr) {
+    if (timestamps.size() != values.size()) throw Error("Uncompressed timestamps and uncompressed values have different lengths.");
+    if (unit_off.empty() || unit_off.size() - 1 != error_bounds.size()) throw Error("One error bound per unit is required.");
+    if (unit_off.back() > timestamps.size()) throw Error("unit_off exceeds the number of data points.");
+    std::vector<uint8_t> kinds;
+    std::vector<float> bounds;
+    for (const ErrorBound &eb : error_bounds) {
+        kinds.push_back(eb.kind());
+        bounds.push_back(eb.value());
+    }
+    mdbcu_segments *segments = nullptr;
+    check(mdbcu_compress(ctx.get(), MDBCU_HOST, timestamps.data(), values.data(), unit_off.data(), error_bounds.size(), kinds.data(), bounds.data(),
+                         &segments));
+    return detail::copy_out(segments, error_bounds.size(), unit_seg_off);
+}
+
+// models/mod.rs:98-124 for every row of a batch, as an exclusive prefix sum (point_off[i+1] - point_off[i] = len of row i).
+inline std::vector<uint64_t> len(Context &ctx, const CompressedSegmentBatch &batch) {
+    std::vector<uint64_t> point_off(batch.num_rows() + 1, 0);
+    uint64_t total = 0;
+    const mdbcu_segments_view v = batch.view();
+    check(mdbcu_grid_count(ctx.get(), MDBCU_HOST, &v, point_off.data(), &total));
+    return point_off;
+}
+
+// models/mod.rs:129-184 for every row of a batch.
+inline std::vector<float> sum(Context &ctx, const CompressedSegmentBatch &batch) {
+    std::vector<float> sums(batch.num_rows());
+    const mdbcu_segments_view v = batch.view();
+    check(mdbcu_segment_sums(ctx.get(), MDBCU_HOST, &v, sums.data()));
+    return sums;
+}
+
+// models/mod.rs:190-251 for every row of a batch: APPENDS to the two builders like the reference does.
+inline void grid(Context &ctx, const CompressedSegmentBatch &batch, std::vector<int64_t> &timestamp_builder, std::vector<float> &value_builder,
+                 std::vector<uint64_t> *point_off_out = nullptr) {
+    std::vector<uint64_t> point_off = len(ctx, batch);
+    const uint64_t total = point_off.back(), before = timestamp_builder.size();
+    timestamp_builder.resize(before + total);
+    value_builder.resize(before + total);
+    uint64_t n = 0;
+    const mdbcu_segments_view v = batch.view();
+    check(mdbcu_grid(ctx.get(), MDBCU_HOST, &v, timestamp_builder.data() + before, value_builder.data() + before, total, &n));
+    if (point_off_out) *point_off_out = std::move(point_off);
+}
+
+// grid_exec.rs:197-430: leftovers of the current batch + the points of the next segment batch, handed out in slices
+// of batch_size rows; `tags` of a segment batch (one value per row and tag column) are repeated for every created row.
+class GridStream {
+public:
+    struct Batch {
+        std::vector<int64_t> timestamps;
+        std::vector<float> values;
+        std::vector<std::vector<std::string>> tags; // one vector per tag column
+    };
+    using Input = std::pair<CompressedSegmentBatch, std::vector<std::vector<std::string>>>; // (segments, tag columns)
+
+    GridStream(Context &ctx, std::vector<Input> input, size_t batch_size, size_t n_tag_columns = 0)
+        : ctx_(ctx), input_(std::move(input)), batch_size_(batch_size), current_{{}, {}, std::vector<std::vector<std::string>>(n_tag_columns)} {}
+
+    // Poll::Ready(Some(batch)) -> true (the batch may be empty, as in the reference); Poll::Ready(None) -> false.
+    bool poll_next(Batch &out) {
+        if (current_.timestamps.size() - offset_ < batch_size_ && next_input_ < input_.size()) grid_and_append_to_leftovers_in_current_batch(input_[next_input_++]);
+        if (next_input_ >= input_.size() && offset_ >= current_.timestamps.size()) return false;
+        const size_t length = std::min(batch_size_, current_.timestamps.size() - offset_);
+        out.timestamps.assign(current_.timestamps.begin() + offset_, current_.timestamps.begin() + offset_ + length);
+        out.values.assign(current_.values.begin() + offset_, current_.values.begin() + offset_ + length);
+        out.tags.assign(current_.tags.size(), {});
+        for (size_t c = 0; c < current_.tags.size(); c++) out.tags[c].assign(current_.tags[c].begin() + offset_, current_.tags[c].begin() + offset_ + length);
+        offset_ += length;
+        return true;
+    }
+
+private:
+    void grid_and_append_to_leftovers_in_current_batch(const Input &in) { // grid_exec.rs:261-391
+        Batch next;
+        next.timestamps.assign(current_.timestamps.begin() + offset_, current_.timestamps.end());
+        next.values.assign(current_.values.begin() + offset_, current_.values.end());
+        next.tags.resize(current_.tags.size());
+        for (size_t c = 0; c < current_.tags.size(); c++) next.tags[c].assign(current_.tags[c].begin() + offset_, current_.tags[c].end());
+        std::vector<uint64_t> point_off;
+        grid(ctx_, in.first, next.timestamps, next.values, &point_off);
+        if (in.second.size() != next.tags.size()) throw Error("every segment batch must carry the same tag columns");
+        for (size_t c = 0; c < next.tags.size(); c++)
+            for (size_t row = 0; row < in.first.num_rows(); row++)
+                next.tags[c].insert(next.tags[c].end(), point_off[row + 1] - point_off[row], in.second[c][row]);
+        current_ = std::move(next);
+        offset_ = 0;
+    }
+
+    Context &ctx_;
+    std::vector<Input> input_;
+    size_t next_input_ = 0, batch_size_, offset_ = 0;
+    Batch current_;
+};
+
+// model_simple_aggregates.rs:336-618: update_batch folds a segment batch into the state, state() returns it and resets.
+// (merge_batch / evaluate are unreachable!() on the model accumulators and are not provided.)
+namespace detail {
+struct BatchAggregate {
+    int64_t count;
+    float min, max;
+    double sum;
+};
+inline BatchAggregate aggregate(Context &ctx, const CompressedSegmentBatch &batch) {
+    BatchAggregate a{0, std::numeric_limits<float>::max(), std::numeric_limits<float>::lowest(), 0.0};
+    if (batch.num_rows() == 0) return a;
+    const mdbcu_segments_view v = batch.view();
+    check(mdbcu_aggregate(ctx.get(), MDBCU_HOST, &v, nullptr, 1, &a.count, &a.min, &a.max, &a.sum));
+    return a;
+}
+// Value::min / Value::max of Rust: NaN-ignoring, the receiver wins ties
+inline float rust_min(float a, float b) { return a != a ? b : (b < a ? b : a); }
+inline float rust_max(float a, float b) { return a != a ? b : (b > a ? b : a); }
+} // namespace detail
+
+class ModelCountAccumulator {
+public:
+    explicit ModelCountAccumulator(Context &ctx) : ctx_(ctx) {}
+    void update_batch(const CompressedSegmentBatch &batch) { count_ += detail::aggregate(ctx_, batch).count; }
+    int64_t state() { return std::exchange(count_, 0); }
+
+private:
+    Context &ctx_;
+    int64_t count_ = 0;
+};
+
+class ModelMinAccumulator {
+public:
+    explicit ModelMinAccumulator(Context &ctx) : ctx_(ctx) {}
+    void update_batch(const CompressedSegmentBatch &batch) { min_ = detail::rust_min(min_, detail::aggregate(ctx_, batch).min); }
+    float state() { return std::exchange(min_, std::numeric_limits<float>::max()); }
+
+private:
+    Context &ctx_;
+    float min_ = std::numeric_limits<float>::max();
+};
+
+class ModelMaxAccumulator {
+public:
+    explicit ModelMaxAccumulator(Context &ctx) : ctx_(ctx) {}
+    void update_batch(const CompressedSegmentBatch &batch) { max_ = detail::rust_max(max_, detail::aggregate(ctx_, batch).max); }
+    float state() { return std::exchange(max_, std::numeric_limits<float>::lowest()); }
+
+private:
+    Context &ctx_;
+    float max_ = std::numeric_limits<float>::lowest();
+};
+
+class ModelSumAccumulator {
+public:
+    explicit ModelSumAccumulator(Context &ctx) : ctx_(ctx) {}
+    void update_batch(const CompressedSegmentBatch &batch) { sum_ += detail::aggregate(ctx_, batch).sum; }
+    double state() { return std::exchange(sum_, 0.0); }
+
+private:
+    Context &ctx_;
+    double sum_ = 0.0;
+};
+
+class ModelAvgAccumulator {
+public:
+    explicit ModelAvgAccumulator(Context &ctx) : ctx_(ctx) {}
+    void update_batch(const CompressedSegmentBatch &batch) {
+        const detail::BatchAggregate a = detail::aggregate(ctx_, batch);
+        sum_ += a.sum;
+        count_ += (uint64_t)a.count;
+    }
+    std::pair<uint64_t, double> state() { return {std::exchange(count_, 0), std::exchange(sum_, 0.0)}; } // (count, sum)
+
+private:
+    Context &ctx_;
+    double sum_ = 0.0;
+    uint64_t count_ = 0;
+};
+
+} // namespace modelardb_cuda

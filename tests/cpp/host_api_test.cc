@@ -1,0 +1,166 @@
+// host_api_test.cc -- the C++ host layer (include/modelardb_cuda.hpp) against the CPU oracle (oracle/mdb_oracle.h) on
+// the same inputs.  Test infrastructure: built and run by tests/test_gpu_cpp_host_api.py on a machine with a GPU.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/modelardb_cuda.hpp"
+#include "../../oracle/mdb_oracle.h"
+
+namespace mc = modelardb_cuda;
+
+static int g_checks = 0, g_failures = 0;
+#define CHECK(cond, what)                                                             \
+    do {                                                                              \
+        g_checks++;                                                                   \
+        if (!(cond)) {                                                                \
+            g_failures++;                                                             \
+            std::printf("FAILED %s:%d: %s (%s)\n", __FILE__, __LINE__, #cond, what);  \
+        }                                                                             \
+    } while (0)
+
+template <typename T> static bool same_bytes(const std::vector<T> &a, const T *b, size_t n) {
+    return a.size() == n && (n == 0 || std::memcmp(a.data(), b, n * sizeof(T)) == 0);
+}
+
+static bool equals_oracle(const mc::CompressedSegmentBatch &got, const mdbo_segments_view &want) {
+    const size_t s = want.n_segments;
+    return got.num_rows() == s && same_bytes(got.model_type_ids, want.model_type_id, s) && same_bytes(got.start_times, want.start_time, s) &&
+           same_bytes(got.end_times, want.end_time, s) && same_bytes(got.min_values, want.min_value, s) &&
+           same_bytes(got.max_values, want.max_value, s) && same_bytes(got.timestamps_off, want.timestamps_off, s + 1) &&
+           same_bytes(got.values_off, want.values_off, s + 1) && same_bytes(got.residuals_off, want.residuals_off, s + 1) &&
+           same_bytes(got.timestamps, want.timestamps_data, want.timestamps_off[s]) && same_bytes(got.values, want.values_data, want.values_off[s]) &&
+           same_bytes(got.residuals, want.residuals_data, want.residuals_off[s]);
+}
+
+int main() {
+    std::mt19937 rng(7);
+    std::normal_distribution<double> noise(0.0, 0.1);
+    std::uniform_real_distribution<float> uniform(-1e3f, 1e3f);
+    const size_t n = 20000;
+    std::vector<int64_t> ts(3 * n);
+    std::vector<float> values(3 * n);
+    for (size_t i = 0; i < n; i++) {
+        ts[i] = ts[n + i] = ts[2 * n + i] = 1600000000000000LL + 1000LL * (int64_t)i;
+        values[i] = (float)(100.0 + 10.0 * std::sin(2.0 * M_PI * (double)i / 1000.0) + noise(rng)); // models
+        values[n + i] = uniform(rng);                                                                // one MacaqueV row
+        values[2 * n + i] = 42.5f;                                                                   // one PMC-Mean model
+    }
+    const std::vector<uint64_t> unit_off = {0, n, 2 * n, 3 * n};
+    const std::vector<mc::ErrorBound> bounds = {mc::ErrorBound::try_new_relative(1.0f), mc::ErrorBound::lossless(),
+                                                mc::ErrorBound::try_new_absolute(0.5f)};
+    const uint8_t kinds[3] = {MDBCU_RELATIVE, MDBCU_LOSSLESS, MDBCU_ABSOLUTE};
+    const float eb_values[3] = {1.0f, 0.0f, 0.5f};
+
+    mc::Context ctx(0);
+
+    // ---- the batch form against the oracle
+    std::vector<uint64_t> unit_seg_off, want_uso(4);
+    const mc::CompressedSegmentBatch batch = mc::try_compress_time_series_batch(ctx, ts, values, unit_off, bounds, &unit_seg_off);
+    mdbo_segments *oracle_segments = mdbo_compress(ts.data(), values.data(), unit_off.data(), 3, kinds, eb_values, 4, want_uso.data());
+    mdbo_segments_view want;
+    mdbo_segments_view_get(oracle_segments, &want);
+    CHECK(equals_oracle(batch, want), "batch compress: every column bit-identical");
+    CHECK(unit_seg_off == want_uso, "rows of each unit");
+
+    // ---- one series at a time (compression.rs:191-275)
+    for (int u = 0; u < 3; u++) {
+        const std::vector<int64_t> uts(ts.begin() + u * n, ts.begin() + (u + 1) * n);
+        const std::vector<float> uval(values.begin() + u * n, values.begin() + (u + 1) * n);
+        const mc::CompressedSegmentBatch one = mc::try_compress_univariate_time_series(ctx, uts, uval, bounds[u]);
+        const mc::CompressedSegmentBatch expected = batch.slice(unit_seg_off[u], unit_seg_off[u + 1]);
+        CHECK(one.num_rows() == expected.num_rows() && one.values == expected.values && one.timestamps == expected.timestamps &&
+                  one.residuals == expected.residuals && one.start_times == expected.start_times && one.model_type_ids == expected.model_type_ids,
+              "univariate compress equals its rows of the batch");
+    }
+
+    // ---- len, grid, sum (models/mod.rs:98-251)
+    const std::vector<uint64_t> point_off = mc::len(ctx, batch);
+    std::vector<uint64_t> want_point_off(want.n_segments + 1);
+    const uint64_t total = mdbo_grid_count(&want, want_point_off.data(), 4);
+    CHECK(point_off == want_point_off && total == 3 * n, "len of every row");
+    std::vector<int64_t> grid_ts;
+    std::vector<float> grid_val;
+    mc::grid(ctx, batch, grid_ts, grid_val);
+    std::vector<int64_t> want_ts(total);
+    std::vector<float> want_val(total);
+    mdbo_grid(&want, want_ts.data(), want_val.data(), total, 4);
+    CHECK(grid_ts == want_ts && grid_ts == ts, "grid timestamps");
+    CHECK(same_bytes(grid_val, want_val.data(), total), "grid values bit-identical");
+    const std::vector<float> sums = mc::sum(ctx, batch);
+    std::vector<float> want_sums(want.n_segments);
+    mdbo_segment_sums(&want, want_sums.data(), 4);
+    CHECK(same_bytes(sums, want_sums.data(), want.n_segments), "sum of every row");
+
+    // ---- GridStream (grid_exec.rs:197-430): two segment batches with one tag column, batch_size 4096
+    {
+        std::vector<mc::GridStream::Input> input;
+        size_t cuts[3] = {0, batch.num_rows() / 2, batch.num_rows()};
+        for (int b = 0; b < 2; b++) {
+            mc::CompressedSegmentBatch part = batch.slice(cuts[b], cuts[b + 1]);
+            std::vector<std::string> tag(part.num_rows(), b == 0 ? "first" : "second");
+            input.push_back({std::move(part), {std::move(tag)}});
+        }
+        mc::GridStream stream(ctx, std::move(input), 4096, 1);
+        std::vector<int64_t> all_ts;
+        std::vector<float> all_val;
+        size_t first_rows = 0, batches = 0;
+        mc::GridStream::Batch out;
+        bool sizes_ok = true;
+        while (stream.poll_next(out)) {
+            batches++;
+            sizes_ok = sizes_ok && out.timestamps.size() <= 4096 && out.tags[0].size() == out.timestamps.size();
+            for (const std::string &t : out.tags[0]) first_rows += t == "first";
+            all_ts.insert(all_ts.end(), out.timestamps.begin(), out.timestamps.end());
+            all_val.insert(all_val.end(), out.values.begin(), out.values.end());
+        }
+        CHECK(sizes_ok && batches >= total / 4096, "batches of at most batch_size rows");
+        CHECK(all_ts == want_ts && same_bytes(all_val, want_val.data(), total), "the stream is the concatenated grid");
+        CHECK(first_rows == point_off[cuts[1]], "tags repeated once per created row");
+    }
+
+    // ---- accumulators (model_simple_aggregates.rs:336-618)
+    {
+        int64_t want_count;
+        float want_min, want_max;
+        double want_sum;
+        mdbo_aggregate(&want, nullptr, 1, &want_count, &want_min, &want_max, &want_sum, 1);
+        mc::ModelCountAccumulator count(ctx);
+        mc::ModelMinAccumulator min(ctx);
+        mc::ModelMaxAccumulator max(ctx);
+        mc::ModelSumAccumulator sum(ctx);
+        mc::ModelAvgAccumulator avg(ctx);
+        for (size_t lo = 0; lo < batch.num_rows(); lo += 100) { // fed in several batches, like DataFusion does
+            const mc::CompressedSegmentBatch part = batch.slice(lo, std::min(batch.num_rows(), lo + 100));
+            count.update_batch(part); min.update_batch(part); max.update_batch(part); sum.update_batch(part); avg.update_batch(part);
+        }
+        const double got_sum = sum.state();
+        const auto avg_state = avg.state();
+        CHECK(count.state() == want_count && (int64_t)avg_state.first == want_count, "COUNT");
+        CHECK(min.state() == want_min && max.state() == want_max, "MIN / MAX");
+        CHECK(std::fabs(got_sum - want_sum) <= 1e-12 * std::fabs(want_sum) && std::fabs(avg_state.second - want_sum) <= 1e-12 * std::fabs(want_sum), "SUM");
+        CHECK(count.state() == 0 && sum.state() == 0.0, "state() resets");
+    }
+
+    // ---- error behaviour
+    {
+        bool threw = false;
+        try { mc::try_compress_univariate_time_series(ctx, std::vector<int64_t>(3), std::vector<float>(2), mc::ErrorBound::lossless()); } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "different lengths are an InvalidArgument (compression.rs:202-206)");
+        threw = false;
+        try { mc::ErrorBound::try_new_relative(101.0f); } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "relative bounds above 100 % are rejected (types.rs:325-334)");
+        threw = false;
+        try { mc::ErrorBound::try_new_absolute(-1.0f); } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "absolute bounds must be positive (types.rs:312-321)");
+        const mc::CompressedSegmentBatch empty = mc::try_compress_univariate_time_series(ctx, {}, {}, mc::ErrorBound::lossless());
+        CHECK(empty.num_rows() == 0, "empty input gives an empty batch (compression.rs:208-211)");
+    }
+
+    mdbo_segments_free(oracle_segments);
+    std::printf("host_api_test: %d checks, %d failures\n", g_checks, g_failures);
+    return g_failures ? 1 : 0;
+}
