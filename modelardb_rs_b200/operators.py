@@ -43,6 +43,49 @@ class GridStreamMetrics:
         self.segments_with_regular_timestamps += int(np.count_nonzero(regular))
 
 
+class _TagRuns:
+    """The tag columns of the points of the current batch as runs: run r covers points [off[r], off[r+1]) and carries
+    values[c][r] for tag column c.  One segment row is one run (its tag values repeated len() times in the reference,
+    grid_exec.rs:340-356), so the replication the reference does per created row becomes arithmetic on offsets."""
+
+    def __init__(self, n_columns: int):
+        self.off = np.zeros(1, np.int64)
+        self.values: List[np.ndarray] = [np.zeros(0, object) for _ in range(n_columns)]
+
+    def tail(self, offset: int) -> "_TagRuns":
+        """The runs of points [offset, end), rebased to 0."""
+        out = _TagRuns(len(self.values))
+        r0 = int(np.searchsorted(self.off, offset, "right")) - 1
+        if offset >= self.off[-1]:
+            return out
+        out.off = np.concatenate([[0], self.off[r0 + 1:] - offset])
+        out.values = [v[r0:] for v in self.values]
+        return out
+
+    def extend(self, lens: np.ndarray, values: Sequence[np.ndarray]):
+        keep = lens > 0
+        self.off = np.concatenate([self.off, self.off[-1] + np.cumsum(lens[keep])])
+        self.values = [np.concatenate([old, np.asarray(new, object)[keep]]) for old, new in zip(self.values, values)]
+
+    def filter(self, keep: np.ndarray):
+        """Only the points with keep[i] survive."""
+        if len(self.off) == 1:
+            return
+        lens = np.add.reduceat(keep.astype(np.int64), self.off[:-1])  # runs are non-empty, so the starts increase
+        alive = lens > 0
+        self.off = np.concatenate([[0], np.cumsum(lens[alive])])
+        self.values = [v[alive] for v in self.values]
+
+    def slice(self, lo: int, hi: int) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """(values, run lengths) per tag column for points [lo, hi)."""
+        if hi <= lo:
+            return [(np.zeros(0, object), np.zeros(0, np.int64)) for _ in self.values]
+        r0 = int(np.searchsorted(self.off, lo, "right")) - 1
+        r1 = int(np.searchsorted(self.off, hi, "left"))
+        lens = np.diff(np.clip(self.off[r0:r1 + 1], lo, hi))
+        return [(v[r0:r1], lens) for v in self.values]
+
+
 class GridStream:
     """Reconstructs data points from batches of segments and hands them out in batches of `batch_size` rows:
     (timestamps int64[], values float32[], tag columns...), sorted as the input is (grid_exec.rs:187-195).
@@ -51,11 +94,13 @@ class GridStream:
     sequence of per-row tag arrays (one array per tag column, possibly none).
     predicate: optional function (timestamps, values) -> bool mask applied to every reconstructed batch, the
     reference's `maybe_predicate` (all points are reconstructed, then pruned: grid_exec.rs:368-386).
+    tag_runs: hand out every tag column as (values, run_lengths) instead of one string per created row (SURVEY 8(f2):
+    tags as run-lengths); np.repeat(values, run_lengths) is the column the reference builds.
     """
 
     def __init__(self, input: Iterable[Tuple[object, Sequence[np.ndarray]]], batch_size: int, n_tag_columns: int = 0,
                  predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None,
-                 time_range: Optional[Tuple[Optional[int], Optional[int]]] = None):
+                 time_range: Optional[Tuple[Optional[int], Optional[int]]] = None, tag_runs: bool = False):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
         self._input: Iterator = iter(input)
@@ -66,12 +111,13 @@ class GridStream:
         # the push-down the reference applies to its Parquet scan (time_series_table.rs:290-373), SURVEY 8(f2).  The
         # caller's predicate must imply the range; points of the surviving segments are still pruned by it.
         self.time_range = time_range
+        self.tag_runs = tag_runs
         self.segments_skipped = 0
         self.ctx = ctx
         self.metrics = GridStreamMetrics()
         self._timestamps = np.zeros(0, np.int64)
         self._values = np.zeros(0, np.float32)
-        self._tags: List[np.ndarray] = [np.zeros(0, object) for _ in range(n_tag_columns)]
+        self._tags = _TagRuns(n_tag_columns)
         self._offset = 0  # current_batch_offset
 
     def __iter__(self):
@@ -83,6 +129,8 @@ class GridStream:
     def _grid_and_append_to_leftovers_in_current_batch(self, segments, tags: Sequence[np.ndarray]):
         # grid_exec.rs:261-391 -- one batched kernel call instead of one grid() per row
         host = segments.to_host() if isinstance(segments, mc.CompressedSegments) else segments
+        if len(tags) != len(self._tags.values):
+            raise ValueError("every batch must carry the same tag columns")
         if self.time_range is not None:
             lo, hi = self.time_range
             keep = np.ones(len(host), bool)
@@ -101,19 +149,17 @@ class GridStream:
             ts, vals = mc.grid(host, ctx=self.ctx)
         self.metrics.add_batch(host, point_off)
         lens = np.diff(point_off).astype(np.int64)
-        new_tags = [np.repeat(np.asarray(t, object), lens) for t in tags]  # each tag value once per created row
-        if len(new_tags) != len(self._tags):
-            raise ValueError("every batch must carry the same tag columns")
+        runs = self._tags.tail(self._offset)
+        runs.extend(lens, tags)  # each tag value once per created row, as one run
         # (the leftovers were filtered when they were created; the predicate is a per-row test, so filtering them again
         # together with the new points changes nothing)
         ts = np.concatenate([self._timestamps[self._offset:], ts])
         vals = np.concatenate([self._values[self._offset:], vals])
-        new_tags = [np.concatenate([old[self._offset:], new]) for old, new in zip(self._tags, new_tags)]
         if self.predicate is not None:
             keep = np.asarray(self.predicate(ts, vals), bool)
             ts, vals = ts[keep], vals[keep]
-            new_tags = [t[keep] for t in new_tags]
-        self._timestamps, self._values, self._tags = ts, vals, new_tags
+            runs.filter(keep)
+        self._timestamps, self._values, self._tags = ts, vals, runs
         self._offset = 0
 
     def __next__(self):
@@ -129,7 +175,9 @@ class GridStream:
         length = min(self.batch_size, self._remaining())
         lo, hi = self._offset, self._offset + length
         self._offset = hi
-        return (self._timestamps[lo:hi], self._values[lo:hi], *[t[lo:hi] for t in self._tags])
+        runs = self._tags.slice(lo, hi)
+        tags = runs if self.tag_runs else [np.repeat(values, lens) for values, lens in runs]
+        return (self._timestamps[lo:hi], self._values[lo:hi], *tags)
 
 
 class _ModelAccumulator:
@@ -219,3 +267,51 @@ class ModelAvgAccumulator(_ModelAccumulator):  # model_simple_aggregates.rs:530-
         state = [self.count, self.sum]
         self.sum, self.count = 0.0, 0
         return state
+
+
+def grouped_model_aggregates(segments, tag_columns: Sequence[np.ndarray], ctx: Optional[mc.Context] = None):
+    """COUNT / MIN / MAX / SUM per distinct combination of tag values, directly from segments (the
+    aggregate rule extended to GROUP BY <tag columns>; the reference's rule only rewrites ungrouped aggregates,
+    model_simple_aggregates.rs:203-334, and answers grouped ones by reconstructing every point).
+
+    Rows with equal tags are contiguous in what compress and the storage layer produce (one series after the other), so
+    each run of equal tags is one group of ONE mdbcu_aggregate call; runs that repeat an earlier key (several files of
+    the same series) are merged on the host in row order with the accumulators' folds.  Returns (keys, count i64[],
+    min f32[], max f32[], sum f64[]) with keys as tuples in order of first appearance; AVG = sum / count."""
+    host = segments.to_host() if isinstance(segments, mc.CompressedSegments) else segments
+    n = len(host)
+    columns = [np.asarray(c, object) for c in tag_columns]
+    if any(len(c) != n for c in columns):
+        raise ValueError("a tag column needs one value per segment")
+    if n == 0:
+        return [], np.zeros(0, np.int64), np.zeros(0, np.float32), np.zeros(0, np.float32), np.zeros(0, np.float64)
+    change = np.zeros(n, bool)
+    change[0] = True
+    for c in columns:
+        change[1:] |= c[1:] != c[:-1]
+    starts = np.flatnonzero(change)
+    group_off = np.concatenate([starts, [n]]).astype(np.uint64)
+    count, mn, mx, sm = mc.aggregate(host, group_off, ctx)
+    keys: List[tuple] = []
+    index = {}
+    slot = np.empty(len(starts), np.int64)
+    for r, row in enumerate(starts):
+        key = tuple(c[row] for c in columns)
+        if key not in index:
+            index[key] = len(keys)
+            keys.append(key)
+        slot[r] = index[key]
+    g = len(keys)
+    out_count, out_sum = np.zeros(g, np.int64), np.zeros(g, np.float64)
+    out_min, out_max = np.full(g, F32_MAX, np.float32), np.full(g, F32_MIN, np.float32)
+    if g == len(starts):  # the usual case: every key is one run
+        return keys, count.astype(np.int64), mn, mx, sm
+    for r in range(len(starts)):
+        k = slot[r]
+        out_count[k] += count[r]
+        out_sum[k] += sm[r]
+        if mn[r] < out_min[k]:
+            out_min[k] = mn[r]
+        if mx[r] > out_max[k]:
+            out_max[k] = mx[r]
+    return keys, out_count, out_min, out_max, out_sum
