@@ -89,6 +89,7 @@ struct mdbcu_context {
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
+    uint32_t lane_rows_min = 4096; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
     int fit_mode = 0;                // 0 automatic (warp per chain), 1 thread per chain, 2 warp per chain
@@ -635,6 +636,48 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsV
     }
 }
 
+// With THOUSANDS of long rows in a batch (100 000 series of 10 000 values; the server path's 64 Ki-point buffers) the
+// rows themselves are parallelism enough, and a warp per row wastes 31 of its 32 issue slots on the serial code walk:
+// from LANE_ROWS_MIN rows on, one THREAD owns a row (MacaqueVDecoder: word-wise reads through a register window,
+// branch-free codes).  A thread's loads and stores walk its own row, so a warp's accesses are scattered over 32 rows:
+// the stream is read and the values are written 16 bytes at a time to keep the number of sector transactions down.
+constexpr uint32_t LANE_ROWS_MIN = 4096;
+
+__global__ void __launch_bounds__(128) k_grid_macaque_lanes(SegmentsView v, const SegDesc *desc, const uint64_t *point_off,
+                                                            const uint32_t *worklist_back, uint32_t n_wide, float *val_out) {
+    const uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_wide) return;
+    const uint64_t s = *(worklist_back - w);
+    const SegDesc d = desc[s];
+    const Row r = load_row(v, s);
+    const uint64_t base = point_off[s];
+    const uint32_t len = (uint32_t)(point_off[s + 1] - base);
+    MacaqueVDecoder dec;
+    float last;
+    // the next n values of the stream to out[0 .. n): single stores up to a 16-byte boundary, then four values per store
+    auto decode_run = [&](float *out, uint32_t n) {
+        uint32_t i = 0;
+        for (; i < n && (reinterpret_cast<uintptr_t>(out + i) & 15); i++) out[i] = last = dec.next();
+        for (; i + 4 <= n; i += 4) {
+            float4 q;
+            q.x = dec.next();
+            q.y = dec.next();
+            q.z = dec.next();
+            q.w = last = dec.next();
+            *reinterpret_cast<float4 *>(out + i) = q;
+        }
+        for (; i < n; i++) out[i] = last = dec.next();
+    };
+    dec.init(r.values, r.n_values, false, 0.0f);
+    last = __uint_as_float(dec.last_value);
+    val_out[base] = last;
+    decode_run(val_out + base + 1, d.model_len - 1);
+    if (d.flags & F_HAS_RESIDUALS) { // models/mod.rs:241-249: seeded with the last gridded model value
+        dec.init(r.residuals, r.n_residuals - 1, true, last);
+        decode_run(val_out + base + d.model_len, len - d.model_len);
+    }
+}
+
 __global__ void __launch_bounds__(256) k_grid_prepare(SegmentsView v, SegDesc *desc, uint32_t *len, uint32_t *worklist, Status *status) {
     uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     bool serial = false, wide = false;
@@ -816,11 +859,12 @@ __global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *
 // One warp per long MacaqueV row: the f32 sum in stream order (macaque_v.rs:220-265), as aggregate_segment computes it.
 // The 32 values of a batch are decoded in parallel; their additions stay a serial chain (one rounding per value).
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsView v, const uint32_t *wide_list, const unsigned int *n_wide_ptr,
-                                                                       float *seg_sum) {
+                                                                       uint32_t lane_rows_min, float *seg_sum) {
     __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
     __shared__ float batch[WIDE_WARPS][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_wide = *n_wide_ptr;
+    if (n_wide >= lane_rows_min) return; // k_agg_macaque_lanes has them
     for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
         const uint64_t s = wide_list[w];
         const Row r = load_row(v, s);
@@ -851,6 +895,21 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsVi
             sum = __fadd_rn(model_sum, sum);
         }
         if (lane == 0) seg_sum[s] = canonical_nan(sum);
+    }
+}
+
+// The same rows with one thread per row when the batch holds at least lane_rows_min of them (see k_grid_macaque_lanes);
+// the count is only known on the device here, so both kernels are launched and one of them returns at once.
+__global__ void __launch_bounds__(128) k_agg_macaque_lanes(SegmentsView v, const uint32_t *wide_list, const unsigned int *n_wide_ptr,
+                                                           uint32_t lane_rows_min, float *seg_sum) {
+    const uint32_t n_wide = *n_wide_ptr;
+    if (n_wide < lane_rows_min) return;
+    for (uint32_t w = blockIdx.x * blockDim.x + threadIdx.x; w < n_wide; w += gridDim.x * blockDim.x) {
+        const uint64_t s = wide_list[w];
+        uint64_t count;
+        float sum;
+        aggregate_segment(v, s, count, sum); // well-formed: k_agg_segments checked the row before deferring it
+        seg_sum[s] = sum;
     }
 }
 
@@ -1086,6 +1145,8 @@ int mdbcu_context_create(int device, mdbcu_context **out) {
         return fail(std::string("mailbox allocation: ") + cudaGetErrorString(e));
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->lane_rows_min = LANE_ROWS_MIN;
+    if (const char *rows = std::getenv("MDBCU_LANE_ROWS_MIN")) ctx->lane_rows_min = (uint32_t)std::max(1l, std::atol(rows)); // tuning and tests
     // keep freed blocks in the pool: steady-state calls then never reach the driver allocator
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1221,7 +1282,10 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     if (pl.h_status.n_seq)
         LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p,
                (uint32_t)pl.h_status.n_seq, d_ts, d_val);
-    if (pl.h_status.n_wide)
+    if (pl.h_status.n_wide >= ctx->lane_rows_min)
+        LAUNCH(ctx, k_grid_macaque_lanes, div_up(pl.h_status.n_wide, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p + (S - 1),
+               (uint32_t)pl.h_status.n_wide, d_val);
+    else if (pl.h_status.n_wide)
         LAUNCH(ctx, k_grid_macaque_warp, div_up(pl.h_status.n_wide, WIDE_WARPS), WIDE_WARPS * 32, 0, st.view, pl.desc.p, pl.point_off.p,
                pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, d_val);
     CUDA_TRY(cudaGetLastError());
@@ -1255,7 +1319,10 @@ int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segmen
     CUDA_TRY(wide_list.alloc(S, s));
     LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, wide_list.p, status.p);
     LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0, st.view,
-           wide_list.p, &status.p->n_wide, d_sum);
+           wide_list.p, &status.p->n_wide, ctx->lane_rows_min, d_sum);
+    if (S >= ctx->lane_rows_min)
+        LAUNCH(ctx, k_agg_macaque_lanes, std::min<unsigned int>(div_up(S, 128), (unsigned int)ctx->sm_count * 16), 128, 0, st.view, wide_list.p,
+               &status.p->n_wide, ctx->lane_rows_min, d_sum);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) CUDA_TRY(d2h_bytes(ctx, sums_out, d_sum, S * sizeof(float)));
     Status h;
@@ -1291,7 +1358,10 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     if (S) {
         LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, seg_count.p, seg_sum.p, wide_list.p, status.p);
         LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
-               st.view, wide_list.p, &status.p->n_wide, seg_sum.p);
+               st.view, wide_list.p, &status.p->n_wide, ctx->lane_rows_min, seg_sum.p);
+        if (S >= ctx->lane_rows_min)
+            LAUNCH(ctx, k_agg_macaque_lanes, std::min<unsigned int>(div_up(S, 128), (unsigned int)ctx->sm_count * 16), 128, 0, st.view,
+                   wide_list.p, &status.p->n_wide, ctx->lane_rows_min, seg_sum.p);
     }
 
     // parts per group: enough blocks to fill the GPU when there are few large groups

@@ -11,11 +11,13 @@
 #ifdef __CUDACC__
 #include <cuda_runtime.h>
 #define MDB_DEV __device__ __forceinline__
+#define MDB_DEV_NOINLINE __device__ __noinline__
 #else
 // Host build of the per-thread bodies, used ONLY by tests/emu (a debugging harness that steps the
 // kernels' thread functions in a loop on this GPU-less build container).  Not part of the product.
 #include "mdb_host_shim.h"
 #define MDB_DEV inline
+#define MDB_DEV_NOINLINE inline
 #endif
 
 namespace mdb {
@@ -341,36 +343,136 @@ MDB_DEV bool are_uncompressed_timestamps_regular(const int64_t *ts, uint64_t n) 
 // MacaqueV (models/macaque_v.rs)
 // ---------------------------------------------------------------------------------------------
 
-// Decoder state machine of macaque_v.rs:272-323 / :220-265.
+// Bit reader of the MacaqueV decoder: the stream as aligned 32-bit words through a 64-bit window in registers.  Words
+// are fetched four at a time (one 16-byte load) into a small queue, a quad ahead of their use: a thread that owns a
+// whole row otherwise waits a memory round trip every few codes, and 4-byte loads scattered over 32 rows cost a full
+// sector transaction each.  Bits past the end of the stream read as zero; only bytes of the stream are touched: words
+// that are not entirely inside it are assembled byte by byte.
+struct WordBitReader {
+    const uint32_t *words;     // 16-byte aligned address at or before the first byte of the stream
+    uint64_t lo_byte, hi_byte; // the stream is bytes [lo_byte, hi_byte) of that word sequence
+    uint64_t full_lo, n_full;  // words [full_lo, full_lo + n_full) lie entirely inside the stream
+    uint64_t next;             // index of the first word after the queued quad
+    uint64_t buf;              // the next `avail` bits of the stream, from the top; zero below them
+    int avail;
+    uint32_t q0, q1, q2, q3;   // queued words (big-endian bit order), q0 first
+    int q_left;
+
+    static MDB_DEV uint32_t big_endian(uint32_t x) {
+#ifdef __CUDA_ARCH__
+        return __byte_perm(x, 0, 0x0123);
+#else
+        return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
+#endif
+    }
+    struct Quad {
+        uint32_t a, b, c, d;
+    };
+    static MDB_DEV uint32_t edge_word(const uint32_t *words, uint64_t lo_byte, uint64_t hi_byte, uint64_t w) {
+        const uint64_t b0 = 4 * w;
+        if (b0 >= hi_byte) return 0;
+        if (b0 >= lo_byte && b0 + 4 <= hi_byte) return big_endian(words[w]);
+        const uint8_t *bytes = reinterpret_cast<const uint8_t *>(words);
+        uint32_t x = 0;
+        for (uint32_t b = 0; b < 4; b++)
+            if (b0 + b >= lo_byte && b0 + b < hi_byte) x |= (uint32_t)bytes[b0 + b] << (24 - 8 * b);
+        return x;
+    }
+    // a quad at the first / last bytes of the stream or past its end (one call, arguments by value: the reader stays in
+    // registers and the rare path is not replicated at every refill site)
+    static MDB_DEV_NOINLINE Quad load_quad_edge(const uint32_t *words, uint64_t lo_byte, uint64_t hi_byte, uint64_t w) {
+        Quad q;
+        q.a = edge_word(words, lo_byte, hi_byte, w);
+        q.b = edge_word(words, lo_byte, hi_byte, w + 1);
+        q.c = edge_word(words, lo_byte, hi_byte, w + 2);
+        q.d = edge_word(words, lo_byte, hi_byte, w + 3);
+        return q;
+    }
+    MDB_DEV void load_quad(uint64_t w) { // w is a multiple of 4
+        if (w - full_lo < n_full && w + 3 - full_lo < n_full) {
+#ifdef __CUDA_ARCH__
+            const uint4 x = __ldg(reinterpret_cast<const uint4 *>(words + w));
+            q0 = big_endian(x.x); q1 = big_endian(x.y); q2 = big_endian(x.z); q3 = big_endian(x.w);
+#else
+            q0 = big_endian(words[w]); q1 = big_endian(words[w + 1]); q2 = big_endian(words[w + 2]); q3 = big_endian(words[w + 3]);
+#endif
+        } else {
+            const Quad q = load_quad_edge(words, lo_byte, hi_byte, w);
+            q0 = q.a; q1 = q.b; q2 = q.c; q3 = q.d;
+        }
+    }
+    MDB_DEV uint32_t pop_word() {
+        const uint32_t x = q0;
+        q0 = q1; q1 = q2; q2 = q3;
+        if (--q_left == 0) {
+            load_quad(next);
+            next += 4;
+            q_left = 4;
+        }
+        return x;
+    }
+    MDB_DEV void init(const uint8_t *bytes, uint64_t n_bytes) {
+        const uintptr_t a = reinterpret_cast<uintptr_t>(bytes);
+        const uint32_t skip = (uint32_t)(a & 15);
+        words = reinterpret_cast<const uint32_t *>(a - skip);
+        lo_byte = skip;
+        hi_byte = skip + n_bytes;
+        full_lo = (lo_byte + 3) / 4;
+        n_full = hi_byte / 4 > full_lo ? hi_byte / 4 - full_lo : 0;
+        load_quad(0);
+        next = 4;
+        q_left = 4;
+        for (uint32_t i = 0; i < skip / 4; i++) pop_word(); // words before the stream
+        const uint32_t sub = 8 * (skip & 3);
+        buf = (uint64_t)pop_word() << (32 + sub);
+        avail = 32 - (int)sub;
+    }
+    MDB_DEV void ensure(int n) { // n <= 32
+        if (avail < n) {
+            buf |= (uint64_t)pop_word() << (32 - avail);
+            avail += 32;
+        }
+    }
+    MDB_DEV uint32_t peek32() const { return (uint32_t)(buf >> 32); }
+    MDB_DEV void skip(int n) { buf <<= n; avail -= n; } // n <= avail
+    MDB_DEV uint32_t read(int n) {                       // n in [0, 32]
+        ensure(n);
+        const uint32_t value = (uint32_t)((buf >> 1) >> (63 - n));
+        skip(n);
+        return value;
+    }
+};
+
+// Decoder state machine of macaque_v.rs:272-323 / :220-265.  next() evaluates the three kinds of code without
+// branching (threads of a warp own different rows and would diverge at every code): `0` = the XOR's meaningful bits in
+// the window in force, `10` = the same value again, `11` = 5 bits of leading zeros, 6 bits of length, the bits.
 struct MacaqueVDecoder {
-    BitReader bits;
-    uint32_t leading_zeros;  // u8 in the reference, starts at u8::MAX
+    WordBitReader bits;
+    uint32_t width_in_force;  // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = u8::MAX at first
     uint32_t trailing_zeros;
     uint32_t last_value;
     // Positions the decoder; when !has_seed the first value is the raw 32 bits and is returned.
     MDB_DEV void init(const uint8_t *b, uint64_t n, bool has_seed, float seed) {
         bits.init(b, n);
-        leading_zeros = 255;
+        width_in_force = 32;
         trailing_zeros = 0;
         last_value = has_seed ? __float_as_uint(seed) : bits.read(32);
     }
     MDB_DEV float next() {
-        if (bits.read(1)) {
-            if (bits.read(1)) {
-                leading_zeros = bits.read(5);
-                uint32_t meaningful_bits = bits.read(6);
-                trailing_zeros = (32u - meaningful_bits - leading_zeros) & 0xffu; // u8 wrapping as in release
-                meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
-                uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits);
-                value = trailing_zeros < 32 ? value << trailing_zeros : 0;
-                last_value ^= value;
-            }
-        } else {
-            uint32_t meaningful_bits = (32u - leading_zeros - trailing_zeros) & 0xffu;
-            uint32_t value = bits.read(meaningful_bits > 32 ? 32 : (int)meaningful_bits);
-            value = trailing_zeros < 32 ? value << trailing_zeros : 0;
-            last_value ^= value;
-        }
+        bits.ensure(13);
+        const uint32_t head = bits.peek32();
+        const bool reuse = !(head & 0x80000000u);
+        const bool fresh = (head & 0xC0000000u) == 0xC0000000u;
+        const uint32_t leading_zeros = (head >> 25) & 31u;
+        const uint32_t stored_len = (head >> 19) & 63u;
+        const uint32_t new_trailing = (32u - stored_len - leading_zeros) & 0xffu; // u8 wrapping as in release builds
+        const uint32_t new_meaningful = (32u - leading_zeros - new_trailing) & 0xffu;
+        trailing_zeros = fresh ? new_trailing : trailing_zeros;
+        width_in_force = fresh ? (new_meaningful > 32u ? 32u : new_meaningful) : width_in_force;
+        bits.skip(reuse ? 1 : (fresh ? 13 : 2));
+        uint32_t value = bits.read((reuse | fresh) ? (int)width_in_force : 0);
+        value = trailing_zeros < 32u ? value << trailing_zeros : 0u;
+        last_value ^= value;
         return __uint_as_float(last_value);
     }
 };

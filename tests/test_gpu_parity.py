@@ -295,6 +295,60 @@ def test_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
     seg.free()
 
 
+@pytest.mark.parametrize("eb", [(0, 0.0), (1, 0.05), (2, 1e-4)], ids=["lossless", "abs0.05", "rel1e-4"])
+def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
+    """From 4096 long MacaqueV rows in a batch on, grid and the aggregates give every row to one thread instead of one
+    warp (k_grid_macaque_lanes / k_agg_macaque_lanes): 5000 series of a few hundred values, no model ever fits (some
+    series hold runs of equal values so that models and residuals sit between the MacaqueV rows)."""
+    rng = np.random.default_rng(23)
+    lens = rng.integers(150, 400, 5000)
+    units = []
+    for u, n in enumerate(lens):
+        x = rng.uniform(-1e3, 1e3, n).astype(np.float32)
+        if u % 7 == 0:
+            x[n // 3: n // 3 + 40] = x[n // 3]  # a constant stretch: a PMC-Mean model, residuals before the next row
+        units.append(x)
+    vals = np.concatenate(units)
+    ts = np.concatenate([syn.regular_timestamps(len(u)) for u in units])
+    off = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+    assert int(np.count_nonzero((want.model_type_id == 2) & (np.diff(want.values_off) > 200))) >= 4096
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    got = seg.to_host()
+    assert_segments_equal(got, want, f"many MacaqueV rows eb={eb}")
+    wts, wval, _ = oracle.grid(want, n_threads=8)
+    gts, gval = mc.grid(got, ctx=ctx)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, f"many MacaqueV rows eb={eb} grid")
+    dts, dval = mc.grid(seg, ctx=ctx)  # device-resident segments and outputs
+    assert np.array_equal(dts.cpu().numpy(), wts)
+    assert_f32_bits_equal(dval.cpu().numpy(), wval, f"many MacaqueV rows eb={eb} device grid")
+    assert_f32_bits_equal(mc.segment_sums(got, ctx), oracle.segment_sums(want, n_threads=8), f"many MacaqueV rows eb={eb} sums",
+                          nan_payload_matters=False)
+    gc, gmn, gmx, gsm = mc.aggregate(got, want.unit_seg_off, ctx)
+    wc, wmn, wmx, wsm = oracle.aggregate(want, want.unit_seg_off, n_threads=8)
+    assert np.array_equal(gc, wc) and gmn.tobytes() == wmn.tobytes() and gmx.tobytes() == wmx.tobytes()
+    _check_sum(gsm, wsm, "many MacaqueV rows aggregate")
+    seg.free()
+
+
+def test_lane_and_warp_decoders_agree(oracle, monkeypatch):
+    """The row count that switches between the two decoders is a tuning knob (MDBCU_LANE_ROWS_MIN, read when a context
+    is created): the same batch through both gives the same bits."""
+    ts, vals, off = syn.multi_series(40, 3000, 77, "walk")
+    want = oracle.compress(ts, vals, off, eb=(0, 0.0), n_threads=4)
+    wts, wval, _ = oracle.grid(want, n_threads=4)
+    host = mc.HostSegments(**{c: getattr(want, c) for c in mc._COLUMNS})
+    for rows_min in ("1", "1000000"):
+        monkeypatch.setenv("MDBCU_LANE_ROWS_MIN", rows_min)
+        c = mc.Context(0)
+        gts, gval = mc.grid(host, ctx=c)
+        assert np.array_equal(gts, wts)
+        assert_f32_bits_equal(gval, wval, f"lane rows min {rows_min}")
+        assert_f32_bits_equal(mc.segment_sums(host, c), oracle.segment_sums(want), f"sums, lane rows min {rows_min}", nan_payload_matters=False)
+        c.close()
+
+
 def test_contexts_on_threads_pipeline_independent_slabs(oracle):
     """One context per host thread (the e2e pattern of bench.py): results do not depend on what the others do."""
     import threading

@@ -129,3 +129,33 @@ def test_eight_point_screen_agrees_with_fit_next_model(case):
         if b - a == 0:
             continue
         assert emu.check_eight_points(ts[a:b], vals[a:b], ebs[u]) == 0, (name, u)
+
+
+@pytest.mark.parametrize("eb", [(0, 0.0), (1, 0.05)], ids=["lossless", "abs0.05"])
+def test_macaque_v_word_reader_at_every_alignment(oracle, eb):
+    """The MacaqueV decoder reads its stream as aligned 16-byte quads (WordBitReader, mdb_device.cuh); the bytes before
+    and after the stream in those quads must neither be read as data nor matter.  Streams of 1 to ~300 bytes (values and
+    residuals), shifted to each of the 16 positions inside a quad, with poisoned bytes around them."""
+    rng = np.random.default_rng(5)
+    units = [rng.uniform(-50, 50, n).astype(np.float32) for n in (1, 2, 3, 5, 8, 13, 40, 77)]
+    units.append(np.concatenate([np.full(30, 2.5, np.float32), rng.uniform(-50, 50, 9).astype(np.float32)]))  # a model, then residuals
+    vals = np.concatenate(units)
+    ts = np.concatenate([syn.regular_timestamps(len(u)) for u in units])
+    off = np.concatenate([[0], np.cumsum([len(u) for u in units])]).astype(np.uint64)
+    want = oracle.compress(ts, vals, off, eb=eb)
+    wts, wval, _ = oracle.grid(want)
+    wsum = oracle.segment_sums(want)
+    for shift in range(16):
+        cols = {c: getattr(want, c) for c in oracle._COLS}
+        for name in ("values", "residuals"):
+            data = cols[name + "_data"]
+            backing = np.full(len(data) + 64, 0xA5, np.uint8)  # 64-byte aligned start is not guaranteed: align by hand
+            start = (-backing.ctypes.data) % 16 + shift
+            backing[start:start + len(data)] = data
+            cols[name + "_data"] = backing[start:start + len(data)]
+            assert cols[name + "_data"].ctypes.data % 16 == shift % 16
+        shifted = oracle.Segments(**cols)
+        gts, gval, _ = emu.grid(shifted)
+        assert np.array_equal(gts, wts), shift
+        assert gval.tobytes() == wval.tobytes(), shift
+        assert emu.segment_sums(shifted)[0].tobytes() == wsum.tobytes(), shift
