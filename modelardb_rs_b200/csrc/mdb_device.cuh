@@ -355,7 +355,9 @@ struct WordBitReader {
     uint64_t next;             // index of the first word after the queued quad
     uint64_t buf;              // the next `avail` bits of the stream, from the top; zero below them
     int avail;
-    uint32_t q0, q1, q2, q3;   // queued words (big-endian bit order), q0 first
+    uint32_t q0, q1, q2, q3;   // the current quad's remaining words (big-endian bit order), q0 first
+    uint32_t a0, a1, a2, a3;   // the quad after it (as loaded), unless ahead_edge
+    bool ahead_edge;
     int q_left;
 
     static MDB_DEV uint32_t big_endian(uint32_t x) {
@@ -388,27 +390,36 @@ struct WordBitReader {
         q.d = edge_word(words, lo_byte, hi_byte, w + 3);
         return q;
     }
-    MDB_DEV void load_quad(uint64_t w) { // w is a multiple of 4
-        if (w - full_lo < n_full && w + 3 - full_lo < n_full) {
+    // The quad after the current one, as loaded (little-endian words): nothing reads these registers until the current
+    // quad is used up, so the load has a whole quad's worth of codes to complete.  A quad at an edge of the stream is
+    // only noted here and assembled when it becomes the current one (its value must not merge into the registers the
+    // 16-byte load targets, or the merge would wait for the load).
+    MDB_DEV void load_ahead(uint64_t w) { // w is a multiple of 4
+        ahead_edge = !(w - full_lo < n_full && w + 3 - full_lo < n_full);
+        if (!ahead_edge) {
 #ifdef __CUDA_ARCH__
             const uint4 x = __ldg(reinterpret_cast<const uint4 *>(words + w));
-            q0 = big_endian(x.x); q1 = big_endian(x.y); q2 = big_endian(x.z); q3 = big_endian(x.w);
+            a0 = x.x; a1 = x.y; a2 = x.z; a3 = x.w;
 #else
-            q0 = big_endian(words[w]); q1 = big_endian(words[w + 1]); q2 = big_endian(words[w + 2]); q3 = big_endian(words[w + 3]);
+            a0 = words[w]; a1 = words[w + 1]; a2 = words[w + 2]; a3 = words[w + 3];
 #endif
-        } else {
-            const Quad q = load_quad_edge(words, lo_byte, hi_byte, w);
-            q0 = q.a; q1 = q.b; q2 = q.c; q3 = q.d;
         }
+    }
+    MDB_DEV void next_quad() {
+        if (ahead_edge) {
+            const Quad q = load_quad_edge(words, lo_byte, hi_byte, next - 4);
+            q0 = q.a; q1 = q.b; q2 = q.c; q3 = q.d;
+        } else {
+            q0 = big_endian(a0); q1 = big_endian(a1); q2 = big_endian(a2); q3 = big_endian(a3);
+        }
+        load_ahead(next);
+        next += 4;
+        q_left = 4;
     }
     MDB_DEV uint32_t pop_word() {
         const uint32_t x = q0;
         q0 = q1; q1 = q2; q2 = q3;
-        if (--q_left == 0) {
-            load_quad(next);
-            next += 4;
-            q_left = 4;
-        }
+        if (--q_left == 0) next_quad();
         return x;
     }
     MDB_DEV void init(const uint8_t *bytes, uint64_t n_bytes) {
@@ -419,9 +430,10 @@ struct WordBitReader {
         hi_byte = skip + n_bytes;
         full_lo = (lo_byte + 3) / 4;
         n_full = hi_byte / 4 > full_lo ? hi_byte / 4 - full_lo : 0;
-        load_quad(0);
+        a0 = a1 = a2 = a3 = 0;
+        load_ahead(0);
         next = 4;
-        q_left = 4;
+        next_quad();
         for (uint32_t i = 0; i < skip / 4; i++) pop_word(); // words before the stream
         const uint32_t sub = 8 * (skip & 3);
         buf = (uint64_t)pop_word() << (32 + sub);
