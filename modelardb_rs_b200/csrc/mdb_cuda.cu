@@ -89,7 +89,7 @@ struct mdbcu_context {
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
-    uint32_t lane_rows_min = 4096; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
+    uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
     int fit_mode = 0;                // 0 automatic (warp per chain), 1 thread per chain, 2 warp per chain
@@ -636,12 +636,14 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsV
     }
 }
 
-// With THOUSANDS of long rows in a batch (100 000 series of 10 000 values; the server path's 64 Ki-point buffers) the
-// rows themselves are parallelism enough, and a warp per row wastes 31 of its 32 issue slots on the serial code walk:
-// from LANE_ROWS_MIN rows on, one THREAD owns a row (MacaqueVDecoder: word-wise reads through a register window,
-// branch-free codes).  A thread's loads and stores walk its own row, so a warp's accesses are scattered over 32 rows:
-// the stream is read and the values are written 16 bytes at a time to keep the number of sector transactions down.
-constexpr uint32_t LANE_ROWS_MIN = 4096;
+// With TENS OF THOUSANDS of long rows in a batch (100 000 series of 10 000 values) the rows themselves are parallelism
+// enough, and a warp per row wastes 31 of its 32 issue slots on the serial code walk: from LANE_ROWS_MIN rows on, one
+// THREAD owns a row (MacaqueVDecoder: word-wise reads through a register window, branch-free codes).  A thread's loads
+// and stores walk its own row, so a warp's accesses are scattered over 32 rows: the stream is read and the values are
+// written 16 bytes at a time to keep the number of sector transactions down.  Measured on 10^9 values: a thread
+// decodes a code in ~1300 cycles, a warp in ~140 but at most ~27 G codes/s in total; 16 000 rows: 42 ms (threads)
+// against 37 ms (warps), 100 000 rows: 7.2 ms against 44.6 ms -- the switch sits where the two cross.
+constexpr uint32_t LANE_ROWS_MIN = 24576;
 
 __global__ void __launch_bounds__(128) k_grid_macaque_lanes(SegmentsView v, const SegDesc *desc, const uint64_t *point_off,
                                                             const uint32_t *worklist_back, uint32_t n_wide, float *val_out) {

@@ -296,10 +296,13 @@ def test_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
 
 
 @pytest.mark.parametrize("eb", [(0, 0.0), (1, 0.05), (2, 1e-4)], ids=["lossless", "abs0.05", "rel1e-4"])
-def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
-    """From 4096 long MacaqueV rows in a batch on, grid and the aggregates give every row to one thread instead of one
-    warp (k_grid_macaque_lanes / k_agg_macaque_lanes): 5000 series of a few hundred values, no model ever fits (some
-    series hold runs of equal values so that models and residuals sit between the MacaqueV rows)."""
+def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, monkeypatch, eb):
+    """From tens of thousands of long MacaqueV rows in a batch on (24 576; lowered to 4096 here), grid and the aggregates
+    give every row to one thread instead of one warp (k_grid_macaque_lanes / k_agg_macaque_lanes): 5000 series of a few
+    hundred values, no model ever fits (some series hold runs of equal values so that models and residuals sit between
+    the MacaqueV rows)."""
+    monkeypatch.setenv("MDBCU_LANE_ROWS_MIN", "4096")
+    ctx = mc.Context(0)
     rng = np.random.default_rng(23)
     lens = rng.integers(150, 400, 5000)
     units = []
@@ -330,6 +333,7 @@ def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, ctx, eb):
     assert np.array_equal(gc, wc) and gmn.tobytes() == wmn.tobytes() and gmx.tobytes() == wmx.tobytes()
     _check_sum(gsm, wsm, "many MacaqueV rows aggregate")
     seg.free()
+    ctx.close()
 
 
 def test_lane_and_warp_decoders_agree(oracle, monkeypatch):
