@@ -91,7 +91,10 @@ const char *mdbcu_version(void);
  * for pageable caller memory, cached pinned blocks for host copies of segments, a mapped mailbox for
  * scalar read-backs).  Calls on one context are blocking and must not overlap: use one context per
  * host thread; contexts on different threads run concurrently on the device.  Free every
- * mdbcu_segments created on a context before destroying it. */
+ * mdbcu_segments created on a context before destroying it.
+ * Tuning knob read when a context is created: MDBCU_LANE_ROWS_MIN (environment) = the number of long MacaqueV rows in a
+ * batch from which grid / aggregate decode one row per thread instead of one row per warp (default 24 576; results
+ * are identical either way). */
 int mdbcu_context_create(int device, mdbcu_context **out);
 void mdbcu_context_destroy(mdbcu_context *ctx);
 /* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of the context's own. */
