@@ -1,6 +1,6 @@
 // warp_emu.h -- DEBUGGING HARNESS: runs warp-cooperative device code (modelardb_rs_b200/csrc/mdb_fit_warp.cuh) on the host.
 //
-// The 32 lanes of a warp are 32 cooperative fibers (ucontext) on one OS thread.  Every warp-level primitive
+// The 32 lanes of a warp are 32 cooperative fibers on one OS thread (each with its own stack; switched by hand).  Every warp-level primitive
 // (__shfl*_sync, __ballot_sync, __any_sync, __reduce_*_sync, __syncwarp) is a rendezvous: the calling lane publishes its
 // operand and yields; the scheduler resumes the lanes round-robin, so when a lane continues, all 32 operands of that
 // primitive are there.  Operands live in two alternating buffers, because a lane may already publish primitive k + 1
@@ -11,7 +11,7 @@
 // Nothing under modelardb_rs_b200/ includes this file; the product is compiled by nvcc only.
 #pragma once
 
-#include <ucontext.h>
+#include <ucontext.h> // only used where the hand-written switch below is not available
 
 #include <climits>
 #include <cmath>
@@ -26,10 +26,47 @@ namespace warp_emu {
 
 constexpr int LANES = 32;
 
+// Switching between the lanes.  swapcontext() saves and restores the signal mask with two system calls per switch, which
+// made the emulated tests the slowest part of the CPU suite; on x86-64 the switch is done by hand instead (callee-saved
+// registers and the stack pointer, System V ABI).  Other architectures keep ucontext.
+#if defined(__x86_64__)
+#define WARP_EMU_FAST_SWITCH 1
+extern "C" void warp_emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.weak warp_emu_switch
+.type warp_emu_switch,@function
+warp_emu_switch:
+    pushq %rbp
+    pushq %rbx
+    pushq %r12
+    pushq %r13
+    pushq %r14
+    pushq %r15
+    movq %rsp, (%rdi)
+    movq %rsi, %rsp
+    popq %r15
+    popq %r14
+    popq %r13
+    popq %r12
+    popq %rbx
+    popq %rbp
+    ret
+.size warp_emu_switch,.-warp_emu_switch
+)");
+#else
+#define WARP_EMU_FAST_SWITCH 0
+#endif
+
 struct Warp {
+#if WARP_EMU_FAST_SWITCH
+    void *sched_sp = nullptr;
+    void *sp[LANES];
+#else
     ucontext_t sched;
     ucontext_t ctx[LANES];
-    std::vector<char> stack[LANES];
+#endif
+    char *stack[LANES]; // from lane_stacks(): allocated once per host thread, reused by every run
     uint64_t buf[2][LANES];
     uint32_t primitives[LANES]; // how many primitives each lane has issued
     bool done[LANES];
@@ -38,7 +75,7 @@ struct Warp {
 };
 
 inline Warp *&current() {
-    static Warp *w = nullptr;
+    static thread_local Warp *w = nullptr;
     return w;
 }
 
@@ -46,7 +83,11 @@ inline int lane() { return current()->cur; }
 
 inline void yield() {
     Warp &w = *current();
+#if WARP_EMU_FAST_SWITCH
+    warp_emu_switch(&w.sp[w.cur], w.sched_sp);
+#else
     swapcontext(&w.ctx[w.cur], &w.sched);
+#endif
 }
 
 // Publishes `v`, waits for the other lanes, returns the 32 operands of this primitive.
@@ -73,12 +114,26 @@ template <typename T> inline T read_slot(const uint64_t *slots, int l) {
     return out;
 }
 
+#if WARP_EMU_FAST_SWITCH
+extern "C" inline void warp_emu_trampoline() {
+#else
 inline void trampoline() {
+#endif
     Warp &w = *current();
     const int me = w.cur;
     w.body(me);
     w.done[me] = true;
     while (true) yield(); // never resumed again
+}
+
+constexpr size_t STACK_BYTES = 512 * 1024;
+
+// The lanes' stacks: one allocation per host thread for the life of the process (a fresh, zero-filled 16 MiB per run
+// cost more in page faults than the emulated code in cycles).
+inline char *lane_stacks() {
+    static thread_local std::vector<char> stacks;
+    if (stacks.empty()) stacks.resize(LANES * STACK_BYTES);
+    return stacks.data();
 }
 
 // Runs body(lane) for the 32 lanes of one warp to completion.
@@ -87,14 +142,25 @@ inline void run(const std::function<void(int)> &body) {
     w.body = body;
     current() = &w;
     for (int l = 0; l < LANES; l++) {
-        w.stack[l].resize(512 * 1024);
+        w.stack[l] = lane_stacks() + (size_t)l * STACK_BYTES;
         w.primitives[l] = 0;
         w.done[l] = false;
+#if WARP_EMU_FAST_SWITCH
+        // a frame warp_emu_switch can "return" into: six callee-saved registers, the entry point, and a null return
+        // address so that the entry point sees the stack alignment of a called function
+        uintptr_t top = reinterpret_cast<uintptr_t>(w.stack[l] + STACK_BYTES) & ~uintptr_t(15);
+        void **sp = reinterpret_cast<void **>(top);
+        *--sp = nullptr;
+        *--sp = reinterpret_cast<void *>(&warp_emu_trampoline);
+        for (int r = 0; r < 6; r++) *--sp = nullptr;
+        w.sp[l] = sp;
+#else
         getcontext(&w.ctx[l]);
-        w.ctx[l].uc_stack.ss_sp = w.stack[l].data();
-        w.ctx[l].uc_stack.ss_size = w.stack[l].size();
+        w.ctx[l].uc_stack.ss_sp = w.stack[l];
+        w.ctx[l].uc_stack.ss_size = STACK_BYTES;
         w.ctx[l].uc_link = nullptr;
         makecontext(&w.ctx[l], trampoline, 0);
+#endif
     }
     while (true) {
         bool any = false;
@@ -102,7 +168,11 @@ inline void run(const std::function<void(int)> &body) {
             if (w.done[l]) continue;
             any = true;
             w.cur = l;
+#if WARP_EMU_FAST_SWITCH
+            warp_emu_switch(&w.sched_sp, w.sp[l]);
+#else
             swapcontext(&w.sched, &w.ctx[l]);
+#endif
         }
         if (!any) break;
     }
