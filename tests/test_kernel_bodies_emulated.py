@@ -159,3 +159,32 @@ def test_macaque_v_word_reader_at_every_alignment(oracle, eb):
         assert np.array_equal(gts, wts), shift
         assert gval.tobytes() == wval.tobytes(), shift
         assert emu.segment_sums(shifted)[0].tobytes() == wsum.tobytes(), shift
+
+
+@pytest.mark.parametrize("block", range(4))
+def test_grid_and_sum_bodies_fuzz(oracle, block):
+    """Random stitched series (constants, ramps, noise, repeats, signed zeros, NaN / inf), random bounds, regular or
+    irregular timestamps: the grid and sum bodies reproduce the oracle from segments whose byte columns sit at a
+    random alignment between poisoned bytes."""
+    from tests.test_warp_fit_emulated import _fuzz_series
+    for seed in range(40 * block, 40 * block + 40):
+        rng = np.random.default_rng(77000 + seed)
+        vals = _fuzz_series(rng)
+        n = len(vals)
+        step = rng.integers(1, 2000, n) if seed % 3 == 0 else np.full(n, int(rng.integers(1, 5000)))
+        ts = (int(rng.integers(0, 2_000_000_000_000_000)) + np.cumsum(step)).astype(np.int64)
+        eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 3))), (2, float(rng.choice([0.01, 0.5, 1.0, 5.0, 30.0, 100.0])))][seed % 3]
+        want = oracle.compress(ts, vals, eb=eb)
+        wts, wval, _ = oracle.grid(want)
+        cols = {c: getattr(want, c) for c in oracle._COLS}
+        for name in ("values", "residuals", "timestamps"):
+            data = cols[name + "_data"]
+            backing = np.full(len(data) + 64, 0x5A, np.uint8)
+            start = (-backing.ctypes.data) % 16 + int(rng.integers(0, 16))
+            backing[start:start + len(data)] = data
+            cols[name + "_data"] = backing[start:start + len(data)]
+        seg = oracle.Segments(**cols)
+        gts, gval, _ = emu.grid(seg)
+        assert np.array_equal(gts, wts), seed
+        assert_f32_bits_equal(gval, wval, f"fuzz grid seed={seed}")
+        assert_f32_bits_equal(emu.segment_sums(seg)[0], oracle.segment_sums(want), f"fuzz sums seed={seed}", nan_payload_matters=False)
