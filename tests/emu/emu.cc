@@ -19,6 +19,7 @@
 #define MDB_WARP_EMU
 #include "warp_emu.h"
 #include "../../modelardb_rs_b200/csrc/mdb_fit_warp.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_macaque_warp.cuh"
 
 using namespace mdb;
 
@@ -252,6 +253,18 @@ void emu_fit_models(const int64_t *ts, const float *values, uint32_t n, uint8_t 
         d.model_type_id = m.model_type_id; d.values_len = m.values_len; d.aborted = aborted; d.irregular = irregular;
         out[k] = d;
     }
+}
+
+// warp_macaque_v_decode (mdb_macaque_warp.cuh) on one stream: out receives `count` values, *last_out the decoder's last value.
+void emu_warp_macaque_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, int has_seed, float seed, float *out, float *last_out) {
+    std::vector<uint32_t> stage(STAGE_WORDS + 1);
+    warp_emu::run([&](int lane) {
+        const float last = warp_macaque_v_decode(bytes, n_bytes, count, has_seed != 0, seed, stage.data(), lane,
+                                                 [&](uint32_t k0, float value, bool valid) {
+                                                     if (valid) out[k0 + lane] = value;
+                                                 });
+        if (lane == 0) *last_out = last;
+    });
 }
 
 uint64_t emu_segments_len(const EmuSegments *s) { return s->model_type_id.size(); }

@@ -1,0 +1,48 @@
+"""The warp-cooperative MacaqueV decoder (csrc/mdb_macaque_warp.cuh: staged stream, branch-free code walk, parallel
+payload extraction, XOR scan) run on the host by the warp emulator against the oracle's serial decoder.  The GPU tests
+cover the same kernel through the C-ABI; this is the inner loop for changing it on a machine without a GPU."""
+import numpy as np
+import pytest
+
+from tests import emu_lib as emu
+
+
+def _streams(rng, n):
+    kind = int(rng.integers(0, 6))
+    if kind == 0:
+        return rng.uniform(-1e3, 1e3, n).astype(np.float32)                       # a new window at almost every value
+    if kind == 1:
+        return (100.0 + np.cumsum(rng.standard_normal(n))).astype(np.float32)     # random walk: reuse and new windows mixed
+    if kind == 2:
+        return np.repeat(rng.uniform(-5, 5, n // 7 + 1).astype(np.float32), 7)[:n]  # runs of equal values: `10` codes
+    if kind == 3:
+        return rng.choice(np.array([0.0, -0.0, 1.0, np.nan, np.inf, -np.inf, 3.4e38, 1e-45], np.float32), n)
+    if kind == 4:
+        return (rng.integers(0, 2**32, n, dtype=np.uint64).astype(np.uint32)).view(np.float32)  # arbitrary bit patterns
+    return np.full(n, np.float32(rng.normal()), np.float32)
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_warp_decoder_equals_serial_decoder(oracle, block):
+    rng = np.random.default_rng(4100 + block)
+    for case in range(25):
+        n = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 500, 1700, 5000])) if case % 2 else int(rng.integers(1, 3000))
+        vals = _streams(rng, n)
+        eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 2))), (2, float(rng.choice([0.1, 1.0, 10.0])))][case % 3]
+        seed = None if case % 4 else np.float32(rng.normal())  # residual streams are seeded with the model's last value
+        stream = oracle.macaque_v_compress(eb, vals, seed=seed)
+        want = oracle.macaque_v_grid(stream.data, n, seed=seed)
+        got, last = emu.warp_macaque_decode(stream.data, n, seed=seed, misalign=int(rng.integers(0, 16)))
+        assert got.tobytes() == want.tobytes(), (block, case, n, eb, seed)
+        assert np.float32(last).tobytes() == want[-1:].tobytes(), (block, case)
+
+
+def test_warp_decoder_refills_its_stage(oracle):
+    """A stream much longer than the 2 KiB stage, decoded from every alignment."""
+    rng = np.random.default_rng(9)
+    vals = rng.uniform(-1e6, 1e6, 20_000).astype(np.float32)
+    stream = oracle.macaque_v_compress((0, 0.0), vals)
+    assert len(stream.data) > 30 * 2048
+    for misalign in (0, 1, 2, 3, 7, 13):
+        got, _ = emu.warp_macaque_decode(stream.data, len(vals), misalign=misalign)
+        assert got.tobytes() == vals.tobytes(), misalign
