@@ -521,171 +521,7 @@ __global__ void __launch_bounds__(128) k_spec_records(const int64_t *__restrict_
     }
 }
 
-// ---- long MacaqueV rows encoded by a whole warp ---------------------------------------------------------
-// The encoder (macaque_v.rs:39-164) looks serial -- the stored value, the XOR window and the bit position of value
-// i all depend on value i - 1 -- but each of the three dependencies is a chain with RESETS whose targets do not
-// depend on history, so 32 values are encoded at once, one per lane:
-//   * lossy bounds: the stored value stays `last_value` while the input is within the bound of it and is otherwise a
-//     function of the input alone (:112-121).  The change points of a batch are found by repeating
-//     "every lane tests its value against the current stored value; ballot; the first failing lane starts a new one".
-//   * the window (leading, trailing) is kept while the XOR fits into it and is otherwise the XOR's own (:134-156):
-//     the same ballot loop, one iteration per new window.
-//   * code lengths are then known per lane; a warp scan gives every code its bit offset, and the lanes OR their codes
-//     into a zeroed shared-memory stage that leaves in coalesced stores.
-// Every decision is the reference's own comparison on the same operands, so the bytes are identical.
-// k_records_macaque_warp runs this on a counter to size the row (and to get min / max, an in-order fold),
-// k_emit_macaque_warp on the writer at the row's final offset.
-struct WarpCodeCounter {
-    uint64_t bits = 0;
-    __device__ __forceinline__ void put(uint64_t, int, uint32_t, uint32_t total_bits) { bits += total_bits; }
-    __device__ __forceinline__ uint64_t bytes() const { return (bits + 7) >> 3; }
-};
-
-struct WarpCodeWriter {
-    static constexpr uint32_t STAGE_BITS = STAGE_WORDS * 32;
-    uint8_t *out;
-    uint32_t *stage; // STAGE_WORDS zeroed words; codes are OR-ed in, MSB first
-    uint32_t bitpos; // bits of the stage in use
-    int lane;
-    __device__ __forceinline__ void init(uint8_t *o, uint32_t *stage_, int lane_) {
-        out = o; stage = stage_; bitpos = 0; lane = lane_;
-        for (int i = lane; i < STAGE_WORDS; i += 32) stage[i] = 0;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void write_bytes(uint32_t n_bytes) {
-        for (uint32_t i = (uint32_t)lane; i < n_bytes; i += 32) out[i] = (uint8_t)(stage[i >> 2] >> (24 - 8 * (i & 3)));
-        out += n_bytes;
-    }
-    __device__ __forceinline__ void drain() { // whole words leave; the partial word moves to the front
-        __syncwarp();
-        const uint32_t n_words = bitpos >> 5;
-        write_bytes(n_words * 4);
-        __syncwarp();
-        const uint32_t partial = stage[n_words & (STAGE_WORDS - 1)];
-        __syncwarp();
-        for (int i = lane; i < STAGE_WORDS; i += 32) stage[i] = (i == 0 && (bitpos & 31)) ? partial : 0u;
-        bitpos &= 31;
-        __syncwarp();
-    }
-    // this lane's code (`len` low bits of `code`, len <= 45) at bit `off` of a batch of `total_bits` bits
-    __device__ __forceinline__ void put(uint64_t code, int len, uint32_t off, uint32_t total_bits) {
-        if (bitpos + total_bits > STAGE_BITS) drain();
-        uint32_t p = bitpos + off;
-        int remaining = len;
-        while (remaining > 0) {
-            const int r = (int)(p & 31), take = min(32 - r, remaining);
-            const uint32_t piece = (uint32_t)(code >> (remaining - take)) & (take == 32 ? 0xFFFFFFFFu : ((1u << take) - 1u));
-            atomicOr(&stage[p >> 5], piece << (32 - r - take));
-            remaining -= take;
-            p += (uint32_t)take;
-        }
-        bitpos += total_bits;
-        __syncwarp();
-    }
-    __device__ __forceinline__ void finish() { // zero padding to a whole byte (macaque_v.rs:160-164)
-        __syncwarp();
-        write_bytes((bitpos + 7) / 8);
-    }
-};
-
-template <typename Sink>
-__device__ __forceinline__ void warp_macaque_v_encode(const ErrorBound &eb, const float *__restrict__ values, uint32_t lo, uint32_t hi, Sink &sink,
-                                                      int lane, float &min_out, float &max_out) {
-    float min_value = __uint_as_float(0x7fc00000u), max_value = min_value; // macaque_v.rs:199-204, folded in order
-    float last_value = 0.0f;                                                // stored value before the batch
-    uint32_t win_l = 255, win_t = 0;                                        // window before the batch
-    for (uint32_t k0 = lo; k0 <= hi; k0 += 32) {
-        const int cnt = (int)min(32u, hi - k0 + 1);
-        const bool in = lane < cnt;
-        const float raw = in ? values[k0 + (uint32_t)lane] : 0.0f;
-        const bool first_batch = k0 == lo;
-        // ---- stored values
-        float stored = raw;
-        if (eb.kind != KIND_LOSSLESS) {
-            float cur = first_batch ? __shfl_sync(FULL_MASK, raw, 0) : last_value; // the first value of a row is stored raw (:79-83)
-            int pos = first_batch ? 1 : 0;
-            if (first_batch && lane == 0) stored = raw;
-            while (true) {
-                const bool changes = in && lane >= pos && !is_value_within_error_bound(eb, raw, cur);
-                const unsigned m = __ballot_sync(FULL_MASK, changes);
-                const int j = m ? __ffs(m) - 1 : 32;
-                if (lane >= pos && lane < j) stored = cur;
-                if (j == 32) break;
-                const float fresh = rewrite_least_mantissa_bits(eb, __shfl_sync(FULL_MASK, raw, j));
-                if (lane == j) stored = fresh;
-                cur = fresh;
-                pos = j + 1;
-            }
-        }
-        // ---- XOR with the previous stored value
-        float prev = __shfl_up_sync(FULL_MASK, stored, 1);
-        if (lane == 0) prev = last_value;
-        const bool is_raw = first_batch && lane == 0; // 32 raw bits, no XOR code
-        const uint32_t x = (in && !is_raw) ? (__float_as_uint(stored) ^ __float_as_uint(prev)) : 0u;
-        const uint32_t lz = x ? (uint32_t)__clz((int)x) : 32u, tz = x ? (uint32_t)(__ffs((int)x) - 1) : 0u;
-        // ---- windows
-        uint32_t my_l = win_l, my_t = win_t;
-        bool is_new = false;
-        {
-            int pos = 0;
-            while (true) {
-                const bool resets = lane >= pos && x != 0u && !(lz >= win_l && tz >= win_t);
-                const unsigned m = __ballot_sync(FULL_MASK, resets);
-                const int j = m ? __ffs(m) - 1 : 32;
-                if (lane >= pos && lane < j) { my_l = win_l; my_t = win_t; }
-                if (j == 32) break;
-                win_l = __shfl_sync(FULL_MASK, lz, j);
-                win_t = __shfl_sync(FULL_MASK, tz, j);
-                if (lane == j) { my_l = win_l; my_t = win_t; is_new = true; }
-                pos = j + 1;
-            }
-        }
-        // ---- codes
-        uint64_t code = 0;
-        int len = 0;
-        if (in) {
-            if (is_raw) {
-                code = __float_as_uint(stored);
-                len = 32;
-            } else if (x == 0u) {
-                code = 0b10;
-                len = 2;
-            } else {
-                const uint32_t meaningful = 32u - my_l - my_t;
-                if (is_new) {
-                    code = ((uint64_t)((0b11u << 11) | (my_l << 6) | meaningful) << meaningful) | (uint64_t)(x >> my_t);
-                    len = 13 + (int)meaningful;
-                } else {
-                    code = (uint64_t)(x >> my_t); // a leading `0` flag, then the meaningful bits
-                    len = 1 + (int)meaningful;
-                }
-            }
-        }
-        uint32_t end = (uint32_t)len; // inclusive scan of the lengths
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(FULL_MASK, end, d);
-            if (lane >= d) end += o;
-        }
-        const uint32_t total = __shfl_sync(FULL_MASK, end, 31);
-        sink.put(code, len, end - (uint32_t)len, total);
-        // ---- min / max over the stored values, in order (rust_minf / rust_maxf are "leftmost" folds: associative)
-        float mn = in ? stored : __uint_as_float(0x7fc00000u), mx = mn;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const float on = __shfl_up_sync(FULL_MASK, mn, d), ox = __shfl_up_sync(FULL_MASK, mx, d);
-            if (lane >= d) {
-                mn = rust_minf(on, mn);
-                mx = rust_maxf(ox, mx);
-            }
-        }
-        min_value = rust_minf(min_value, __shfl_sync(FULL_MASK, mn, 31));
-        max_value = rust_maxf(max_value, __shfl_sync(FULL_MASK, mx, 31));
-        last_value = __shfl_sync(FULL_MASK, stored, cnt - 1);
-    }
-    min_out = min_value;
-    max_out = max_value;
-}
+// ---- long MacaqueV rows encoded by a whole warp: warp_macaque_v_encode, WarpCodeCounter, WarpCodeWriter (mdb_macaque_warp.cuh)
 
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_records_macaque_warp(const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
                                                                            const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,

@@ -267,6 +267,33 @@ void emu_warp_macaque_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t co
     });
 }
 
+// warp_macaque_v_encode (mdb_macaque_warp.cuh) on one series: first through the counter (how k_records_macaque_warp sizes a
+// row), then through the writer (k_emit_macaque_warp).  Returns the bytes written to out (capacity >= 6 * count + 8).
+uint64_t emu_warp_macaque_encode(uint8_t eb_kind, float eb_value, const float *values, uint32_t count, uint8_t *out, float *min_out,
+                                 float *max_out, uint64_t *counted_bytes) {
+    const ErrorBound eb = make_error_bound(eb_kind, eb_value);
+    std::vector<uint32_t> stage(STAGE_WORDS + 1);
+    uint64_t written = 0;
+    warp_emu::run([&](int lane) {
+        WarpCodeCounter counter;
+        float mn, mx;
+        warp_macaque_v_encode(eb, values, 0, count - 1, counter, lane, mn, mx);
+        WarpCodeWriter writer;
+        writer.init(out, stage.data(), lane);
+        float mn2, mx2;
+        warp_macaque_v_encode(eb, values, 0, count - 1, writer, lane, mn2, mx2);
+        writer.finish();
+        if (lane == 0) {
+            *counted_bytes = counter.bytes();
+            *min_out = mn2;
+            *max_out = mx2;
+            written = (uint64_t)(writer.out - out);
+            if (!(__float_as_uint(mn) == __float_as_uint(mn2) && __float_as_uint(mx) == __float_as_uint(mx2))) written = ~0ull; // both passes agree
+        }
+    });
+    return written;
+}
+
 uint64_t emu_segments_len(const EmuSegments *s) { return s->model_type_id.size(); }
 void emu_segments_view(const EmuSegments *s, SegmentsView *v, const uint64_t **unit_seg_off) {
     v->n_segments = s->model_type_id.size();

@@ -199,3 +199,18 @@ def warp_macaque_decode(data: bytes, count: int, seed=None, misalign: int = 0):
     lib().emu_warp_macaque_decode(_p(stream), C.c_uint64(len(raw)), C.c_uint32(count), 0 if seed is None else 1,
                                   C.c_float(0.0 if seed is None else float(np.float32(seed))), _p(out), _p(last))
     return out, last[0]
+
+
+def warp_macaque_encode(values, eb=(0, 0.0)):
+    """warp_macaque_v_encode (csrc/mdb_macaque_warp.cuh) run by 32 emulated lanes: returns (bytes, min, max, the size the
+    counting pass predicted)."""
+    vals = np.ascontiguousarray(values, np.float32)
+    out = np.full(6 * len(vals) + 8, 0xEE, np.uint8)
+    mn, mx = np.zeros(1, np.float32), np.zeros(1, np.float32)
+    counted = np.zeros(1, np.uint64)
+    L = lib()
+    L.emu_warp_macaque_encode.restype = C.c_uint64
+    n = L.emu_warp_macaque_encode(C.c_uint8(eb[0]), C.c_float(eb[1]), _p(vals), C.c_uint32(len(vals)), _p(out), _p(mn), _p(mx), _p(counted))
+    if n == 2**64 - 1:
+        raise AssertionError("the counting and the writing pass disagree on min / max")
+    return out[:n].tobytes(), mn[0], mx[0], int(counted[0])

@@ -1,6 +1,7 @@
-"""The warp-cooperative MacaqueV decoder (csrc/mdb_macaque_warp.cuh: staged stream, branch-free code walk, parallel
-payload extraction, XOR scan) run on the host by the warp emulator against the oracle's serial decoder.  The GPU tests
-cover the same kernel through the C-ABI; this is the inner loop for changing it on a machine without a GPU."""
+"""The warp-cooperative MacaqueV decoder and encoder (csrc/mdb_macaque_warp.cuh: staged stream, branch-free code walk,
+parallel payload extraction, XOR scan; ballot loops for stored values and windows, scanned bit offsets, OR-ed stage) run
+on the host by the warp emulator against the oracle's serial coder.  The GPU tests cover the same code through the
+C-ABI; this is the inner loop for changing it on a machine without a GPU."""
 import numpy as np
 import pytest
 
@@ -46,3 +47,32 @@ def test_warp_decoder_refills_its_stage(oracle):
     for misalign in (0, 1, 2, 3, 7, 13):
         got, _ = emu.warp_macaque_decode(stream.data, len(vals), misalign=misalign)
         assert got.tobytes() == vals.tobytes(), misalign
+
+
+@pytest.mark.parametrize("block", range(6))
+def test_warp_encoder_equals_serial_encoder(oracle, block):
+    rng = np.random.default_rng(5200 + block)
+    for case in range(25):
+        n = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 500, 1700, 5000])) if case % 2 else int(rng.integers(1, 3000))
+        vals = _streams(rng, n)
+        eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 2))), (2, float(rng.choice([0.1, 1.0, 10.0, 100.0])))][case % 3]
+        want = oracle.macaque_v_compress(eb, vals)
+        data, mn, mx, counted = emu.warp_macaque_encode(vals, eb)
+        assert data == want.data, (block, case, n, eb)
+        assert counted == len(want.data), (block, case)
+        # min / max of the STORED values (macaque_v.rs:199-204); NaN payloads are not part of the contract
+        for got, ref in ((mn, want.min_value), (mx, want.max_value)):
+            assert (np.isnan(got) and np.isnan(ref)) or np.float32(got).tobytes() == np.float32(ref).tobytes(), (block, case, got, ref)
+
+
+def test_warp_encoder_drains_its_stage(oracle):
+    """A stream much longer than the 2 KiB stage (several drains, a partial word carried over each time), lossless and
+    lossy; decoding the emulated encoder's bytes with the emulated decoder closes the loop."""
+    rng = np.random.default_rng(10)
+    vals = rng.uniform(-1e6, 1e6, 12_000).astype(np.float32)
+    for eb in [(0, 0.0), (2, 0.5)]:
+        want = oracle.macaque_v_compress(eb, vals)
+        data, _, _, counted = emu.warp_macaque_encode(vals, eb)
+        assert data == want.data and counted == len(data) and len(data) > 10 * 2048
+        got, _ = emu.warp_macaque_decode(data, len(vals), misalign=5)
+        assert got.tobytes() == oracle.macaque_v_grid(want.data, len(vals)).tobytes()
