@@ -96,13 +96,24 @@ class GridStream:
     reference's `maybe_predicate` (all points are reconstructed, then pruned: grid_exec.rs:368-386).
     tag_runs: hand out every tag column as (values, run_lengths) instead of one string per created row (SURVEY 8(f2):
     tags as run-lengths); np.repeat(values, run_lengths) is the column the reference builds.
+    limit: like the reference's, batch_size becomes min(limit, batch_size) (grid_exec.rs:239-246).  The reference leaves
+    stopping to the LimitExec above it; here the stream also ends after `limit` rows and -- the push-down of SURVEY
+    8(f2) -- reconstructs only the leading segments of an input batch that are needed to reach it (when there is no
+    predicate, whose selectivity is unknown).  The first `limit` rows are the reference's first `limit` rows.
     """
 
     def __init__(self, input: Iterable[Tuple[object, Sequence[np.ndarray]]], batch_size: int, n_tag_columns: int = 0,
                  predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None,
-                 time_range: Optional[Tuple[Optional[int], Optional[int]]] = None, tag_runs: bool = False):
+                 time_range: Optional[Tuple[Optional[int], Optional[int]]] = None, tag_runs: bool = False,
+                 limit: Optional[int] = None):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
+        if limit is not None:
+            if limit <= 0:
+                raise ValueError("limit must be positive")
+            batch_size = min(limit, batch_size)
+        self.limit = limit
+        self._handed_out = 0
         self._input: Iterator = iter(input)
         self._input_done = False
         self.batch_size = batch_size
@@ -146,7 +157,19 @@ class GridStream:
             point_off, ts, vals = np.zeros(1, np.uint64), np.zeros(0, np.int64), np.zeros(0, np.float32)
         else:
             point_off, _ = mc.grid_count(host, self.ctx)
-            ts, vals = mc.grid(host, ctx=self.ctx)
+            if self.limit is not None and self.predicate is None:
+                # rows still owed beyond the leftovers; the first segments that cover them are enough
+                owed = self.limit - self._handed_out - self._remaining()
+                needed = int(np.searchsorted(point_off[1:], max(owed, 0), "left")) + 1 if owed > 0 else 0
+                if needed < len(host):
+                    self.segments_skipped += len(host) - needed
+                    host = host.slice(0, needed)
+                    tags = [np.asarray(t, object)[:needed] for t in tags]
+                    point_off = point_off[:needed + 1]
+            if len(host) == 0:
+                ts, vals = np.zeros(0, np.int64), np.zeros(0, np.float32)
+            else:
+                ts, vals = mc.grid(host, ctx=self.ctx)
         self.metrics.add_batch(host, point_off)
         lens = np.diff(point_off).astype(np.int64)
         runs = self._tags.tail(self._offset)
@@ -164,6 +187,8 @@ class GridStream:
 
     def __next__(self):
         # grid_exec.rs:394-430
+        if self.limit is not None and self._handed_out >= self.limit:
+            raise StopIteration
         if self._remaining() < self.batch_size and not self._input_done:
             try:
                 segments, tags = next(self._input)
@@ -173,8 +198,11 @@ class GridStream:
         if self._input_done and self._remaining() == 0:
             raise StopIteration
         length = min(self.batch_size, self._remaining())
+        if self.limit is not None:
+            length = min(length, self.limit - self._handed_out)
         lo, hi = self._offset, self._offset + length
         self._offset = hi
+        self._handed_out += length
         runs = self._tags.slice(lo, hi)
         tags = runs if self.tag_runs else [np.repeat(values, lens) for values, lens in runs]
         return (self._timestamps[lo:hi], self._values[lo:hi], *tags)

@@ -151,3 +151,26 @@ def _take_any(host, order):
         cols[name + "_off"] = np.concatenate([[0], np.cumsum(lens)]).astype(np.uint64)
         cols[name + "_data"] = np.concatenate([getattr(p, name + "_data") for p in parts]) if len(parts) else np.zeros(0, np.uint8)
     return mc.HostSegments(**cols)
+
+
+@pytest.mark.parametrize("limit", [1, 7, 4096, 5000, 20000])
+def test_limit_gives_the_first_rows_and_skips_the_rest(oracle_behind_the_cabi, limit):
+    """LIMIT: batch_size = min(limit, batch_size) as in the reference (grid_exec.rs:239-246); the stream also ends after
+    `limit` rows and only reconstructs the segments it needs for them."""
+    batches, want_ts, want_val, want_tag, hosts = _batches(oracle_behind_the_cabi)
+    stream = ops.GridStream(batches, 4096, n_tag_columns=1, limit=limit)
+    out = list(stream)
+    assert stream.batch_size == min(limit, 4096) and all(len(b[0]) <= stream.batch_size for b in out)
+    n = min(limit, len(want_ts))
+    assert np.array_equal(np.concatenate([b[0] for b in out]), want_ts[:n])
+    assert np.concatenate([b[1] for b in out]).tobytes() == want_val[:n].tobytes()
+    assert np.array_equal(np.concatenate([b[2] for b in out]), want_tag[:n])
+    if limit < len(want_ts) // 2:
+        assert stream.segments_skipped > 0 and stream.metrics.rows_created < len(want_ts)
+    # with a predicate nothing can be skipped up front, but the first `limit` surviving rows are the same
+    keep = (want_ts % 5000) < 2500
+    filtered = list(ops.GridStream(batches, 4096, n_tag_columns=1, limit=limit, predicate=lambda t, v: (t % 5000) < 2500))
+    m = min(limit, int(keep.sum()))
+    assert np.array_equal(np.concatenate([b[0] for b in filtered]), want_ts[keep][:m])
+    with pytest.raises(ValueError, match="limit"):
+        ops.GridStream(batches, 4096, limit=0)
