@@ -96,3 +96,14 @@ def test_emulated_warp_engine_fuzz(oracle, seed):
     want = oracle.compress(ts, vals, eb=eb)
     got = emu.compress(ts, vals, eb=eb, chunk_len=int(rng.choice([8, 100, 700])), sched_seed=seed + 1, in_flight=int(rng.choice([1, 2, 9])), engine=2)
     assert_segments_equal(got, want, f"fuzz seed={seed} eb={eb} n={n}")
+
+
+@pytest.mark.parametrize("chunk_len,sched", [(4096, (3, 4)), (700, (9, 2))], ids=["async-4096", "async-700"])
+def test_emulated_warp_engine_on_long_models(oracle, chunk_len, sched):
+    """The long-model series of the GPU tests (models of thousands of points, values right around the bounds, zeros, sign
+    changes, special values, extreme magnitudes) through the emulated warp engine and the asynchronous scheduler."""
+    for name, ts, vals, eb in long_model_cases():
+        want = oracle.compress(ts, vals, eb=eb)
+        got = emu.compress(ts, vals, eb=eb, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2)
+        assert_segments_equal(got, want, f"{name} chunk_len={chunk_len}")
+    assert emu.division_mismatches() == 0
