@@ -10,6 +10,13 @@
 
 #if defined(__CUDACC__) || defined(MDB_WARP_EMU)
 
+// 1: the decoder takes whole runs of `0` codes (the XOR in the window in force) in one step instead of walking them one by
+// one.  Exact (every code of a run is verified by its flag bit) and emulated against the oracle, but not yet run or
+// measured on a GPU: compiled out until it has been.
+#ifndef MDB_MACAQUE_SPECULATE_RUNS
+#define MDB_MACAQUE_SPECULATE_RUNS 0
+#endif
+
 #ifdef MDB_WARP_EMU
 #define MDB_WARP_FN inline
 static inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t shift) {
@@ -103,6 +110,10 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
     uint32_t trailing_zeros = 0;
     uint32_t width_in_force = 32; // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = 255 at first
     uint32_t last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
+#if MDB_MACAQUE_SPECULATE_RUNS
+    bool speculate = true; // the same in every lane
+    int reuse_codes = 0;   // `0` codes among those walked one by one in the current batch
+#endif
     for (uint32_t k0 = 0; k0 < count; k0 += 32) {
         const int cnt = (int)(count - k0 < 32u ? count - k0 : 32u);
         bits.cover(p, 32u * 45u + 64u, lane);
@@ -127,6 +138,9 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
             const uint32_t packed = (reuse | fresh) ? ((rel + header) | (width << 15) | (trailing_zeros << 21)) : 0u;
             rel += header + width;
             if (k == lane) mine = packed;
+#if MDB_MACAQUE_SPECULATE_RUNS
+            reuse_codes += reuse ? 1 : 0;
+#endif
         };
         int k_begin = 0;
         if (!has_seed && k0 == 0) { // macaque_v.rs:282-285: the first value is stored raw
@@ -134,12 +148,42 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
             rel += 32;
             k_begin = 1;
         }
+#if MDB_MACAQUE_SPECULATE_RUNS
+        if (speculate) {
+            // Runs of `0` codes in one step: lane l looks at the bit where its code starts IF all codes from k up to it are
+            // `0` codes of the width in force; the first set bit ends the run (every `0` code before it is thereby verified,
+            // and fixes where the next code starts).  The code that ended the run is walked serially, then the next run.
+            int k = k_begin, serial_codes = 0;
+            while (k < cnt) {
+                const uint32_t stride = 1u + width_in_force;
+                const bool candidate = lane >= k && lane < cnt;
+                const uint32_t my_rel = candidate ? rel + (uint32_t)(lane - k) * stride : rel;
+                const bool ends_run = candidate && (bits.peek32(my_rel) & 0x80000000u);
+                const unsigned enders = __ballot_sync(0xffffffffu, ends_run);
+                const int good = enders ? __ffs((int)enders) - 1 : cnt;
+                if (candidate && lane < good) mine = (my_rel + 1u) | (width_in_force << 15) | (trailing_zeros << 21);
+                rel += (uint32_t)(good - k) * stride;
+                k = good;
+                if (k < cnt) {
+                    walk_one(k);
+                    k++;
+                    serial_codes++;
+                }
+            }
+            speculate = serial_codes <= 12; // mostly `10` / `11` codes: the plain walk is cheaper
+        } else {
+            reuse_codes = 0;
+            for (int k = k_begin; k < cnt; k++) walk_one(k);
+            speculate = reuse_codes >= 24; // back to runs when nearly every code of this batch was a `0` code
+        }
+#else
         if (cnt == 32 && k_begin == 0) {
 #pragma unroll
             for (int k = 0; k < 32; k++) walk_one(k);
         } else {
             for (int k = k_begin; k < cnt; k++) walk_one(k);
         }
+#endif
         p += rel - rel0;
         uint32_t x = 0;
         const uint32_t my_width = (mine >> 15) & 63u, my_shift = mine >> 21;

@@ -63,7 +63,8 @@ _variants = {}
 
 
 def variant(*defines):
-    """A separate build of emu.cc with extra -D flags (e.g. "MDB_FIT_WIDE_ENABLED=1"); only emu_fit_models is bound."""
+    """A separate build of emu.cc with extra -D flags (e.g. "MDB_FIT_WIDE_ENABLED=1"); emu_fit_models and
+    emu_warp_macaque_decode are the entry points used on variants."""
     key = tuple(defines)
     if key not in _variants:
         lib()  # (builds the default library first, so compile errors show up there)
@@ -186,9 +187,9 @@ def check_eight_points(ts, values, eb) -> int:
     return int(lib().emu_check_eight_points(_p(ts), _p(vals), len(ts), eb[0], eb[1]))
 
 
-def warp_macaque_decode(data: bytes, count: int, seed=None, misalign: int = 0):
+def warp_macaque_decode(data: bytes, count: int, seed=None, misalign: int = 0, library=None):
     """warp_macaque_v_decode (csrc/mdb_macaque_warp.cuh) run by 32 emulated lanes on one MacaqueV stream placed `misalign`
-    bytes past a 16-byte boundary between poisoned bytes; returns (values, last value)."""
+    bytes past a 16-byte boundary between poisoned bytes; returns (values, last value).  library: a variant() build."""
     raw = np.frombuffer(data, np.uint8)
     backing = np.full(len(raw) + 64, 0xC3, np.uint8)
     start = (-backing.ctypes.data) % 16 + misalign
@@ -196,7 +197,7 @@ def warp_macaque_decode(data: bytes, count: int, seed=None, misalign: int = 0):
     stream = backing[start:start + len(raw)]
     out = np.zeros(count, np.float32)
     last = np.zeros(1, np.float32)
-    lib().emu_warp_macaque_decode(_p(stream), C.c_uint64(len(raw)), C.c_uint32(count), 0 if seed is None else 1,
+    (library or lib()).emu_warp_macaque_decode(_p(stream), C.c_uint64(len(raw)), C.c_uint32(count), 0 if seed is None else 1,
                                   C.c_float(0.0 if seed is None else float(np.float32(seed))), _p(out), _p(last))
     return out, last[0]
 

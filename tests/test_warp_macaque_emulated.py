@@ -23,8 +23,16 @@ def _streams(rng, n):
     return np.full(n, np.float32(rng.normal()), np.float32)
 
 
+def _library(runs):
+    """The product's decoder, or the build that takes runs of `0` codes in one step (MDB_MACAQUE_SPECULATE_RUNS=1: exact,
+    emulated here, compiled out of the product until it has been measured on a GPU)."""
+    return emu.variant("MDB_MACAQUE_SPECULATE_RUNS=1") if runs else None
+
+
+@pytest.mark.parametrize("runs", [False, True], ids=["walk", "runs"])
 @pytest.mark.parametrize("block", range(6))
-def test_warp_decoder_equals_serial_decoder(oracle, block):
+def test_warp_decoder_equals_serial_decoder(oracle, block, runs):
+    library = _library(runs)
     rng = np.random.default_rng(4100 + block)
     for case in range(25):
         n = int(rng.choice([1, 2, 31, 32, 33, 64, 65, 500, 1700, 5000])) if case % 2 else int(rng.integers(1, 3000))
@@ -33,20 +41,43 @@ def test_warp_decoder_equals_serial_decoder(oracle, block):
         seed = None if case % 4 else np.float32(rng.normal())  # residual streams are seeded with the model's last value
         stream = oracle.macaque_v_compress(eb, vals, seed=seed)
         want = oracle.macaque_v_grid(stream.data, n, seed=seed)
-        got, last = emu.warp_macaque_decode(stream.data, n, seed=seed, misalign=int(rng.integers(0, 16)))
+        got, last = emu.warp_macaque_decode(stream.data, n, seed=seed, misalign=int(rng.integers(0, 16)), library=library)
         assert got.tobytes() == want.tobytes(), (block, case, n, eb, seed)
         assert np.float32(last).tobytes() == want[-1:].tobytes(), (block, case)
 
 
-def test_warp_decoder_refills_its_stage(oracle):
+@pytest.mark.parametrize("runs", [False, True], ids=["walk", "runs"])
+def test_warp_decoder_refills_its_stage(oracle, runs):
     """A stream much longer than the 2 KiB stage, decoded from every alignment."""
     rng = np.random.default_rng(9)
     vals = rng.uniform(-1e6, 1e6, 20_000).astype(np.float32)
     stream = oracle.macaque_v_compress((0, 0.0), vals)
     assert len(stream.data) > 30 * 2048
     for misalign in (0, 1, 2, 3, 7, 13):
-        got, _ = emu.warp_macaque_decode(stream.data, len(vals), misalign=misalign)
+        got, _ = emu.warp_macaque_decode(stream.data, len(vals), misalign=misalign, library=_library(runs))
         assert got.tobytes() == vals.tobytes(), misalign
+
+
+def test_run_decoder_on_streams_that_switch_between_kinds_of_code(oracle):
+    """Stretches of noise (`0` codes), of repeated values (`10` codes) and of values of wildly different magnitude (`11`
+    codes) in one stream: the run decoder changes between its two modes and must stay exact across the switches."""
+    rng = np.random.default_rng(12)
+    parts = []
+    for _ in range(60):
+        kind, m = int(rng.integers(0, 3)), int(rng.integers(5, 300))
+        if kind == 0:
+            parts.append(100.0 + rng.standard_normal(m))
+        elif kind == 1:
+            parts.append(np.full(m, rng.normal()))
+        else:
+            parts.append(rng.standard_normal(m) * 10.0 ** rng.integers(-20, 20, m))
+    vals = np.concatenate(parts).astype(np.float32)
+    for eb in [(0, 0.0), (2, 1.0)]:
+        for seed in (None, np.float32(3.5)):
+            stream = oracle.macaque_v_compress(eb, vals, seed=seed)
+            want = oracle.macaque_v_grid(stream.data, len(vals), seed=seed)
+            got, _ = emu.warp_macaque_decode(stream.data, len(vals), seed=seed, misalign=3, library=_library(True))
+            assert got.tobytes() == want.tobytes(), (eb, seed)
 
 
 @pytest.mark.parametrize("block", range(6))
