@@ -10,9 +10,9 @@
 
 #if defined(__CUDACC__) || defined(MDB_WARP_EMU)
 
-// 1: the decoder takes whole runs of `0` codes (the XOR in the window in force) in one step instead of walking them one by
-// one.  Exact (every code of a run is verified by its flag bit) and emulated against the oracle, but not yet run or
-// measured on a GPU: compiled out until it has been.
+// 1: the decoder takes whole runs of `0` codes (the XOR in the window in force) and of `10` codes (the same value again)
+// in one step instead of walking them one by one.  Exact (every code of a run is verified by its own flag bits) and
+// emulated against the oracle, but not yet run or measured on a GPU: compiled out until it has been.
 #ifndef MDB_MACAQUE_SPECULATE_RUNS
 #define MDB_MACAQUE_SPECULATE_RUNS 0
 #endif
@@ -111,8 +111,8 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
     uint32_t width_in_force = 32; // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = 255 at first
     uint32_t last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
 #if MDB_MACAQUE_SPECULATE_RUNS
-    bool speculate = true; // the same in every lane
-    int reuse_codes = 0;   // `0` codes among those walked one by one in the current batch
+    bool speculate = true;   // the same in every lane
+    int batches_walked = 0;  // batches since the plain walk took over
 #endif
     for (uint32_t k0 = 0; k0 < count; k0 += 32) {
         const int cnt = (int)(count - k0 < 32u ? count - k0 : 32u);
@@ -138,9 +138,6 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
             const uint32_t packed = (reuse | fresh) ? ((rel + header) | (width << 15) | (trailing_zeros << 21)) : 0u;
             rel += header + width;
             if (k == lane) mine = packed;
-#if MDB_MACAQUE_SPECULATE_RUNS
-            reuse_codes += reuse ? 1 : 0;
-#endif
         };
         int k_begin = 0;
         if (!has_seed && k0 == 0) { // macaque_v.rs:282-285: the first value is stored raw
@@ -150,31 +147,37 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
         }
 #if MDB_MACAQUE_SPECULATE_RUNS
         if (speculate) {
-            // Runs of `0` codes in one step: lane l looks at the bit where its code starts IF all codes from k up to it are
-            // `0` codes of the width in force; the first set bit ends the run (every `0` code before it is thereby verified,
-            // and fixes where the next code starts).  The code that ended the run is walked serially, then the next run.
-            int k = k_begin, serial_codes = 0;
+            // Runs of equal kinds of code in one step.  The code at `rel` says what kind of run starts there: `0` codes of
+            // the width in force (1 + width bits each) or `10` codes (2 bits each); lane l looks at the bits where its
+            // code starts IF all codes from k up to it belong to that run, and the first lane whose bits say otherwise
+            // ends it (every code before it is thereby verified, and fixes where the next one starts).  A `11` code
+            // changes the window and is walked on its own.
+            int k = k_begin, steps = 0;
             while (k < cnt) {
-                const uint32_t stride = 1u + width_in_force;
-                const bool candidate = lane >= k && lane < cnt;
-                const uint32_t my_rel = candidate ? rel + (uint32_t)(lane - k) * stride : rel;
-                const bool ends_run = candidate && (bits.peek32(my_rel) & 0x80000000u);
-                const unsigned enders = __ballot_sync(0xffffffffu, ends_run);
-                const int good = enders ? __ffs((int)enders) - 1 : cnt;
-                if (candidate && lane < good) mine = (my_rel + 1u) | (width_in_force << 15) | (trailing_zeros << 21);
-                rel += (uint32_t)(good - k) * stride;
-                k = good;
-                if (k < cnt) {
+                steps++;
+                const uint32_t first = bits.peek32(rel) >> 30;
+                if (first == 3u) {
                     walk_one(k);
                     k++;
-                    serial_codes++;
+                    continue;
                 }
+                const bool zero_run = first < 2u;
+                const uint32_t stride = zero_run ? 1u + width_in_force : 2u;
+                const bool candidate = lane >= k && lane < cnt;
+                const uint32_t my_rel = candidate ? rel + (uint32_t)(lane - k) * stride : rel;
+                const uint32_t my_bits = bits.peek32(my_rel) >> 30;
+                const bool ends_run = candidate && (zero_run ? my_bits >= 2u : my_bits != 2u);
+                const unsigned enders = __ballot_sync(0xffffffffu, ends_run);
+                const int good = enders ? __ffs((int)enders) - 1 : cnt;
+                if (candidate && lane < good) mine = zero_run ? ((my_rel + 1u) | (width_in_force << 15) | (trailing_zeros << 21)) : 0u;
+                rel += (uint32_t)(good - k) * stride;
+                k = good;
             }
-            speculate = serial_codes <= 12; // mostly `10` / `11` codes: the plain walk is cheaper
+            speculate = steps <= 12; // short runs everywhere: the plain walk is cheaper
+            batches_walked = 0;
         } else {
-            reuse_codes = 0;
             for (int k = k_begin; k < cnt; k++) walk_one(k);
-            speculate = reuse_codes >= 24; // back to runs when nearly every code of this batch was a `0` code
+            speculate = ++batches_walked >= 8; // try runs again every few batches
         }
 #else
         if (cnt == 32 && k_begin == 0) {
