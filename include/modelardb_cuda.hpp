@@ -9,6 +9,9 @@
 //   query operators
 //     GridStream                                    crates/modelardb_storage/src/query/grid_exec.rs:197-430
 //     Model{Count,Min,Max,Sum,Avg}Accumulator       crates/modelardb_storage/src/optimizer/model_simple_aggregates.rs:336-618
+//     grouped_model_aggregates                      the aggregate rule (:203-334) extended to GROUP BY <tag columns>
+//   server compressor
+//     compress_finished_buffers                     crates/modelardb_server/src/storage/uncompressed_data_manager.rs:530-581
 //
 // The reference is Rust and its toolchain is not in this image, so the host side is C++ (the Python package under
 // modelardb_rs_b200/ is the same mirror for the tests and the benchmark).  Header only; link libmodelardb_cuda.so.
@@ -18,7 +21,10 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <functional>
 #include <limits>
+#include <map>
+#include <optional>
 #include <stdexcept>
 #include <string>
 #include <utility>
@@ -116,6 +122,26 @@ struct CompressedSegmentBatch {
         cut(timestamps_off, timestamps, out.timestamps_off, out.timestamps);
         cut(values_off, values, out.values_off, out.values);
         cut(residuals_off, residuals, out.residuals_off, out.residuals);
+        return out;
+    }
+    // The rows with keep[row] != 0, in their original order.
+    CompressedSegmentBatch take(const std::vector<uint8_t> &keep) const {
+        CompressedSegmentBatch out;
+        for (size_t row = 0; row < num_rows(); row++) {
+            if (!keep[row]) continue;
+            out.model_type_ids.push_back(model_type_ids[row]);
+            out.start_times.push_back(start_times[row]);
+            out.end_times.push_back(end_times[row]);
+            out.min_values.push_back(min_values[row]);
+            out.max_values.push_back(max_values[row]);
+            auto append = [&](const std::vector<uint64_t> &off, const std::vector<uint8_t> &data, std::vector<uint64_t> &o, std::vector<uint8_t> &d) {
+                d.insert(d.end(), data.begin() + off[row], data.begin() + off[row + 1]);
+                o.push_back(d.size());
+            };
+            append(timestamps_off, timestamps, out.timestamps_off, out.timestamps);
+            append(values_off, values, out.values_off, out.values);
+            append(residuals_off, residuals, out.residuals_off, out.residuals);
+        }
         return out;
     }
 };
@@ -221,43 +247,143 @@ public:
         std::vector<std::vector<std::string>> tags; // one vector per tag column
     };
     using Input = std::pair<CompressedSegmentBatch, std::vector<std::vector<std::string>>>; // (segments, tag columns)
+    // keep[i] != 0 for the reconstructed points that survive (the reference's maybe_predicate, grid_exec.rs:368-386)
+    using Predicate = std::function<std::vector<uint8_t>(const std::vector<int64_t> &, const std::vector<float> &)>;
+
+    struct Options {
+        size_t batch_size = 8192;
+        size_t n_tag_columns = 0;
+        Predicate predicate;
+        // Segments that end before the first or start after the second are not reconstructed at all (the push-down the
+        // reference applies to its Parquet scan, time_series_table.rs:290-373); the predicate must imply the range.
+        std::optional<int64_t> time_range_start, time_range_end;
+        // batch_size becomes min(limit, batch_size) as in the reference (grid_exec.rs:239-246); the stream also ends after
+        // `limit` rows and, without a predicate, reconstructs only the leading segments needed to reach it.
+        std::optional<size_t> limit;
+    };
 
     GridStream(Context &ctx, std::vector<Input> input, size_t batch_size, size_t n_tag_columns = 0)
-        : ctx_(ctx), input_(std::move(input)), batch_size_(batch_size), current_{{}, {}, std::vector<std::vector<std::string>>(n_tag_columns)} {}
+        : GridStream(ctx, std::move(input), make_options(batch_size, n_tag_columns)) {}
+
+    GridStream(Context &ctx, std::vector<Input> input, Options options)
+        : ctx_(ctx), input_(std::move(input)), options_(std::move(options)), current_{{}, {}, std::vector<std::vector<std::string>>(options_.n_tag_columns)} {
+        if (options_.batch_size == 0) throw Error("batch_size must be positive");
+        if (options_.limit) {
+            if (*options_.limit == 0) throw Error("limit must be positive");
+            options_.batch_size = std::min(options_.batch_size, *options_.limit);
+        }
+    }
 
     // Poll::Ready(Some(batch)) -> true (the batch may be empty, as in the reference); Poll::Ready(None) -> false.
     bool poll_next(Batch &out) {
-        if (current_.timestamps.size() - offset_ < batch_size_ && next_input_ < input_.size()) grid_and_append_to_leftovers_in_current_batch(input_[next_input_++]);
-        if (next_input_ >= input_.size() && offset_ >= current_.timestamps.size()) return false;
-        const size_t length = std::min(batch_size_, current_.timestamps.size() - offset_);
+        if (options_.limit && handed_out_ >= *options_.limit) return false;
+        if (remaining() < options_.batch_size && next_input_ < input_.size()) grid_and_append_to_leftovers_in_current_batch(input_[next_input_++]);
+        if (next_input_ >= input_.size() && remaining() == 0) return false;
+        size_t length = std::min(options_.batch_size, remaining());
+        if (options_.limit) length = std::min(length, *options_.limit - handed_out_);
         out.timestamps.assign(current_.timestamps.begin() + offset_, current_.timestamps.begin() + offset_ + length);
         out.values.assign(current_.values.begin() + offset_, current_.values.begin() + offset_ + length);
         out.tags.assign(current_.tags.size(), {});
         for (size_t c = 0; c < current_.tags.size(); c++) out.tags[c].assign(current_.tags[c].begin() + offset_, current_.tags[c].begin() + offset_ + length);
         offset_ += length;
+        handed_out_ += length;
         return true;
     }
 
+    size_t batch_size() const { return options_.batch_size; }
+    size_t segments_skipped() const { return segments_skipped_; } // by the time range or the limit
+    uint64_t rows_created() const { return rows_created_; }       // GridStreamMetrics (grid_exec.rs:433-520)
+
 private:
+    static Options make_options(size_t batch_size, size_t n_tag_columns) {
+        Options o;
+        o.batch_size = batch_size;
+        o.n_tag_columns = n_tag_columns;
+        return o;
+    }
+    size_t remaining() const { return current_.timestamps.size() - offset_; }
+
     void grid_and_append_to_leftovers_in_current_batch(const Input &in) { // grid_exec.rs:261-391
+        if (in.second.size() != current_.tags.size()) throw Error("every segment batch must carry the same tag columns");
+        const CompressedSegmentBatch *segments = &in.first;
+        const std::vector<std::vector<std::string>> *tags = &in.second;
+        CompressedSegmentBatch kept;
+        std::vector<std::vector<std::string>> kept_tags;
+        auto keep_rows = [&](const std::vector<uint8_t> &keep) {
+            CompressedSegmentBatch next_kept = segments->take(keep);
+            std::vector<std::vector<std::string>> next_tags(tags->size());
+            for (size_t c = 0; c < tags->size(); c++)
+                for (size_t row = 0; row < keep.size(); row++)
+                    if (keep[row]) next_tags[c].push_back((*tags)[c][row]);
+            segments_skipped_ += keep.size() - next_kept.num_rows();
+            kept = std::move(next_kept);
+            kept_tags = std::move(next_tags);
+            segments = &kept;
+            tags = &kept_tags;
+        };
+        if (options_.time_range_start || options_.time_range_end) {
+            std::vector<uint8_t> keep(segments->num_rows(), 1);
+            bool all = true;
+            for (size_t row = 0; row < keep.size(); row++) {
+                if (options_.time_range_start && segments->end_times[row] < *options_.time_range_start) keep[row] = 0;
+                if (options_.time_range_end && segments->start_times[row] > *options_.time_range_end) keep[row] = 0;
+                all = all && keep[row];
+            }
+            if (!all) keep_rows(keep);
+        }
+        std::vector<uint64_t> point_off(1, 0);
+        if (options_.limit && !options_.predicate && segments->num_rows()) {
+            // rows still owed beyond the leftovers: the first segments that cover them are enough
+            point_off = len(ctx_, *segments);
+            const size_t have = handed_out_ + remaining();
+            const uint64_t owed = *options_.limit > have ? *options_.limit - have : 0;
+            size_t needed = 0;
+            while (needed < segments->num_rows() && point_off[needed] < owed) needed++;
+            if (needed < segments->num_rows()) {
+                std::vector<uint8_t> keep(segments->num_rows(), 0);
+                std::fill(keep.begin(), keep.begin() + needed, 1);
+                keep_rows(keep);
+            }
+        }
         Batch next;
         next.timestamps.assign(current_.timestamps.begin() + offset_, current_.timestamps.end());
         next.values.assign(current_.values.begin() + offset_, current_.values.end());
         next.tags.resize(current_.tags.size());
         for (size_t c = 0; c < current_.tags.size(); c++) next.tags[c].assign(current_.tags[c].begin() + offset_, current_.tags[c].end());
-        std::vector<uint64_t> point_off;
-        grid(ctx_, in.first, next.timestamps, next.values, &point_off);
-        if (in.second.size() != next.tags.size()) throw Error("every segment batch must carry the same tag columns");
+        point_off.assign(1, 0);
+        if (segments->num_rows()) grid(ctx_, *segments, next.timestamps, next.values, &point_off);
+        rows_created_ += point_off.back();
         for (size_t c = 0; c < next.tags.size(); c++)
-            for (size_t row = 0; row < in.first.num_rows(); row++)
-                next.tags[c].insert(next.tags[c].end(), point_off[row + 1] - point_off[row], in.second[c][row]);
+            for (size_t row = 0; row < segments->num_rows(); row++)
+                next.tags[c].insert(next.tags[c].end(), point_off[row + 1] - point_off[row], (*tags)[c][row]);
+        if (options_.predicate) {
+            // (the leftovers were filtered when they were created; the predicate is a per-row test, so filtering them
+            // again together with the new points changes nothing)
+            const std::vector<uint8_t> keep = options_.predicate(next.timestamps, next.values);
+            if (keep.size() != next.timestamps.size()) throw Error("the predicate must return one flag per data point");
+            size_t w = 0;
+            for (size_t i = 0; i < keep.size(); i++) {
+                if (!keep[i]) continue;
+                if (w != i) {
+                    next.timestamps[w] = next.timestamps[i];
+                    next.values[w] = next.values[i];
+                    for (auto &column : next.tags) column[w] = std::move(column[i]);
+                }
+                w++;
+            }
+            next.timestamps.resize(w);
+            next.values.resize(w);
+            for (auto &column : next.tags) column.resize(w);
+        }
         current_ = std::move(next);
         offset_ = 0;
     }
 
     Context &ctx_;
     std::vector<Input> input_;
-    size_t next_input_ = 0, batch_size_, offset_ = 0;
+    Options options_;
+    size_t next_input_ = 0, offset_ = 0, handed_out_ = 0, segments_skipped_ = 0;
+    uint64_t rows_created_ = 0;
     Batch current_;
 };
 
@@ -340,5 +466,112 @@ private:
     double sum_ = 0.0;
     uint64_t count_ = 0;
 };
+
+// COUNT / MIN / MAX / SUM per distinct combination of tag values straight from segments (the aggregate rule of
+// model_simple_aggregates.rs:203-334 extended to GROUP BY <tag columns>).  Rows with equal tags are
+// contiguous in what compress and the storage layer produce, so each run of equal tags is one group of ONE
+// mdbcu_aggregate call; runs that repeat an earlier key are merged in row order with the accumulators' folds.
+// Keys come back in order of first appearance; AVG = sum / count.
+struct GroupedAggregates {
+    std::vector<std::vector<std::string>> keys;
+    std::vector<int64_t> count;
+    std::vector<float> min, max;
+    std::vector<double> sum;
+};
+
+inline GroupedAggregates grouped_model_aggregates(Context &ctx, const CompressedSegmentBatch &batch,
+                                                  const std::vector<std::vector<std::string>> &tag_columns) {
+    const size_t n = batch.num_rows();
+    for (const auto &column : tag_columns)
+        if (column.size() != n) throw Error("a tag column needs one value per segment");
+    GroupedAggregates out;
+    if (n == 0) return out;
+    std::vector<uint64_t> group_off;
+    for (size_t row = 0; row < n; row++) {
+        bool change = row == 0;
+        for (const auto &column : tag_columns) change = change || column[row] != column[row - 1];
+        if (change) group_off.push_back(row);
+    }
+    const size_t runs = group_off.size();
+    group_off.push_back(n);
+    std::vector<int64_t> count(runs);
+    std::vector<float> min(runs), max(runs);
+    std::vector<double> sum(runs);
+    const mdbcu_segments_view v = batch.view();
+    check(mdbcu_aggregate(ctx.get(), MDBCU_HOST, &v, group_off.data(), runs, count.data(), min.data(), max.data(), sum.data()));
+    std::map<std::vector<std::string>, size_t> slot_of;
+    for (size_t r = 0; r < runs; r++) {
+        std::vector<std::string> key;
+        for (const auto &column : tag_columns) key.push_back(column[group_off[r]]);
+        auto found = slot_of.find(key);
+        if (found == slot_of.end()) {
+            slot_of.emplace(key, out.keys.size());
+            out.keys.push_back(std::move(key));
+            out.count.push_back(count[r]);
+            out.min.push_back(min[r]);
+            out.max.push_back(max[r]);
+            out.sum.push_back(sum[r]);
+        } else {
+            const size_t k = found->second;
+            out.count[k] += count[r];
+            out.min[k] = detail::rust_min(out.min[k], min[r]);
+            out.max[k] = detail::rust_max(out.max[k], max[r]);
+            out.sum[k] += sum[r];
+        }
+    }
+    return out;
+}
+
+// The server's compressor (crates/modelardb_server/src/storage/uncompressed_data_manager.rs:530-581) takes one finished
+// buffer at a time -- the data points of ONE series for all fields of its table -- and compresses each field with its
+// own error bound.  One buffer per call would starve a GPU: compress_finished_buffers takes every buffer that is waiting
+// and compresses all their (buffer, field) pairs with ONE mdbcu_compress; what comes back is what the
+// reference sends on, one CompressedSegmentBatch per buffer and field, in the order of the buffers.
+struct UncompressedDataBuffer {
+    std::vector<int64_t> timestamps;
+    std::vector<std::vector<float>> field_columns; // one per field
+    std::vector<int> field_column_indices;         // index of each field in the table's schema
+    std::vector<ErrorBound> error_bounds;          // one per field
+    std::vector<std::string> tag_values;
+};
+
+struct CompressedBuffer {
+    std::vector<std::string> tag_values;
+    std::vector<std::pair<int, CompressedSegmentBatch>> compressed_segments; // (field_column_index, segments), in field order
+};
+
+inline std::vector<CompressedBuffer> compress_finished_buffers(Context &ctx, const std::vector<UncompressedDataBuffer> &buffers) {
+    std::vector<int64_t> timestamps;
+    std::vector<float> values;
+    std::vector<uint64_t> unit_off(1, 0);
+    std::vector<ErrorBound> bounds;
+    for (const UncompressedDataBuffer &b : buffers) {
+        if (b.field_columns.size() != b.field_column_indices.size() || b.field_columns.size() != b.error_bounds.size())
+            throw Error("one index and one error bound per field column");
+        for (size_t f = 0; f < b.field_columns.size(); f++) {
+            if (b.field_columns[f].size() != b.timestamps.size())
+                throw Error("Uncompressed timestamps and uncompressed values have different lengths.");
+            // the C-ABI pairs one timestamp with every value, so a buffer's timestamps are repeated once per field
+            timestamps.insert(timestamps.end(), b.timestamps.begin(), b.timestamps.end());
+            values.insert(values.end(), b.field_columns[f].begin(), b.field_columns[f].end());
+            unit_off.push_back(timestamps.size());
+            bounds.push_back(b.error_bounds[f]);
+        }
+    }
+    std::vector<CompressedBuffer> out;
+    std::vector<uint64_t> unit_seg_off(unit_off.size(), 0);
+    CompressedSegmentBatch all;
+    if (!bounds.empty()) all = try_compress_time_series_batch(ctx, timestamps, values, unit_off, bounds, &unit_seg_off);
+    size_t u = 0;
+    for (const UncompressedDataBuffer &b : buffers) {
+        CompressedBuffer compressed{b.tag_values, {}};
+        for (int index : b.field_column_indices) {
+            compressed.compressed_segments.emplace_back(index, all.slice(unit_seg_off[u], unit_seg_off[u + 1]));
+            u++;
+        }
+        out.push_back(std::move(compressed));
+    }
+    return out;
+}
 
 } // namespace modelardb_cuda

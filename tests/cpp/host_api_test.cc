@@ -122,6 +122,149 @@ int main() {
         CHECK(first_rows == point_off[cuts[1]], "tags repeated once per created row");
     }
 
+#ifdef HOST_API_EXTENDED // (see tests/test_gpu_cpp_host_api.py for which run defines it)
+    // ---- GridStream options: predicate after reconstruction, time range and limit pushed down to whole segments
+    {
+        const std::vector<std::string> series_of_row = [&] {
+            std::vector<std::string> t;
+            for (int u = 0; u < 3; u++) t.insert(t.end(), unit_seg_off[u + 1] - unit_seg_off[u], "series-" + std::to_string(u));
+            return t;
+        }();
+        auto run = [&](mc::GridStream::Options options, std::vector<int64_t> &all_ts, std::vector<float> &all_val, std::vector<std::string> &all_tag,
+                       size_t &skipped, uint64_t &created) {
+            options.n_tag_columns = 1;
+            std::vector<mc::GridStream::Input> input;
+            const size_t cut = batch.num_rows() / 3;
+            input.push_back({batch.slice(0, cut), {std::vector<std::string>(series_of_row.begin(), series_of_row.begin() + cut)}});
+            input.push_back({batch.slice(cut, batch.num_rows()), {std::vector<std::string>(series_of_row.begin() + cut, series_of_row.end())}});
+            mc::GridStream stream(ctx, std::move(input), options);
+            mc::GridStream::Batch out;
+            bool sizes_ok = true;
+            while (stream.poll_next(out)) {
+                sizes_ok = sizes_ok && out.timestamps.size() <= stream.batch_size() && out.tags[0].size() == out.timestamps.size();
+                all_ts.insert(all_ts.end(), out.timestamps.begin(), out.timestamps.end());
+                all_val.insert(all_val.end(), out.values.begin(), out.values.end());
+                all_tag.insert(all_tag.end(), out.tags[0].begin(), out.tags[0].end());
+            }
+            skipped = stream.segments_skipped();
+            created = stream.rows_created();
+            return sizes_ok;
+        };
+        std::vector<std::string> want_tag;
+        for (size_t row = 0; row < batch.num_rows(); row++) want_tag.insert(want_tag.end(), point_off[row + 1] - point_off[row], series_of_row[row]);
+        // (all three series share their timestamps: a time window selects the same stretch of each)
+        const int64_t lo = ts[n / 3], hi = ts[n / 2];
+        mc::GridStream::Options pruned_options, pushed_options;
+        pruned_options.batch_size = pushed_options.batch_size = 5000;
+        pruned_options.predicate = pushed_options.predicate = [&](const std::vector<int64_t> &t, const std::vector<float> &) {
+            std::vector<uint8_t> keep(t.size());
+            for (size_t i = 0; i < t.size(); i++) keep[i] = t[i] >= lo && t[i] <= hi;
+            return keep;
+        };
+        pushed_options.time_range_start = lo;
+        pushed_options.time_range_end = hi;
+        std::vector<int64_t> a_ts, b_ts, expect_ts;
+        std::vector<float> a_val, b_val, expect_val;
+        std::vector<std::string> a_tag, b_tag, expect_tag;
+        size_t a_skipped, b_skipped;
+        uint64_t a_created, b_created;
+        const bool a_ok = run(pruned_options, a_ts, a_val, a_tag, a_skipped, a_created);
+        const bool b_ok = run(pushed_options, b_ts, b_val, b_tag, b_skipped, b_created);
+        for (size_t i = 0; i < want_ts.size(); i++)
+            if (want_ts[i] >= lo && want_ts[i] <= hi) {
+                expect_ts.push_back(want_ts[i]);
+                expect_val.push_back(want_val[i]);
+                expect_tag.push_back(want_tag[i]);
+            }
+        CHECK(a_ok && b_ok, "batch sizes with a predicate");
+        CHECK(a_ts == expect_ts && same_bytes(a_val, expect_val.data(), expect_val.size()) && a_tag == expect_tag, "predicate after reconstruction");
+        CHECK(b_ts == expect_ts && same_bytes(b_val, expect_val.data(), expect_val.size()) && b_tag == expect_tag, "time range pushed down: same rows");
+        CHECK(a_skipped == 0 && a_created == total && b_skipped > 0 && b_created < total, "segments outside the range are never reconstructed");
+
+        for (size_t limit : {size_t(1), size_t(4097), size_t(30000)}) {
+            mc::GridStream::Options options;
+            options.batch_size = 4096;
+            options.limit = limit;
+            std::vector<int64_t> l_ts;
+            std::vector<float> l_val;
+            std::vector<std::string> l_tag;
+            size_t l_skipped;
+            uint64_t l_created;
+            const bool l_ok = run(options, l_ts, l_val, l_tag, l_skipped, l_created);
+            CHECK(l_ok && l_ts.size() == limit && std::equal(l_ts.begin(), l_ts.end(), want_ts.begin()) && same_bytes(l_val, want_val.data(), limit) &&
+                      std::equal(l_tag.begin(), l_tag.end(), want_tag.begin()),
+                  "LIMIT: the first rows of the stream");
+            CHECK(l_skipped > 0 && l_created < total, "LIMIT: later segments are not reconstructed");
+        }
+        bool threw = false;
+        try {
+            mc::GridStream::Options options;
+            options.limit = 0;
+            mc::GridStream stream(ctx, {}, options);
+        } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "a limit of zero is rejected");
+    }
+
+    // ---- GROUP BY tag straight from segments
+    {
+        std::vector<std::string> tag;
+        for (int u = 0; u < 3; u++) tag.insert(tag.end(), unit_seg_off[u + 1] - unit_seg_off[u], u == 2 ? "a" : (u == 0 ? "a" : "b")); // units 0 and 2 share a key
+        const mc::GroupedAggregates g = mc::grouped_model_aggregates(ctx, batch, {tag});
+        std::vector<int64_t> unit_count(3);
+        std::vector<float> unit_min(3), unit_max(3);
+        std::vector<double> unit_sum(3);
+        mdbo_aggregate(&want, want_uso.data(), 3, unit_count.data(), unit_min.data(), unit_max.data(), unit_sum.data(), 1);
+        CHECK(g.keys.size() == 2 && g.keys[0] == std::vector<std::string>{"a"} && g.keys[1] == std::vector<std::string>{"b"}, "keys in order of first appearance");
+        CHECK(g.count[0] == unit_count[0] + unit_count[2] && g.count[1] == unit_count[1], "grouped COUNT");
+        CHECK(g.min[0] == std::min(unit_min[0], unit_min[2]) && g.max[0] == std::max(unit_max[0], unit_max[2]) && g.min[1] == unit_min[1] && g.max[1] == unit_max[1],
+              "grouped MIN / MAX");
+        CHECK(std::fabs(g.sum[0] - (unit_sum[0] + unit_sum[2])) <= 1e-12 * std::fabs(unit_sum[0] + unit_sum[2]) && std::fabs(g.sum[1] - unit_sum[1]) <= 1e-12 * std::fabs(unit_sum[1]),
+              "grouped SUM");
+        bool threw = false;
+        try { mc::grouped_model_aggregates(ctx, batch, {std::vector<std::string>(3, "x")}); } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "a tag column needs one value per segment");
+    }
+
+    // ---- the server compressor's finished buffers, many per call (uncompressed_data_manager.rs:530-581)
+    {
+        std::vector<mc::UncompressedDataBuffer> buffers;
+        for (int b = 0; b < 4; b++) {
+            const size_t m = 500 + 1500 * b;
+            mc::UncompressedDataBuffer buffer;
+            buffer.timestamps.assign(ts.begin(), ts.begin() + m);
+            buffer.field_columns = {std::vector<float>(values.begin() + b * 100, values.begin() + b * 100 + m),
+                                    std::vector<float>(values.begin() + n, values.begin() + n + m)};
+            buffer.field_column_indices = {1, 3};
+            buffer.error_bounds = {mc::ErrorBound::try_new_relative(1.0f), mc::ErrorBound::lossless()};
+            buffer.tag_values = {"buffer-" + std::to_string(b)};
+            buffers.push_back(std::move(buffer));
+        }
+        const std::vector<mc::CompressedBuffer> compressed = mc::compress_finished_buffers(ctx, buffers);
+        bool all_equal = compressed.size() == buffers.size();
+        for (size_t b = 0; all_equal && b < buffers.size(); b++) {
+            all_equal = compressed[b].tag_values == buffers[b].tag_values && compressed[b].compressed_segments.size() == 2 &&
+                        compressed[b].compressed_segments[0].first == 1 && compressed[b].compressed_segments[1].first == 3;
+            for (size_t f = 0; all_equal && f < 2; f++) { // each (buffer, field) pair is what one call of the reference produces
+                const uint64_t one_off[2] = {0, buffers[b].timestamps.size()};
+                const uint8_t kind = buffers[b].error_bounds[f].kind();
+                const float value = buffers[b].error_bounds[f].value();
+                mdbo_segments *alone = mdbo_compress(buffers[b].timestamps.data(), buffers[b].field_columns[f].data(), one_off, 1, &kind, &value, 1, nullptr);
+                mdbo_segments_view alone_view;
+                mdbo_segments_view_get(alone, &alone_view);
+                all_equal = equals_oracle(compressed[b].compressed_segments[f].second, alone_view);
+                mdbo_segments_free(alone);
+            }
+        }
+        CHECK(all_equal, "many finished buffers in one call: one segment batch per buffer and field, bit-identical");
+        CHECK(mc::compress_finished_buffers(ctx, {}).empty(), "no buffers, no call");
+        bool threw = false;
+        buffers[1].field_columns[0].pop_back();
+        try { mc::compress_finished_buffers(ctx, buffers); } catch (const mc::Error &) { threw = true; }
+        CHECK(threw, "different lengths are the reference's error");
+    }
+
+#endif // HOST_API_EXTENDED
+
     // ---- accumulators (model_simple_aggregates.rs:336-618)
     {
         int64_t want_count;
