@@ -151,6 +151,13 @@ int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timestamps, const 
  * They only count in a library built with -DMDB_FIT_COUNTERS. */
 int mdbcu_debug_counters(mdbcu_context *ctx, uint64_t *out8);
 
+/* Diagnostics: `23 - floor(|log2(x)|) as i32` of rewrite_least_mantissa_bits (macaque_v.rs:185) evaluated on the
+ * device for every f32 bit pattern in [first_bits, last_bits], reported as a step function: the patterns at which
+ * the position changes (first_bits always listed), unordered; *n_steps may exceed cap.  Host space only.  The tests
+ * compare it with libm's log2f, which the reference uses, over all non-negative patterns. */
+int mdbcu_debug_rewrite_position_steps(mdbcu_context *ctx, uint32_t first_bits, uint32_t last_bits,
+                                       uint32_t *bits_out, int32_t *pos_out, uint32_t cap, uint32_t *n_steps);
+
 uint64_t mdbcu_segments_len(const mdbcu_segments *segments);
 /* Columns of an owned batch in `space` (a host copy is made on first request).  unit_seg_off
  * (nullable) receives a pointer to n_units + 1 row offsets: unit u produced rows

@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmodelardb_cuda.so")
+# MODELARDB_CUDA_LIB: another build of the same library (a tuning variant made by build.py), never another implementation
+LIB_PATH = os.environ.get("MODELARDB_CUDA_LIB") or os.path.join(_HERE, "libmodelardb_cuda.so")
 
 HOST, DEVICE = 0, 1
 
@@ -18,6 +19,7 @@ SYMBOLS = (
     "mdbcu_context_create", "mdbcu_context_destroy", "mdbcu_context_set_stream", "mdbcu_context_stream",
     "mdbcu_context_launch_count", "mdbcu_context_set_profiling", "mdbcu_context_kernel_stat",
     "mdbcu_context_set_chunk_len", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models", "mdbcu_debug_counters",
+    "mdbcu_debug_rewrite_position_steps",
     "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
     "mdbcu_grid_count", "mdbcu_grid", "mdbcu_segment_sums", "mdbcu_aggregate",
 )
@@ -84,6 +86,8 @@ def lib():
     L.mdbcu_debug_fit_models.restype = i32
     L.mdbcu_debug_counters.argtypes = [vp, vp]
     L.mdbcu_debug_counters.restype = i32
+    L.mdbcu_debug_rewrite_position_steps.argtypes = [vp, C.c_uint32, C.c_uint32, vp, vp, C.c_uint32, vp]
+    L.mdbcu_debug_rewrite_position_steps.restype = i32
     L.mdbcu_compress.argtypes = [vp, i32, vp, vp, vp, u64, vp, vp, C.POINTER(vp)]
     L.mdbcu_compress.restype = i32
     L.mdbcu_segments_len.argtypes = [vp]

@@ -36,14 +36,19 @@ def is_stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    if not force and not is_stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str = LIB) -> str:
+    """`defines` / `out`: an experimental variant beside the product library (tuning runs on the GPU box select it
+    with MODELARDB_CUDA_LIB, see _native.py); the product is always the default build."""
+    if not force and out == LIB and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + [
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-D" + d for d in defines] + ["-o", out] + [
         os.path.join(CSRC, s) for s in SOURCES]
     subprocess.check_call(cmd, cwd=CSRC)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
-    print(build_library(force=True, verbose=True))
+    import sys
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith("-D")]
+    outs = [a for a in sys.argv[1:] if not a.startswith("-D")]
+    print(build_library(force=True, verbose=True, defines=defs, out=os.path.join(_HERE, outs[0]) if outs else LIB))

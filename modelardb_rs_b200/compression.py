@@ -196,6 +196,31 @@ class HostSegments:
         return HostSegments(**cols)
 
 
+class DeviceSegments:
+    """A caller-assembled batch of compressed segments in device memory: the same columns as HostSegments as
+    contiguous CUDA tensors (int8 / int64 / float32 / uint8; the offset columns as int64).  Batches that compress
+    produced are CompressedSegments; this is for segment columns that reached the device some other way."""
+
+    space = DEVICE
+
+    def __init__(self, **cols):
+        for c in _COLUMNS:
+            t = cols[c]
+            if not (_is_torch(t) and t.is_cuda and t.is_contiguous()):
+                raise ValueError(f"{c}: a contiguous CUDA tensor is required")
+            setattr(self, c, t)
+
+    def __len__(self):
+        return len(self.model_type_id)
+
+    def view(self) -> SegmentsView:
+        v = SegmentsView()
+        v.n_segments = len(self)
+        for c in _COLUMNS:
+            setattr(v, c, getattr(self, c).data_ptr())
+        return v
+
+
 class CompressedSegments:
     """An owned device-resident batch produced by compress (mdbcu_segments)."""
 
@@ -412,6 +437,15 @@ def _view_of(segments):
     return segments.view(), segments.space
 
 
+def _order_streams(space: int):
+    """Device space: the context launches on its own non-blocking stream, while the outputs were just taken from
+    torch's caching allocator (which may hand out a block that a kernel still queued on torch's stream uses) and
+    caller tensors may still be being written there: let torch's current stream drain before the library runs."""
+    if space == DEVICE:
+        import torch
+        torch.cuda.current_stream().synchronize()
+
+
 def grid_count(segments, ctx: Optional[Context] = None):
     """len() per row (models/mod.rs:98-124) as an exclusive prefix sum: returns (point_off, total)."""
     ctx = ctx or getattr(segments, "ctx", None) or default_context()
@@ -423,6 +457,7 @@ def grid_count(segments, ctx: Optional[Context] = None):
         import torch
         # torch.empty, never torch.zeros: a fill kernel on torch's stream is unordered w.r.t. the context's stream
         off = torch.empty(v.n_segments + 1, dtype=torch.int64, device=f"cuda:{ctx.device}")
+    _order_streams(space)
     _native.check(_native.lib().mdbcu_grid_count(ctx._h, space, C.byref(v), _ptr(off), C.byref(total)))
     return off, total.value
 
@@ -443,6 +478,7 @@ def grid(segments, timestamps_out=None, values_out=None, ctx: Optional[Context] 
             timestamps_out = torch.empty(total, dtype=torch.int64, device=dev)
             values_out = torch.empty(total, dtype=torch.float32, device=dev)
     n = C.c_uint64()
+    _order_streams(space)
     _native.check(_native.lib().mdbcu_grid(ctx._h, space, C.byref(v), _ptr(timestamps_out), _ptr(values_out),
                                            len(timestamps_out), C.byref(n)))
     return timestamps_out[: n.value], values_out[: n.value]
@@ -457,6 +493,7 @@ def segment_sums(segments, ctx: Optional[Context] = None):
     else:
         import torch
         out = torch.empty(v.n_segments, dtype=torch.float32, device=f"cuda:{ctx.device}")
+    _order_streams(space)
     _native.check(_native.lib().mdbcu_segment_sums(ctx._h, space, C.byref(v), _ptr(out)))
     return out
 
@@ -482,6 +519,7 @@ def aggregate(segments, group_off=None, ctx: Optional[Context] = None):
         mx = torch.empty(g, dtype=torch.float32, device=dev)
         sm = torch.empty(g, dtype=torch.float64, device=dev)
     gp = group_off if isinstance(group_off, int) else _ptr(group_off)
+    _order_streams(space)
     _native.check(_native.lib().mdbcu_aggregate(ctx._h, space, C.byref(v), gp, g if group_off is not None else 1,
                                                 _ptr(count), _ptr(mn), _ptr(mx), _ptr(sm)))
     return count, mn, mx, sm

@@ -952,6 +952,51 @@ extern "C" int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timesta
     return MDBCU_SUCCESS;
 }
 
+// Diagnostics: rewrite_position (mdb_device.cuh) as a step function of the f32 bit pattern, computed ON THE DEVICE for every
+// pattern in [first_bits, last_bits]: the patterns at which the position differs from the one before (first_bits is always
+// listed).  The tests compare the list with the oracle's libm form (oracle/mdb_oracle.cc: mdbo_rewrite_position_steps).
+__global__ void __launch_bounds__(256) k_debug_rewrite_steps(uint32_t first_bits, uint64_t count, uint32_t *bits_out, int32_t *pos_out, uint32_t cap,
+                                                             unsigned int *n_out) {
+    const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+    for (uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; k < count; k += stride) {
+        const uint32_t b = first_bits + (uint32_t)k;
+        const int32_t p = rewrite_position(__uint_as_float(b));
+        if (k == 0 || rewrite_position(__uint_as_float(b - 1u)) != p) {
+            const unsigned int slot = atomicAdd(n_out, 1u);
+            if (slot < cap) {
+                bits_out[slot] = b;
+                pos_out[slot] = p;
+            }
+        }
+    }
+}
+
+extern "C" int mdbcu_debug_rewrite_position_steps(mdbcu_context *ctx, uint32_t first_bits, uint32_t last_bits, uint32_t *bits_out, int32_t *pos_out,
+                                                  uint32_t cap, uint32_t *n_steps) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (last_bits < first_bits || !bits_out || !pos_out || !n_steps) return fail("rewrite_position_steps: bad arguments");
+    cudaStream_t s = ctx->stream;
+    DBuf<uint32_t> d_bits;
+    DBuf<int32_t> d_pos;
+    DBuf<unsigned int> d_n;
+    CUDA_TRY(d_bits.alloc(cap, s));
+    CUDA_TRY(d_pos.alloc(cap, s));
+    CUDA_TRY(d_n.alloc(1, s));
+    CUDA_TRY(cudaMemsetAsync(d_n.p, 0, sizeof(unsigned int), s));
+    const uint64_t count = (uint64_t)last_bits - first_bits + 1;
+    LAUNCH(ctx, k_debug_rewrite_steps, (unsigned int)ctx->sm_count * 16, 256, 0, first_bits, count, d_bits.p, d_pos.p, cap, d_n.p);
+    CUDA_TRY(cudaGetLastError());
+    unsigned int n = 0;
+    CUDA_TRY(cudaMemcpyAsync(&n, d_n.p, sizeof(n), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(sync_stream(ctx));
+    *n_steps = n;
+    const uint32_t m = n < cap ? n : cap;
+    CUDA_TRY(d2h_bytes(ctx, bits_out, d_bits.p, m * sizeof(uint32_t)));
+    CUDA_TRY(d2h_bytes(ctx, pos_out, d_pos.p, m * sizeof(int32_t)));
+    CUDA_TRY(sync_stream(ctx));
+    return MDBCU_SUCCESS; // (the entries are in completion order: the caller sorts them by bit pattern)
+}
+
 // Diagnostics: reads (and clears) the fit event counters; all zero unless built with -DMDB_FIT_COUNTERS.
 extern "C" int mdbcu_debug_counters(mdbcu_context *ctx, uint64_t *out8 /* 16 entries */) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;

@@ -607,19 +607,30 @@ struct Row {
     const uint8_t *residuals; uint64_t n_residuals;
 };
 
+// The three offset columns are caller data: a row whose offsets run backwards or past the column's last offset
+// (off[n_segments], the byte length the caller states for the data array) is loaded as an empty row of an unknown
+// model type, which row_is_well_formed rejects -- no decoder ever sees a length derived from a bad offset.
 MDB_DEV Row load_row(const SegmentsView &v, uint64_t i) {
     Row r;
     r.model_type_id = v.model_type_id[i];
     r.start_time = v.start_time[i];
     r.end_time = v.end_time[i];
+    const uint64_t S = v.n_segments;
     uint64_t a = v.timestamps_off[i], b = v.timestamps_off[i + 1];
+    bool ok = a <= b && b <= v.timestamps_off[S];
     r.timestamps = v.timestamps_data + a; r.n_timestamps = b - a;
     r.min_value = v.min_value[i];
     r.max_value = v.max_value[i];
     a = v.values_off[i]; b = v.values_off[i + 1];
+    ok = ok && a <= b && b <= v.values_off[S];
     r.values = v.values_data + a; r.n_values = b - a;
     a = v.residuals_off[i]; b = v.residuals_off[i + 1];
+    ok = ok && a <= b && b <= v.residuals_off[S];
     r.residuals = v.residuals_data + a; r.n_residuals = b - a;
+    if (!ok) {
+        r.model_type_id = -1;
+        r.n_timestamps = r.n_values = r.n_residuals = 0;
+    }
     return r;
 }
 

@@ -996,6 +996,40 @@ float mdbo_rewrite_least_mantissa_bits(int kind, float eb, float value) {
 int32_t mdbo_rewrite_position_libm(float e) { return rewrite_position_libm(e); }
 int32_t mdbo_rewrite_position_f64(float e) { return rewrite_position_f64(e); }
 
+// rewrite_position as a step function of the bit pattern: every bit pattern b in [first_bits, last_bits] at which the
+// position differs from the position at b - 1 (first_bits itself is always listed), in ascending order.  Scans every
+// pattern of the range with `which` = 0 (libm log2f, the reference) or 1 (f64 log2 rounded once, the GPU's form) on
+// n_threads threads; two step functions with the same list are the same function on the whole range.
+size_t mdbo_rewrite_position_steps(int which, uint32_t first_bits, uint32_t last_bits, int n_threads, uint32_t *bits_out,
+                                   int32_t *pos_out, size_t cap) {
+    if (last_bits < first_bits) return 0;
+    if (n_threads < 1) n_threads = 1;
+    auto pos_of = [which](uint32_t b) { return which ? rewrite_position_f64(f32_from_bits(b)) : rewrite_position_libm(f32_from_bits(b)); };
+    const uint64_t total = (uint64_t)last_bits - first_bits + 1;
+    std::vector<std::vector<std::pair<uint32_t, int32_t>>> found((size_t)n_threads);
+    std::vector<std::thread> threads;
+    for (int t = 0; t < n_threads; t++) {
+        threads.emplace_back([&, t] {
+            const uint64_t lo = first_bits + total * (uint64_t)t / (uint64_t)n_threads, hi = first_bits + total * (uint64_t)(t + 1) / (uint64_t)n_threads;
+            if (lo >= hi) return;
+            int32_t prev = lo == first_bits ? pos_of((uint32_t)lo) + 1 : pos_of((uint32_t)(lo - 1)); // (first_bits is always a step)
+            for (uint64_t b = lo; b < hi; b++) {
+                const int32_t p = pos_of((uint32_t)b);
+                if (p != prev) found[(size_t)t].emplace_back((uint32_t)b, p);
+                prev = p;
+            }
+        });
+    }
+    for (auto &th : threads) th.join();
+    size_t n = 0;
+    for (auto &f : found)
+        for (auto &e : f) {
+            if (n < cap) { bits_out[n] = e.first; pos_out[n] = e.second; }
+            n++;
+        }
+    return n;
+}
+
 static void model_to_c(const CompressedSegmentBuilder &b, mdbo_model *out) {
     std::memset(out, 0, sizeof(*out));
     out->model_type_id = b.model_type_id;

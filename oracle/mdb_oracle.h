@@ -55,6 +55,10 @@ float mdbo_rewrite_least_mantissa_bits(int kind, float eb, float value);
 /* 23 - floor(|log2f(x)|) as i32, the reference way (libm log2f) and the f64 way used on the GPU. */
 int32_t mdbo_rewrite_position_libm(float factorized_epsilon);
 int32_t mdbo_rewrite_position_f64(float factorized_epsilon);
+/* The position as a step function of the bit pattern over [first_bits, last_bits]: the patterns at which it changes
+ * (first_bits always listed), ascending; which = 0 libm, 1 f64.  Returns the number of steps (may exceed cap). */
+size_t mdbo_rewrite_position_steps(int which, uint32_t first_bits, uint32_t last_bits, int n_threads,
+                                   uint32_t *bits_out, int32_t *pos_out, size_t cap);
 
 /* ---- model fitting (types.rs:40-145, pmc_mean.rs, swing.rs) ---- */
 typedef struct {

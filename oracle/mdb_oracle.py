@@ -95,6 +95,8 @@ def lib():
     L.mdbo_rewrite_position_libm.restype = C.c_int32
     L.mdbo_rewrite_position_f64.argtypes = [f32]
     L.mdbo_rewrite_position_f64.restype = C.c_int32
+    L.mdbo_rewrite_position_steps.argtypes = [i32, C.c_uint32, C.c_uint32, i32, vp, vp, sz]
+    L.mdbo_rewrite_position_steps.restype = sz
     L.mdbo_fit_next_model.argtypes = [u64, i32, f32, vp, vp, u64, C.POINTER(_Model)]
     L.mdbo_fit_next_model.restype = None
     L.mdbo_pmc_fit_prefix.argtypes = [i32, f32, vp, u64, vp]
@@ -233,6 +235,19 @@ def macaque_v_sum(b: bytes, n_values: int, seed=None) -> np.float32:
 def rewrite_least_mantissa_bits(eb, value) -> np.float32:
     k, v = eb
     return np.float32(lib().mdbo_rewrite_least_mantissa_bits(k, v, float(np.float32(value))))
+
+
+def rewrite_position_steps(which: int, first_bits: int = 0, last_bits: int = 0x7F800000, n_threads: int = 0):
+    """`23 - floor(|log2(x)|) as i32` (macaque_v.rs:185) as a step function of the f32 bit pattern over
+    [first_bits, last_bits]: (bits, position) at every pattern where it changes.  which = 0: libm log2f (the
+    reference), 1: f64 log2 rounded once (the form the GPU uses)."""
+    n_threads = n_threads or (os.cpu_count() or 1)
+    cap = 4096
+    bits = np.empty(cap, np.uint32)
+    pos = np.empty(cap, np.int32)
+    n = lib().mdbo_rewrite_position_steps(which, first_bits, last_bits, n_threads, bits.ctypes.data, pos.ctypes.data, cap)
+    assert n <= cap
+    return bits[:n].copy(), pos[:n].copy()
 
 
 # --------------------------------------------------------------------------- models

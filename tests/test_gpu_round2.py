@@ -1,0 +1,142 @@
+"""GPU parity tests added in round 2: the device's own rewrite position for every f32, caller offsets that run
+backwards or out of range, and two BASELINE.json configs at their exact / slab size against the oracle."""
+import numpy as np
+import pytest
+
+from modelardb_rs_b200 import _native
+from modelardb_rs_b200 import compression as mc
+from modelardb_rs_b200 import operators as ops
+from modelardb_rs_b200 import synthetic as syn
+from tests.parity_cases import assert_f32_bits_equal, assert_segments_equal
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    return mc.Context(0)
+
+
+def test_rewrite_position_on_the_device(oracle, ctx):
+    """`23 - floor(|log2(x)|) as i32` (macaque_v.rs:185) decides which mantissa bits of every lossy MacaqueV value are
+    cleared.  The reference calls libm's log2f, the device CUDA's f64 log2 rounded once (mdb_device.cuh:
+    rewrite_position).  Both are step functions of the input: the device's steps over EVERY bit pattern from +0 to +inf
+    must be the reference's, pattern for pattern (tests/test_oracle_log2.py is the host half of this check)."""
+    want_bits, want_pos = oracle.rewrite_position_steps(0)
+    cap = 4096
+    bits = np.empty(cap, np.uint32)
+    pos = np.empty(cap, np.int32)
+    import ctypes as C
+    n = C.c_uint32()
+    _native.check(_native.lib().mdbcu_debug_rewrite_position_steps(ctx._h, 0, 0x7F800000, bits.ctypes.data, pos.ctypes.data, cap, C.byref(n)))
+    assert n.value <= cap
+    order = np.argsort(bits[: n.value])
+    got_bits, got_pos = bits[: n.value][order], pos[: n.value][order]
+    assert np.array_equal(got_bits, want_bits), (len(got_bits), len(want_bits))
+    assert np.array_equal(got_pos, want_pos)
+
+
+def _segments(oracle, n_series=4, n=3000, kind="sine", eb=(2, 1.0)):
+    ts, vals, off = syn.multi_series(n_series, n, 11, kind)
+    seg = oracle.compress(ts, vals, off, eb=eb)
+    return seg, mc.HostSegments(unit_seg_off=seg.unit_seg_off, **{c: getattr(seg, c) for c in mc._COLUMNS})
+
+
+@pytest.mark.parametrize("column", ["timestamps_off", "values_off", "residuals_off"])
+@pytest.mark.parametrize("space", ["host", "device"])
+def test_bad_offsets_fail_instead_of_reading_out_of_bounds(oracle, ctx, column, space):
+    """The three offset columns are caller data.  Offsets that run backwards or point past the column's last offset make
+    the call fail with the row's index; nothing is decoded from a length derived from them, and the context (and the
+    process: no sticky CUDA error) stays usable."""
+    import torch
+    seg, host = _segments(oracle, kind="walk", eb=(2, 1.0))  # rows with values and residual bytes
+    S = len(host)
+    assert S > 8
+
+    def run(bad_host):
+        if space == "host":
+            batch = bad_host
+        else:
+            cols = {}
+            for c in mc._COLUMNS:
+                a = getattr(bad_host, c)
+                cols[c] = torch.from_numpy(a.view(np.int64) if a.dtype == np.uint64 else a).cuda()
+            batch = mc.DeviceSegments(**cols)
+        with pytest.raises(mc.ModelarDbCudaError, match="malformed segment row"):
+            mc.grid(batch, ctx=ctx)
+        with pytest.raises(mc.ModelarDbCudaError, match="malformed segment row"):
+            mc.segment_sums(batch, ctx)
+        with pytest.raises(mc.ModelarDbCudaError, match="malformed segment row"):
+            mc.aggregate(batch, None, ctx)
+
+    off = getattr(host, column).copy()
+    # (1) backwards: two interior offsets swapped (only when they differ)
+    k = next(i for i in range(1, S - 1) if off[i] != off[i + 1])
+    swapped = off.copy()
+    swapped[k], swapped[k + 1] = swapped[k + 1], swapped[k]
+    # (2) an interior offset far past the end of the data
+    huge = off.copy()
+    huge[S // 2] = np.uint64(1) << np.uint64(40)
+    for bad_off in (swapped, huge):
+        cols = {c: getattr(host, c) for c in mc._COLUMNS}
+        cols[column] = bad_off
+        run(mc.HostSegments(unit_seg_off=host.unit_seg_off, **cols))
+    # the context still works
+    gts, gval = mc.grid(host, ctx=ctx)
+    wts, wval, _ = oracle.grid(seg)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, "grid after failed calls")
+
+
+def test_config1_full_size_on_the_gpu(oracle, ctx):
+    """BASELINE.json configs[0] at its exact size through the CUDA library: one series of 2^20 points (sine + noise,
+    seed 1), lossless compress bit-identical to the oracle, then SELECT SUM / AVG through the model accumulators
+    (crates/modelardb_embedded/src/operations/data_folder.rs:214-217, model_simple_aggregates.rs:473-618)."""
+    n = 1 << 20
+    ts = syn.regular_timestamps(n)
+    vals = syn.sine_noise(n, 1)
+    want = oracle.compress(ts, vals, eb=(0, 0.0))
+    got = mc.try_compress_univariate_time_series(ts, vals, mc.Lossless, ctx)
+    assert_segments_equal(got, want, "configs[0] compress")
+    gts, gval = mc.grid(got, ctx=ctx)
+    assert np.array_equal(gts, ts)
+    assert_f32_bits_equal(gval, vals, "configs[0] grid")  # lossless: the input, bit for bit
+    assert_f32_bits_equal(mc.segment_sums(got, ctx), oracle.segment_sums(want), "configs[0] row sums", nan_payload_matters=False)
+    total, average = ops.ModelSumAccumulator(), ops.ModelAvgAccumulator()
+    for lo in range(0, len(got), 1000):  # DataFusion feeds the accumulators batch by batch
+        part = got.slice(lo, min(len(got), lo + 1000))
+        total.update_batch(part)
+        average.update_batch(part)
+    (sum_state,), (count_state, avg_sum_state) = total.state(), average.state()
+    assert count_state == n
+    want_sum = 0.0
+    for s in oracle.segment_sums(want):  # the reference's left fold of f32 row sums into f64
+        want_sum += float(s)
+    assert abs(sum_state - want_sum) <= 1e-12 * abs(want_sum) and abs(avg_sum_state - want_sum) <= 1e-12 * abs(want_sum)
+    exact = float(vals.astype(np.float64).sum())
+    assert abs(sum_state - exact) <= 1e-5 * abs(exact)  # integration_test.rs:1128-1171: 0.001 %
+
+
+def test_config2_slab_of_1000_series_matches_oracle(oracle, ctx):
+    """BASELINE.json configs[1] shape at a tenth of the series length: 1000 series x 10^5 points, 1 % relative bound,
+    compress + full grid + GROUP BY series, every column and every point against the oracle."""
+    n_series, n = 1000, 100_000
+    ts, vals, off = syn.multi_series(n_series, n, 2, "sine")
+    eb = (2, 1.0)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=16)
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    got = seg.to_host()
+    assert_segments_equal(got, want, "configs[1] slab")
+    wts, wval, _ = oracle.grid(want, n_threads=16)
+    gts, gval = mc.grid(got, ctx=ctx)
+    assert np.array_equal(gts, wts) and np.array_equal(gts, ts)
+    assert_f32_bits_equal(gval, wval, "configs[1] slab grid")
+    wc, wmn, wmx, wsm = oracle.aggregate(want, want.unit_seg_off, n_threads=16)
+    gc, gmn, gmx, gsm = mc.aggregate(got, want.unit_seg_off, ctx)
+    assert np.array_equal(gc, wc) and (gc == n).all()
+    assert_f32_bits_equal(gmn, wmn)
+    assert_f32_bits_equal(gmx, wmx)
+    assert (np.abs(gsm - wsm) <= 1e-12 * np.abs(wsm)).all()
+    rel = np.abs((vals.astype(np.float64) - gval.astype(np.float64)) / vals.astype(np.float64)) * 100.0
+    assert float(rel.max()) <= 1.0  # within the user's bound of the raw input (compression.rs:914-928)
+    seg.free()
