@@ -24,9 +24,9 @@ def _streams(rng, n):
 
 
 def _library(runs):
-    """The product's decoder, or the build that takes runs of `0` codes in one step (MDB_MACAQUE_SPECULATE_RUNS=1: exact,
-    emulated here, compiled out of the product until it has been measured on a GPU)."""
-    return emu.variant("MDB_MACAQUE_SPECULATE_RUNS=1") if runs else None
+    """The product's decoder (takes runs of `0` / `10` codes in one step), or the build with the plain code walk
+    (MDB_MACAQUE_SPECULATE_RUNS=0)."""
+    return None if runs else emu.variant("MDB_MACAQUE_SPECULATE_RUNS=0")
 
 
 @pytest.mark.parametrize("runs", [False, True], ids=["walk", "runs"])
