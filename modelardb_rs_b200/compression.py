@@ -103,8 +103,9 @@ class Context:
         _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
 
     def set_fit_engine(self, engine: int):
-        """0 automatic (= 3), 1 one thread per chain in rounds, 2 one warp per chain in rounds, 3 one warp per chain with
-        the asynchronous scheduler; results are identical."""
+        """0 automatic (= 4), 1 one thread per chain in rounds, 2 one warp per chain in rounds, 3 one warp per chain with
+        the asynchronous scheduler, 4 one lane per chain for the bulk of the chains and 3 for the stitching; results are
+        identical."""
         _native.check(_native.lib().mdbcu_context_set_fit_engine(self._h, engine))
 
     @property

@@ -133,6 +133,168 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
     if (lane == 0) st[g] = s;
 }
 
+// ---- one lane per chain (mdb_fit_lanes.cuh): the bulk of the chains, before the exact stitching ------------------
+//
+// k_lanes_units    one thread per unit: LaneUnit (first timestamp, interval, bound constants) and whether the unit
+//                  qualifies at all (at least two points, positive interval, |timestamps| < 2^53, exact relative test)
+// k_lanes_regular  one block per chunk, coalesced: every interval of the chunk equals the unit's first one, else the
+//                  unit is marked irregular (the lanes then leave it alone)
+// k_spec_lanes     persistent warps; every LANE claims chunks from a counter and runs the chunk's chain from its first
+//                  index (LaneChain), reading its values through a 16-value ring in shared memory that is refilled a
+//                  16-byte quad at a time, one quad ahead of the cursor
+// k_sched_kick     one thread per unit: the first sched_advance, which finds the first chunk whose chain did not start
+//                  at the exact entry and queues its re-run for k_spec_async
+
+__global__ void __launch_bounds__(128) k_lanes_units(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off, uint64_t n_units,
+                                                     const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value, LaneUnit *info,
+                                                     unsigned int *kind_units) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const uint64_t a = unit_off[u], n = unit_off[u + 1] - a;
+    const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+    const LaneUnit lu = lane_unit_init(ts + a, n, eb);
+    info[u] = lu;
+    if (lu.ok) atomicAdd(&kind_units[eb.kind], 1u);
+}
+
+constexpr int REGULAR_THREADS = 256;
+__global__ void __launch_bounds__(REGULAR_THREADS) k_lanes_regular(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off,
+                                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
+                                                                   uint32_t chunk_len, LaneUnit *info) {
+    const uint64_t g = blockIdx.x;
+    const uint32_t u = chunk_unit[g];
+    if (!info[u].ok) return;
+    const uint64_t a = unit_off[u];
+    const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+    const uint32_t c = (uint32_t)(g - chunk_base[u]);
+    const uint32_t lo = c * chunk_len, hi = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
+    const int64_t *uts = ts + a;
+    const int64_t t0 = uts[0], delta = uts[1] - t0;
+    bool bad = false;
+    for (uint32_t i = lo + threadIdx.x; i < hi; i += REGULAR_THREADS) bad |= uts[i] != t0 + (int64_t)i * delta;
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(&info[u].irregular, 1u);
+}
+
+constexpr int LANES_WARPS = 4;
+constexpr int LANES_RING = 16; // values per lane: four 16-byte quads (the one before the cursor's, the cursor's, one or two ahead)
+#ifndef MDB_LANES_MIN_BLOCKS
+#define MDB_LANES_MIN_BLOCKS 4
+#endif
+
+template <int KIND>
+__global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec_lanes(const float *__restrict__ values, uint64_t n_total,
+                                                                  const uint64_t *__restrict__ unit_off, const LaneUnit *__restrict__ info,
+                                                                  const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
+                                                                  uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, FittedModel *lists,
+                                                                  const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                                  unsigned int *next_chunk) {
+    __shared__ float ring_s[LANES_WARPS][LANES_RING][32]; // [slot][lane]: a lane's slot k is in bank `lane` whatever k is
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float(*ring)[32] = ring_s[warp];
+    // the values array in 16-byte quads: element e of the quad space is values[e - skew]
+    const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(values) >> 2) & 3u);
+    const float4 *quads = reinterpret_cast<const float4 *>(values - skew);
+
+    bool have = false;       // this lane owns a chunk
+    uint32_t g = 0;          // the chunk
+    const float4 *uq = quads; // the quad that holds the unit's point 0 ...
+    uint32_t sk = 0;         // ... at element sk of it: point i of the unit is element sk + i from there
+    uint64_t eb4 = 0;        // quad-space element index of uq[0] (bounds of the array's first and last quad)
+    LaneUnit lu;
+    LaneChain chain;
+    FittedModel *list = nullptr;
+    // ring: quads [ring_lo, loaded] (relative to uq) are in slots (q & 3) * 4 ..; `pend` is the quad in flight
+    int32_t ring_lo = 0, loaded = -1, pend_q = -1;
+    float4 pend = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool exhausted = false;  // the chunk counter has run out
+
+    auto load_quad = [&](int32_t q) -> float4 {
+        const uint64_t e = eb4 + (uint64_t)q * 4;
+        if (e >= skew && e + 4 <= n_total + skew) return __ldg(uq + q);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f); // first / last quad of the array: the elements that exist
+        float *rp = reinterpret_cast<float *>(&r);
+        for (int k = 0; k < 4; k++)
+            if (e + k >= skew && e + k < n_total + skew) rp[k] = __ldg(values + (e + k - skew));
+        return r;
+    };
+
+    for (uint32_t iter = 0;; iter++) {
+        if ((iter & 3u) == 0u) {
+            // ---- claim a chunk if this lane has none
+            if (!have && !exhausted) {
+                while (true) {
+                    const unsigned int w = atomicAdd(next_chunk, 1u);
+                    if (w >= n_chunks) {
+                        exhausted = true;
+                        break;
+                    }
+                    const uint32_t u = chunk_unit[w];
+                    lu = info[u];
+                    if (!lu.ok || lu.irregular || lu.kind != KIND) continue;
+                    g = w;
+                    const uint64_t a = unit_off[u];
+                    const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+                    const uint32_t c = (uint32_t)(g - chunk_base[u]);
+                    const uint32_t lo = c * chunk_len;
+                    const uint32_t chunk_end = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
+                    const uint32_t limit = (uint64_t)chunk_end + chunk_len < n ? chunk_end + chunk_len : n;
+                    chain.begin(lo, chunk_end, limit, n);
+                    list = lists + list_base[g] + (size_t)(list_cap[g] / 2); // the chunk's second buffer (st.buf is 0 before the first chain)
+                    sk = (uint32_t)((a + skew) & 3u);
+                    eb4 = (a + skew) & ~(uint64_t)3;
+                    uq = quads + (eb4 >> 2);
+                    have = true;
+                    loaded = -1;
+                    pend_q = -1;
+                    ring_lo = 0;
+                    break;
+                }
+            }
+            if (!__any_sync(FULL_MASK, have)) break;
+            // ---- ring refill: land the quad in flight, then request the next one
+            if (pend_q >= 0) {
+                const int s4 = (pend_q & 3) * 4;
+                ring[s4 + 0][lane] = pend.x;
+                ring[s4 + 1][lane] = pend.y;
+                ring[s4 + 2][lane] = pend.z;
+                ring[s4 + 3][lane] = pend.w;
+                loaded = pend_q;
+                pend_q = -1;
+            }
+            if (have) {
+                const int32_t cq = (int32_t)((sk + chain.fit.idx) >> 2);
+                if (loaded < 0 || cq < ring_lo || cq < loaded - 3 || cq > loaded + 1) { // seek: nothing in the ring is of use
+                    loaded = -1;
+                    ring_lo = cq;
+                    pend_q = cq;
+                } else if (loaded < cq + 2) {
+                    pend_q = loaded + 1;
+                }
+                if (pend_q >= 0) {
+                    if ((uint32_t)pend_q * 4u < sk + chain.limit) pend = load_quad(pend_q);
+                    else pend_q = -1; // nothing of this chunk lies there
+                }
+            }
+        }
+        if (have) {
+            const uint32_t e = sk + chain.fit.idx;
+            const int32_t cq = (int32_t)(e >> 2);
+            if (loaded >= 0 && cq >= ring_lo && cq <= loaded && cq >= loaded - 3) {
+                const float v = ring[(int)(e & 15u)][lane];
+                if (chain.template step<KIND>(lu, v, list)) {
+                    if (!chain.bailed) {
+                        ChunkState s = st[g];
+                        lane_chain_publish(chain, s);
+                        s.phase = PH_DONE;
+                        st[g] = s;
+                    }
+                    have = false;
+                }
+            }
+        }
+    }
+}
+
 // ---- asynchronous scheduling (mdb_compress.cuh: sched_advance) ------------------------------------------
 struct SchedQueue {
     uint32_t head;       // oldest queued slot
@@ -148,15 +310,18 @@ struct SchedQueue {
 // Initial queue order: chunk 0 of every unit, then chunk 1 of every unit, ...: the exact frontiers (chunk 0 is
 // exact by definition) start moving in the first wave, and later chunks are still unstarted -- and can be
 // re-aimed at their exact entry -- when the frontier reaches them.
-__global__ void __launch_bounds__(256) k_sched_count(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, uint32_t *per_index) {
+// (Chunks whose chain a lane has already run -- phase PH_DONE -- are not queued: the frontier reaches them through
+// sched_advance, which re-queues those that turn out to have started from the wrong entry.)
+__global__ void __launch_bounds__(256) k_sched_count(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, const ChunkState *st,
+                                                     uint32_t *per_index) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_chunks) return;
+    if (g >= n_chunks || st[g].phase != PH_QUEUED) return;
     atomicAdd(&per_index[(uint32_t)(g - chunk_base[chunk_unit[g]])], 1u);
 }
-__global__ void __launch_bounds__(256) k_sched_fill(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, const uint64_t *index_base,
-                                                    uint32_t *cursor, uint32_t *items) {
+__global__ void __launch_bounds__(256) k_sched_fill(const uint64_t *chunk_base, const uint32_t *chunk_unit, uint64_t n_chunks, const ChunkState *st,
+                                                    const uint64_t *index_base, uint32_t *cursor, uint32_t *items) {
     uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= n_chunks) return;
+    if (g >= n_chunks || st[g].phase != PH_QUEUED) return;
     const uint32_t c = (uint32_t)(g - chunk_base[chunk_unit[g]]);
     items[index_base[c] + atomicAdd(&cursor[c], 1u)] = (uint32_t)g + 1u;
 }
@@ -178,6 +343,28 @@ __global__ void __launch_bounds__(128) k_sched_units(const uint64_t *chunk_base,
     s.finished = 0;
     units[u] = s;
     if (chunk_base[u + 1] > chunk_base[u]) atomicAdd(&q->live_units, 1u);
+}
+
+// The first sched_advance of every unit after the lanes: walks the chunks whose chains started at the exact entry and queues
+// the re-run of the first one that did not (or re-aims it, if no chain has run it: a chunk the lanes left alone).
+__global__ void __launch_bounds__(128) k_sched_kick(const uint64_t *__restrict__ unit_off, uint64_t n_units, const uint64_t *__restrict__ chunk_base,
+                                                    uint32_t chunk_len, ChunkState *st, UnitSched *units, SchedQueue *q, uint32_t *items) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u >= n_units) return;
+    const uint64_t g0 = chunk_base[u];
+    const uint32_t C = (uint32_t)(chunk_base[u + 1] - g0);
+    if (C == 0) return;
+    const uint32_t n = (uint32_t)(unit_off[u + 1] - unit_off[u]);
+    const bool unit_final = sched_advance(units[u], n, chunk_len, C, st + g0, [&](uint32_t cc) {
+        __threadfence();
+        const uint32_t slot = atomicAdd(&q->tail, 1u);
+        if (slot < sync_load(&q->capacity)) sync_store(&items[slot], (uint32_t)(g0 + cc) + 1u);
+        else sync_store(&q->finished, 2u);
+    });
+    if (unit_final && atomicAdd(&q->units_done, 1u) + 1u == sync_load(&q->live_units)) {
+        __threadfence();
+        atomicCAS(&q->finished, 0u, 1u);
+    }
 }
 
 // Workers: one warp = one worker.  Worker w starts with queue slot w; afterwards it pops the oldest queued chunk,
@@ -624,9 +811,9 @@ uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return c
 
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
-    if (engine < 0 || engine > 3)
-        return fail("fit engine must be 0 (automatic), 1 (one thread per chain, rounds), 2 (one warp per chain, rounds) or 3 (one warp per chain, "
-                    "asynchronous scheduling)");
+    if (engine < 0 || engine > 4)
+        return fail("fit engine must be 0 (automatic), 1 (one thread per chain, rounds), 2 (one warp per chain, rounds), 3 (one warp per chain, "
+                    "asynchronous scheduling) or 4 (one lane per chain, then 3 for the stitching)");
     ctx->fit_mode = engine;
     return MDBCU_SUCCESS;
 }
@@ -737,7 +924,42 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         DBuf<FittedModel> lists;
         TRY_SG(lists.alloc(n_models_cap, s));
 
-        const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3;
+        const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3 || ctx->fit_mode == 4;
+        const bool use_lanes = ctx->fit_mode == 0 || ctx->fit_mode == 4;
+        if (use_lanes && G) {
+            // ---- one lane per chunk: the bulk of the chains (mdb_fit_lanes.cuh); what they leave open is stitched below
+            DBuf<LaneUnit> lane_units;
+            DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
+            TRY_SG(lane_units.alloc(n_units, s));
+            TRY_SG(lane_words.alloc(4, s));
+            TRY_SG(cudaMemsetAsync(lane_words.p, 0, 4 * sizeof(unsigned int), s));
+            LAUNCH(ctx, k_lanes_units, div_up(n_units, 128), 128, 0, d_ts, d_off, n_units, d_kind, d_ebv, lane_units.p, lane_words.p);
+            LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
+            TRY_SG(post(ctx, 0, lane_words.p, 2));
+            TRY_SG(sync_stream(ctx));
+            unsigned int kind_units[4];
+            std::memcpy(kind_units, ctx->mailbox, sizeof(kind_units));
+            for (int kind = 0; kind < 3; kind++) {
+                if (!kind_units[kind]) continue;
+                int blocks_per_sm = 0;
+                const void *fn = kind == KIND_LOSSLESS ? (const void *)k_spec_lanes<KIND_LOSSLESS>
+                                 : kind == KIND_ABSOLUTE ? (const void *)k_spec_lanes<KIND_ABSOLUTE> : (const void *)k_spec_lanes<KIND_RELATIVE>;
+                TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, LANES_WARPS * 32, 0));
+                if (blocks_per_sm < 1) return bail(fail("compress: the lane kernel does not fit on this device"));
+                const unsigned int n_blocks = (unsigned int)std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, LANES_WARPS * 32));
+                TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
+                if (kind == KIND_LOSSLESS)
+                    LAUNCH(ctx, k_spec_lanes<KIND_LOSSLESS>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
+                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                else if (kind == KIND_ABSOLUTE)
+                    LAUNCH(ctx, k_spec_lanes<KIND_ABSOLUTE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
+                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                else
+                    LAUNCH(ctx, k_spec_lanes<KIND_RELATIVE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
+                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+            }
+            TRY_SG(cudaGetLastError());
+        }
         if (async_sched && G) {
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
             int blocks_per_sm = 0;
@@ -760,11 +982,14 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             TRY_SG(cudaMemsetAsync(items.p, 0, capacity * sizeof(uint32_t), s));
             TRY_SG(cudaMemsetAsync(per_index.p, 0, G * sizeof(uint32_t), s));
             TRY_SG(cudaMemsetAsync(cursor.p, 0, G * sizeof(uint32_t), s));
-            LAUNCH(ctx, k_sched_count, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, per_index.p);
+            LAUNCH(ctx, k_sched_count, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, st.p, per_index.p);
             if (exclusive_scan<uint32_t>(ctx, per_index.p, G, index_base.p)) return bail(MDBCU_FAILURE);
-            LAUNCH(ctx, k_sched_fill, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, index_base.p, cursor.p, items.p);
-            const uint32_t n_initial = (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G); // slots handed out without the queue
+            LAUNCH(ctx, k_sched_fill, div_up(G, 256), 256, 0, chunk_base.p, chunk_unit.p, G, st.p, index_base.p, cursor.p, items.p);
+            // slots handed out without the queue (after the lanes only the chunks they left alone are pre-filled: their
+            // number is known on the device alone, so every worker takes a ticket)
+            const uint32_t n_initial = use_lanes ? 0u : (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G);
             LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, n_initial, units.p, queue.p);
+            if (use_lanes) LAUNCH(ctx, k_sched_kick, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, units.p, queue.p, items.p);
             LAUNCH(ctx, k_spec_async, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p,
                    chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
             static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");

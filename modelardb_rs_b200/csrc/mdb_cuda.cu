@@ -27,6 +27,7 @@
 #include "mdb_aggregate.cuh"
 #include "mdb_compress.cuh"
 #include "mdb_fit_warp.cuh"
+#include "mdb_fit_lanes.cuh"
 #include "mdb_grid.cuh"
 #include "mdb_macaque_warp.cuh"
 

@@ -19,6 +19,7 @@
 #define MDB_WARP_EMU
 #include "warp_emu.h"
 #include "../../modelardb_rs_b200/csrc/mdb_fit_warp.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_fit_lanes.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_macaque_warp.cuh"
 
 using namespace mdb;
@@ -52,6 +53,39 @@ static void emu_run_chain(int engine, const ErrorBound &eb, const int64_t *uts, 
     st = after;
 }
 static int g_emu_engine = 1;
+static int g_emu_lanes = 0; // 1: one lane per chunk first (mdb_fit_lanes.cuh: k_lanes_units, k_lanes_regular, k_spec_lanes), then the stitching
+static uint64_t g_emu_lane_chunks = 0, g_emu_lane_bailed = 0;
+
+// k_lanes_units + k_lanes_regular + k_spec_lanes for one unit: every chunk's chain from the chunk's first index, one point
+// per step, values read straight from the array (the kernel reads the same values through its ring).
+template <int KIND>
+static void emu_unit_lanes_kind(const LaneUnit &lu, const float *uval, uint32_t n, uint32_t L, uint32_t C, uint32_t cap, std::vector<ChunkState> &st,
+                                std::vector<FittedModel> &lists) {
+    for (uint32_t c = 0; c < C; c++) {
+        const uint32_t lo = c * L, chunk_end = (uint32_t)std::min<uint64_t>((uint64_t)lo + L, n), limit = (uint32_t)std::min<uint64_t>((uint64_t)chunk_end + L, n);
+        LaneChain chain;
+        chain.begin(lo, chunk_end, limit, n);
+        FittedModel *list = lists.data() + ((size_t)c * 2 + 1) * cap;
+        while (!chain.template step<KIND>(lu, uval[chain.fit.idx], list)) {}
+        g_emu_lane_chunks++;
+        if (chain.bailed) {
+            g_emu_lane_bailed++;
+            continue;
+        }
+        lane_chain_publish(chain, st[c]);
+        st[c].phase = PH_DONE;
+    }
+}
+static void emu_unit_lanes(const ErrorBound &eb, const int64_t *uts, const float *uval, uint32_t n, uint32_t L, uint32_t C, uint32_t cap,
+                           std::vector<ChunkState> &st, std::vector<FittedModel> &lists) {
+    LaneUnit lu = lane_unit_init(uts, n, eb);
+    if (!lu.ok) return;
+    for (uint32_t i = 0; i < n; i++)
+        if (uts[i] != uts[0] + (int64_t)i * (uts[1] - uts[0])) return; // k_lanes_regular
+    if (eb.kind == KIND_LOSSLESS) emu_unit_lanes_kind<KIND_LOSSLESS>(lu, uval, n, L, C, cap, st, lists);
+    else if (eb.kind == KIND_ABSOLUTE) emu_unit_lanes_kind<KIND_ABSOLUTE>(lu, uval, n, L, C, cap, st, lists);
+    else emu_unit_lanes_kind<KIND_RELATIVE>(lu, uval, n, L, C, cap, st, lists);
+}
 
 // The asynchronous scheduler (k_spec_async + sched_advance) for one unit, single-threaded: up to `in_flight`
 // "workers" hold a claimed chunk at a time, and a seeded generator decides whether the next event is a worker
@@ -62,10 +96,12 @@ static bool emu_unit_async(const ErrorBound &eb, const int64_t *uts, const float
     uint64_t rng = 0x9E3779B97F4A7C15ull * (seed + 1);
     auto next = [&]() { rng ^= rng << 13; rng ^= rng >> 7; rng ^= rng << 17; return rng; };
     std::vector<uint32_t> queue;
-    for (uint32_t c = 0; c < C; c++) queue.push_back(c);
+    for (uint32_t c = 0; c < C; c++)
+        if (st[c].phase == PH_QUEUED) queue.push_back(c); // k_sched_count / k_sched_fill: chunks no lane has run
     size_t head = 0;
     UnitSched us;
     us.lock = 0; us.next_c = 0; us.entry = 0; us.finished = 0;
+    if (g_emu_lanes) sched_advance(us, n, L, C, st.data(), [&](uint32_t cc) { queue.push_back(cc); }); // k_sched_kick
     struct Claimed { uint32_t c; ChunkState s; };
     std::vector<Claimed> claimed;
     uint32_t runs = 0;
@@ -139,6 +175,7 @@ EmuSegments *emu_compress_sched(const int64_t *ts, const float *values, const ui
         uint32_t rounds = 0, resume_c = 0, resume_e = 0;
         if (sched_seed) {
             for (uint32_t c = 0; c < C; c++) st[c].phase = PH_QUEUED;
+            if (g_emu_lanes) emu_unit_lanes(eb, uts, uval, n, L, C, cap, st, lists);
             if (!emu_unit_async(eb, uts, uval, n, L, C, cap, st, lists, sched_seed + (uint32_t)u, in_flight ? in_flight : 1, &rounds)) return nullptr;
         }
         while (!sched_seed) { // rounds: k_spec_chain over dirty chunks, then k_spec_propagate per unit
@@ -216,6 +253,9 @@ uint64_t emu_check_eight_points(const int64_t *ts, const float *values, uint32_t
 
 // Engine of the chains in emu_compress*: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers.
 void emu_set_engine(int engine) { g_emu_engine = engine; }
+// 1: with the asynchronous scheduler, every chunk's chain is first run by a "lane" (mdb_fit_lanes.cuh) and the scheduler only stitches.
+void emu_set_lanes(int on) { g_emu_lanes = on; }
+void emu_lane_counters(uint64_t *chunks, uint64_t *bailed) { *chunks = g_emu_lane_chunks; *bailed = g_emu_lane_bailed; }
 uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
 
 // mdbcu_debug_fit_models on the host: fit_next_model at each start with either engine (records of 40 bytes).

@@ -35,6 +35,10 @@ def lib():
     L.emu_check_eight_points.restype = u64
     L.emu_set_engine.argtypes = [C.c_int]
     L.emu_set_engine.restype = None
+    L.emu_set_lanes.argtypes = [C.c_int]
+    L.emu_set_lanes.restype = None
+    L.emu_lane_counters.argtypes = [vp, vp]
+    L.emu_lane_counters.restype = None
     L.emu_division_mismatches.restype = u64
     L.emu_fit_models.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_float, C.c_int, vp, vp, C.c_uint32, vp]
     L.emu_fit_models.restype = None
@@ -102,11 +106,21 @@ def division_mismatches() -> int:
     return int(lib().emu_division_mismatches())
 
 
-def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0, engine=1) -> O.Segments:
+def lane_counters():
+    """(chunks run by emulated lanes so far, chunks a lane abandoned because of a non-finite value)."""
+    a, b = C.c_uint64(), C.c_uint64()
+    lib().emu_lane_counters(C.byref(a), C.byref(b))
+    return a.value, b.value
+
+
+def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0, engine=1, lanes=False) -> O.Segments:
     """sched_seed == 0: the round scheme; otherwise the asynchronous scheduler stepped in a seeded random order with
     `in_flight` concurrent workers (rounds then receives the largest number of chain runs of any unit).
-    engine: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers."""
+    engine: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers.
+    lanes (asynchronous scheduler only): every chunk's chain is first run by the one-lane-per-chain engine
+    (csrc/mdb_fit_lanes.cuh), the scheduler then only stitches, as mdbcu_compress does by default."""
     lib().emu_set_engine(engine)
+    lib().emu_set_lanes(1 if lanes else 0)
     ts = np.ascontiguousarray(ts, np.int64)
     vals = np.ascontiguousarray(values, np.float32)
     if unit_off is None:
