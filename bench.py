@@ -56,6 +56,7 @@ def parse_args():
     p.add_argument("--e2e-up-gate", type=int, default=2, help="workers allowed at once in the upload-heavy call (compress)")
     p.add_argument("--e2e-down-gate", type=int, default=1, help="workers allowed at once in the download-heavy call (grid)")
     p.add_argument("--chunk-len", type=int, default=0, help="chunk length of the parallel segmentation (0 = automatic); tuning only")
+    p.add_argument("--lane-warmup", type=int, default=-1, help="warm-up points of the lane engine (-1 = library default); tuning only")
     p.add_argument("--fit-engine", type=int, default=0, help="compress engine (0 = automatic); tuning only, results are identical")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -278,6 +279,8 @@ def main():
         ctx.set_chunk_len(args.chunk_len)
     if args.fit_engine:
         ctx.set_fit_engine(args.fit_engine)
+    if args.lane_warmup >= 0:
+        ctx.set_lane_warmup(args.lane_warmup)
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
     # ---- inputs resident in HBM

@@ -128,14 +128,19 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
  * greedy chains concurrently and are stitched by a fixpoint that reproduces the sequential chain
  * exactly (csrc/mdb_compress.cuh); results never depend on the chunk length.  0 = automatic. */
 int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len);
+/* How many points before its chunk a speculative one-lane-per-chain chain starts (engine 4; csrc/mdb_fit_lanes.cuh).
+ * Tuning only: results never depend on it. */
+int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points);
 /* Number of chain rounds the last mdbcu_compress on this context needed (1 = no re-run at all; always
  * 1 with the asynchronous scheduler, which has no rounds). */
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
-/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (= 3), 1 one
+/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (= 4), 1 one
  * thread per chain in global rounds, 2 one warp per chain (32 lanes fit 128 points per step,
  * csrc/mdb_fit_warp.cuh) in global rounds, 3 one warp per chain served from a device-side work queue
  * by persistent warps, each unit advancing its own exact frontier (csrc/mdb_compress.cuh,
- * sched_advance).  Results are identical. */
+ * sched_advance), 4 one LANE per chain for the bulk of the chains (every thread walks its own chunk point by point,
+ * csrc/mdb_fit_lanes.cuh; regular units with finite values) followed by 3 for the exact stitching and for everything
+ * the lanes leave alone.  Results are identical. */
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine);
 
 /* Diagnostics: fit_next_model (compression.rs:280-301) at each of `starts` with the chosen engine

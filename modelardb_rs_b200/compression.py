@@ -102,6 +102,10 @@ class Context:
         """Chunk length of the parallel segmentation (0 = automatic); results never depend on it."""
         _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
 
+    def set_lane_warmup(self, points: int):
+        """Points a speculative lane chain starts before its chunk (engine 4); results never depend on it."""
+        _native.check(_native.lib().mdbcu_context_set_lane_warmup(self._h, points))
+
     def set_fit_engine(self, engine: int):
         """0 automatic (= 4), 1 one thread per chain in rounds, 2 one warp per chain in rounds, 3 one warp per chain with
         the asynchronous scheduler, 4 one lane per chain for the bulk of the chains and 3 for the stitching; results are

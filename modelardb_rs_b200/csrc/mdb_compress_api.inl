@@ -185,9 +185,9 @@ template <int KIND>
 __global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec_lanes(const float *__restrict__ values, uint64_t n_total,
                                                                   const uint64_t *__restrict__ unit_off, const LaneUnit *__restrict__ info,
                                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
-                                                                  uint32_t chunk_len, uint32_t n_chunks, ChunkState *st, FittedModel *lists,
-                                                                  const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
-                                                                  unsigned int *next_chunk) {
+                                                                  uint32_t chunk_len, uint32_t warmup, uint32_t n_chunks, ChunkState *st,
+                                                                  FittedModel *lists, const uint64_t *__restrict__ list_base,
+                                                                  const uint32_t *__restrict__ list_cap, unsigned int *next_chunk) {
     __shared__ float ring_s[LANES_WARPS][LANES_RING][32]; // [slot][lane]: a lane's slot k is in bank `lane` whatever k is
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float(*ring)[32] = ring_s[warp];
@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec
                     const uint32_t lo = c * chunk_len;
                     const uint32_t chunk_end = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
                     const uint32_t limit = (uint64_t)chunk_end + chunk_len < n ? chunk_end + chunk_len : n;
-                    chain.begin(lo, chunk_end, limit, n);
+                    chain.begin(lo > warmup ? lo - warmup : 0u, lo, chunk_end, limit, n); // (see LaneChain: warm-up)
                     list = lists + list_base[g] + (size_t)(list_cap[g] / 2); // the chunk's second buffer (st.buf is 0 before the first chain)
                     sk = (uint32_t)((a + skew) & 3u);
                     eb4 = (a + skew) & ~(uint64_t)3;
@@ -381,11 +381,15 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
     __shared__ double smem[CHAIN_WARPS][WarpFit::SMEM_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     bool first = true, initial_phase = true;
+    uint32_t carry = 0; // (lane 0) the chunk this worker's own sched_advance queued last: taken next, without the queue
     while (true) {
         uint32_t item = 0;
         if (lane == 0) {
             const uint32_t w = blockIdx.x * CHAIN_WARPS + warp;
-            if (first && w < n_initial) { // (init_head starts at n_initial)
+            if (carry) { // stay with the unit: its frontier advances one chunk after the other, and a queue shared by
+                item = carry; // every worker serialises at about a microsecond per item
+                carry = 0;
+            } else if (first && w < n_initial) { // (init_head starts at n_initial)
                 item = sync_load(&items[w]);
             } else {
                 // the pushed part first: those are frontier chunks, the critical path of their unit.  Popped exactly
@@ -447,6 +451,10 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
             atomicExch(&st[g].phase, PH_DONE);
             const bool unit_final = sched_advance(units[u], n, chunk_len, C, st + g0, [&](uint32_t cc) {
                 __threadfence();
+                if (!carry) {
+                    carry = (uint32_t)(g0 + cc) + 1u;
+                    return;
+                }
                 const uint32_t slot = atomicAdd(&q->tail, 1u);
                 if (slot < sync_load(&q->capacity)) sync_store(&items[slot], (uint32_t)(g0 + cc) + 1u);
                 else sync_store(&q->finished, 2u); // cannot happen (a chunk is queued at most three times); stops the workers
@@ -789,9 +797,13 @@ __global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict_
 // longer chunks mean fewer fixpoint rounds for units whose chains do not re-synchronise (measured on
 // 4e8 points: 4096 -> 140 ms, 16384 -> 74 ms, 65536 -> 81 ms).  The one-thread engine wants 32x more
 // chains (one per lane).  Within [4096, 65536] points.
-static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points) {
+// With one lane per chain (`lanes`) every chain is a thread: ~1024 chains per SM, i.e. 32x shorter chunks -- but a
+// speculative lane spends a warm-up of a few thousand points before its chunk (LaneChain), so chunks stay >= 4096 points.
+// With units enough to occupy the lanes by themselves, chunks are as long as they get: no speculation, no warm-up.
+static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points, uint64_t n_units, bool lanes) {
     if (ctx->chunk_len_override) return ctx->chunk_len_override;
-    uint64_t target_chains = (uint64_t)ctx->sm_count * 128 * (ctx->fit_mode == 1 ? 32 : 1);
+    uint64_t target_chains = (uint64_t)ctx->sm_count * 128 * (ctx->fit_mode == 1 ? 32 : lanes ? 8 : 1);
+    if (lanes && n_units >= target_chains / 2) return 65536;
     uint64_t len = n_points / target_chains;
     uint32_t l = 4096;
     while (l < len && l < 65536) l <<= 1;
@@ -808,6 +820,12 @@ int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len) {
 }
 
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return ctx ? ctx->last_rounds : 0; }
+
+int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    ctx->lane_warmup = points;
+    return MDBCU_SUCCESS;
+}
 
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
@@ -888,7 +906,22 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 
     if (n_units) {
         // ---- chunks
-        const uint32_t chunk_len = choose_chunk_len(ctx, n_points - first);
+        // one lane per chain (mdb_fit_lanes.cuh) if any unit qualifies: decided first, because the chunks are shorter then
+        bool use_lanes = ctx->fit_mode == 0 || ctx->fit_mode == 4;
+        DBuf<LaneUnit> lane_units;
+        DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
+        unsigned int kind_units[4] = {0, 0, 0, 0};
+        if (use_lanes) {
+            TRY_SG(lane_units.alloc(n_units, s));
+            TRY_SG(lane_words.alloc(4, s));
+            TRY_SG(cudaMemsetAsync(lane_words.p, 0, 4 * sizeof(unsigned int), s));
+            LAUNCH(ctx, k_lanes_units, div_up(n_units, 128), 128, 0, d_ts, d_off, n_units, d_kind, d_ebv, lane_units.p, lane_words.p);
+            TRY_SG(post(ctx, 0, lane_words.p, 2));
+            TRY_SG(sync_stream(ctx));
+            std::memcpy(kind_units, ctx->mailbox, sizeof(kind_units));
+            use_lanes = kind_units[0] + kind_units[1] + kind_units[2] > 0;
+        }
+        const uint32_t chunk_len = choose_chunk_len(ctx, n_points - first, n_units, use_lanes);
         DBuf<Status> status;
         if (new_status(ctx, status)) return bail(MDBCU_FAILURE);
         DBuf<uint32_t> unit_chunks;
@@ -925,20 +958,9 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(lists.alloc(n_models_cap, s));
 
         const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3 || ctx->fit_mode == 4;
-        const bool use_lanes = ctx->fit_mode == 0 || ctx->fit_mode == 4;
         if (use_lanes && G) {
-            // ---- one lane per chunk: the bulk of the chains (mdb_fit_lanes.cuh); what they leave open is stitched below
-            DBuf<LaneUnit> lane_units;
-            DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
-            TRY_SG(lane_units.alloc(n_units, s));
-            TRY_SG(lane_words.alloc(4, s));
-            TRY_SG(cudaMemsetAsync(lane_words.p, 0, 4 * sizeof(unsigned int), s));
-            LAUNCH(ctx, k_lanes_units, div_up(n_units, 128), 128, 0, d_ts, d_off, n_units, d_kind, d_ebv, lane_units.p, lane_words.p);
+            // ---- one lane per chunk: the bulk of the chains; what they leave open is stitched below
             LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
-            TRY_SG(post(ctx, 0, lane_words.p, 2));
-            TRY_SG(sync_stream(ctx));
-            unsigned int kind_units[4];
-            std::memcpy(kind_units, ctx->mailbox, sizeof(kind_units));
             for (int kind = 0; kind < 3; kind++) {
                 if (!kind_units[kind]) continue;
                 int blocks_per_sm = 0;
@@ -950,13 +972,13 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
                 TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
                 if (kind == KIND_LOSSLESS)
                     LAUNCH(ctx, k_spec_lanes<KIND_LOSSLESS>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
                 else if (kind == KIND_ABSOLUTE)
                     LAUNCH(ctx, k_spec_lanes<KIND_ABSOLUTE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
                 else
                     LAUNCH(ctx, k_spec_lanes<KIND_RELATIVE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
             }
             TRY_SG(cudaGetLastError());
         }

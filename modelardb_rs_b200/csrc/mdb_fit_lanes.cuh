@@ -227,28 +227,38 @@ MDB_DEV bool lane_finish(const LaneFit &f, FittedModel &m) {
 }
 
 // One lane's chain over one chunk: the control flow of spec_chain (mdb_compress.cuh) for a chunk that has no earlier
-// chain to splice into.  `value_at(i)` returns the unit's value i (the kernel reads it from the lane's ring, the host
-// emulation from the array); it is only called for i < limit.
+// chain to splice into.
+//
+// Warm-up.  A chain that starts at an arbitrary index is not the unit's sequential chain: the two only coincide from the
+// first fit start they have in common, and on the benchmark's data that takes about eight fits (measured: mean 2500
+// points, 90 % within 5800).  A speculative lane therefore starts `warm-up` points BEFORE its chunk and only keeps what
+// happens from its first fit start at or after the chunk's first index (`store_from`): that start is the chain's ENTRY.
+// The stitching compares it with the exit of the final chain before the chunk -- equal means the lane's chain is the
+// sequential chain from there on, as for any other speculative chain; different means the chunk is re-run from the exact
+// entry until the new chain meets the lane's.
 struct LaneChain {
-    uint32_t chunk_end, limit, n; // fit starts lie in [entry, chunk_end); a fit may read up to `limit` (<= n)
+    uint32_t store_from, chunk_end, limit, n; // fit starts in [store_from, chunk_end) are kept; a fit may read up to `limit` (<= n)
+    uint32_t entry;               // first fit start >= store_from (IDX_NONE: not reached yet)
     uint32_t n_models, first_start;
     uint32_t exit, truncated_at;
-    bool bailed;                  // met a non-finite value: the chunk is left to the cooperative engine
+    bool bailed;                  // met a non-finite value, or was cut before reaching its chunk: the chunk is left to the cooperative engine
     LaneFit fit;
 
-    MDB_DEV void begin(uint32_t entry, uint32_t chunk_end_, uint32_t limit_, uint32_t n_) {
+    MDB_DEV void begin(uint32_t start, uint32_t store_from_, uint32_t chunk_end_, uint32_t limit_, uint32_t n_) {
+        store_from = store_from_;
         chunk_end = chunk_end_;
         limit = limit_;
         n = n_;
+        entry = start >= store_from_ ? start : IDX_NONE;
         n_models = 0;
         first_start = IDX_NONE;
         exit = IDX_NONE;
         truncated_at = 0;
         bailed = false;
-        fit.begin(entry);
+        fit.begin(start);
     }
 
-    // Feeds one point.  Returns true when the chain is complete (exit / truncated_at / bailed are final).
+    // Feeds one point.  Returns true when the chain is complete (entry / exit / truncated_at / bailed are final).
     template <int KIND> MDB_DEV bool step(const LaneUnit &u, float v, FittedModel *list) {
         if (!(fabsf(v) <= 3.402823466e+38f)) {
             bailed = true;
@@ -258,17 +268,21 @@ struct LaneChain {
         if (fit.growing() && fit.idx < limit) return false;
         if (fit.growing() && limit < n) { // still growing where a speculative chain's budget ends: cut (spec_chain: aborted)
             truncated_at = fit.start;
+            bailed = entry == IDX_NONE;
             return true;
         }
         FittedModel m;
         uint32_t next;
         if (lane_finish(fit, m)) {
-            if (n_models == 0) first_start = m.start_index;
-            list[n_models++] = m;
+            if (entry != IDX_NONE) {
+                if (n_models == 0) first_start = m.start_index;
+                list[n_models++] = m;
+            }
             next = m.end_index + 1;
         } else {
             next = fit.start + 1; // compression.rs:261: the point becomes a residual
         }
+        if (entry == IDX_NONE && next >= store_from) entry = next;
         if (next >= chunk_end) {
             exit = next;
             return true;
@@ -280,7 +294,7 @@ struct LaneChain {
 
 // The chunk state a completed lane chain leaves behind (what spec_chain stores for a fresh chunk).
 MDB_DEV void lane_chain_publish(const LaneChain &c, ChunkState &st) {
-    st.entry = st.new_entry;
+    st.entry = c.entry;
     st.exit = c.exit;
     st.truncated_at = c.truncated_at;
     st.n_models = c.n_models;

@@ -55,6 +55,7 @@ static void emu_run_chain(int engine, const ErrorBound &eb, const int64_t *uts, 
 static int g_emu_engine = 1;
 static int g_emu_lanes = 0; // 1: one lane per chunk first (mdb_fit_lanes.cuh: k_lanes_units, k_lanes_regular, k_spec_lanes), then the stitching
 static uint64_t g_emu_lane_chunks = 0, g_emu_lane_bailed = 0;
+static uint32_t g_emu_lane_warmup = 0;
 
 // k_lanes_units + k_lanes_regular + k_spec_lanes for one unit: every chunk's chain from the chunk's first index, one point
 // per step, values read straight from the array (the kernel reads the same values through its ring).
@@ -64,7 +65,7 @@ static void emu_unit_lanes_kind(const LaneUnit &lu, const float *uval, uint32_t 
     for (uint32_t c = 0; c < C; c++) {
         const uint32_t lo = c * L, chunk_end = (uint32_t)std::min<uint64_t>((uint64_t)lo + L, n), limit = (uint32_t)std::min<uint64_t>((uint64_t)chunk_end + L, n);
         LaneChain chain;
-        chain.begin(lo, chunk_end, limit, n);
+        chain.begin(lo > g_emu_lane_warmup ? lo - g_emu_lane_warmup : 0u, lo, chunk_end, limit, n);
         FittedModel *list = lists.data() + ((size_t)c * 2 + 1) * cap;
         while (!chain.template step<KIND>(lu, uval[chain.fit.idx], list)) {}
         g_emu_lane_chunks++;
@@ -255,6 +256,7 @@ uint64_t emu_check_eight_points(const int64_t *ts, const float *values, uint32_t
 void emu_set_engine(int engine) { g_emu_engine = engine; }
 // 1: with the asynchronous scheduler, every chunk's chain is first run by a "lane" (mdb_fit_lanes.cuh) and the scheduler only stitches.
 void emu_set_lanes(int on) { g_emu_lanes = on; }
+void emu_set_lane_warmup(uint32_t points) { g_emu_lane_warmup = points; }
 void emu_lane_counters(uint64_t *chunks, uint64_t *bailed) { *chunks = g_emu_lane_chunks; *bailed = g_emu_lane_bailed; }
 uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
 

@@ -12,12 +12,13 @@ from tests.parity_cases import assert_segments_equal, long_model_cases, small_ca
 from tests.test_warp_fit_emulated import _fuzz_series
 
 
-@pytest.mark.parametrize("chunk_len,sched", [(64, (2, 1)), (1000, (5, 3)), (4096, (7, 8))], ids=["64", "1000", "4096"])
+@pytest.mark.parametrize("chunk_len,warmup,sched", [(64, 0, (2, 1)), (64, 100, (3, 2)), (1000, 300, (5, 3)), (1000, 5000, (6, 2)), (4096, 0, (7, 8))],
+                         ids=["64", "64+100", "1000+300", "1000+5000", "4096"])
 @pytest.mark.parametrize("case", [c for c in small_cases() if len(c[1]) <= 30000], ids=lambda c: c[0])
-def test_emulated_lanes_compress_matches_oracle(oracle, case, chunk_len, sched):
+def test_emulated_lanes_compress_matches_oracle(oracle, case, chunk_len, warmup, sched):
     name, ts, vals, off, ebs = case
     want = oracle.compress(ts, vals, off, eb=ebs)
-    got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2, lanes=True)
+    got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2, lanes=True, lane_warmup=warmup)
     assert_segments_equal(got, want, f"{name} chunk_len={chunk_len} sched={sched}")
     assert emu.division_mismatches() == 0
 
@@ -42,7 +43,7 @@ def test_lanes_run_regular_units_and_leave_the_others(oracle):
         for eb in ((2, 0.5), (0, 0.0), (1, 0.05)):
             want = oracle.compress(ts, v, eb=eb)
             before = emu.lane_counters()
-            got = emu.compress(ts, v, eb=eb, chunk_len=512, sched_seed=11, in_flight=3, engine=2, lanes=True)
+            got = emu.compress(ts, v, eb=eb, chunk_len=512, sched_seed=11, in_flight=3, engine=2, lanes=True, lane_warmup=200)
             after = emu.lane_counters()
             assert_segments_equal(got, want, f"{name} {eb}")
             assert (after[0] > before[0]) == runs, name
@@ -60,7 +61,7 @@ def test_emulated_lanes_fuzz(oracle, seed):
     eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 3))), (2, float(rng.choice([0.01, 0.5, 1.0, 5.0, 30.0, 100.0])))][seed % 3]
     want = oracle.compress(ts, vals, eb=eb)
     got = emu.compress(ts, vals, eb=eb, chunk_len=int(rng.choice([8, 24, 100, 700])), sched_seed=seed + 1, in_flight=int(rng.choice([1, 2, 9])),
-                       engine=2, lanes=True)
+                       engine=2, lanes=True, lane_warmup=int(rng.choice([0, 5, 60, 1000])))
     assert_segments_equal(got, want, f"fuzz seed={seed} eb={eb} n={n}")
 
 
@@ -70,6 +71,6 @@ def test_emulated_lanes_on_long_models(oracle):
     for name, ts, vals, eb in long_model_cases():
         want = oracle.compress(ts, vals, eb=eb)
         for chunk_len in (700, 4096):
-            got = emu.compress(ts, vals, eb=eb, chunk_len=chunk_len, sched_seed=3, in_flight=4, engine=2, lanes=True)
+            got = emu.compress(ts, vals, eb=eb, chunk_len=chunk_len, sched_seed=3, in_flight=4, engine=2, lanes=True, lane_warmup=chunk_len // 2)
             assert_segments_equal(got, want, f"{name} chunk_len={chunk_len}")
     assert emu.division_mismatches() == 0
