@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(REGULAR_THREADS) k_lanes_regular(const int64_t
 constexpr int LANES_WARPS = 4;
 constexpr int LANES_RING = 16; // values per lane: four 16-byte quads (the one before the cursor's, the cursor's, one or two ahead)
 #ifndef MDB_LANES_MIN_BLOCKS
-#define MDB_LANES_MIN_BLOCKS 4
+#define MDB_LANES_MIN_BLOCKS 5
 #endif
 
 template <int KIND>
@@ -195,100 +195,113 @@ __global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec
     const uint32_t skew = (uint32_t)((reinterpret_cast<uintptr_t>(values) >> 2) & 3u);
     const float4 *quads = reinterpret_cast<const float4 *>(values - skew);
 
-    bool have = false;       // this lane owns a chunk
-    uint32_t g = 0;          // the chunk
+    bool have = false;        // this lane owns a chunk
+    uint32_t g = 0;           // the chunk
     const float4 *uq = quads; // the quad that holds the unit's point 0 ...
-    uint32_t sk = 0;         // ... at element sk of it: point i of the unit is element sk + i from there
-    uint64_t eb4 = 0;        // quad-space element index of uq[0] (bounds of the array's first and last quad)
+    uint32_t sk = 0;          // ... at element sk of it: point i of the unit is element sk + i from there
+    uint32_t vec_lo = 0, vec_n = 0; // quads [vec_lo, vec_lo + vec_n) (relative to uq) lie entirely inside the values array
+    uint64_t eb4 = 0;         // quad-space element index of uq[0]
     LaneUnit lu;
     LaneChain chain;
     FittedModel *list = nullptr;
-    // ring: quads [ring_lo, loaded] (relative to uq) are in slots (q & 3) * 4 ..; `pend` is the quad in flight
-    int32_t ring_lo = 0, loaded = -1, pend_q = -1;
+    // Ring: the elements [win_lo, win_lo + win_n) (relative to uq[0]) are in the ring, element e in slot e & 15.  Quads are
+    // loaded in order, one per refill, `next_q` next; `pend` is the quad requested at the previous refill.
+    uint32_t win_lo = 0, win_n = 0, next_q = 0;
+    bool pending = false;
     float4 pend = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool exhausted = false;  // the chunk counter has run out
+    bool exhausted = false;   // the chunk counter has run out
 
-    auto load_quad = [&](int32_t q) -> float4 {
-        const uint64_t e = eb4 + (uint64_t)q * 4;
-        if (e >= skew && e + 4 <= n_total + skew) return __ldg(uq + q);
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f); // first / last quad of the array: the elements that exist
+    auto load_quad = [&](uint32_t q) -> float4 {
+        if (q - vec_lo < vec_n) return __ldg(uq + q);
+        const uint64_t e = eb4 + (uint64_t)q * 4; // first / last quad of the array: the elements that exist
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
         float *rp = reinterpret_cast<float *>(&r);
         for (int k = 0; k < 4; k++)
             if (e + k >= skew && e + k < n_total + skew) rp[k] = __ldg(values + (e + k - skew));
         return r;
     };
 
-    for (uint32_t iter = 0;; iter++) {
-        if ((iter & 3u) == 0u) {
-            // ---- claim a chunk if this lane has none
-            if (!have && !exhausted) {
-                while (true) {
-                    const unsigned int w = atomicAdd(next_chunk, 1u);
-                    if (w >= n_chunks) {
-                        exhausted = true;
-                        break;
-                    }
-                    const uint32_t u = chunk_unit[w];
-                    lu = info[u];
-                    if (!lu.ok || lu.irregular || lu.kind != KIND) continue;
-                    g = w;
-                    const uint64_t a = unit_off[u];
-                    const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
-                    const uint32_t c = (uint32_t)(g - chunk_base[u]);
-                    const uint32_t lo = c * chunk_len;
-                    const uint32_t chunk_end = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
-                    const uint32_t limit = (uint64_t)chunk_end + chunk_len < n ? chunk_end + chunk_len : n;
-                    chain.begin(lo > warmup ? lo - warmup : 0u, lo, chunk_end, limit, n); // (see LaneChain: warm-up)
-                    list = lists + list_base[g] + (size_t)(list_cap[g] / 2); // the chunk's second buffer (st.buf is 0 before the first chain)
-                    sk = (uint32_t)((a + skew) & 3u);
-                    eb4 = (a + skew) & ~(uint64_t)3;
-                    uq = quads + (eb4 >> 2);
-                    have = true;
-                    loaded = -1;
-                    pend_q = -1;
-                    ring_lo = 0;
+    while (true) {
+        // ---- claim a chunk if this lane has none
+        if (!have && !exhausted) {
+            while (true) {
+                const unsigned int w = atomicAdd(next_chunk, 1u);
+                if (w >= n_chunks) {
+                    exhausted = true;
                     break;
                 }
+                const uint32_t u = chunk_unit[w];
+                lu = info[u];
+                if (!lu.ok || lu.irregular || lu.kind != KIND) continue;
+                g = w;
+                const uint64_t a = unit_off[u];
+                const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+                const uint32_t c = (uint32_t)(g - chunk_base[u]);
+                const uint32_t lo = c * chunk_len;
+                const uint32_t chunk_end = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
+                const uint32_t limit = (uint64_t)chunk_end + chunk_len < n ? chunk_end + chunk_len : n;
+                chain.begin(lo > warmup ? lo - warmup : 0u, lo, chunk_end, limit, n); // (see LaneChain: warm-up)
+                list = lists + list_base[g] + (size_t)(list_cap[g] / 2); // the chunk's second buffer (st.buf is 0 before the first chain)
+                sk = (uint32_t)((a + skew) & 3u);
+                eb4 = (a + skew) & ~(uint64_t)3;
+                uq = quads + (eb4 >> 2);
+                // quads of this unit's span that can be read with one 16-byte load (all but, at most, the array's first and last)
+                const uint64_t q_first = eb4 >= skew ? 0 : 1;                       // quad 0 starts before values[0]
+                const uint64_t q_end = (n_total + skew - eb4) / 4;                   // first quad that reaches past the array
+                vec_lo = (uint32_t)q_first;
+                vec_n = q_end > q_first ? (q_end - q_first < 0xFFFFFFF0ull ? (uint32_t)(q_end - q_first) : 0xFFFFFFF0u) : 0u;
+                have = true;
+                win_n = 0;
+                pending = false;
+                next_q = (sk + chain.fit.idx) >> 2;
+                win_lo = next_q * 4;
+                break;
             }
-            if (!__any_sync(FULL_MASK, have)) break;
-            // ---- ring refill: land the quad in flight, then request the next one
-            if (pend_q >= 0) {
-                const int s4 = (pend_q & 3) * 4;
-                ring[s4 + 0][lane] = pend.x;
-                ring[s4 + 1][lane] = pend.y;
-                ring[s4 + 2][lane] = pend.z;
-                ring[s4 + 3][lane] = pend.w;
-                loaded = pend_q;
-                pend_q = -1;
+        }
+        if (!__any_sync(FULL_MASK, have)) break;
+        // ---- ring refill: land the quad requested at the previous refill, then request the next one
+        if (pending) {
+            const uint32_t s4 = ((next_q - 1u) & 3u) * 4u;
+            ring[s4 + 0][lane] = pend.x;
+            ring[s4 + 1][lane] = pend.y;
+            ring[s4 + 2][lane] = pend.z;
+            ring[s4 + 3][lane] = pend.w;
+            win_n += 4;
+            if (win_n > 16) { // the quad just landed took the slot of the oldest one
+                win_lo += 4;
+                win_n = 16;
             }
-            if (have) {
-                const int32_t cq = (int32_t)((sk + chain.fit.idx) >> 2);
-                if (loaded < 0 || cq < ring_lo || cq < loaded - 3 || cq > loaded + 1) { // seek: nothing in the ring is of use
-                    loaded = -1;
-                    ring_lo = cq;
-                    pend_q = cq;
-                } else if (loaded < cq + 2) {
-                    pend_q = loaded + 1;
-                }
-                if (pend_q >= 0) {
-                    if ((uint32_t)pend_q * 4u < sk + chain.limit) pend = load_quad(pend_q);
-                    else pend_q = -1; // nothing of this chunk lies there
-                }
-            }
+            pending = false;
         }
         if (have) {
             const uint32_t e = sk + chain.fit.idx;
-            const int32_t cq = (int32_t)(e >> 2);
-            if (loaded >= 0 && cq >= ring_lo && cq <= loaded && cq >= loaded - 3) {
-                const float v = ring[(int)(e & 15u)][lane];
-                if (chain.template step<KIND>(lu, v, list)) {
-                    if (!chain.bailed) {
-                        ChunkState s = st[g];
-                        lane_chain_publish(chain, s);
-                        s.phase = PH_DONE;
-                        st[g] = s;
+            if (e - win_lo > win_n) { // the cursor is outside the ring and not at its end (a jump back, or a new chunk): start over there
+                next_q = e >> 2;
+                win_lo = next_q * 4;
+                win_n = 0;
+            }
+            // keep two quads ahead of the cursor's
+            if (next_q <= (e >> 2) + 2 && next_q * 4 < sk + chain.limit) {
+                pend = load_quad(next_q);
+                next_q += 1;
+                pending = true;
+            }
+        }
+#pragma unroll
+        for (int it = 0; it < 4; it++) {
+            if (have) {
+                const uint32_t e = sk + chain.fit.idx;
+                if (e - win_lo < win_n) {
+                    const float v = ring[e & 15u][lane];
+                    if (chain.template step<KIND>(lu, v, list)) {
+                        if (!chain.bailed) {
+                            ChunkState s = st[g];
+                            lane_chain_publish(chain, s);
+                            s.phase = PH_DONE;
+                            st[g] = s;
+                        }
+                        have = false;
                     }
-                    have = false;
                 }
             }
         }
@@ -371,6 +384,7 @@ __global__ void __launch_bounds__(128) k_sched_kick(const uint64_t *__restrict__
 // claims it, runs its chain (the same spec_chain as the round scheme) and advances the unit.  A worker that finds
 // the queue empty EXITS: every later push is made by a worker that is still alive and pops right afterwards, so
 // nothing is ever stranded, and the SM slots of a draining kernel become free for other streams.
+template <typename Fit>
 __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_async(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                  const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
                                                                  const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
@@ -378,7 +392,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
                                                                  FittedModel *lists, const uint64_t *__restrict__ list_base,
                                                                  const uint32_t *__restrict__ list_cap, UnitSched *units, SchedQueue *q, uint32_t *items,
                                                                  uint32_t n_initial, uint32_t n_chunks) {
-    __shared__ double smem[CHAIN_WARPS][WarpFit::SMEM_DOUBLES];
+    __shared__ double smem[CHAIN_WARPS][Fit::SMEM_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     bool first = true, initial_phase = true;
     uint32_t carry = 0; // (lane 0) the chunk this worker's own sched_advance queued last: taken next, without the queue
@@ -440,7 +454,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
         const uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
         ChunkState s = load_shared_record(st + g);
         ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-        WarpFit fitter(eb, ts + a, values + a, n, smem[warp]);
+        Fit fitter(eb, ts + a, values + a, n, smem[warp]);
         spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
         __threadfence(); // this lane's list writes, before lane 0 publishes the chunk
         __syncwarp();
@@ -797,13 +811,22 @@ __global__ void __launch_bounds__(64) k_compress_emit(const int64_t *__restrict_
 // longer chunks mean fewer fixpoint rounds for units whose chains do not re-synchronise (measured on
 // 4e8 points: 4096 -> 140 ms, 16384 -> 74 ms, 65536 -> 81 ms).  The one-thread engine wants 32x more
 // chains (one per lane).  Within [4096, 65536] points.
-// With one lane per chain (`lanes`) every chain is a thread: ~1024 chains per SM, i.e. 32x shorter chunks -- but a
-// speculative lane spends a warm-up of a few thousand points before its chunk (LaneChain), so chunks stay >= 4096 points.
+// With one lane per chain every chain is a thread, and the chains of a call should fill the resident lanes ONCE: a lane that
+// finishes its chunk can only start another whole chunk, so 1.3 waves of chunks take as long as 2.  The chunk length is
+// therefore (points / resident lanes), allowing for one partial chunk per unit; within [4096, 65536] points (a speculative
+// lane spends a warm-up of a few thousand points before its chunk, LaneChain), in k equal waves when the call is that big.
 // With units enough to occupy the lanes by themselves, chunks are as long as they get: no speculation, no warm-up.
-static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points, uint64_t n_units, bool lanes) {
+static uint32_t choose_chunk_len(const mdbcu_context *ctx, uint64_t n_points, uint64_t n_units, uint64_t resident_lanes) {
     if (ctx->chunk_len_override) return ctx->chunk_len_override;
-    uint64_t target_chains = (uint64_t)ctx->sm_count * 128 * (ctx->fit_mode == 1 ? 32 : lanes ? 8 : 1);
-    if (lanes && n_units >= target_chains / 2) return 65536;
+    if (resident_lanes) {
+        if (n_units >= resident_lanes / 2) return 65536;
+        for (uint64_t waves = 1;; waves++) {
+            const uint64_t chains = waves * resident_lanes - n_units;
+            const uint64_t len = ((n_points + chains - 1) / chains + 63) / 64 * 64;
+            if (len <= 65536) return (uint32_t)std::max<uint64_t>(len, 4096);
+        }
+    }
+    uint64_t target_chains = (uint64_t)ctx->sm_count * 128 * (ctx->fit_mode == 1 ? 32 : 1);
     uint64_t len = n_points / target_chains;
     uint32_t l = 4096;
     while (l < len && l < 65536) l <<= 1;
@@ -921,7 +944,19 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             std::memcpy(kind_units, ctx->mailbox, sizeof(kind_units));
             use_lanes = kind_units[0] + kind_units[1] + kind_units[2] > 0;
         }
-        const uint32_t chunk_len = choose_chunk_len(ctx, n_points - first, n_units, use_lanes);
+        uint64_t resident_lanes = 0; // of the lane kernel (the smallest over the bound kinds present)
+        int lane_blocks_per_sm[3] = {0, 0, 0};
+        if (use_lanes) {
+            const void *fns[3] = {(const void *)k_spec_lanes<KIND_LOSSLESS>, (const void *)k_spec_lanes<KIND_ABSOLUTE>, (const void *)k_spec_lanes<KIND_RELATIVE>};
+            for (int kind = 0; kind < 3; kind++) {
+                if (!kind_units[kind]) continue;
+                TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&lane_blocks_per_sm[kind], fns[kind], LANES_WARPS * 32, 0));
+                if (lane_blocks_per_sm[kind] < 1) return bail(fail("compress: the lane kernel does not fit on this device"));
+                const uint64_t r = (uint64_t)ctx->sm_count * lane_blocks_per_sm[kind] * LANES_WARPS * 32;
+                resident_lanes = resident_lanes ? std::min(resident_lanes, r) : r;
+            }
+        }
+        const uint32_t chunk_len = choose_chunk_len(ctx, n_points - first, n_units, resident_lanes);
         DBuf<Status> status;
         if (new_status(ctx, status)) return bail(MDBCU_FAILURE);
         DBuf<uint32_t> unit_chunks;
@@ -963,12 +998,8 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
             for (int kind = 0; kind < 3; kind++) {
                 if (!kind_units[kind]) continue;
-                int blocks_per_sm = 0;
-                const void *fn = kind == KIND_LOSSLESS ? (const void *)k_spec_lanes<KIND_LOSSLESS>
-                                 : kind == KIND_ABSOLUTE ? (const void *)k_spec_lanes<KIND_ABSOLUTE> : (const void *)k_spec_lanes<KIND_RELATIVE>;
-                TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, fn, LANES_WARPS * 32, 0));
-                if (blocks_per_sm < 1) return bail(fail("compress: the lane kernel does not fit on this device"));
-                const unsigned int n_blocks = (unsigned int)std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, LANES_WARPS * 32));
+                const unsigned int n_blocks =
+                    (unsigned int)std::min<uint64_t>((uint64_t)ctx->sm_count * lane_blocks_per_sm[kind], div_up(G, LANES_WARPS * 32));
                 TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
                 if (kind == KIND_LOSSLESS)
                     LAUNCH(ctx, k_spec_lanes<KIND_LOSSLESS>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
@@ -985,7 +1016,8 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         if (async_sched && G) {
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
             int blocks_per_sm = 0;
-            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, k_spec_async, CHAIN_WARPS * 32, 0));
+            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, use_lanes ? k_spec_async<WarpFitWide> : k_spec_async<WarpFit>,
+                                                                 CHAIN_WARPS * 32, 0));
             if (blocks_per_sm < 1) return bail(fail("compress: the chain kernel does not fit on this device"));
             const uint64_t n_blocks = std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, CHAIN_WARPS));
             const uint64_t capacity = 3 * G + n_blocks * CHAIN_WARPS + 8;
@@ -1012,8 +1044,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             const uint32_t n_initial = use_lanes ? 0u : (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G);
             LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, n_initial, units.p, queue.p);
             if (use_lanes) LAUNCH(ctx, k_sched_kick, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, units.p, queue.p, items.p);
-            LAUNCH(ctx, k_spec_async, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p, chunk_unit.p,
-                   chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
+            if (use_lanes) // what the lanes left: stitching, and the long models they cut -- the engine with the wide steps
+                LAUNCH(ctx, k_spec_async<WarpFitWide>, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
+                       chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
+            else
+                LAUNCH(ctx, k_spec_async<WarpFit>, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
+                       chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
             static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");
             TRY_SG(post(ctx, 0, queue.p, 4));
             TRY_SG(sync_stream(ctx));

@@ -24,8 +24,8 @@
 //
 // Arithmetic: the same operations in the same order as the one-thread fit (mdb_compress.cuh), with the divisions done
 // by ddiv_fast_in_range (operands in range by construction for finite f32 values, see mdb_fit_warp.cuh) and PMC-Mean's
-// relative test in its division-free exact form (RelTest).  Swing's two error sums are not needed to find where a fit
-// ends: accepted Swing models are left `pending` and completed by k_swing_finish, as with the cooperative engine.
+// relative test in its division-free exact form (RelTest).  Swing's two error sums (swing.rs:212-228) are accumulated
+// point by point like everything else, so a lane's models are complete (nothing is left `pending` for k_swing_finish).
 #pragma once
 
 #if defined(__CUDACC__) || defined(MDB_WARP_EMU)
@@ -99,7 +99,9 @@ MDB_DEV LaneUnit lane_unit_init(const int64_t *uts, uint64_t n, const ErrorBound
     return lu;
 }
 
-// The state of one fit (ModelBuilder, types.rs:61-144) as a lane keeps it.
+// The state of one fit (ModelBuilder, types.rs:61-144) as a lane keeps it.  While a model accepts every point, its length
+// is the number of points fed so far (idx - start): plen / slen only hold a value once the model has rejected a point.
+constexpr uint32_t LEN_ALIVE = 0xFFFFFFFFu;
 struct LaneFit {
     uint32_t start;  // first point of the fit
     uint32_t idx;    // next point to feed
@@ -110,11 +112,9 @@ struct LaneFit {
     float mn, mx;
     double sum;
     uint32_t plen;
-    bool pmc_ok;
-    // Swing (swing.rs:34-80): the intercepts are functions of the slopes (icpt_of)
-    double v0, t0d, us, ls;
+    // Swing (swing.rs:34-80): the intercepts are functions of the slopes (icpt_of); num / den are the two error sums
+    double v0, t0d, us, ls, num, den;
     uint32_t slen;
-    bool swing_ok;
 
     MDB_DEV void begin(uint32_t at) {
         start = at;
@@ -124,13 +124,13 @@ struct LaneFit {
         mn = __uint_as_float(0x7f800000u);
         mx = __uint_as_float(0xff800000u);
         sum = 0.0;
-        plen = 0;
-        pmc_ok = true;
-        v0 = t0d = us = ls = 0.0;
-        slen = 0;
-        swing_ok = true;
+        plen = LEN_ALIVE;
+        v0 = t0d = us = ls = num = den = 0.0;
+        slen = LEN_ALIVE;
     }
-    MDB_DEV bool growing() const { return pmc_ok | swing_ok; }
+    MDB_DEV bool growing() const { return (plen == LEN_ALIVE) | (slen == LEN_ALIVE); }
+    MDB_DEV uint32_t pmc_len() const { return plen == LEN_ALIVE ? idx - start : plen; }
+    MDB_DEV uint32_t swing_len() const { return slen == LEN_ALIVE ? idx - start : slen; }
 };
 
 // models/mod.rs:53-80 for finite values, branch-free.
@@ -152,76 +152,91 @@ template <int KIND> MDB_DEV bool lane_within(float eb_value, double rel_mid, boo
 template <int KIND> MDB_DEV void lane_feed(const LaneUnit &u, LaneFit &f, float v) {
     const double vd = (double)v;
     const double td = __fma_rn(f.i_d, u.delta_d, u.t0d);
-    // ---- PMC-Mean (pmc_mean.rs:58-75)
+    const uint32_t k = f.idx - f.start;       // points fed before this one
+    const double k1_d = __dadd_rn(f.k_d, 1.0);
+    // ---- PMC-Mean (pmc_mean.rs:58-75); alive: it has accepted all k points, so its length is k
     {
+        const bool alive = f.plen == LEN_ALIVE;
         const float nmn = v < f.mn ? v : f.mn, nmx = v > f.mx ? v : f.mx;
         const double nsum = __dadd_rn(f.sum, vd);
-        const uint32_t nlen = f.plen + 1;
-        const float avg = __double2float_rn(ddiv_fast_in_range(nsum, (double)nlen));
-        const bool ok = f.pmc_ok & lane_within<KIND>(u.eb_value, u.rel_mid, u.rel_mid_passes != 0, nmn, avg) &
+        const float avg = __double2float_rn(ddiv_fast_in_range(nsum, k1_d));
+        const bool ok = lane_within<KIND>(u.eb_value, u.rel_mid, u.rel_mid_passes != 0, nmn, avg) &
                         lane_within<KIND>(u.eb_value, u.rel_mid, u.rel_mid_passes != 0, nmx, avg);
-        if (ok) {
+        if (alive & ok) {
             f.mn = nmn;
             f.mx = nmx;
             f.sum = nsum;
-            f.plen = nlen;
         }
-        f.pmc_ok = ok;
+        if (alive & !ok) f.plen = k;
     }
     // ---- Swing (swing.rs:101-198)
     {
-        const bool first = f.slen == 0, second = f.slen == 1, has = f.slen >= 2;
+        const bool alive = f.slen == LEN_ALIVE;
+        const bool first = k == 0, second = k == 1, has = k >= 2;
         const double v0 = first ? vd : f.v0, t0d = first ? td : f.t0d;
         const double dev = max_dev_k<KIND>(ErrorBound{KIND, u.eb_value, u.eb_dev}, vd);
         // the candidate lines through (t0, v0) and (t, v +- dev): swing.rs:323-340.  When v +- dev equals v0 the
         // difference is +0 and so is the quotient, which is the slope the reference's equal-values branch returns.
-        const double den = first ? 1.0 : __dmul_rn(f.k_d, u.delta_d);
+        const double dt = __dmul_rn(f.k_d, u.delta_d);
         double su, sl;
-        ddiv_fast2_in_range(__dsub_rn(__dadd_rn(vd, dev), v0), __dsub_rn(__dsub_rn(vd, dev), v0), den, su, sl);
+        ddiv_fast2_in_range(__dsub_rn(__dadd_rn(vd, dev), v0), __dsub_rn(__dsub_rn(vd, dev), v0), first ? 1.0 : dt, su, sl);
         // the bounds in force (zero lines before the second point; never used then)
         const double up = __dadd_rn(__dmul_rn(f.us, td), icpt_of(f.us, v0, t0d));
         const double lw = __dadd_rn(__dmul_rn(f.ls, td), icpt_of(f.ls, v0, t0d));
         const bool rejected = has & ((__dadd_rn(up, dev) < vd) | (__dsub_rn(lw, dev) > vd));
         const bool take_u = second | (has & (__dsub_rn(up, dev) > vd)), take_l = second | (has & (__dadd_rn(lw, dev) < vd));
-        if (f.swing_ok & !rejected) {
+        // the terms of the two error sums (swing.rs:180-193, 212-228): from the third point on, (0, 0) when v equals v0
+        const bool term = has & !(vd == v0);
+        const double x = __dmul_rn(__dsub_rn(vd, v0), dt), y = __dmul_rn(dt, dt);
+        if (alive & !rejected) {
             f.v0 = v0;
             f.t0d = t0d;
             if (take_u) f.us = su;
             if (take_l) f.ls = sl;
-            f.slen += 1;
+            if (has) {
+                f.num = __dadd_rn(f.num, term ? x : 0.0);
+                f.den = __dadd_rn(f.den, term ? y : 0.0);
+            }
         }
-        f.swing_ok = f.swing_ok & !rejected;
+        if (alive & rejected) f.slen = k;
     }
     f.idx += 1;
     f.i_d = __dadd_rn(f.i_d, 1.0);
-    f.k_d = __dadd_rn(f.k_d, 1.0);
+    f.k_d = k1_d;
 }
 
 // ModelBuilder::finish (types.rs:88-144) of a fit that ended on its own (both models failed, or the data ended).
 // Returns false when the model would not be stored (bytes_per_value > 4, compression.rs:238): fewer than 8 points.
-MDB_DEV bool lane_finish(const LaneFit &f, FittedModel &m) {
-    if (f.plen < 8 && f.slen < 8) return false; // 29 / len and 30 / len both exceed 4 bytes per value
-    const float pmc_bpv = __fdiv_rn(29.0f, (float)f.plen);    // pmc_mean.rs:83-87
-    const float swing_bpv = __fdiv_rn(30.0f, (float)f.slen);  // swing.rs:236-239
+MDB_DEV bool lane_finish(const LaneUnit &u, const LaneFit &f, FittedModel &m) {
+    const uint32_t plen = f.pmc_len(), slen = f.swing_len();
+    if (plen < 8 && slen < 8) return false; // 29 / len and 30 / len both exceed 4 bytes per value
+    const float pmc_bpv = __fdiv_rn(29.0f, (float)plen);    // pmc_mean.rs:83-87
+    const float swing_bpv = __fdiv_rn(30.0f, (float)slen);  // swing.rs:236-239
     m.start_index = f.start;
     m.pad = 0;
-    m.values_len = 0;
+    m.pending = 0;
+    m.lower_slope = m.upper_slope = 0.0;
     if (swing_bpv < pmc_bpv) { // min_by keeps the first minimum: PMC-Mean wins ties (types.rs:90-94)
+        // Swing::model (swing.rs:246-259) and select_swing (types.rs:122-144), as swing_finish_from_sums
+        const double projected = __ddiv_rn(f.num, f.den);
+        const double slope = rust_maxd(f.ls, rust_mind(projected, f.us));
+        const double dt_end = __dmul_rn((double)(slen - 1), u.delta_d); // (double)(end_time - start_time)
+        const float first = canonical_nan(__double2float_rn(f.v0));
+        const float last = canonical_nan(__double2float_rn(__dadd_rn(__dmul_rn(slope, dt_end), f.v0)));
         m.model_type_id = SWING;
-        m.end_index = f.start + f.slen - 1;
-        m.min_value = m.max_value = m.model_last_value = 0.0f;
+        m.end_index = f.start + slen - 1;
+        m.min_value = rust_minf(first, last);
+        m.max_value = rust_maxf(first, last);
+        m.values_len = (first < last) ? 0 : 1;
+        m.model_last_value = last;
         m.bytes_per_value = swing_bpv;
-        m.pending = 1; // boundaries and bounds are final; k_swing_finish adds the two error sums (swing.rs:212-259)
-        m.lower_slope = f.ls;
-        m.upper_slope = f.us;
     } else {
-        const float value = canonical_nan(__double2float_rn(__ddiv_rn(f.sum, (double)f.plen))); // pmc_mean.rs:91-93
+        const float value = canonical_nan(__double2float_rn(__ddiv_rn(f.sum, (double)plen))); // pmc_mean.rs:91-93
         m.model_type_id = PMC_MEAN;
-        m.end_index = f.start + f.plen - 1;
+        m.end_index = f.start + plen - 1;
         m.min_value = m.max_value = m.model_last_value = value;
+        m.values_len = 0;
         m.bytes_per_value = pmc_bpv;
-        m.pending = 0;
-        m.lower_slope = m.upper_slope = 0.0;
     }
     return m.bytes_per_value <= 4.0f;
 }
@@ -273,7 +288,7 @@ struct LaneChain {
         }
         FittedModel m;
         uint32_t next;
-        if (lane_finish(fit, m)) {
+        if (lane_finish(u, fit, m)) {
             if (entry != IDX_NONE) {
                 if (n_models == 0) first_start = m.start_index;
                 list[n_models++] = m;
