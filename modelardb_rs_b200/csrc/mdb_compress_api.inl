@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(REGULAR_THREADS) k_lanes_regular(const int64_t
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicExch(&info[u].irregular, 1u);
 }
 
+constexpr uint32_t LANE_ROUNDS = 4; // repair rounds after the first pass (see mdbcu_compress)
 constexpr int LANES_WARPS = 4;
 constexpr int LANES_RING = 16; // values per lane: four 16-byte quads (the one before the cursor's, the cursor's, one or two ahead)
 #ifndef MDB_LANES_MIN_BLOCKS
@@ -185,9 +186,10 @@ template <int KIND>
 __global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec_lanes(const float *__restrict__ values, uint64_t n_total,
                                                                   const uint64_t *__restrict__ unit_off, const LaneUnit *__restrict__ info,
                                                                   const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
-                                                                  uint32_t chunk_len, uint32_t warmup, uint32_t n_chunks, ChunkState *st,
-                                                                  FittedModel *lists, const uint64_t *__restrict__ list_base,
-                                                                  const uint32_t *__restrict__ list_cap, unsigned int *next_chunk) {
+                                                                  uint32_t chunk_len, uint32_t warmup, const uint32_t *__restrict__ worklist,
+                                                                  uint32_t n_chunks, ChunkState *st, FittedModel *lists,
+                                                                  const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                                  unsigned int *next_chunk) {
     __shared__ float ring_s[LANES_WARPS][LANES_RING][32]; // [slot][lane]: a lane's slot k is in bank `lane` whatever k is
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float(*ring)[32] = ring_s[warp];
@@ -230,18 +232,36 @@ __global__ void __launch_bounds__(LANES_WARPS * 32, MDB_LANES_MIN_BLOCKS) k_spec
                     exhausted = true;
                     break;
                 }
-                const uint32_t u = chunk_unit[w];
+                // worklist == nullptr: the first pass, every chunk from (a warm-up before) its first index.  Otherwise a round:
+                // the listed chunks are re-run from the entry k_spec_propagate gave them until they meet their old chain.
+                g = worklist ? worklist[w] : w;
+                const uint32_t u = chunk_unit[g];
                 lu = info[u];
                 if (!lu.ok || lu.irregular || lu.kind != KIND) continue;
-                g = w;
+                const ChunkState s0 = st[g];
+                if (worklist && (!s0.dirty || s0.entry == IDX_NONE || (s0.new_entry == s0.entry && s0.exit == IDX_NONE)))
+                    continue; // never run, or a cut chain to be resumed: the cooperative engine's
                 const uint64_t a = unit_off[u];
                 const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
                 const uint32_t c = (uint32_t)(g - chunk_base[u]);
                 const uint32_t lo = c * chunk_len;
                 const uint32_t chunk_end = (uint64_t)lo + chunk_len < n ? lo + chunk_len : n;
                 const uint32_t limit = (uint64_t)chunk_end + chunk_len < n ? chunk_end + chunk_len : n;
-                chain.begin(lo > warmup ? lo - warmup : 0u, lo, chunk_end, limit, n); // (see LaneChain: warm-up)
-                list = lists + list_base[g] + (size_t)(list_cap[g] / 2); // the chunk's second buffer (st.buf is 0 before the first chain)
+                const uint32_t cap = list_cap[g] / 2;
+                list = lists + list_base[g] + (size_t)(s0.buf ^ 1) * cap; // the buffer the chunk's current chain is not in
+                if (worklist) {
+                    chain.begin(s0.new_entry, lo, chunk_end, limit, n);
+                    chain.set_old_chain(lists + list_base[g] + (size_t)s0.buf * cap, s0.n_models, s0.entry, s0.exit, s0.truncated_at);
+                    if (chain.splice_at(s0.new_entry, list)) { // the old chain started a fit at the new entry: nothing to run
+                        ChunkState s = s0;
+                        lane_chain_publish(chain, s);
+                        s.phase = PH_DONE;
+                        st[g] = s;
+                        continue;
+                    }
+                } else {
+                    chain.begin(lo > warmup ? lo - warmup : 0u, lo, chunk_end, limit, n); // (see LaneChain: warm-up)
+                }
                 sk = (uint32_t)((a + skew) & 3u);
                 eb4 = (a + skew) & ~(uint64_t)3;
                 uq = quads + (eb4 >> 2);
@@ -455,7 +475,17 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
         ChunkState s = load_shared_record(st + g);
         ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
         Fit fitter(eb, ts + a, values + a, n, smem[warp]);
+#ifdef MDB_FIT_COUNTERS
+        const long long tc0 = clock64();
+#endif
         spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
+#ifdef MDB_FIT_COUNTERS
+        const long long tc1 = clock64();
+        if (lane == 0) {
+            atomicAdd(&g_fit_counters[13], 1ull);
+            atomicAdd(&g_fit_counters[14], (unsigned long long)(tc1 - tc0));
+        }
+#endif
         __threadfence(); // this lane's list writes, before lane 0 publishes the chunk
         __syncwarp();
         if (lane == 0) {
@@ -477,6 +507,9 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
                 __threadfence();
                 atomicCAS(&q->finished, 0u, 1u);
             }
+#ifdef MDB_FIT_COUNTERS
+            atomicAdd(&g_fit_counters[15], (unsigned long long)(clock64() - tc1));
+#endif
         }
         __syncwarp();
     }
@@ -996,20 +1029,48 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         if (use_lanes && G) {
             // ---- one lane per chunk: the bulk of the chains; what they leave open is stitched below
             LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
-            for (int kind = 0; kind < 3; kind++) {
-                if (!kind_units[kind]) continue;
-                const unsigned int n_blocks =
-                    (unsigned int)std::min<uint64_t>((uint64_t)ctx->sm_count * lane_blocks_per_sm[kind], div_up(G, LANES_WARPS * 32));
-                TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
-                if (kind == KIND_LOSSLESS)
-                    LAUNCH(ctx, k_spec_lanes<KIND_LOSSLESS>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
-                else if (kind == KIND_ABSOLUTE)
-                    LAUNCH(ctx, k_spec_lanes<KIND_ABSOLUTE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
-                else
-                    LAUNCH(ctx, k_spec_lanes<KIND_RELATIVE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p, chunk_unit.p,
-                           chunk_len, ctx->lane_warmup, (uint32_t)G, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+            DBuf<uint32_t> lane_worklist;
+            DBuf<uint2> lane_resume;
+            DBuf<CompressCounters> lane_counters;
+            TRY_SG(lane_worklist.alloc(G, s));
+            TRY_SG(lane_resume.alloc(n_units, s));
+            TRY_SG(lane_counters.alloc(1, s));
+            TRY_SG(cudaMemsetAsync(lane_resume.p, 0, n_units * sizeof(uint2), s));
+            const uint32_t *d_list = nullptr; // the first pass runs every chunk
+            uint64_t n_list = G;
+            // Pass 0, then rounds: k_spec_propagate gives every chunk whose chain did not start where the chain before it ends
+            // that end as its new entry (optimistically: the chunk before may itself be re-run in the same round), and the lanes
+            // re-run those chunks until they meet their old chains.  Chains of one unit are thus repaired in parallel, not one
+            // after the other; a joint is still wrong afterwards only if the chunk before it changed its exit.  What is left
+            // after a few rounds (and everything the lanes do not handle) is the stitching below, which alone decides what is final.
+            for (uint32_t pass = 0; pass <= LANE_ROUNDS && n_list; pass++) {
+                for (int kind = 0; kind < 3; kind++) {
+                    if (!kind_units[kind]) continue;
+                    const unsigned int n_blocks =
+                        (unsigned int)std::min<uint64_t>((uint64_t)ctx->sm_count * lane_blocks_per_sm[kind], div_up(n_list, LANES_WARPS * 32));
+                    TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
+                    if (kind == KIND_LOSSLESS)
+                        LAUNCH(ctx, k_spec_lanes<KIND_LOSSLESS>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p,
+                               chunk_unit.p, chunk_len, ctx->lane_warmup, d_list, (uint32_t)n_list, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                    else if (kind == KIND_ABSOLUTE)
+                        LAUNCH(ctx, k_spec_lanes<KIND_ABSOLUTE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p,
+                               chunk_unit.p, chunk_len, ctx->lane_warmup, d_list, (uint32_t)n_list, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                    else
+                        LAUNCH(ctx, k_spec_lanes<KIND_RELATIVE>, n_blocks, LANES_WARPS * 32, 0, d_val, n_points, d_off, lane_units.p, chunk_base.p,
+                               chunk_unit.p, chunk_len, ctx->lane_warmup, d_list, (uint32_t)n_list, st.p, lists.p, list_base.p, list_cap.p, lane_words.p + 3);
+                }
+                if (pass == LANE_ROUNDS) break;
+                TRY_SG(cudaMemsetAsync(lane_counters.p, 0, sizeof(CompressCounters), s));
+                LAUNCH(ctx, k_spec_propagate, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, 1, lane_resume.p,
+                       lane_worklist.p, lane_counters.p);
+                TRY_SG(post(ctx, 0, lane_counters.p, 1));
+                TRY_SG(sync_stream(ctx));
+                CompressCounters hc;
+                std::memcpy(&hc, ctx->mailbox, sizeof(hc));
+                const uint64_t n_next = hc.dirty;
+                if (pass >= 1 && n_next * 10 > n_list * 9) break; // the rounds no longer help (chunks the lanes do not handle)
+                n_list = n_next;
+                d_list = lane_worklist.p;
             }
             TRY_SG(cudaGetLastError());
         }

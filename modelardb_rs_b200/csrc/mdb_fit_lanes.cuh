@@ -257,6 +257,11 @@ struct LaneChain {
     uint32_t n_models, first_start;
     uint32_t exit, truncated_at;
     bool bailed;                  // met a non-finite value, or was cut before reaching its chunk: the chunk is left to the cooperative engine
+    // Re-run of a chunk that already has a chain (a "round", see k_spec_lanes): the new chain runs from its entry only UNTIL it
+    // starts a fit where the old chain also started one -- from there on the two are the same chain (fit_next_model is a
+    // function of the start index), so the old chain's tail is copied.  The same rule as spec_chain's (mdb_compress.cuh).
+    const FittedModel *old_list;  // nullptr: no earlier chain
+    uint32_t old_n, old_entry, old_exit, old_trunc, sync_limit, old_p;
     LaneFit fit;
 
     MDB_DEV void begin(uint32_t start, uint32_t store_from_, uint32_t chunk_end_, uint32_t limit_, uint32_t n_) {
@@ -270,7 +275,33 @@ struct LaneChain {
         exit = IDX_NONE;
         truncated_at = 0;
         bailed = false;
+        old_list = nullptr;
+        old_n = old_entry = old_exit = old_trunc = sync_limit = old_p = 0;
         fit.begin(start);
+    }
+
+    // The old chain visited [old_entry, sync_limit) and stored old_n models there; it left the chunk at old_exit (IDX_NONE: cut at old_trunc).
+    MDB_DEV void set_old_chain(const FittedModel *list, uint32_t n_old, uint32_t entry_old, uint32_t exit_old, uint32_t trunc_old) {
+        old_list = list;
+        old_n = n_old;
+        old_entry = entry_old;
+        old_exit = exit_old;
+        old_trunc = trunc_old;
+        sync_limit = exit_old == IDX_NONE ? trunc_old : chunk_end;
+        old_p = 0;
+    }
+
+    // A fit is about to start at `cur`: did the old chain start one there too?  Then its tail is this chain's: returns true, chain complete.
+    MDB_DEV bool splice_at(uint32_t cur, FittedModel *list) {
+        if (old_list == nullptr || cur < old_entry || cur >= sync_limit) return false;
+        while (old_p < old_n && old_list[old_p].end_index < cur) old_p++;
+        if (old_p < old_n && old_list[old_p].start_index < cur) return false; // strictly inside an old model: the old chain did not stop here
+        if (n_models == 0 && old_p < old_n) first_start = old_list[old_p].start_index;
+        for (uint32_t k = old_p; k < old_n; k++) list[n_models + (k - old_p)] = old_list[k];
+        n_models += old_n - old_p;
+        exit = old_exit;
+        truncated_at = old_trunc;
+        return true;
     }
 
     // Feeds one point.  Returns true when the chain is complete (entry / exit / truncated_at / bailed are final).
@@ -302,6 +333,7 @@ struct LaneChain {
             exit = next;
             return true;
         }
+        if (splice_at(next, list)) return true;
         fit.begin(next);
         return false;
     }

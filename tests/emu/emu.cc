@@ -55,26 +55,48 @@ static void emu_run_chain(int engine, const ErrorBound &eb, const int64_t *uts, 
 static int g_emu_engine = 1;
 static int g_emu_lanes = 0; // 1: one lane per chunk first (mdb_fit_lanes.cuh: k_lanes_units, k_lanes_regular, k_spec_lanes), then the stitching
 static uint64_t g_emu_lane_chunks = 0, g_emu_lane_bailed = 0;
-static uint32_t g_emu_lane_warmup = 0;
+static uint32_t g_emu_lane_warmup = 0, g_emu_lane_rounds = 4;
+static uint64_t g_emu_lane_reruns = 0;
 
 // k_lanes_units + k_lanes_regular + k_spec_lanes for one unit: every chunk's chain from the chunk's first index, one point
 // per step, values read straight from the array (the kernel reads the same values through its ring).
 template <int KIND>
 static void emu_unit_lanes_kind(const LaneUnit &lu, const float *uval, uint32_t n, uint32_t L, uint32_t C, uint32_t cap, std::vector<ChunkState> &st,
                                 std::vector<FittedModel> &lists) {
-    for (uint32_t c = 0; c < C; c++) {
+    // one chunk's chain, as a lane of k_spec_lanes runs it (rerun: a round, from the entry spec_propagate_unit gave the chunk)
+    auto run = [&](uint32_t c, bool rerun) {
         const uint32_t lo = c * L, chunk_end = (uint32_t)std::min<uint64_t>((uint64_t)lo + L, n), limit = (uint32_t)std::min<uint64_t>((uint64_t)chunk_end + L, n);
+        const ChunkState s0 = st[c];
+        if (rerun && (!s0.dirty || s0.entry == IDX_NONE || (s0.new_entry == s0.entry && s0.exit == IDX_NONE))) return;
         LaneChain chain;
-        chain.begin(lo > g_emu_lane_warmup ? lo - g_emu_lane_warmup : 0u, lo, chunk_end, limit, n);
-        FittedModel *list = lists.data() + ((size_t)c * 2 + 1) * cap;
-        while (!chain.template step<KIND>(lu, uval[chain.fit.idx], list)) {}
+        FittedModel *list = lists.data() + ((size_t)c * 2 + (s0.buf ^ 1)) * cap;
+        bool done = false;
+        if (rerun) {
+            chain.begin(s0.new_entry, lo, chunk_end, limit, n);
+            chain.set_old_chain(lists.data() + ((size_t)c * 2 + s0.buf) * cap, s0.n_models, s0.entry, s0.exit, s0.truncated_at);
+            done = chain.splice_at(s0.new_entry, list);
+        } else {
+            chain.begin(lo > g_emu_lane_warmup ? lo - g_emu_lane_warmup : 0u, lo, chunk_end, limit, n);
+        }
+        while (!done) done = chain.template step<KIND>(lu, uval[chain.fit.idx], list);
         g_emu_lane_chunks++;
         if (chain.bailed) {
             g_emu_lane_bailed++;
-            continue;
+            return;
         }
         lane_chain_publish(chain, st[c]);
         st[c].phase = PH_DONE;
+    };
+    for (uint32_t c = 0; c < C; c++) run(c, false);
+    uint32_t resume_c = 0, resume_e = 0;
+    size_t last = C;
+    for (uint32_t round = 0; round < g_emu_lane_rounds; round++) { // k_spec_propagate + k_spec_lanes over its worklist
+        std::vector<uint32_t> work;
+        spec_propagate_unit(n, L, C, st.data(), true, resume_c, resume_e, [&](uint32_t c) { work.push_back(c); });
+        if (work.empty() || (round >= 1 && work.size() * 10 > last * 9)) break;
+        for (uint32_t c : work) run(c, true);
+        g_emu_lane_reruns += work.size();
+        last = work.size();
     }
 }
 static void emu_unit_lanes(const ErrorBound &eb, const int64_t *uts, const float *uval, uint32_t n, uint32_t L, uint32_t C, uint32_t cap,
@@ -257,6 +279,8 @@ void emu_set_engine(int engine) { g_emu_engine = engine; }
 // 1: with the asynchronous scheduler, every chunk's chain is first run by a "lane" (mdb_fit_lanes.cuh) and the scheduler only stitches.
 void emu_set_lanes(int on) { g_emu_lanes = on; }
 void emu_set_lane_warmup(uint32_t points) { g_emu_lane_warmup = points; }
+void emu_set_lane_rounds(uint32_t rounds) { g_emu_lane_rounds = rounds; }
+uint64_t emu_lane_reruns() { return g_emu_lane_reruns; }
 void emu_lane_counters(uint64_t *chunks, uint64_t *bailed) { *chunks = g_emu_lane_chunks; *bailed = g_emu_lane_bailed; }
 uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
 

@@ -39,6 +39,9 @@ def lib():
     L.emu_set_lanes.restype = None
     L.emu_set_lane_warmup.argtypes = [C.c_uint32]
     L.emu_set_lane_warmup.restype = None
+    L.emu_set_lane_rounds.argtypes = [C.c_uint32]
+    L.emu_set_lane_rounds.restype = None
+    L.emu_lane_reruns.restype = u64
     L.emu_lane_counters.argtypes = [vp, vp]
     L.emu_lane_counters.restype = None
     L.emu_division_mismatches.restype = u64
@@ -116,7 +119,7 @@ def lane_counters():
 
 
 def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, sched_seed=0, in_flight=0, engine=1, lanes=False,
-             lane_warmup=0) -> O.Segments:
+             lane_warmup=0, lane_rounds=4) -> O.Segments:
     """sched_seed == 0: the round scheme; otherwise the asynchronous scheduler stepped in a seeded random order with
     `in_flight` concurrent workers (rounds then receives the largest number of chain runs of any unit).
     engine: 1 the one-thread fit, 2 the warp-cooperative fit on 32 fibers.
@@ -125,6 +128,7 @@ def compress(ts, values, unit_off=None, eb=(0, 0.0), chunk_len=0, rounds=None, s
     lib().emu_set_engine(engine)
     lib().emu_set_lanes(1 if lanes else 0)
     lib().emu_set_lane_warmup(lane_warmup)
+    lib().emu_set_lane_rounds(lane_rounds)
     ts = np.ascontiguousarray(ts, np.int64)
     vals = np.ascontiguousarray(values, np.float32)
     if unit_off is None:

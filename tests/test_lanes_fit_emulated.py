@@ -18,7 +18,8 @@ from tests.test_warp_fit_emulated import _fuzz_series
 def test_emulated_lanes_compress_matches_oracle(oracle, case, chunk_len, warmup, sched):
     name, ts, vals, off, ebs = case
     want = oracle.compress(ts, vals, off, eb=ebs)
-    got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2, lanes=True, lane_warmup=warmup)
+    got = emu.compress(ts, vals, off, eb=ebs, chunk_len=chunk_len, sched_seed=sched[0], in_flight=sched[1], engine=2, lanes=True, lane_warmup=warmup,
+                       lane_rounds=sched[0] % 5)
     assert_segments_equal(got, want, f"{name} chunk_len={chunk_len} sched={sched}")
     assert emu.division_mismatches() == 0
 
@@ -61,7 +62,7 @@ def test_emulated_lanes_fuzz(oracle, seed):
     eb = [(0, 0.0), (1, float(10.0 ** rng.integers(-3, 3))), (2, float(rng.choice([0.01, 0.5, 1.0, 5.0, 30.0, 100.0])))][seed % 3]
     want = oracle.compress(ts, vals, eb=eb)
     got = emu.compress(ts, vals, eb=eb, chunk_len=int(rng.choice([8, 24, 100, 700])), sched_seed=seed + 1, in_flight=int(rng.choice([1, 2, 9])),
-                       engine=2, lanes=True, lane_warmup=int(rng.choice([0, 5, 60, 1000])))
+                       engine=2, lanes=True, lane_warmup=int(rng.choice([0, 5, 60, 1000])), lane_rounds=int(rng.integers(0, 5)))
     assert_segments_equal(got, want, f"fuzz seed={seed} eb={eb} n={n}")
 
 
