@@ -49,6 +49,7 @@ def parse_args():
                    help="series: one compress unit per series (bulk / embedded path); "
                         "buffers: 65 536-point buffers (server ingestion path)")
     p.add_argument("--kind", default="sine", choices=["sine", "walk"])
+    p.add_argument("--sine", default="50:150,1:20,500:2000", help="per-series ranges of the sine generator: base LO:HI, amplitude LO:HI, period LO:HI")
     p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
     p.add_argument("--e2e-steps", type=int, default=3, help="slabs per worker in the timed e2e region")
     p.add_argument("--e2e-workers", type=int, default=4, help="host threads pipelining slabs (one context each)")
@@ -73,8 +74,17 @@ def parse_eb(text):
 
 # ----------------------------------------------------------------------------------------------- data
 
+SINE_RANGES = ((50.0, 150.0), (1.0, 20.0), (500.0, 2000.0))  # base, amplitude, period (set from --sine)
+
+
+def set_sine_ranges(text):
+    global SINE_RANGES
+    SINE_RANGES = tuple(tuple(float(x) for x in part.split(":")) for part in text.split(","))
+
+
 def gen_values_device(torch, n_series, n_points, seed, kind, device):
     """Per-series sine + noise (or random walk) as f32, generated on the device in chunks of series."""
+    (b0, b1), (a0, a1), (p0, p1) = SINE_RANGES
     out = torch.empty(n_series * n_points, dtype=torch.float32, device=device)
     g = torch.Generator(device=device).manual_seed(seed)
     i = torch.arange(n_points, device=device, dtype=torch.float64)
@@ -82,9 +92,9 @@ def gen_values_device(torch, n_series, n_points, seed, kind, device):
     for s0 in range(0, n_series, chunk):
         k = min(chunk, n_series - s0)
         if kind == "sine":
-            base = 50.0 + 100.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
-            amp = 1.0 + 19.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
-            period = 500.0 + 1500.0 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            base = b0 + (b1 - b0) * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            amp = a0 + (a1 - a0) * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
+            period = p0 + (p1 - p0) * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
             phase = 6.28 * torch.rand(k, 1, device=device, generator=g, dtype=torch.float64)
             v = base + amp * torch.sin(2.0 * torch.pi * i / period + phase)
             v += 0.1 * torch.randn(k, n_points, device=device, generator=g, dtype=torch.float64)
@@ -99,11 +109,12 @@ def gen_values_host(n_series, n_points, seed, kind):
     from modelardb_rs_b200 import synthetic as syn
     rng = np.random.default_rng(seed)
     out = np.empty(n_series * n_points, np.float32)
+    (b0, b1), (a0, a1), (p0, p1) = SINE_RANGES
     for s in range(n_series):
         sl = slice(s * n_points, (s + 1) * n_points)
         if kind == "sine":
-            out[sl] = syn.sine_noise(n_points, seed + s, base=float(rng.uniform(50, 150)), amp=float(rng.uniform(1, 20)),
-                                     period=float(rng.uniform(500, 2000)), phase=float(rng.uniform(0, 6.28)))
+            out[sl] = syn.sine_noise(n_points, seed + s, base=float(rng.uniform(b0, b1)), amp=float(rng.uniform(a0, a1)),
+                                     period=float(rng.uniform(p0, p1)), phase=float(rng.uniform(0, 6.28)))
         else:
             out[sl] = syn.random_walk(n_points, seed + s)
     return out
@@ -248,6 +259,7 @@ def workload_config(args, per_gpu_series):
 
 def main():
     args = parse_args()
+    set_sine_ranges(args.sine)
     if args.impl == "reference":
         run_reference_arm(args)
         return

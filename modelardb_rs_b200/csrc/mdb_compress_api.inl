@@ -130,6 +130,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
     WarpFit fitter(eb, ts + a, values + a, n, smem[warp]);
     spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, chunk_len, s, lists + list_base[g], list_cap[g] / 2);
     __syncwarp();
+    s.phase = PH_DONE; // (only read by the asynchronous scheduler, when these rounds run before it: the chunk has a chain now)
     if (lane == 0) st[g] = s;
 }
 
@@ -879,7 +880,8 @@ uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx) { return c
 
 int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
-    ctx->lane_warmup = points;
+    ctx->lane_rounds_by_lanes = (points & 0x80000000u) != 0; // (tuning switch in the top bit: repair rounds by lanes instead of warps)
+    ctx->lane_warmup = points & 0x7FFFFFFFu;
     return MDBCU_SUCCESS;
 }
 
@@ -962,8 +964,14 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 
     if (n_units) {
         // ---- chunks
-        // one lane per chain (mdb_fit_lanes.cuh) if any unit qualifies: decided first, because the chunks are shorter then
-        bool use_lanes = ctx->fit_mode == 0 || ctx->fit_mode == 4;
+        // One lane per chain (mdb_fit_lanes.cuh) if any unit qualifies: decided first, because the chunks are shorter then.
+        // Automatic choice (measured on B200, round 2): with units enough to occupy the lanes by themselves (100 000 series of
+        // 10 000 points: 14.3 ms against 20.2 ms per 10^9 points) the lanes win -- no speculation, no stitching.  With few long
+        // units they win on units whose models are a few hundred points (17.0 against 20.4 ms, homogeneous sine + noise), but a
+        // handful of units with models of many thousands of points, which the lanes cut and the cooperative engine then has to
+        // walk alone, AFTER the lanes, cost more than they save (33 against 22 ms on the benchmark's mixed units): those
+        // chains are the critical path either way, and the cooperative engine hides it behind the other units' work.
+        bool use_lanes = ctx->fit_mode == 4 || (ctx->fit_mode == 0 && n_units * 4 >= (uint64_t)ctx->sm_count * 5 * LANES_WARPS * 32);
         DBuf<LaneUnit> lane_units;
         DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
         unsigned int kind_units[4] = {0, 0, 0, 0};
@@ -1044,6 +1052,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             // after the other; a joint is still wrong afterwards only if the chunk before it changed its exit.  What is left
             // after a few rounds (and everything the lanes do not handle) is the stitching below, which alone decides what is final.
             for (uint32_t pass = 0; pass <= LANE_ROUNDS && n_list; pass++) {
+                if (pass >= 1 && !ctx->lane_rounds_by_lanes) {
+                    // a round's duration is its longest re-run (up to two chunk lengths): the cooperative engine walks a single
+                    // chain ~15x faster than a lane does (measured: ~20 ns against ~300 ns per point when little else runs)
+                    LAUNCH(ctx, k_spec_chain_warp, div_up(n_list, CHAIN_WARPS), CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
+                           chunk_unit.p, d_list, n_list, chunk_len, st.p, lists.p, list_base.p, list_cap.p);
+                } else
                 for (int kind = 0; kind < 3; kind++) {
                     if (!kind_units[kind]) continue;
                     const unsigned int n_blocks =

@@ -93,6 +93,7 @@ struct mdbcu_context {
     int sm_count = 148;
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
+    bool lane_rounds_by_lanes = false; // repair rounds after the lanes' first pass: by lanes too, or (default) by the cooperative engine
     uint32_t lane_warmup = 4096;     // points a speculative lane chain starts before its chunk (LaneChain, mdb_fit_lanes.cuh)
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
     int fit_mode = 0;                // 0 automatic (warp per chain), 1 thread per chain, 2 warp per chain

@@ -18,6 +18,8 @@ ns = int(sys.argv[2]) if len(sys.argv) > 2 else 1000
 ebs = sys.argv[3:] or ["rel:1.0"]
 ctx = mc.Context(0)
 ctx.set_fit_engine(engine)
+import os
+if os.environ.get("WARMUP"): ctx.set_lane_warmup(int(os.environ["WARMUP"]))
 names = ["fits", "scalar", "steps", "quiet", "spec", "mismatch", "pmc_inorder", "wide", "cyc_load", "cyc_pmc", "cyc_quiet", "cyc_cand", "cyc_scan", "items", "cyc_chain", "cyc_sched"]
 for ebs_ in ebs:
     eb = mc.ErrorBound(*bench.parse_eb(ebs_))
