@@ -38,17 +38,20 @@ STEP_US = 1000
 
 def parse_args():
     p = argparse.ArgumentParser()
+    p.add_argument("--config", default="cfg2", choices=list(CONFIGS),
+                   help="BASELINE.json config: cfg2 = configs[1] (default), cfg3 = configs[2], cfg4 = configs[3], cfg5 = configs[4]; "
+                        "--series / --points / --eb / --kind given explicitly override the preset")
     p.add_argument("--gpus", type=int, default=1)
     p.add_argument("--steps", type=int, default=5)
     p.add_argument("--warmup", type=int, default=3)
     p.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    p.add_argument("--series", type=int, default=1000, help="series per slab (per GPU)")
-    p.add_argument("--points", type=int, default=1_000_000, help="points per series")
-    p.add_argument("--eb", default="rel:1.0", help="lossless | abs:X | rel:X")
+    p.add_argument("--series", type=int, default=None, help="series per slab (per GPU; cfg4: in total)")
+    p.add_argument("--points", type=int, default=None, help="points per series")
+    p.add_argument("--eb", default=None, help="lossless | abs:X | rel:X")
     p.add_argument("--units", default="series", choices=["series", "buffers"],
                    help="series: one compress unit per series (bulk / embedded path); "
                         "buffers: 65 536-point buffers (server ingestion path)")
-    p.add_argument("--kind", default="sine", choices=["sine", "walk"])
+    p.add_argument("--kind", default=None, choices=["sine", "walk"])
     p.add_argument("--sine", default="50:150,1:20,500:2000", help="per-series ranges of the sine generator: base LO:HI, amplitude LO:HI, period LO:HI")
     p.add_argument("--e2e-series", type=int, default=200, help="series per slab of the host-buffer (e2e) measurement")
     p.add_argument("--e2e-steps", type=int, default=3, help="slabs per worker in the timed e2e region")
@@ -62,7 +65,29 @@ def parse_args():
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
-    return p.parse_args()
+    args = p.parse_args()
+    preset = CONFIGS[args.config]
+    args.preset_overridden = any(getattr(args, k) is not None for k in ("series", "points", "eb", "kind"))
+    for k in ("series", "points", "eb", "kind"):
+        if getattr(args, k) is None:
+            setattr(args, k, preset[k])
+    args.scaling = preset["scaling"]
+    return args
+
+
+# BASELINE.json `configs` as slabs that fit one GPU next to their own reconstruction.  cfg2 / cfg3 / cfg5
+# are tables of independent series streamed slab by slab: every rank works on its own slab (weak scaling).  cfg4 is ONE
+# 10^9-point table: its 1000 series are sharded over the ranks (strong scaling) and the per-series aggregates gathered.
+CONFIGS = {
+    "cfg2": dict(series=1000, points=1_000_000, eb="rel:1.0", kind="sine", scaling="weak", name="BASELINE.json configs[1]",
+                 what="10k series x 1M points, 1 % relative bound, compress + full grid, streamed in slabs"),
+    "cfg3": dict(series=1000, points=1_000_000, eb="lossless", kind="walk", scaling="weak", name="BASELINE.json configs[2]",
+                 what="high-entropy random walk, lossless (MacaqueV-heavy), compress + grid, streamed in slabs"),
+    "cfg4": dict(series=1000, points=1_000_000, eb="rel:5.0", kind="sine", scaling="strong", name="BASELINE.json configs[3]",
+                 what="1B-point table, 5 % relative bound, SUM/MIN/MAX/AVG GROUP BY series from segments, series sharded over the GPUs"),
+    "cfg5": dict(series=100_000, points=10_000, eb="rel:1.0", kind="sine", scaling="weak", name="BASELINE.json configs[4]",
+                 what="bulk ingest: 100k series x 10k points per slab (bounds 0 / 1 / 5 / 10 % with --eb)"),
+}
 
 
 def parse_eb(text):
@@ -246,12 +271,21 @@ def run_reference_arm(args):
 
 
 def workload_config(args, per_gpu_series):
+    preset = CONFIGS[args.config]
+    if args.preset_overridden:  # name the shape that actually ran, not the preset it started from
+        name = (f"custom shape (preset {args.config} overridden): {per_gpu_series} series x {args.points} points per GPU per step, "
+                f"{args.kind}, error bound {args.eb}")
+    else:
+        name = f"{preset['name']} ({preset['what']}): {per_gpu_series} series x {args.points} points per GPU per step"
+    gen = (f"sine + noise f32, per-series base/amplitude/period in {args.sine}" if args.kind == "sine" else "random walk f32 (100 + cumsum N(0,1))")
     return {
-        "workload": f"BASELINE.json configs[1] streamed in slabs: {per_gpu_series} series x {args.points} points per GPU per step, "
-                    f"{args.kind}+noise f32, regular 1 ms timestamps, error bound {args.eb}, compress + full grid + aggregates GROUP BY series",
-        "series_per_gpu_per_step": per_gpu_series, "points_per_series": args.points, "error_bound": args.eb,
+        "workload": f"{name}; {gen}, regular 1 ms timestamps at epoch scale, error bound {args.eb}; a step = compress -> full grid -> "
+                    f"aggregates GROUP BY series of one slab",
+        "config": args.config if not args.preset_overridden else "custom", "series_per_gpu_per_step": per_gpu_series,
+        "points_per_series": args.points, "error_bound": args.eb, "kind": args.kind,
         "compress_units": args.units, "l2": "inputs (12 B/point x slab) far larger than the 126 MB L2; no flush needed",
-        "parallelism": f"series sharded over {args.gpus} GPU(s), no data-path collective; per-series aggregates all-gathered",
+        "parallelism": (f"series sharded over {args.gpus} GPU(s), no data-path collective; per-series aggregates all-gathered (one packed NCCL all-gather)"),
+        "scaling": args.scaling,
     }
 
 
@@ -282,11 +316,26 @@ def main():
 
     eb_t = parse_eb(args.eb)
     eb = mc.ErrorBound(*eb_t)
-    n_series, n_points = args.series, args.points
+    from modelardb_rs_b200.sharding import Communicator, shard_units
+    n_points = args.points
+    if args.scaling == "strong":  # one table: its series are sharded over the ranks (mdbcu_shard_units)
+        table_series = args.series
+        s_lo, s_hi = shard_units(table_series, rank, world)
+        n_series = s_hi - s_lo
+    else:                         # independent slabs: every rank has its own
+        n_series = args.series
+        table_series = world * n_series
     n = n_series * n_points
+    total_points_per_step = table_series * n_points
 
-    from modelardb_rs_b200.sharding import gather_group_aggregates
     ctx = mc.Context(local_rank)
+    comm = None
+    if world > 1:  # the library's own NCCL communicator (what a Rust host would use); torch.distributed only hands the id around
+        uid = torch.zeros(128, dtype=torch.uint8, device=device)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(Communicator.unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        comm = Communicator.create(ctx, world, rank, bytes(uid.cpu().numpy().tobytes()))
     if args.chunk_len:
         ctx.set_chunk_len(args.chunk_len)
     if args.fit_engine:
@@ -322,10 +371,11 @@ def main():
             group = (seg.unit_seg_off_device_ptr(), n_units)
         else:
             group = series_group_off_of(seg)
-        count, mn, mx, sm = mc.aggregate(seg, group, ctx)
-        if world > 1:  # only the per-series aggregate partials travel (disjoint groups -> all-gather)
-            with torch.cuda.stream(stream):  # weak scaling: every rank owns n_series series of the world * n_series table
-                count, mn, mx, sm = gather_group_aggregates(count, mn, mx, sm, world * n_series)
+        if comm is not None:  # only the per-series aggregate records travel: one packed all-gather inside the library
+            gp = group if isinstance(group, tuple) else (group.data_ptr(), n_series)
+            count, mn, mx, sm = comm.aggregate_sharded(seg, gp, n_series, table_series)
+        else:
+            count, mn, mx, sm = mc.aggregate(seg, group, ctx)
         ev[3].record(stream)
         if record:
             ev[3].synchronize()
@@ -358,7 +408,6 @@ def main():
     for _ in range(args.warmup):
         step(False)
     barrier()
-    ctx.set_profiling(True)
     launches0 = ctx.launch_count
     clocks = ClockSampler(local_rank)
     clocks.start()
@@ -373,6 +422,13 @@ def main():
     clock_info = clocks.stop()
     total_ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0
+    # per-kernel device times: a separate, untimed pass with the library's event bracketing switched on (two CUDA events per
+    # launch would otherwise sit inside the timed region)
+    prof_steps = max(1, min(2, args.steps))
+    ctx.set_profiling(True)
+    for _ in range(prof_steps):
+        step(False)
+    torch.cuda.synchronize()
     kstats = ctx.kernel_stats()
     ctx.set_profiling(False)
 
@@ -381,7 +437,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms = float(t.item())
     ms_per_step = total_ms / args.steps
-    value = world * n * args.steps / (total_ms / 1000.0)
+    value = total_points_per_step * args.steps / (total_ms / 1000.0)
 
     # ---- e2e: same path through the C-ABI with HOST (pinned) buffers
     e2e = None
@@ -482,6 +538,8 @@ def main():
             b["ctx"].close()
         del bufs
 
+    if comm is not None:
+        comm.close()
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -503,7 +561,10 @@ def main():
     }
     # The chain kernel runs once per fixpoint round; its unit of work is one SLAB (one step), so every
     # kernel is accounted per step: algorithmic bytes of one slab / device time the kernel took in one step.
-    algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_async"] = algo_bytes["k_spec_chain"]
+    algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_async"] = algo_bytes["k_spec_lanes"] = algo_bytes["k_spec_chain"]
+
+    def algo_of(kernel):  # template instances report as e.g. "k_spec_async<WarpFit>"
+        return algo_bytes.get(kernel.split("<")[0], 12 * n)
     # dram bytes per launch from the committed ncu --set full captures (default workload only), scaled by points
     traffic_of = {}
     traffic_path = os.path.join(ROOT, "profiles", "traffic.json")
@@ -511,23 +572,38 @@ def main():
         for k, v in json.load(open(traffic_path)).items():
             if isinstance(v, dict):
                 traffic_of[k] = (v["dram_bytes"] * n / v["points"], v["source"])
-    per_step_ms = {k: v[0] / args.steps for k, v in kstats.items()}
+    per_step_ms = {k: v[0] / prof_steps for k, v in kstats.items()}
     dominant = max(per_step_ms.items(), key=lambda kv: kv[1])[0] if per_step_ms else None
     roofline = None
     if dominant:
-        ab = algo_bytes.get(dominant, 12 * n)
+        ab = algo_of(dominant)
         achieved = ab / (per_step_ms[dominant] / 1000.0) / 1e9
         roofline = {"bound": "hbm", "kernel": dominant, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                     "traffic": traffic_of.get(dominant, (None, None))[0], "traffic_source": traffic_of.get(dominant, (None, None))[1],
                     "algorithmic_bytes_per_step": ab, "kernel_ms_per_step": per_step_ms[dominant],
-                    "launches_per_step": kstats[dominant][1] / args.steps, "peak_source": peak_src,
+                    "launches_per_step": kstats[dominant][1] / prof_steps, "peak_source": peak_src,
                     "kernel_share_of_step": per_step_ms[dominant] / ms_per_step,
                     "all_kernels_ms_per_step": dict(sorted(per_step_ms.items(), key=lambda kv: -kv[1]))}
-        for k in ("k_grid_tile", "k_spec_async", "k_spec_chain", "k_spec_chain_warp", "k_agg_segments"):
-            if k in per_step_ms and per_step_ms[k] > 0:
-                a_ = algo_bytes[k] / (per_step_ms[k] / 1000.0) / 1e9
+        for k in per_step_ms:
+            if k.split("<")[0] in ("k_grid_tile", "k_spec_async", "k_spec_lanes", "k_spec_chain", "k_spec_chain_warp", "k_agg_segments", "k_agg_groups") \
+                    and per_step_ms[k] > 0:
+                a_ = algo_of(k) / (per_step_ms[k] / 1000.0) / 1e9
                 roofline[f"{k}_GBps"] = a_
                 roofline[f"{k}_frac"] = a_ / peak
+        # what a caller sees: whole stages (median device time of the timed steps) against the same peak;
+        # algorithmic bytes per stage as in SURVEY.md 8(d)
+        med_ = {k: statistics.median(v) for k, v in stage_ms.items() if v}
+        stage_bytes = {"compress": 12 * n + seg_bytes, "grid": seg_bytes + 12 * n, "aggregate": seg_bytes}
+        stages = {}
+        for k, b in stage_bytes.items():
+            if k in med_ and med_[k] > 0:
+                a_ = b / (med_[k] / 1000.0) / 1e9
+                stages[k] = {"ms": med_[k], "algorithmic_bytes": b, "achieved": a_, "frac": a_ / peak}
+        if "grid" in med_ and "aggregate" in med_:
+            b, t_ = stage_bytes["grid"] + stage_bytes["aggregate"], med_["grid"] + med_["aggregate"]
+            a_ = b / (t_ / 1000.0) / 1e9
+            stages["grid+aggregate"] = {"ms": t_, "algorithmic_bytes": b, "achieved": a_, "frac": a_ / peak}
+        roofline["stages"] = stages
 
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:  # (rank 0 at N = 1 only: the other ranks' processes would wait on it)
@@ -542,11 +618,11 @@ def main():
     med = {k: statistics.median(v) for k, v in stage_ms.items() if v}
     line = {
         "metric": "compress+grid+aggregate data points/s", "value": value, "unit": "points/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": args.scaling,
         "vs_baseline": None, "dtype": "f32 values, f64 fitting, i64 timestamps", "data": "synthetic",
         "config": workload_config(args, n_series),
         "stage_ms_median": med,
-        "stage_points_per_s": {k: world * n / (v / 1000.0) for k, v in med.items()},
+        "stage_points_per_s": {k: total_points_per_step / (v / 1000.0) for k, v in med.items()},
         "compress_chain_rounds": ctx.last_compress_rounds,
         "segments": {"rows_per_slab": n_rows, "segment_bytes_per_point": seg_bytes / n if n else None,
                      "compression_ratio": 12 * n / seg_bytes if seg_bytes else None},

@@ -195,6 +195,40 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
                     const uint64_t *group_off, uint64_t n_groups, int64_t *count, float *min,
                     float *max, double *sum);
 
+/* ---- multi-GPU ----------------------------------------------------------------------------- */
+
+/* The path shards by unit (time series): a rank compresses, grids and aggregates the units it owns and nothing of
+ * that crosses GPUs (the reference treats every series independently: compression.rs:95-104, grid_exec.rs:323-356).
+ * Only the small result of an aggregate query travels, over NCCL / NVLink: what DataFusion's final aggregation merges
+ * from the partial states of model_simple_aggregates.rs:367-606.  One communicator per context (= per GPU); NCCL is
+ * loaded at run time, so a host that never creates a communicator does not need it. */
+typedef struct mdbcu_comm mdbcu_comm;
+
+/* Contiguous, balanced range [*lo, *hi) of the units rank `rank` of `world` owns (the first n_units % world ranks
+ * get one more). */
+int mdbcu_shard_units(uint64_t n_units, int world, int rank, uint64_t *lo, uint64_t *hi);
+/* One process (or thread) per GPU: rank 0 obtains 128 bytes, hands them to the others by any means, and every rank
+ * joins with its context. */
+int mdbcu_comm_unique_id(uint8_t *id128);
+int mdbcu_comm_create(mdbcu_context *ctx, int world, int rank, const uint8_t *id128, mdbcu_comm **out);
+/* One process driving n GPUs: communicators for n contexts (one per device) at once; out receives n handles.  Calls
+ * on different communicators must come from different host threads (each call blocks until its stream is done). */
+int mdbcu_comm_create_all(mdbcu_context *const *ctxs, int n, mdbcu_comm **out);
+void mdbcu_comm_destroy(mdbcu_comm *comm);
+int mdbcu_comm_world(const mdbcu_comm *comm);
+int mdbcu_comm_rank(const mdbcu_comm *comm);
+/* mdbcu_aggregate GROUP BY unit over a table whose n_total units are sharded with mdbcu_shard_units: `segments` and
+ * group_off (n_local + 1 entries) describe THIS rank's units; count / min / max / sum receive all n_total groups in
+ * unit order on every rank.  The ranks' 24-byte records are exchanged by ONE ncclAllGather.  Collective: every rank
+ * of the communicator must call it. */
+int mdbcu_aggregate_sharded(mdbcu_comm *comm, mdbcu_space space, const mdbcu_segments_view *segments,
+                            const uint64_t *group_off, uint64_t n_local, uint64_t n_total, int64_t *count,
+                            float *min, float *max, double *sum);
+/* The ungrouped aggregate over rows sharded across the ranks: one record per rank, folded in rank order (= row
+ * order, so the f64 sum does not depend on a reduction tree); single values, identical on every rank.  Collective. */
+int mdbcu_aggregate_all_sharded(mdbcu_comm *comm, mdbcu_space space, const mdbcu_segments_view *segments,
+                                int64_t *count, float *min, float *max, double *sum);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,8 @@ SYMBOLS = (
     "mdbcu_debug_rewrite_position_steps",
     "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
     "mdbcu_grid_count", "mdbcu_grid", "mdbcu_segment_sums", "mdbcu_aggregate",
+    "mdbcu_shard_units", "mdbcu_comm_unique_id", "mdbcu_comm_create", "mdbcu_comm_create_all", "mdbcu_comm_destroy",
+    "mdbcu_comm_world", "mdbcu_comm_rank", "mdbcu_aggregate_sharded", "mdbcu_aggregate_all_sharded",
 )
 
 
@@ -106,6 +108,24 @@ def lib():
     L.mdbcu_segment_sums.restype = i32
     L.mdbcu_aggregate.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, u64, vp, vp, vp, vp]
     L.mdbcu_aggregate.restype = i32
+    L.mdbcu_shard_units.argtypes = [u64, i32, i32, C.POINTER(u64), C.POINTER(u64)]
+    L.mdbcu_shard_units.restype = i32
+    L.mdbcu_comm_unique_id.argtypes = [vp]
+    L.mdbcu_comm_unique_id.restype = i32
+    L.mdbcu_comm_create.argtypes = [vp, i32, i32, vp, C.POINTER(vp)]
+    L.mdbcu_comm_create.restype = i32
+    L.mdbcu_comm_create_all.argtypes = [vp, i32, vp]
+    L.mdbcu_comm_create_all.restype = i32
+    L.mdbcu_comm_destroy.argtypes = [vp]
+    L.mdbcu_comm_destroy.restype = None
+    L.mdbcu_comm_world.argtypes = [vp]
+    L.mdbcu_comm_world.restype = i32
+    L.mdbcu_comm_rank.argtypes = [vp]
+    L.mdbcu_comm_rank.restype = i32
+    L.mdbcu_aggregate_sharded.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, u64, u64, vp, vp, vp, vp]
+    L.mdbcu_aggregate_sharded.restype = i32
+    L.mdbcu_aggregate_all_sharded.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, vp, vp, vp]
+    L.mdbcu_aggregate_all_sharded.restype = i32
     _lib = L
     return L
 

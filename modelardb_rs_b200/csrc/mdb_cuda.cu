@@ -1356,3 +1356,4 @@ int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_vie
 } // extern "C"
 
 #include "mdb_compress_api.inl"
+#include "mdb_comm.inl"

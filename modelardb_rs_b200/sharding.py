@@ -8,7 +8,13 @@ tests.
 """
 from __future__ import annotations
 
-from typing import Tuple
+import ctypes as C
+from typing import Optional, Tuple
+
+import numpy as np
+
+from . import _native
+from ._native import DEVICE, HOST
 
 
 def shard_units(n_units: int, rank: int, world: int) -> Tuple[int, int]:
@@ -66,3 +72,73 @@ def combine_global_aggregates(count, mn, mx, sm, group=None):
     for r in range(world):  # rank order = row order
         total_sum = total_sum + sums[r:r + 1]
     return total_count, total_min, total_max, total_sum
+
+
+# ------------------------------------------------------------------------------------------------ in-library NCCL path
+class Communicator:
+    """mdbcu_comm (include/modelardb_cuda.h, "multi-GPU"): the library's own NCCL communicator, one per context / GPU.
+    This is what a Rust host uses -- no torch.distributed involved; the functions above are the same exchange written
+    with torch.distributed (gloo in the CPU tests) and define the expected result."""
+
+    def __init__(self, handle, ctx, world: int, rank: int):
+        self._h, self.ctx, self.world, self.rank = handle, ctx, world, rank
+
+    @staticmethod
+    def unique_id() -> bytes:
+        """Rank 0 calls this and hands the 128 bytes to the other ranks by any means."""
+        buf = (C.c_uint8 * 128)()
+        _native.check(_native.lib().mdbcu_comm_unique_id(buf))
+        return bytes(buf)
+
+    @classmethod
+    def create(cls, ctx, world: int, rank: int, unique_id: bytes) -> "Communicator":
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        out = C.c_void_p()
+        _native.check(_native.lib().mdbcu_comm_create(ctx._h, world, rank, buf, C.byref(out)))
+        return cls(out, ctx, world, rank)
+
+    def close(self):
+        if self._h:
+            _native.lib().mdbcu_comm_destroy(self._h)
+            self._h = None
+
+    def shard(self, n_units: int) -> Tuple[int, int]:
+        lo, hi = C.c_uint64(), C.c_uint64()
+        _native.check(_native.lib().mdbcu_shard_units(n_units, self.world, self.rank, C.byref(lo), C.byref(hi)))
+        return lo.value, hi.value
+
+    def aggregate_sharded(self, segments, group_off, n_local: int, n_total: int):
+        """GROUP BY unit over a table sharded by mdbcu_shard_units: this rank's segments and group offsets in, all
+        n_total groups out (count i64, min f32, max f32, sum f64) in unit order, on every rank.  One ncclAllGather."""
+        from .compression import _order_streams, _ptr
+        v, space = segments.view(), segments.space
+        if isinstance(group_off, tuple):
+            group_off = group_off[0]
+        if space == HOST:
+            if group_off is not None and not isinstance(group_off, int):
+                group_off = np.ascontiguousarray(group_off, np.uint64)
+            out = (np.zeros(n_total, np.int64), np.zeros(n_total, np.float32), np.zeros(n_total, np.float32), np.zeros(n_total, np.float64))
+        else:
+            import torch
+            dev = f"cuda:{self.ctx.device}"
+            out = (torch.empty(n_total, dtype=torch.int64, device=dev), torch.empty(n_total, dtype=torch.float32, device=dev),
+                   torch.empty(n_total, dtype=torch.float32, device=dev), torch.empty(n_total, dtype=torch.float64, device=dev))
+        gp = group_off if isinstance(group_off, int) else _ptr(group_off)
+        _order_streams(space)
+        _native.check(_native.lib().mdbcu_aggregate_sharded(self._h, space, C.byref(v), gp, n_local, n_total, *[_ptr(o) for o in out]))
+        return out
+
+    def aggregate_all_sharded(self, segments):
+        """The ungrouped aggregate over rows sharded across the ranks (folded in rank order); one-element arrays."""
+        from .compression import _order_streams, _ptr
+        v, space = segments.view(), segments.space
+        if space == HOST:
+            out = (np.zeros(1, np.int64), np.zeros(1, np.float32), np.zeros(1, np.float32), np.zeros(1, np.float64))
+        else:
+            import torch
+            dev = f"cuda:{self.ctx.device}"
+            out = (torch.empty(1, dtype=torch.int64, device=dev), torch.empty(1, dtype=torch.float32, device=dev),
+                   torch.empty(1, dtype=torch.float32, device=dev), torch.empty(1, dtype=torch.float64, device=dev))
+        _order_streams(space)
+        _native.check(_native.lib().mdbcu_aggregate_all_sharded(self._h, space, C.byref(v), *[_ptr(o) for o in out]))
+        return out
