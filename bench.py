@@ -61,6 +61,7 @@ def parse_args():
     p.add_argument("--e2e-down-gate", type=int, default=1, help="workers allowed at once in the download-heavy call (grid)")
     p.add_argument("--chunk-len", type=int, default=0, help="chunk length of the parallel segmentation (0 = automatic); tuning only")
     p.add_argument("--lane-warmup", type=int, default=-1, help="warm-up points of the lane engine (-1 = library default); tuning only")
+    p.add_argument("--option", action="append", default=[], help="library tuning knob name=value (mdbcu_context_set_option); repeatable")
     p.add_argument("--fit-engine", type=int, default=0, help="compress engine (0 = automatic); tuning only, results are identical")
     p.add_argument("--cpu-seconds", type=float, default=20.0, help="rough budget of the CPU baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
@@ -342,6 +343,9 @@ def main():
         ctx.set_fit_engine(args.fit_engine)
     if args.lane_warmup >= 0:
         ctx.set_lane_warmup(args.lane_warmup)
+    for opt in args.option:
+        k_, v_ = opt.split("=")
+        ctx.set_option(k_, int(v_))
     stream = torch.cuda.ExternalStream(ctx.stream, device=device)
 
     # ---- inputs resident in HBM

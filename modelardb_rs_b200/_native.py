@@ -18,7 +18,7 @@ SYMBOLS = (
     "mdbcu_last_error", "mdbcu_device_count", "mdbcu_version",
     "mdbcu_context_create", "mdbcu_context_destroy", "mdbcu_context_set_stream", "mdbcu_context_stream",
     "mdbcu_context_launch_count", "mdbcu_context_set_profiling", "mdbcu_context_kernel_stat",
-    "mdbcu_context_set_chunk_len", "mdbcu_context_set_lane_warmup", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models", "mdbcu_debug_counters",
+    "mdbcu_context_set_chunk_len", "mdbcu_context_set_lane_warmup", "mdbcu_context_set_option", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models", "mdbcu_debug_counters",
     "mdbcu_debug_rewrite_position_steps",
     "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
     "mdbcu_grid_count", "mdbcu_grid", "mdbcu_segment_sums", "mdbcu_aggregate",
@@ -80,6 +80,8 @@ def lib():
     L.mdbcu_context_kernel_stat.restype = i32
     L.mdbcu_context_set_chunk_len.argtypes = [vp, C.c_uint32]
     L.mdbcu_context_set_chunk_len.restype = i32
+    L.mdbcu_context_set_option.argtypes = [vp, C.c_char_p, C.c_int64]
+    L.mdbcu_context_set_option.restype = i32
     L.mdbcu_context_set_lane_warmup.argtypes = [vp, C.c_uint32]
     L.mdbcu_context_set_lane_warmup.restype = i32
     L.mdbcu_context_last_compress_rounds.argtypes = [vp]

@@ -102,6 +102,10 @@ class Context:
         """Chunk length of the parallel segmentation (0 = automatic); results never depend on it."""
         _native.check(_native.lib().mdbcu_context_set_chunk_len(self._h, chunk_len))
 
+    def set_option(self, name: str, value: int):
+        """Tuning knob by name (mdbcu_context_set_option); results never depend on it."""
+        _native.check(_native.lib().mdbcu_context_set_option(self._h, name.encode(), int(value)))
+
     def set_lane_warmup(self, points: int):
         """Points a speculative lane chain starts before its chunk (engine 4); results never depend on it."""
         _native.check(_native.lib().mdbcu_context_set_lane_warmup(self._h, points))

@@ -50,8 +50,9 @@ MDB_DEV float macaque_v_sum(const uint8_t *bytes, uint64_t n_bytes, uint64_t len
 // COUNT (len) and SUM (sum) of row s. Returns false for a row the reference would panic on.
 // defer_min / deferred: a MacaqueV row of at least defer_min (> 0) model values only gets its COUNT here and is
 // reported through *deferred; its SUM is left to the kernel that decodes long streams with a whole warp.
+// count_only: stop once it is known whether the row is deferred (k_agg_find_wide).
 MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &count, float &sum, uint32_t defer_min = 0,
-                               bool *deferred = nullptr) {
+                               bool *deferred = nullptr, bool count_only = false) {
     Row r = load_row(v, s);
     count = 0;
     sum = 0.0f;
@@ -76,6 +77,7 @@ MDB_DEV bool aggregate_segment(const SegmentsView &v, uint64_t s, uint64_t &coun
             *deferred = true;
             return true;
         }
+        if (count_only) return true;
         model_last_value = __uint_as_float(0x7fc00000u);
         model_sum = macaque_v_sum(r.values, r.n_values, model_length, false, 0.0f);
     }

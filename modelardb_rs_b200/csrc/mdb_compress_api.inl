@@ -885,6 +885,21 @@ int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points) {
     return MDBCU_SUCCESS;
 }
 
+// Tuning knobs by name (tests and benchmarks; results never depend on them).
+int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    if (!name) return fail("set_option: name is null");
+    const std::string n(name);
+    if (n == "grid_plain_stores") ctx->grid_plain_stores = value != 0;
+    else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
+    else if (n == "lane_warmup") ctx->lane_warmup = (uint32_t)std::max<int64_t>(0, value);
+    else if (n == "lane_rounds_by_lanes") ctx->lane_rounds_by_lanes = value != 0;
+    else if (n == "chunk_len") return mdbcu_context_set_chunk_len(ctx, (uint32_t)value);
+    else if (n == "fit_engine") return mdbcu_context_set_fit_engine(ctx, (int)value);
+    else return fail("set_option: unknown option '" + n + "'");
+    return MDBCU_SUCCESS;
+}
+
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
     if (engine < 0 || engine > 4)

@@ -93,6 +93,7 @@ struct mdbcu_context {
     int sm_count = 148;
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
+    bool grid_plain_stores = false;  // tuning / tests: k_grid_tile (per-thread stores) instead of k_grid_tile_tma
     bool lane_rounds_by_lanes = false; // repair rounds after the lanes' first pass: by lanes too, or (default) by the cooperative engine
     uint32_t lane_warmup = 4096;     // points a speculative lane chain starts before its chunk (LaneChain, mdb_fit_lanes.cuh)
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
@@ -701,6 +702,157 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__res
     }
 }
 
+// ---- the same tile, staged in shared memory and written by the TMA engine ------------------------------------------
+// k_grid_tile's stores are issued by the threads themselves: three 16-byte STG per four points, each waiting in the LSU
+// pipe behind the descriptor loads of the same thread.  Here a block assembles the whole tile (2048 timestamps = 16 KiB,
+// 2048 values = 8 KiB) in shared memory and ONE thread hands the two arrays to the TMA engine as bulk copies
+// (cp.async.bulk.global.shared::cta, SASS UBLKCP): the stores leave the SM as full 128-byte lines without occupying
+// issue slots, and the block goes on with its next tile while they drain (the kernel is persistent: a block walks tiles
+// blockIdx.x, blockIdx.x + gridDim.x, ... and only waits for the engine to have READ the buffer before refilling it).
+// The descriptors of the rows overlapping the tile are staged in shared memory once (a tile overlaps ~10 rows on the
+// benchmark) instead of being fetched per quad.  Positions of the tile that belong to the serial kernels (irregular
+// rows, MacaqueV values, residual values) are written as zeros here and overwritten by those kernels, which run after
+// this one on the same stream.  Needs 16-byte aligned outputs (mdbcu_grid falls back to k_grid_tile otherwise).
+constexpr int TILE_DESC_CACHE = 48;
+
+__device__ __forceinline__ void bulk_store(void *gmem, const void *smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem), "r"((uint32_t)__cvta_generic_to_shared(smem)), "r"(bytes)
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(TILE_THREADS) k_grid_tile_tma(const SegDesc *__restrict__ desc, const uint64_t *__restrict__ point_off,
+                                                                const uint32_t *__restrict__ tile_first, uint64_t n_segments, uint64_t total,
+                                                                uint32_t n_tiles, int64_t *__restrict__ ts_out, float *__restrict__ val_out) {
+    __shared__ __align__(128) int64_t ts_tile[TILE];
+    __shared__ __align__(128) float val_tile[TILE];
+    __shared__ uint16_t po_rel[TILE + 2];   // start of local row i >= 1, relative to the tile (rows have >= 1 point: < TILE inside the tile)
+    __shared__ uint16_t seg_of[TILE];       // local row index of every point of the tile
+    __shared__ uint32_t warp_max[TILE_THREADS / 32];
+    __shared__ SegDesc desc_s[TILE_DESC_CACHE];
+    __shared__ uint64_t po0_s;              // first point of local row 0 (it may start before the tile)
+    __shared__ uint32_t n_rows_s;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const uint64_t tile_start = (uint64_t)tile * TILE;
+        const uint64_t tile_end = min(total, tile_start + TILE);
+        const uint32_t tile_n = (uint32_t)(tile_end - tile_start);
+        const uint64_t s0 = tile_first[tile];
+        // the previous tile's bulk stores must have read the buffers before they are refilled
+        if (tid == 0) {
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            n_rows_s = 1;
+        }
+        for (int p = tid; p < TILE; p += TILE_THREADS) seg_of[p] = 0;
+        __syncthreads();
+        // rows s0 .. overlapping the tile: head flags where rows i >= 1 start
+        for (int base = 0; base < TILE + 2; base += TILE_THREADS) {
+            const int i = base + tid;
+            uint64_t x = ~0ull;
+            if (i < TILE + 2) {
+                if (s0 + i <= n_segments) x = point_off[s0 + i];
+                if (i == 0) po0_s = x;
+                if (i >= 1 && x < tile_end) {
+                    po_rel[i] = (uint16_t)(x - tile_start);
+                    seg_of[x - tile_start] = (uint16_t)i;
+                    atomicMax(&n_rows_s, (uint32_t)i + 1u);
+                }
+            }
+            if (!__syncthreads_or(tid == TILE_THREADS - 1 && x < tile_end)) break;
+        }
+        __syncthreads();
+        const uint32_t n_rows = n_rows_s;
+        if (tid < TILE_DESC_CACHE && (uint32_t)tid < n_rows) desc_s[tid] = desc[s0 + tid];
+        // inclusive max-scan over seg_of: thread owns 8 consecutive entries
+        uint32_t loc[TILE_POINTS_PER_THREAD];
+        uint32_t run = 0;
+#pragma unroll
+        for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) {
+            run = max(run, (uint32_t)seg_of[tid * TILE_POINTS_PER_THREAD + k]);
+            loc[k] = run;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (lane >= d) incl = max(incl, y);
+        }
+        if (lane == 31) warp_max[warp] = incl;
+        uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
+        if (lane == 0) prev = 0;
+        __syncthreads();
+        for (int w = 0; w < warp; w++) prev = max(prev, warp_max[w]);
+#pragma unroll
+        for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) seg_of[tid * TILE_POINTS_PER_THREAD + k] = (uint16_t)max(prev, loc[k]);
+        __syncthreads();
+
+        // four consecutive points per thread into the shared tile
+        const uint64_t po0 = po0_s;
+#pragma unroll
+        for (int k = 0; k < TILE_POINTS_PER_THREAD / 4; k++) {
+            const int p = 4 * (tid + k * TILE_THREADS);
+            if ((uint32_t)p >= tile_n) continue;
+            const uint32_t i = seg_of[p];
+            const bool one_row = (uint32_t)p + 3 < tile_n && seg_of[p + 3] == i;
+            longlong2 t01 = make_longlong2(0, 0), t23 = make_longlong2(0, 0);
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (one_row) {
+                const SegDesc d = i < TILE_DESC_CACHE ? desc_s[i] : desc[s0 + i];
+                if (d.flags & F_REGULAR) {
+                    const uint32_t j = i == 0 ? (uint32_t)(tile_start + p - po0) : (uint32_t)p - po_rel[i];
+                    const int64_t t0 = d.start + (int64_t)j * d.interval;
+                    const int64_t t1 = t0 + d.interval, t2 = t1 + d.interval, t3 = t2 + d.interval;
+                    t01 = make_longlong2(t0, t1);
+                    t23 = make_longlong2(t2, t3);
+                    if (d.flags & F_TILE_VALUES) {
+                        const bool pmc = (d.flags & F_TYPE_MASK) == PMC_MEAN;
+                        const float c = (float)d.a;
+                        if (j + 0 < d.model_len) v.x = pmc ? c : swing_value(d.a, d.b, t0); // pmc_mean.rs:104-108, swing.rs:304-319
+                        if (j + 1 < d.model_len) v.y = pmc ? c : swing_value(d.a, d.b, t1);
+                        if (j + 2 < d.model_len) v.z = pmc ? c : swing_value(d.a, d.b, t2);
+                        if (j + 3 < d.model_len) v.w = pmc ? c : swing_value(d.a, d.b, t3);
+                    }
+                }
+            } else { // the quad straddles rows or the end of the output: point by point
+                int64_t tt[4] = {0, 0, 0, 0};
+                float vv[4] = {0.f, 0.f, 0.f, 0.f};
+                for (int q = 0; q < 4; q++) {
+                    if ((uint32_t)(p + q) >= tile_n) break;
+                    const uint32_t iq = seg_of[p + q];
+                    const SegDesc d = iq < TILE_DESC_CACHE ? desc_s[iq] : desc[s0 + iq];
+                    if (!(d.flags & F_REGULAR)) continue;
+                    const uint32_t j = iq == 0 ? (uint32_t)(tile_start + p + q - po0) : (uint32_t)(p + q) - po_rel[iq];
+                    tt[q] = d.start + (int64_t)j * d.interval;
+                    if ((d.flags & F_TILE_VALUES) && j < d.model_len) vv[q] = (d.flags & F_TYPE_MASK) == PMC_MEAN ? (float)d.a : swing_value(d.a, d.b, tt[q]);
+                }
+                t01 = make_longlong2(tt[0], tt[1]);
+                t23 = make_longlong2(tt[2], tt[3]);
+                v = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            }
+            reinterpret_cast<longlong2 *>(ts_tile + p)[0] = t01;
+            reinterpret_cast<longlong2 *>(ts_tile + p)[1] = t23;
+            *reinterpret_cast<float4 *>(val_tile + p) = v;
+        }
+        // shared-memory writes of the generic proxy, made visible to the async proxy (the TMA engine) before the copy is issued
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
+            const uint32_t bulk_n = tile_n & ~3u; // sizes are multiples of 16 bytes; the last tile's tail (<= 3 points) is stored directly
+            if (bulk_n) {
+                bulk_store(ts_out + tile_start, ts_tile, bulk_n * 8u);
+                bulk_store(val_out + tile_start, val_tile, bulk_n * 4u);
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+            for (uint32_t q = bulk_n; q < tile_n; q++) {
+                ts_out[tile_start + q] = ts_tile[q];
+                val_out[tile_start + q] = val_tile[q];
+            }
+        }
+    }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the copies are complete before the block retires
+}
+
 __global__ void __launch_bounds__(128) k_grid_sequential(SegmentsView v, const SegDesc *desc, const uint64_t *point_off, const uint32_t *worklist,
                                                          uint32_t n_work, int64_t *ts_out, float *val_out) {
     uint32_t w = blockIdx.x * blockDim.x + threadIdx.x;
@@ -792,6 +944,33 @@ __global__ void __launch_bounds__(128) k_agg_macaque_lanes(SegmentsView v, const
     }
 }
 
+// ---- the fused aggregate: no per-row round trip through global memory --------------------------------------------
+// k_agg_find_wide  one thread per row: only MacaqueV rows are looked at further (1 byte per row otherwise); long ones are
+//                  listed for the warp / lane decoders, which leave their f32 sums in seg_sum (sparse)
+// k_agg_groups     block (part, group): every thread parses rows part_lo + tid, + 256, ... of its slice (coalesced column
+//                  reads), computes COUNT and SUM of each from the model in registers (aggregate_segment) and folds them;
+//                  a fixed shuffle tree then combines the block.  Nothing per row is written.
+// The shape of the reduction depends only on (rows of the group, parts), and parts only on the batch: results do not
+// depend on the device.  COUNT / MIN / MAX are exact; the f64 SUM is a fixed tree over f32 row sums (the reference adds
+// them row by row, model_simple_aggregates.rs:481-511: 1e-12 relative, see modelardb_cuda.h).
+__global__ void __launch_bounds__(256) k_agg_find_wide(SegmentsView v, uint32_t *wide_list, Status *status) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool wide = false;
+    if (s < v.n_segments && v.model_type_id[s] == MACAQUE_V) {
+        uint64_t c;
+        float sum;
+        aggregate_segment(v, s, c, sum, WIDE_ROW_MIN, &wide, /*count_only=*/true);
+    }
+    const unsigned int mask = __ballot_sync(0xffffffffu, wide);
+    if (mask) {
+        const int lane = threadIdx.x & 31, leader = __ffs(mask) - 1;
+        unsigned int base = 0;
+        if (lane == leader) base = atomicAdd(&status->n_wide, (unsigned int)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, leader);
+        if (wide) wide_list[base + __popc(mask & ((1u << lane) - 1))] = (uint32_t)s;
+    }
+}
+
 constexpr int AGG_THREADS = 256;
 
 // In-order tree reduction of a block's per-thread partials (thread t holds rows EARLIER than t + 1).
@@ -814,6 +993,34 @@ __device__ __forceinline__ GroupAgg block_reduce_in_order(GroupAgg a) {
         for (int w = 1; w < AGG_THREADS / 32; w++) r = group_agg_combine(r, warp_part[w]);
     __syncthreads();
     return r; // valid in thread 0
+}
+
+// Block (part, group) of the fused aggregate: see k_agg_find_wide above.
+__global__ void __launch_bounds__(AGG_THREADS) k_agg_groups(SegmentsView v, const uint64_t *group_off, uint64_t n_groups, uint32_t parts,
+                                                            const float *wide_sum, GroupAgg *partial, Status *status) {
+    for (uint64_t g = blockIdx.y; g < n_groups; g += gridDim.y) {
+        uint64_t lo = group_off ? group_off[g] : 0, hi = group_off ? group_off[g + 1] : v.n_segments;
+        hi = min(hi, v.n_segments); // never read past the batch, whatever the caller passed
+        lo = min(lo, hi);
+        const uint64_t rows = hi - lo, part = blockIdx.x;
+        const uint64_t plo = lo + rows * part / parts, phi = lo + rows * (part + 1) / parts;
+        GroupAgg a = group_agg_identity();
+        for (uint64_t s = plo + threadIdx.x; s < phi; s += AGG_THREADS) {
+            GroupAgg row;
+            uint64_t c;
+            float sum;
+            bool wide = false;
+            if (!aggregate_segment(v, s, c, sum, WIDE_ROW_MIN, &wide)) report_bad(status, s);
+            if (wide) sum = wide_sum[s]; // a long MacaqueV row: decoded by k_agg_macaque_warp / _lanes before this kernel
+            row.count = (int64_t)c;
+            row.min = v.min_value[s];
+            row.max = v.max_value[s];
+            row.sum = (double)sum;
+            a = group_agg_combine(a, row);
+        }
+        a = block_reduce_in_order(a);
+        if (threadIdx.x == 0) partial[g * parts + part] = a;
+    }
 }
 
 // Block (part, group): folds the part-th contiguous slice of the group's rows.
@@ -1024,8 +1231,7 @@ int mdbcu_context_create(int device, mdbcu_context **out) {
         return fail(std::string("mailbox allocation: ") + cudaGetErrorString(e));
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
-    ctx->lane_rows_min = LANE_ROWS_MIN;
-    if (const char *rows = std::getenv("MDBCU_LANE_ROWS_MIN")) ctx->lane_rows_min = (uint32_t)std::max(1l, std::atol(rows)); // tuning and tests
+    ctx->lane_rows_min = LANE_ROWS_MIN; // (tuning and tests change it with mdbcu_context_set_option: the library reads no environment variables)
     // keep freed blocks in the pool: steady-state calls then never reach the driver allocator
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -1157,7 +1363,14 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     DBuf<uint32_t> tile_first;
     CUDA_TRY(tile_first.alloc(n_tiles, s));
     LAUNCH(ctx, k_grid_tile_index, div_up(S, 256), 256, 0, pl.point_off.p, S, tile_first.p);
-    LAUNCH(ctx, k_grid_tile, n_tiles, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, d_ts, d_val);
+    if ((((uintptr_t)d_ts | (uintptr_t)d_val) & 15) == 0 && !ctx->grid_plain_stores) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_tile_tma, TILE_THREADS, 0));
+        const unsigned int blocks = std::min<unsigned int>(n_tiles, (unsigned int)(ctx->sm_count * std::max(per_sm, 1)));
+        LAUNCH(ctx, k_grid_tile_tma, blocks, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, n_tiles, d_ts, d_val);
+    } else {
+        LAUNCH(ctx, k_grid_tile, n_tiles, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, d_ts, d_val);
+    }
     if (pl.h_status.n_seq)
         LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p,
                (uint32_t)pl.h_status.n_seq, d_ts, d_val);
@@ -1228,30 +1441,28 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     }
     DBuf<Status> status;
     if (new_status(ctx, status)) return MDBCU_FAILURE;
-    DBuf<uint64_t> seg_count;
-    DBuf<float> seg_sum;
-    CUDA_TRY(seg_count.alloc(S, s));
-    CUDA_TRY(seg_sum.alloc(S, s));
+    DBuf<float> wide_sum; // f32 sums of the long MacaqueV rows only (sparse; every other row is folded in registers)
     DBuf<uint32_t> wide_list;
+    CUDA_TRY(wide_sum.alloc(S, s));
     CUDA_TRY(wide_list.alloc(S, s));
     if (S) {
-        LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, seg_count.p, seg_sum.p, wide_list.p, status.p);
+        LAUNCH(ctx, k_agg_find_wide, div_up(S, 256), 256, 0, st.view, wide_list.p, status.p);
         LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
-               st.view, wide_list.p, &status.p->n_wide, ctx->lane_rows_min, seg_sum.p);
+               st.view, wide_list.p, &status.p->n_wide, ctx->lane_rows_min, wide_sum.p);
         if (S >= ctx->lane_rows_min)
             LAUNCH(ctx, k_agg_macaque_lanes, std::min<unsigned int>(div_up(S, 128), (unsigned int)ctx->sm_count * 16), 128, 0, st.view,
-                   wide_list.p, &status.p->n_wide, ctx->lane_rows_min, seg_sum.p);
+                   wide_list.p, &status.p->n_wide, ctx->lane_rows_min, wide_sum.p);
     }
 
-    // parts per group: enough blocks to fill the GPU when there are few large groups
+    // parts per group: enough blocks to fill a GPU when there are few large groups (a function of the batch alone, so that
+    // the reduction tree -- and with it the last bits of SUM -- does not depend on the device)
     uint64_t avg_rows = S / n_groups + 1;
     uint32_t parts = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(1, avg_rows / 4096));
-    if (n_groups >= (uint64_t)ctx->sm_count * 8) parts = 1;
+    if (n_groups >= 1184) parts = 1;
     DBuf<GroupAgg> partial;
     CUDA_TRY(partial.alloc(n_groups * parts, s));
     dim3 grid(parts, (unsigned int)std::min<uint64_t>(n_groups, 65535));
-    LAUNCH(ctx, k_agg_partial, grid, AGG_THREADS, 0, d_group_off, n_groups, S, parts, seg_count.p, seg_sum.p, st.view.min_value,
-           st.view.max_value, partial.p);
+    LAUNCH(ctx, k_agg_groups, grid, AGG_THREADS, 0, st.view, d_group_off, n_groups, parts, wide_sum.p, partial.p, status.p);
 
     DBuf<int64_t> count_buf;
     DBuf<float> min_buf, max_buf;

@@ -301,8 +301,8 @@ def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, monkeypatch, eb):
     give every row to one thread instead of one warp (k_grid_macaque_lanes / k_agg_macaque_lanes): 5000 series of a few
     hundred values, no model ever fits (some series hold runs of equal values so that models and residuals sit between
     the MacaqueV rows)."""
-    monkeypatch.setenv("MDBCU_LANE_ROWS_MIN", "4096")
     ctx = mc.Context(0)
+    ctx.set_option("lane_rows_min", 4096)
     rng = np.random.default_rng(23)
     lens = rng.integers(150, 400, 5000)
     units = []
@@ -337,15 +337,19 @@ def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, monkeypatch, eb):
 
 
 def test_lane_and_warp_decoders_agree(oracle, monkeypatch):
-    """The row count that switches between the two decoders is a tuning knob (MDBCU_LANE_ROWS_MIN, read when a context
-    is created): the same batch through both gives the same bits."""
+    """The row count that switches between the two decoders is a tuning knob (mdbcu_context_set_option "lane_rows_min"): the
+    same batch through both gives the same bits.  The tile kernel with per-thread stores and the one that hands whole tiles
+    to the TMA engine are compared the same way ("grid_plain_stores")."""
     ts, vals, off = syn.multi_series(40, 3000, 77, "walk")
     want = oracle.compress(ts, vals, off, eb=(0, 0.0), n_threads=4)
     wts, wval, _ = oracle.grid(want, n_threads=4)
     host = mc.HostSegments(**{c: getattr(want, c) for c in mc._COLUMNS})
-    for rows_min in ("1", "1000000"):
-        monkeypatch.setenv("MDBCU_LANE_ROWS_MIN", rows_min)
+    for rows_min in (1, 1000000):
         c = mc.Context(0)
+        c.set_option("lane_rows_min", rows_min)
+        c.set_option("grid_plain_stores", 1 if rows_min == 1 else 0)
+        with pytest.raises(mc.ModelarDbCudaError, match="unknown option"):
+            c.set_option("no_such_knob", 1)
         gts, gval = mc.grid(host, ctx=c)
         assert np.array_equal(gts, wts)
         assert_f32_bits_equal(gval, wval, f"lane rows min {rows_min}")
