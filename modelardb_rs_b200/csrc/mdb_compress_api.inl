@@ -890,7 +890,7 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
     if (check_ctx(ctx)) return MDBCU_FAILURE;
     if (!name) return fail("set_option: name is null");
     const std::string n(name);
-    if (n == "grid_plain_stores") ctx->grid_plain_stores = value != 0;
+    if (n == "grid_tma_stores") ctx->grid_tma_stores = value != 0;
     else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
     else if (n == "lane_warmup") ctx->lane_warmup = (uint32_t)std::max<int64_t>(0, value);
     else if (n == "lane_rounds_by_lanes") ctx->lane_rounds_by_lanes = value != 0;

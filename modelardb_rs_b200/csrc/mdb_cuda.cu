@@ -93,7 +93,7 @@ struct mdbcu_context {
     int sm_count = 148;
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
-    bool grid_plain_stores = false;  // tuning / tests: k_grid_tile (per-thread stores) instead of k_grid_tile_tma
+    bool grid_tma_stores = false;    // k_grid_tile_tma (tiles staged in shared memory, stored by the TMA engine) instead of k_grid_tile: measured slower, see there
     bool lane_rounds_by_lanes = false; // repair rounds after the lanes' first pass: by lanes too, or (default) by the cooperative engine
     uint32_t lane_warmup = 4096;     // points a speculative lane chain starts before its chunk (LaneChain, mdb_fit_lanes.cuh)
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
@@ -712,7 +712,15 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__res
 // The descriptors of the rows overlapping the tile are staged in shared memory once (a tile overlaps ~10 rows on the
 // benchmark) instead of being fetched per quad.  Positions of the tile that belong to the serial kernels (irregular
 // rows, MacaqueV values, residual values) are written as zeros here and overwritten by those kernels, which run after
-// this one on the same stream.  Needs 16-byte aligned outputs (mdbcu_grid falls back to k_grid_tile otherwise).
+// this one on the same stream.  Needs 16-byte aligned outputs.
+//
+// MEASURED (B200, round 2, 10^9 points of PMC-Mean / Swing rows): k_grid_tile 2.86 ms; this kernel 3.9 ms as first written,
+// 3.57 ms with the binary-search row lookup, 3.64 ms with the metadata pipeline added, 4.04 ms with the loops rolled.  ncu
+// (profiles/r02_grid_tile_tma_ncu_full.txt): both kernels are instruction-issue bound (2.0e9 against 2.4e9-2.8e9 warp
+// instructions per 10^9 points at IPC 2.4-2.7), neither is near the store bandwidth, and this one adds a pass through
+// shared memory and two more barriers per tile (top stall: barrier, 5.4 cycles per instruction).  The plain kernel
+// therefore stays the default; this one is selected with mdbcu_context_set_option("grid_tma_stores", 1) and is covered
+// by the same tests.
 constexpr int TILE_DESC_CACHE = 48;
 
 __device__ __forceinline__ void bulk_store(void *gmem, const void *smem, uint32_t bytes) {
@@ -720,111 +728,143 @@ __device__ __forceinline__ void bulk_store(void *gmem, const void *smem, uint32_
                  : "memory");
 }
 
+// Rows of a tile are found by a binary search over the tile's row starts (a tile overlaps ~10 rows on the benchmark, at most
+// TILE + 1): k_grid_tile's head flags + block-wide max-scan cost ~40 of its 64 thread instructions per point.
+//
+// Software pipeline.  What a tile needs before it can compute -- its first row (tile_first), that row's and the following
+// rows' point offsets, their descriptors -- is three DEPENDENT global round trips, and under several TB/s of store traffic a
+// round trip takes microseconds.  They are therefore taken off the critical path: while tile k is computed, the point offsets
+// and descriptors of the block's NEXT tile are copied into a second staging buffer with cp.async (LDGSTS, 8-byte pieces: the
+// arrays are only 8-byte aligned at s0), and the first row of the tile after that is loaded into a register.
+constexpr int TILE_PO_WINDOW = 256; // point offsets staged per tile; tiles that overlap more rows read the rest from global memory
+
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+
 __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile_tma(const SegDesc *__restrict__ desc, const uint64_t *__restrict__ point_off,
                                                                 const uint32_t *__restrict__ tile_first, uint64_t n_segments, uint64_t total,
                                                                 uint32_t n_tiles, int64_t *__restrict__ ts_out, float *__restrict__ val_out) {
     __shared__ __align__(128) int64_t ts_tile[TILE];
     __shared__ __align__(128) float val_tile[TILE];
-    __shared__ uint16_t po_rel[TILE + 2];   // start of local row i >= 1, relative to the tile (rows have >= 1 point: < TILE inside the tile)
-    __shared__ uint16_t seg_of[TILE];       // local row index of every point of the tile
-    __shared__ uint32_t warp_max[TILE_THREADS / 32];
-    __shared__ SegDesc desc_s[TILE_DESC_CACHE];
-    __shared__ uint64_t po0_s;              // first point of local row 0 (it may start before the tile)
-    __shared__ uint32_t n_rows_s;
+    __shared__ uint16_t po_rel[TILE + 2];   // po_rel[i], i >= 1: start of local row i relative to the tile (< TILE); po_rel[0] = 0
+    __shared__ __align__(8) uint64_t po_stage[2][TILE_PO_WINDOW];                       // point_off[s0 .. s0 + 256) of this / the next tile
+    __shared__ __align__(8) uint64_t desc_stage[2][TILE_DESC_CACHE * sizeof(SegDesc) / 8]; // desc[s0 .. s0 + 48) likewise
+    static_assert(sizeof(SegDesc) == 40 && TILE_DESC_CACHE * 5 <= TILE_THREADS, "one 8-byte piece of a descriptor per thread");
 
     const int tid = threadIdx.x;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // stage the metadata of the tile whose first row is s0 into buffer `buf` (asynchronously; one commit group)
+    auto prefetch = [&](int buf, uint64_t s0) {
+        if (s0 + tid <= n_segments) cp_async_8(&po_stage[buf][tid], point_off + s0 + tid);
+        if (tid < TILE_DESC_CACHE * 5 && s0 + (uint64_t)(tid / 5) < n_segments)
+            cp_async_8(&desc_stage[buf][tid], reinterpret_cast<const uint64_t *>(desc + s0) + tid);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    uint32_t tile = blockIdx.x;
+    if (tile >= n_tiles) return;
+    uint64_t s0 = tile_first[tile];
+    prefetch(0, s0);
+    uint64_t s0_next = tile + gridDim.x < n_tiles ? tile_first[tile + gridDim.x] : 0;
+    for (int buf = 0; tile < n_tiles; buf ^= 1) {
+        const uint32_t next_tile = tile + gridDim.x;
         const uint64_t tile_start = (uint64_t)tile * TILE;
         const uint64_t tile_end = min(total, tile_start + TILE);
         const uint32_t tile_n = (uint32_t)(tile_end - tile_start);
-        const uint64_t s0 = tile_first[tile];
-        // the previous tile's bulk stores must have read the buffers before they are refilled
-        if (tid == 0) {
-            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-            n_rows_s = 1;
-        }
-        for (int p = tid; p < TILE; p += TILE_THREADS) seg_of[p] = 0;
+        // this tile's metadata has landed (every thread waits for its own pieces; the barrier below publishes them) ...
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        // ... and the previous tile's bulk stores have READ the tile buffers before they are refilled
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         __syncthreads();
-        // rows s0 .. overlapping the tile: head flags where rows i >= 1 start
+        // the next tile's metadata, and the first row of the one after it
+        uint64_t s0_after = 0;
+        if (next_tile < n_tiles) {
+            prefetch(buf ^ 1, s0_next);
+            const uint32_t after = next_tile + gridDim.x;
+            if (after < n_tiles) s0_after = tile_first[after];
+        }
+        // rows s0 .. that start inside the tile: from the staged window, then (rarely) 256 at a time from global memory
+        const uint64_t *po_w = po_stage[buf];
+        uint32_t n_rows = 1;
         for (int base = 0; base < TILE + 2; base += TILE_THREADS) {
             const int i = base + tid;
             uint64_t x = ~0ull;
-            if (i < TILE + 2) {
-                if (s0 + i <= n_segments) x = point_off[s0 + i];
-                if (i == 0) po0_s = x;
-                if (i >= 1 && x < tile_end) {
-                    po_rel[i] = (uint16_t)(x - tile_start);
-                    seg_of[x - tile_start] = (uint16_t)i;
-                    atomicMax(&n_rows_s, (uint32_t)i + 1u);
-                }
-            }
-            if (!__syncthreads_or(tid == TILE_THREADS - 1 && x < tile_end)) break;
+            if (i < TILE + 2 && s0 + i <= n_segments) x = base == 0 ? po_w[tid] : point_off[s0 + i];
+            const bool inside = i >= 1 && x < tile_end;
+            if (i == 0) po_rel[0] = 0;
+            if (inside) po_rel[i] = (uint16_t)(x - tile_start);
+            const int cnt = __syncthreads_count(inside);
+            n_rows += (uint32_t)cnt;
+            if (cnt < TILE_THREADS - (base == 0 ? 1 : 0)) break; // (row starts increase: the first entry outside ends the list)
         }
-        __syncthreads();
-        const uint32_t n_rows = n_rows_s;
-        if (tid < TILE_DESC_CACHE && (uint32_t)tid < n_rows) desc_s[tid] = desc[s0 + tid];
-        // inclusive max-scan over seg_of: thread owns 8 consecutive entries
-        uint32_t loc[TILE_POINTS_PER_THREAD];
-        uint32_t run = 0;
-#pragma unroll
-        for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) {
-            run = max(run, (uint32_t)seg_of[tid * TILE_POINTS_PER_THREAD + k]);
-            loc[k] = run;
-        }
-        uint32_t incl = run;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (lane >= d) incl = max(incl, y);
-        }
-        if (lane == 31) warp_max[warp] = incl;
-        uint32_t prev = __shfl_up_sync(0xffffffffu, incl, 1);
-        if (lane == 0) prev = 0;
-        __syncthreads();
-        for (int w = 0; w < warp; w++) prev = max(prev, warp_max[w]);
-#pragma unroll
-        for (int k = 0; k < TILE_POINTS_PER_THREAD; k++) seg_of[tid * TILE_POINTS_PER_THREAD + k] = (uint16_t)max(prev, loc[k]);
-        __syncthreads();
+        const uint64_t po0 = po_w[0]; // first point of local row 0 (it may start before the tile)
+        const SegDesc *desc_w = reinterpret_cast<const SegDesc *>(desc_stage[buf]);
+        const bool staged = n_rows <= (uint32_t)TILE_DESC_CACHE; // every descriptor of the tile is in shared memory (the usual case)
 
-        // four consecutive points per thread into the shared tile
-        const uint64_t po0 = po0_s;
-#pragma unroll
+        // Four consecutive points per thread and pass; lane l of a warp owns quads l, l + 32 of the warp's 256 points, so that a
+        // warp's 16-byte shared stores are contiguous.  The row of the first quad is found by binary search, the row of the
+        // second by walking on from it.
+        uint32_t row = 0;
+#pragma unroll 1
         for (int k = 0; k < TILE_POINTS_PER_THREAD / 4; k++) {
-            const int p = 4 * (tid + k * TILE_THREADS);
-            if ((uint32_t)p >= tile_n) continue;
-            const uint32_t i = seg_of[p];
-            const bool one_row = (uint32_t)p + 3 < tile_n && seg_of[p + 3] == i;
+            const uint32_t p = 4u * (uint32_t)(tid + k * TILE_THREADS);
+            if (p >= tile_n) break;
+            if (k == 0) {
+                uint32_t lo = 0, hi = n_rows; // the last local row that starts at or before p
+                while (hi - lo > 1) {
+                    const uint32_t mid = (lo + hi) >> 1;
+                    if (po_rel[mid] <= p) lo = mid;
+                    else hi = mid;
+                }
+                row = lo;
+            } else {
+                while (row + 1 < n_rows && po_rel[row + 1] <= p) row++;
+            }
+            const uint32_t next_start = row + 1 < n_rows ? po_rel[row + 1] : 0xFFFFu;
             longlong2 t01 = make_longlong2(0, 0), t23 = make_longlong2(0, 0);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (one_row) {
-                const SegDesc d = i < TILE_DESC_CACHE ? desc_s[i] : desc[s0 + i];
+            if (p + 3 < next_start && p + 3 < tile_n) { // the quad lies in one row
+                const SegDesc d = staged ? desc_w[row] : desc[s0 + row];
                 if (d.flags & F_REGULAR) {
-                    const uint32_t j = i == 0 ? (uint32_t)(tile_start + p - po0) : (uint32_t)p - po_rel[i];
+                    const uint32_t j = row == 0 ? (uint32_t)(tile_start + p - po0) : p - po_rel[row];
                     const int64_t t0 = d.start + (int64_t)j * d.interval;
                     const int64_t t1 = t0 + d.interval, t2 = t1 + d.interval, t3 = t2 + d.interval;
                     t01 = make_longlong2(t0, t1);
                     t23 = make_longlong2(t2, t3);
                     if (d.flags & F_TILE_VALUES) {
-                        const bool pmc = (d.flags & F_TYPE_MASK) == PMC_MEAN;
-                        const float c = (float)d.a;
-                        if (j + 0 < d.model_len) v.x = pmc ? c : swing_value(d.a, d.b, t0); // pmc_mean.rs:104-108, swing.rs:304-319
-                        if (j + 1 < d.model_len) v.y = pmc ? c : swing_value(d.a, d.b, t1);
-                        if (j + 2 < d.model_len) v.z = pmc ? c : swing_value(d.a, d.b, t2);
-                        if (j + 3 < d.model_len) v.w = pmc ? c : swing_value(d.a, d.b, t3);
+                        if ((d.flags & F_TYPE_MASK) == PMC_MEAN) {
+                            v.x = v.y = v.z = v.w = (float)d.a;                       // pmc_mean.rs:104-108
+                        } else {
+                            v.x = swing_value(d.a, d.b, t0);                          // swing.rs:304-319
+                            v.y = swing_value(d.a, d.b, t1);
+                            v.z = swing_value(d.a, d.b, t2);
+                            v.w = swing_value(d.a, d.b, t3);
+                        }
+                        if (j + 3 >= d.model_len) { // the model part ends inside the quad: the rest are residual values (k_grid_sequential)
+                            if (j + 0 >= d.model_len) v.x = 0.f;
+                            if (j + 1 >= d.model_len) v.y = 0.f;
+                            if (j + 2 >= d.model_len) v.z = 0.f;
+                            v.w = 0.f;
+                        }
                     }
                 }
             } else { // the quad straddles rows or the end of the output: point by point
                 int64_t tt[4] = {0, 0, 0, 0};
                 float vv[4] = {0.f, 0.f, 0.f, 0.f};
-                for (int q = 0; q < 4; q++) {
-                    if ((uint32_t)(p + q) >= tile_n) break;
-                    const uint32_t iq = seg_of[p + q];
-                    const SegDesc d = iq < TILE_DESC_CACHE ? desc_s[iq] : desc[s0 + iq];
+                uint32_t iq = row;
+#pragma unroll 1
+                for (uint32_t q = 0; q < 4 && p + q < tile_n; q++) {
+                    while (iq + 1 < n_rows && po_rel[iq + 1] <= p + q) iq++;
+                    const SegDesc d = staged ? desc_w[iq] : desc[s0 + iq];
                     if (!(d.flags & F_REGULAR)) continue;
-                    const uint32_t j = iq == 0 ? (uint32_t)(tile_start + p + q - po0) : (uint32_t)(p + q) - po_rel[iq];
-                    tt[q] = d.start + (int64_t)j * d.interval;
-                    if ((d.flags & F_TILE_VALUES) && j < d.model_len) vv[q] = (d.flags & F_TYPE_MASK) == PMC_MEAN ? (float)d.a : swing_value(d.a, d.b, tt[q]);
+                    const uint32_t j = iq == 0 ? (uint32_t)(tile_start + p + q - po0) : p + q - po_rel[iq];
+                    const int64_t t = d.start + (int64_t)j * d.interval;
+                    float x = 0.f;
+                    if ((d.flags & F_TILE_VALUES) && j < d.model_len) x = (d.flags & F_TYPE_MASK) == PMC_MEAN ? (float)d.a : swing_value(d.a, d.b, t);
+                    // (q is a loop variable: select the slot without indexing a register array dynamically)
+                    if (q == 0) { tt[0] = t; vv[0] = x; }
+                    if (q == 1) { tt[1] = t; vv[1] = x; }
+                    if (q == 2) { tt[2] = t; vv[2] = x; }
+                    if (q == 3) { tt[3] = t; vv[3] = x; }
                 }
                 t01 = make_longlong2(tt[0], tt[1]);
                 t23 = make_longlong2(tt[2], tt[3]);
@@ -849,6 +889,9 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile_tma(const SegDesc *_
                 val_out[tile_start + q] = val_tile[q];
             }
         }
+        tile = next_tile;
+        s0 = s0_next;
+        s0_next = s0_after;
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); // the copies are complete before the block retires
 }
@@ -1020,6 +1063,47 @@ __global__ void __launch_bounds__(AGG_THREADS) k_agg_groups(SegmentsView v, cons
         }
         a = block_reduce_in_order(a);
         if (threadIdx.x == 0) partial[g * parts + part] = a;
+    }
+}
+
+// The same with one WARP per group, for batches of many small groups (GROUP BY series over 100 000 short series): lane l folds
+// rows lo + l, lo + l + 32, ...; a fixed shuffle tree combines the lanes.
+__global__ void __launch_bounds__(AGG_THREADS) k_agg_groups_warp(SegmentsView v, const uint64_t *group_off, uint64_t n_groups, const float *wide_sum,
+                                                                 int64_t *count, float *mn, float *mx, double *sum, Status *status) {
+    const int lane = threadIdx.x & 31;
+    const uint64_t g = (uint64_t)blockIdx.x * (AGG_THREADS / 32) + (threadIdx.x >> 5);
+    if (g >= n_groups) return;
+    uint64_t lo = group_off ? group_off[g] : 0, hi = group_off ? group_off[g + 1] : v.n_segments;
+    hi = min(hi, v.n_segments);
+    lo = min(lo, hi);
+    GroupAgg a = group_agg_identity();
+    for (uint64_t s = lo + lane; s < hi; s += 32) {
+        GroupAgg row;
+        uint64_t c;
+        float rs;
+        bool wide = false;
+        if (!aggregate_segment(v, s, c, rs, WIDE_ROW_MIN, &wide)) report_bad(status, s);
+        if (wide) rs = wide_sum[s];
+        row.count = (int64_t)c;
+        row.min = v.min_value[s];
+        row.max = v.max_value[s];
+        row.sum = (double)rs;
+        a = group_agg_combine(a, row);
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        GroupAgg o;
+        o.count = __shfl_down_sync(0xffffffffu, a.count, d);
+        o.min = __shfl_down_sync(0xffffffffu, a.min, d);
+        o.max = __shfl_down_sync(0xffffffffu, a.max, d);
+        o.sum = __shfl_down_sync(0xffffffffu, a.sum, d);
+        if (lane + d < 32) a = group_agg_combine(a, o);
+    }
+    if (lane == 0) {
+        count[g] = a.count;
+        mn[g] = a.min;
+        mx[g] = a.max;
+        sum[g] = a.sum;
     }
 }
 
@@ -1363,7 +1447,7 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     DBuf<uint32_t> tile_first;
     CUDA_TRY(tile_first.alloc(n_tiles, s));
     LAUNCH(ctx, k_grid_tile_index, div_up(S, 256), 256, 0, pl.point_off.p, S, tile_first.p);
-    if ((((uintptr_t)d_ts | (uintptr_t)d_val) & 15) == 0 && !ctx->grid_plain_stores) {
+    if ((((uintptr_t)d_ts | (uintptr_t)d_val) & 15) == 0 && ctx->grid_tma_stores) {
         int per_sm = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_tile_tma, TILE_THREADS, 0));
         const unsigned int blocks = std::min<unsigned int>(n_tiles, (unsigned int)(ctx->sm_count * std::max(per_sm, 1)));
@@ -1454,15 +1538,18 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
                    wide_list.p, &status.p->n_wide, ctx->lane_rows_min, wide_sum.p);
     }
 
-    // parts per group: enough blocks to fill a GPU when there are few large groups (a function of the batch alone, so that
-    // the reduction tree -- and with it the last bits of SUM -- does not depend on the device)
-    uint64_t avg_rows = S / n_groups + 1;
-    uint32_t parts = (uint32_t)std::min<uint64_t>(1024, std::max<uint64_t>(1, avg_rows / 4096));
-    if (n_groups >= 1184) parts = 1;
+    // Shape of the reduction: a function of the batch alone (never of the device), so that the tree -- and with it the last
+    // bits of SUM -- is the same everywhere.  Small groups: one warp each.  Large groups: blocks of 256 threads over slices of
+    // ~2048 rows (parts per group), then a fold of the parts.
+    const uint64_t avg_rows = S / n_groups + 1;
+    const bool warp_groups = avg_rows < 512;
+    const uint32_t parts = warp_groups ? 1u : (uint32_t)std::min<uint64_t>(1024, (avg_rows + 2047) / 2048);
     DBuf<GroupAgg> partial;
-    CUDA_TRY(partial.alloc(n_groups * parts, s));
-    dim3 grid(parts, (unsigned int)std::min<uint64_t>(n_groups, 65535));
-    LAUNCH(ctx, k_agg_groups, grid, AGG_THREADS, 0, st.view, d_group_off, n_groups, parts, wide_sum.p, partial.p, status.p);
+    if (!warp_groups) {
+        CUDA_TRY(partial.alloc(n_groups * parts, s));
+        dim3 grid(parts, (unsigned int)std::min<uint64_t>(n_groups, 65535));
+        LAUNCH(ctx, k_agg_groups, grid, AGG_THREADS, 0, st.view, d_group_off, n_groups, parts, wide_sum.p, partial.p, status.p);
+    }
 
     DBuf<int64_t> count_buf;
     DBuf<float> min_buf, max_buf;
@@ -1477,7 +1564,11 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
         CUDA_TRY(sum_buf.alloc(n_groups, s));
         d_count = count_buf.p; d_min = min_buf.p; d_max = max_buf.p; d_sum = sum_buf.p;
     }
-    LAUNCH(ctx, k_agg_final, div_up(n_groups, AGG_THREADS), AGG_THREADS, 0, partial.p, n_groups, parts, d_count, d_min, d_max, d_sum);
+    if (warp_groups)
+        LAUNCH(ctx, k_agg_groups_warp, div_up(n_groups, AGG_THREADS / 32), AGG_THREADS, 0, st.view, d_group_off, n_groups, wide_sum.p, d_count, d_min,
+               d_max, d_sum, status.p);
+    else
+        LAUNCH(ctx, k_agg_final, div_up(n_groups, AGG_THREADS), AGG_THREADS, 0, partial.p, n_groups, parts, d_count, d_min, d_max, d_sum);
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
         CUDA_TRY(d2h_bytes(ctx, count, d_count, n_groups * sizeof(int64_t)));

@@ -339,7 +339,7 @@ def test_thousands_of_long_macaque_v_rows_match_oracle(oracle, monkeypatch, eb):
 def test_lane_and_warp_decoders_agree(oracle, monkeypatch):
     """The row count that switches between the two decoders is a tuning knob (mdbcu_context_set_option "lane_rows_min"): the
     same batch through both gives the same bits.  The tile kernel with per-thread stores and the one that hands whole tiles
-    to the TMA engine are compared the same way ("grid_plain_stores")."""
+    to the TMA engine are compared the same way ("grid_tma_stores")."""
     ts, vals, off = syn.multi_series(40, 3000, 77, "walk")
     want = oracle.compress(ts, vals, off, eb=(0, 0.0), n_threads=4)
     wts, wval, _ = oracle.grid(want, n_threads=4)
@@ -347,7 +347,7 @@ def test_lane_and_warp_decoders_agree(oracle, monkeypatch):
     for rows_min in (1, 1000000):
         c = mc.Context(0)
         c.set_option("lane_rows_min", rows_min)
-        c.set_option("grid_plain_stores", 1 if rows_min == 1 else 0)
+        c.set_option("grid_tma_stores", 1 if rows_min == 1 else 0)
         with pytest.raises(mc.ModelarDbCudaError, match="unknown option"):
             c.set_option("no_such_knob", 1)
         gts, gval = mc.grid(host, ctx=c)

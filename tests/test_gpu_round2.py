@@ -140,3 +140,31 @@ def test_config2_slab_of_1000_series_matches_oracle(oracle, ctx):
     rel = np.abs((vals.astype(np.float64) - gval.astype(np.float64)) / vals.astype(np.float64)) * 100.0
     assert float(rel.max()) <= 1.0  # within the user's bound of the raw input (compression.rs:914-928)
     seg.free()
+
+
+@pytest.mark.parametrize("kind,eb", [("sine", (2, 1.0)), ("mixed", (2, 5.0)), ("walk", (2, 1.0)), ("sine", (0, 0.0))])
+def test_tma_tile_kernel_matches_oracle(oracle, kind, eb):
+    """k_grid_tile_tma (tiles staged in shared memory and stored by the TMA engine, metadata prefetched with cp.async; an
+    option, the per-thread stores are the default) writes the same points as the oracle: PMC-Mean / Swing rows of every
+    length, residual tails and MacaqueV rows that the serial kernels overwrite afterwards, a last tile that is not a multiple
+    of four points, and -- device space -- outputs that are not 16-byte aligned (which take the plain kernel)."""
+    import torch
+    ctx = mc.Context(0)
+    ctx.set_option("grid_tma_stores", 1)
+    ts, vals, off = syn.multi_series(7, 30_001, 19, kind)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+    wts, wval, _ = oracle.grid(want, n_threads=8)
+    host = mc.HostSegments(unit_seg_off=want.unit_seg_off, **{c: getattr(want, c) for c in mc._COLUMNS})
+    gts, gval = mc.grid(host, ctx=ctx)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, f"tma tile {kind} {eb}")
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    n = len(wts)
+    for shift in (0, 1):  # shift 1: the outputs start 8 / 4 bytes past a 16-byte boundary
+        tbuf = torch.zeros(n + 2, dtype=torch.int64, device="cuda:0")
+        vbuf = torch.zeros(n + 4, dtype=torch.float32, device="cuda:0")
+        dts, dval = mc.grid(seg, tbuf[shift:shift + n], vbuf[shift:shift + n], ctx)
+        assert np.array_equal(dts.cpu().numpy(), wts), shift
+        assert_f32_bits_equal(dval.cpu().numpy(), wval, f"tma tile device {kind} {eb} shift {shift}")
+    seg.free()
+    ctx.close()
