@@ -130,7 +130,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 int mdbcu_context_set_chunk_len(mdbcu_context *ctx, uint32_t chunk_len);
 /* Tuning knobs by name, for tests and benchmarks (results never depend on them): "chunk_len", "fit_engine",
  * "lane_warmup", "lane_rounds_by_lanes", "lane_rows_min" (long MacaqueV rows per batch from which one thread decodes a
- * row), "grid_tma_stores" (the tile kernel that stages tiles in shared memory and stores them with the TMA engine; measured
+ * row), "block_row_min" (MacaqueV values from which a row is decoded by a whole block), "grid_tma_stores" (the tile kernel that stages tiles in shared memory and stores them with the TMA engine; measured
  * slower than per-thread stores on B200, which stay the default).  Unknown names fail. */
 int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value);
 /* How many points before its chunk a speculative one-lane-per-chain chain starts (engine 4; csrc/mdb_fit_lanes.cuh).

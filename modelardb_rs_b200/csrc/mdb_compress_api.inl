@@ -892,6 +892,8 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
     const std::string n(name);
     if (n == "grid_tma_stores") ctx->grid_tma_stores = value != 0;
     else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
+    else if (n == "block_row_warps") ctx->block_row_warps = (int)value;
+    else if (n == "block_row_min") ctx->block_row_min = (uint32_t)std::max<int64_t>(512, value);
     else if (n == "lane_warmup") ctx->lane_warmup = (uint32_t)std::max<int64_t>(0, value);
     else if (n == "lane_rounds_by_lanes") ctx->lane_rounds_by_lanes = value != 0;
     else if (n == "chunk_len") return mdbcu_context_set_chunk_len(ctx, (uint32_t)value);

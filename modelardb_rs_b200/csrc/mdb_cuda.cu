@@ -91,6 +91,8 @@ struct mdbcu_context {
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
+    int block_row_warps = 4;        // warps per row of k_macaque_block (2, 4, 8 or 16)
+    uint32_t block_row_min = 0;     // MacaqueV values from which a row is decoded by a whole block (set to BLOCK_ROW_MIN at creation)
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
     bool grid_tma_stores = false;    // k_grid_tile_tma (tiles staged in shared memory, stored by the TMA engine) instead of k_grid_tile: measured slower, see there
@@ -488,10 +490,19 @@ __device__ __forceinline__ void report_bad(Status *status, uint64_t index) {
 // with the one-thread-per-row kernels.
 // ------------------------------------------------------------------------------------------------
 
+constexpr uint32_t BLOCK_ROW_MIN = 32768;           // model values from which a row is given to a block (mdbcu_context::block_row_min)
+// Rows k_macaque_block takes (the warp kernels skip them): MacaqueV, no residuals (model 2 rows never carry any), long.
+__device__ __forceinline__ bool macaque_block_row(const Row &r, uint32_t block_row_min) {
+    if (r.model_type_id != MACAQUE_V || r.n_residuals || r.n_values < 4) return false;
+    const uint64_t length = segment_len(r.start_time, r.end_time, r.timestamps, r.n_timestamps);
+    return length >= block_row_min && length <= 0xFFFFFFF0ull;
+}
+
 // One warp per wide row (the worklist's back part): the row's MacaqueV values, then its residuals if it has any.
 // Timestamps of these rows are regular and were written by the tile kernel.
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsView v, const SegDesc *desc, const uint64_t *point_off,
-                                                                        const uint32_t *worklist_back, uint32_t n_wide, float *val_out) {
+                                                                        const uint32_t *worklist_back, uint32_t n_wide, uint32_t block_row_min,
+                                                                        float *val_out) {
     __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t w = blockIdx.x * WIDE_WARPS + warp;
@@ -499,12 +510,25 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsV
     const uint64_t s = *(worklist_back - w);
     const SegDesc d = desc[s];
     const Row r = load_row(v, s);
+    if (macaque_block_row(r, block_row_min)) return; // a whole block decodes it (k_macaque_block)
     const uint64_t base = point_off[s];
     const uint32_t len = (uint32_t)(point_off[s + 1] - base);
-    const float last = warp_macaque_v_decode(r.values, r.n_values, d.model_len, false, 0.0f, stage[warp], lane,
-                                             [&](uint32_t k0, float value, bool valid) {
-                                                 if (valid) val_out[base + k0 + lane] = value; // 32 consecutive values, one store
-                                             });
+    float *row_out = val_out + base;
+    const float last = warp_macaque_v_decode(
+        r.values, r.n_values, d.model_len, false, 0.0f, stage[warp], lane,
+        [&](uint32_t k0, float value, bool valid) {
+            if (valid) row_out[k0 + lane] = value; // 32 consecutive values, one store
+        },
+        [&](uint32_t k0, const uint32_t(&v)[WIDE_RUN_PER_LANE]) { // a verified run of 256 `0` codes: eight consecutive values per lane
+            float *o = row_out + k0 + WIDE_RUN_PER_LANE * lane;
+            if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                reinterpret_cast<uint4 *>(o)[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                reinterpret_cast<uint4 *>(o)[1] = make_uint4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int j = 0; j < WIDE_RUN_PER_LANE; j++) o[j] = __uint_as_float(v[j]);
+            }
+        });
     if (d.flags & F_HAS_RESIDUALS) { // models/mod.rs:241-249: seeded with the last gridded model value
         const uint64_t res_base = base + d.model_len;
         warp_macaque_v_decode(r.residuals, r.n_residuals - 1, len - d.model_len, true, last, stage[warp], lane,
@@ -512,6 +536,155 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_grid_macaque_warp(SegmentsV
                                   if (valid) val_out[res_base + k0 + lane] = value;
                               });
     }
+}
+
+// ---- one BLOCK per very long MacaqueV row ---------------------------------------------------------------------------
+// A lossless high-entropy series is ONE row of 10^6 values (BASELINE.json configs[2]: 1000 such rows), and a warp per row is
+// 1000 warps on 148 SMs, each walking its stream alone.  Inside a run of `0` codes the stream is fixed width (see
+// wide_run_at), so the warps of a block take consecutive stretches of 256 slots each from the row's cursor, verify
+// their own flag bits and XOR their own payloads; the block then combines: everything before the first stretch with a
+// failed flag is proven (by induction over the slots, stretch after stretch) and is written out, with every stretch's first
+// value known from the XOR of the stretches before it.  Where a run breaks (a `11` code widens the window, a value
+// repeats) warp 0 walks the next 256 codes the ordinary way and the block carries on from the state it reaches.
+// SUM: the f32 additions of a row remain ONE chain in stream order (macaque_v.rs:228-264: one rounding per value); the
+// block decodes 4096 values into shared memory and warp 0 adds them in order.
+
+template <bool SUM, int ROW_WARPS>
+__global__ void __launch_bounds__(ROW_WARPS * 32) k_macaque_block(SegmentsView v, const uint32_t *list, int list_step, const unsigned int *n_list_ptr,
+                                                                        uint32_t n_list_max, uint32_t lane_rows_min, uint32_t block_row_min, const uint64_t *point_off,
+                                                                        float *out) {
+    __shared__ uint32_t stage[ROW_WARPS][STAGE_WORDS + 1];
+    __shared__ uint32_t totals[ROW_WARPS];
+    __shared__ uint32_t oks[ROW_WARPS];
+    __shared__ float sum_buf[32]; // (SUM: a batch of 32 values decoded the ordinary way; the stretches' values go through `stage`)
+    __shared__ uint64_t m_p;                         // the row's cursor: bit position, window, last value, values done
+    __shared__ uint32_t m_width, m_tz, m_last, m_k;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_list = n_list_ptr ? min(*n_list_ptr, n_list_max) : n_list_max;
+    if (n_list >= lane_rows_min) return; // one thread per row then (k_grid_macaque_lanes / k_agg_macaque_lanes)
+    for (uint32_t item = blockIdx.x; item < n_list; item += gridDim.x) {
+    __syncthreads(); // (the previous row's cursor has been read by everybody)
+    const uint64_t s = *(list + (int64_t)list_step * (int64_t)item);
+    const Row r = load_row(v, s);
+    if (!macaque_block_row(r, block_row_min)) continue; // shorter rows: k_grid_macaque_warp / k_agg_macaque_warp
+    const uint32_t count = (uint32_t)segment_len(r.start_time, r.end_time, r.timestamps, r.n_timestamps);
+    float *row_out = SUM ? nullptr : out + point_off[s];
+    float sum = 0.0f; // (warp 0)
+
+    WarpMacaqueDecoder dec; // every warp: its own window onto the row's bytes; warp 0 also decodes the ordinary way with it (the
+    dec.init(r.values, r.n_values, false, 0.0f, stage[warp]); // warm-up, the breaks of a run, the tail)
+    WarpBitStage &bits = dec.bits;
+    auto emit_batch = [&](uint32_t k0, uint32_t value, int cnt) { // warp 0: 32 values decoded the ordinary way
+        if (SUM) {
+            __syncwarp();
+            sum_buf[lane] = __uint_as_float(value);
+            __syncwarp();
+            for (int j = 0; j < cnt; j++) sum = (k0 == 0 && j == 0) ? sum_buf[0] : __fadd_rn(sum, sum_buf[j]); // the first value STARTS the sum
+        } else if (lane < cnt) {
+            row_out[k0 + lane] = __uint_as_float(value);
+        }
+    };
+    auto walk = [&](uint32_t k0, uint32_t n_values) { // warp 0: n_values from the cursor, 32 at a time; publishes the new cursor
+        for (uint32_t k = 0; k < n_values; k += 32) {
+            const int cnt = (int)min(32u, n_values - k);
+            emit_batch(k0 + k, dec.batch(cnt, lane), cnt);
+        }
+        if (lane == 0) {
+            m_p = dec.p;
+            m_width = dec.width_in_force;
+            m_tz = dec.trailing_zeros;
+            m_last = dec.last_value;
+            m_k = k0 + n_values;
+        }
+    };
+    if (warp == 0) walk(0, min(count, WIDE_RUN)); // warm-up: the raw first value and the first windows
+    __syncthreads();
+    while (true) {
+        const uint32_t k = m_k, width = m_width, tz = m_tz, last = m_last;
+        const uint64_t p = m_p;
+        if (count - k < (ROW_WARPS * WIDE_RUN)) break;
+        const uint32_t stride = 1u + width;
+        uint32_t x[WIDE_RUN_PER_LANE];
+        const bool ok = wide_run_at(bits, p + (uint64_t)warp * WIDE_RUN * stride, width, tz, lane, x);
+        // this warp's stretch of the NEXT step, if the run goes on: requested now, moved into the stage at the end of the step
+        uint32_t pre[WarpBitStage::PRE_WORDS];
+        uint64_t pre_w0;
+        bits.prefetch_issue(p + (uint64_t)(ROW_WARPS + warp) * WIDE_RUN * stride, lane, pre, pre_w0);
+        uint32_t t = x[WIDE_RUN_PER_LANE - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { // inclusive XOR scan of the lanes' totals
+            const uint32_t o = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t ^= o;
+        }
+        if (lane == 31) {
+            totals[warp] = t;
+            oks[warp] = ok ? 1u : 0u;
+        }
+        __syncthreads();
+        int good = 0; // stretches proven: all before the first one with a failed flag
+        uint32_t before_warp = last, after_good = last;
+        for (int w = 0; w < ROW_WARPS; w++) {
+            if (!oks[w]) break;
+            good = w + 1;
+            if (w < warp) before_warp ^= totals[w];
+            after_good ^= totals[w];
+        }
+        if (warp < good) {
+            const uint32_t before = before_warp ^ t ^ x[WIDE_RUN_PER_LANE - 1]; // the value before this lane's first one
+            const uint32_t k0 = k + (uint32_t)warp * WIDE_RUN + (uint32_t)(WIDE_RUN_PER_LANE * lane);
+            if (SUM) { // the stretch's bits have been used: its values take their place in this warp's stage (reloaded next step anyway)
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < WIDE_RUN_PER_LANE; j++) stage[warp][WIDE_RUN_PER_LANE * lane + j] = before ^ x[j];
+                bits.first_word = ~0ull;
+            } else {
+                float *o = row_out + k0;
+                if ((reinterpret_cast<uintptr_t>(o) & 15) == 0) {
+                    reinterpret_cast<uint4 *>(o)[0] = make_uint4(before ^ x[0], before ^ x[1], before ^ x[2], before ^ x[3]);
+                    reinterpret_cast<uint4 *>(o)[1] = make_uint4(before ^ x[4], before ^ x[5], before ^ x[6], before ^ x[7]);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < WIDE_RUN_PER_LANE; j++) o[j] = __uint_as_float(before ^ x[j]);
+                }
+            }
+        }
+        __syncthreads(); // totals / oks / cursor have been read by everybody; the values for SUM are in sum_buf
+        if (warp == 0) {
+            if (SUM) {
+                for (int w = 0; w < good; w++) { // one addition chain, in stream order
+                    const uint32_t *b = stage[w];
+#pragma unroll 16
+                    for (int j = 0; j < (int)WIDE_RUN; j++) sum = __fadd_rn(sum, __uint_as_float(b[j]));
+                }
+            }
+            const uint32_t k_new = k + (uint32_t)good * WIDE_RUN;
+            if (good < ROW_WARPS) { // the run broke in the next stretch: walk 256 codes the ordinary way from there
+                dec.p = p + (uint64_t)good * WIDE_RUN * stride;
+                dec.last_value = after_good;
+                dec.width_in_force = width;
+                dec.trailing_zeros = tz;
+                dec.first_raw = false;
+                walk(k_new, WIDE_RUN); // (count - k >= (ROW_WARPS * WIDE_RUN): these values exist)
+            } else if (lane == 0) {
+                m_p = p + (uint64_t)(ROW_WARPS * WIDE_RUN) * stride;
+                m_last = after_good;
+                m_k = k_new;
+            }
+        }
+        __syncthreads();
+        if (good == ROW_WARPS) bits.prefetch_commit(lane, pre, pre_w0); // (after a break the cursor is elsewhere: cover() loads)
+    }
+    if (warp == 0) { // the tail, the ordinary way
+        const uint32_t k = m_k;
+        dec.p = m_p;
+        dec.last_value = m_last;
+        dec.width_in_force = m_width;
+        dec.trailing_zeros = m_tz;
+        dec.first_raw = false;
+        if (k < count) walk(k, count - k);
+        if (SUM && lane == 0) out[s] = canonical_nan(sum);
+    }
+    } // rows
 }
 
 // With TENS OF THOUSANDS of long rows in a batch (100 000 series of 10 000 values) the rows themselves are parallelism
@@ -933,15 +1106,17 @@ __global__ void __launch_bounds__(128) k_agg_segments(SegmentsView v, uint64_t *
 // One warp per long MacaqueV row: the f32 sum in stream order (macaque_v.rs:220-265), as aggregate_segment computes it.
 // The 32 values of a batch are decoded in parallel; their additions stay a serial chain (one rounding per value).
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsView v, const uint32_t *wide_list, const unsigned int *n_wide_ptr,
-                                                                       uint32_t lane_rows_min, float *seg_sum) {
+                                                                       uint32_t lane_rows_min, uint32_t block_row_min, float *seg_sum) {
     __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
     __shared__ float batch[WIDE_WARPS][32];
+    __shared__ __align__(16) float wide_batch[WIDE_WARPS][WIDE_RUN];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_wide = *n_wide_ptr;
     if (n_wide >= lane_rows_min) return; // k_agg_macaque_lanes has them
     for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
         const uint64_t s = wide_list[w];
         const Row r = load_row(v, s);
+        if (macaque_block_row(r, block_row_min)) continue; // a whole block decodes it (k_macaque_block)
         const uint64_t res_len = r.n_residuals ? r.residuals[r.n_residuals - 1] : 0;
         const uint64_t length = segment_len(r.start_time, r.end_time, r.timestamps, r.n_timestamps);
         const uint32_t model_length = (uint32_t)(length - res_len);
@@ -958,8 +1133,22 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_agg_macaque_warp(SegmentsVi
                 first = false;
             }
         };
-        warp_macaque_v_decode(r.values, r.n_values, model_length, false, 0.0f, stage[warp], lane,
-                              [&](uint32_t k0, float value, bool valid) { add_in_order(k0, value, valid, model_length); });
+        warp_macaque_v_decode(
+            r.values, r.n_values, model_length, false, 0.0f, stage[warp], lane,
+            [&](uint32_t k0, float value, bool valid) { add_in_order(k0, value, valid, model_length); },
+            [&](uint32_t, const uint32_t(&v)[WIDE_RUN_PER_LANE]) { // 256 values at once: still ONE addition chain in stream order
+                __syncwarp();
+                uint4 *slot = reinterpret_cast<uint4 *>(&wide_batch[warp][WIDE_RUN_PER_LANE * lane]);
+                slot[0] = make_uint4(v[0], v[1], v[2], v[3]);
+                slot[1] = make_uint4(v[4], v[5], v[6], v[7]);
+                __syncwarp();
+                const float4 *b4 = reinterpret_cast<const float4 *>(wide_batch[warp]);
+#pragma unroll 8
+                for (int j = 0; j < (int)WIDE_RUN / 4; j++) { // (never the stream's first value: wide runs start after it)
+                    const float4 q = b4[j];
+                    sum = __fadd_rn(__fadd_rn(__fadd_rn(__fadd_rn(sum, q.x), q.y), q.z), q.w);
+                }
+            });
         if (r.n_residuals) { // models/mod.rs:173-183: seeded with the "last value" a MacaqueV model reports there, NaN
             const float model_sum = sum;
             sum = 0.0f;
@@ -1278,6 +1467,18 @@ static int new_status(mdbcu_context *ctx, DBuf<Status> &st) {
     return MDBCU_SUCCESS;
 }
 
+// Warps per row of k_macaque_block: more warps finish a row sooner, fewer warps keep more rows resident (mdbcu_context::block_row_warps).
+template <bool SUM>
+static void launch_macaque_block(mdbcu_context *ctx, unsigned int blocks, SegmentsView v, const uint32_t *list, int step, const unsigned int *n_ptr,
+                                 uint32_t n_max, const uint64_t *point_off, float *out) {
+    switch (ctx->block_row_warps) {
+    case 16: LAUNCH(ctx, (k_macaque_block<SUM, 16>), blocks, 16 * 32, 0, v, list, step, n_ptr, n_max, ctx->lane_rows_min, ctx->block_row_min, point_off, out); break;
+    case 8: LAUNCH(ctx, (k_macaque_block<SUM, 8>), blocks, 8 * 32, 0, v, list, step, n_ptr, n_max, ctx->lane_rows_min, ctx->block_row_min, point_off, out); break;
+    case 2: LAUNCH(ctx, (k_macaque_block<SUM, 2>), blocks, 2 * 32, 0, v, list, step, n_ptr, n_max, ctx->lane_rows_min, ctx->block_row_min, point_off, out); break;
+    default: LAUNCH(ctx, (k_macaque_block<SUM, 4>), blocks, 4 * 32, 0, v, list, step, n_ptr, n_max, ctx->lane_rows_min, ctx->block_row_min, point_off, out); break;
+    }
+}
+
 extern "C" {
 
 const char *mdbcu_last_error(void) { return g_last_error.c_str(); }
@@ -1315,6 +1516,7 @@ int mdbcu_context_create(int device, mdbcu_context **out) {
         return fail(std::string("mailbox allocation: ") + cudaGetErrorString(e));
     }
     cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device);
+    ctx->block_row_min = BLOCK_ROW_MIN;
     ctx->lane_rows_min = LANE_ROWS_MIN; // (tuning and tests change it with mdbcu_context_set_option: the library reads no environment variables)
     // keep freed blocks in the pool: steady-state calls then never reach the driver allocator
     cudaMemPool_t pool;
@@ -1461,9 +1663,12 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     if (pl.h_status.n_wide >= ctx->lane_rows_min)
         LAUNCH(ctx, k_grid_macaque_lanes, div_up(pl.h_status.n_wide, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p + (S - 1),
                (uint32_t)pl.h_status.n_wide, d_val);
-    else if (pl.h_status.n_wide)
+    else if (pl.h_status.n_wide) {
         LAUNCH(ctx, k_grid_macaque_warp, div_up(pl.h_status.n_wide, WIDE_WARPS), WIDE_WARPS * 32, 0, st.view, pl.desc.p, pl.point_off.p,
-               pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, d_val);
+               pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, ctx->block_row_min, d_val);
+        launch_macaque_block<false>(ctx, std::min<unsigned int>(pl.h_status.n_wide, (unsigned int)ctx->sm_count * 16), st.view, pl.worklist.p + (S - 1), -1,
+                                    (const unsigned int *)nullptr, (uint32_t)pl.h_status.n_wide, pl.point_off.p, d_val);
+    }
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
         CUDA_TRY(d2h_bytes(ctx, timestamps_out, d_ts, pl.total * sizeof(int64_t)));
@@ -1495,7 +1700,9 @@ int mdbcu_segment_sums(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segmen
     CUDA_TRY(wide_list.alloc(S, s));
     LAUNCH(ctx, k_agg_segments, div_up(S, 128), 128, 0, st.view, (uint64_t *)nullptr, d_sum, wide_list.p, status.p);
     LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0, st.view,
-           wide_list.p, &status.p->n_wide, ctx->lane_rows_min, d_sum);
+           wide_list.p, &status.p->n_wide, ctx->lane_rows_min, ctx->block_row_min, d_sum);
+    launch_macaque_block<true>(ctx, std::min<unsigned int>((unsigned int)std::min<uint64_t>(S, 1u << 20), (unsigned int)ctx->sm_count * 16), st.view, wide_list.p, 1,
+                               &status.p->n_wide, (uint32_t)std::min<uint64_t>(S, 0xFFFFFFFFull), (const uint64_t *)nullptr, d_sum);
     if (S >= ctx->lane_rows_min)
         LAUNCH(ctx, k_agg_macaque_lanes, std::min<unsigned int>(div_up(S, 128), (unsigned int)ctx->sm_count * 16), 128, 0, st.view, wide_list.p,
                &status.p->n_wide, ctx->lane_rows_min, d_sum);
@@ -1532,7 +1739,9 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
     if (S) {
         LAUNCH(ctx, k_agg_find_wide, div_up(S, 256), 256, 0, st.view, wide_list.p, status.p);
         LAUNCH(ctx, k_agg_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
-               st.view, wide_list.p, &status.p->n_wide, ctx->lane_rows_min, wide_sum.p);
+               st.view, wide_list.p, &status.p->n_wide, ctx->lane_rows_min, ctx->block_row_min, wide_sum.p);
+        launch_macaque_block<true>(ctx, std::min<unsigned int>((unsigned int)std::min<uint64_t>(S, 1u << 20), (unsigned int)ctx->sm_count * 16), st.view, wide_list.p, 1,
+                                   &status.p->n_wide, (uint32_t)std::min<uint64_t>(S, 0xFFFFFFFFull), (const uint64_t *)nullptr, wide_sum.p);
         if (S >= ctx->lane_rows_min)
             LAUNCH(ctx, k_agg_macaque_lanes, std::min<unsigned int>(div_up(S, 128), (unsigned int)ctx->sm_count * 16), 128, 0, st.view,
                    wide_list.p, &status.p->n_wide, ctx->lane_rows_min, wide_sum.p);

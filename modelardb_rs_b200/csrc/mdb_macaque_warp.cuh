@@ -8,6 +8,8 @@
 
 #include "mdb_device.cuh"
 
+#include <type_traits>
+
 #if defined(__CUDACC__) || defined(MDB_WARP_EMU)
 
 // 1 (default): the decoder takes whole runs of `0` codes (the XOR in the window in force) and of `10` codes (the same value
@@ -89,6 +91,27 @@ struct WarpBitStage {
         first_word = w0;
         __syncwarp();
     }
+    // Software prefetch of the window that starts at bit p: the loads are issued here and land in registers while the caller
+    // does something else; prefetch_commit moves them into the stage.  Only whole words of the stream's interior are
+    // prefetched (a window that touches the stream's first or last, partial word is left to cover()).
+    static constexpr int PRE_WORDS = STAGE_WORDS / 32;
+    MDB_WARP_FN void prefetch_issue(uint64_t p, int lane, uint32_t (&pre)[PRE_WORDS], uint64_t &pre_w0) const {
+        const uint64_t w0 = p >> 5;
+        const bool interior = 4 * w0 >= lo_byte && 4 * (w0 + STAGE_WORDS) <= hi_byte;
+        pre_w0 = interior ? w0 : ~0ull;
+        if (interior) {
+#pragma unroll
+            for (int i = 0; i < PRE_WORDS; i++) pre[i] = __ldg(words + w0 + (uint64_t)(i * 32 + lane));
+        }
+    }
+    MDB_WARP_FN void prefetch_commit(int lane, const uint32_t (&pre)[PRE_WORDS], uint64_t pre_w0) {
+        if (pre_w0 == ~0ull) return;
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < PRE_WORDS; i++) stage[i * 32 + lane] = __byte_perm(pre[i], 0, 0x0123);
+        first_word = pre_w0;
+        __syncwarp();
+    }
     // the 32 bits starting at bit `rel` of the stage (rel = absolute position - 32 * first_word; covered)
     MDB_WARP_FN uint32_t peek32(uint32_t rel) const {
         const uint32_t i = rel >> 5;
@@ -102,21 +125,65 @@ struct WarpBitStage {
 // lane k keeps the position, width and shift of the k-th payload (packed into one register).  The payloads are then
 // extracted by the 32 lanes at once, and the values are an exclusive-or prefix scan over them
 // (value k = value k - 1 XOR payload k).  on_batch(k0, value, valid): this lane's value k0 + lane of the stream.
-template <typename OnBatch>
-MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, bool has_seed, float seed,
-                                                       uint32_t *stage_words, int lane, OnBatch &&on_batch) {
+//
+// Wide runs.  On high-entropy lossless data the window only ever widens, so after a short warm-up practically every code is a
+// `0` code of the same width: the stream is FIXED WIDTH there.  If the code at the cursor is a `0` code, the next 256 codes are
+// assumed to be too: lane l looks at the eight slots 8 l .. 8 l + 7 (slot k starts at cursor + k * (1 + width)); a slot whose
+// first bit is 0 IS a `0` code provided every slot before it is one, so "all 256 flag bits are zero" proves the whole run, by
+// induction over the slots.  Then each lane extracts its eight payloads, XORs them into a lane-local prefix, and ONE warp scan of
+// the lanes' totals (instead of eight) turns them into values.  One failed flag anywhere and nothing is used: the ordinary
+// 32-value batches take over for a while.  on_wide(k0, v): this lane's values k0 + 8 * lane + 0..7 of the stream.
+// Because a run's slots are at known positions, DIFFERENT warps can take different stretches of the same run
+// (wide_run_at from any slot boundary): k_grid_macaque_block / k_agg_macaque_block give a long row to a whole block.
+struct NoWideRuns {};
+constexpr int WIDE_RUN_PER_LANE = 8;
+constexpr uint32_t WIDE_RUN = 32 * WIDE_RUN_PER_LANE;
+
+// The 256 slots starting at bit `at` as `0` codes of `width` payload bits: x[j] = XOR of this lane's payloads 0..j (already
+// shifted into place).  Returns false (in every lane) if some slot is not a `0` code.
+MDB_WARP_FN bool wide_run_at(WarpBitStage &bits, uint64_t at, uint32_t width, uint32_t trailing_zeros, int lane, uint32_t (&x)[WIDE_RUN_PER_LANE]) {
+    const uint32_t stride = 1u + width;
+    bits.cover(at, WIDE_RUN * 33u + 64u, lane);
+    const uint32_t rel = (uint32_t)(at - 32u * bits.first_word);
+    uint32_t flags = 0;
+#pragma unroll
+    for (int j = 0; j < WIDE_RUN_PER_LANE; j++) {
+        const uint32_t slot = rel + (uint32_t)(WIDE_RUN_PER_LANE * lane + j) * stride;
+        flags |= bits.peek32(slot); // bit 31: the slot's first bit
+        uint32_t y = width ? bits.peek32(slot + 1u) >> (32u - width) : 0u;
+        y = trailing_zeros < 32u ? y << trailing_zeros : 0u;
+        x[j] = j ? x[j - 1] ^ y : y;
+    }
+    return !__any_sync(0xffffffffu, (flags & 0x80000000u) != 0u);
+}
+
+struct WarpMacaqueDecoder {
     WarpBitStage bits;
-    bits.init(bytes, n_bytes, stage_words);
-    uint64_t p = bits.start_bit;
-    uint32_t trailing_zeros = 0;
-    uint32_t width_in_force = 32; // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = 255 at first
-    uint32_t last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
+    uint64_t p;              // bit position of the next code
+    uint32_t trailing_zeros;
+    uint32_t width_in_force; // payload width of a `0` code: min(32, (32 - leading - trailing) & 0xff), leading = 255 at first
+    uint32_t last_value;
+    bool first_raw;          // the stream starts with a raw 32-bit value that has not been read yet
 #if MDB_MACAQUE_SPECULATE_RUNS
-    bool speculate = true;   // the same in every lane
-    int batches_walked = 0;  // batches since the plain walk took over
+    bool speculate;          // the same in every lane
+    int batches_walked;      // batches since the plain walk took over
 #endif
-    for (uint32_t k0 = 0; k0 < count; k0 += 32) {
-        const int cnt = (int)(count - k0 < 32u ? count - k0 : 32u);
+
+    MDB_WARP_FN void init(const uint8_t *bytes, uint64_t n_bytes, bool has_seed, float seed, uint32_t *stage_words) {
+        bits.init(bytes, n_bytes, stage_words);
+        p = bits.start_bit;
+        trailing_zeros = 0;
+        width_in_force = 32;
+        last_value = has_seed ? __float_as_uint(seed) : 0u; // (the first value is "0 XOR 32 raw bits")
+        first_raw = !has_seed;
+#if MDB_MACAQUE_SPECULATE_RUNS
+        speculate = true;
+        batches_walked = 0;
+#endif
+    }
+
+    // The next `cnt` (<= 32) values; returns this lane's (lane < cnt).
+    MDB_WARP_FN uint32_t batch(int cnt, int lane) {
         bits.cover(p, 32u * 45u + 64u, lane);
         const uint32_t rel0 = (uint32_t)(p - 32u * bits.first_word); // positions inside the batch are relative to the stage
         uint32_t rel = rel0;
@@ -141,10 +208,11 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
             if (k == lane) mine = packed;
         };
         int k_begin = 0;
-        if (!has_seed && k0 == 0) { // macaque_v.rs:282-285: the first value is stored raw
+        if (first_raw) { // macaque_v.rs:282-285: the first value is stored raw
             if (lane == 0) mine = rel | (32u << 15);
             rel += 32;
             k_begin = 1;
+            first_raw = false;
         }
 #if MDB_MACAQUE_SPECULATE_RUNS
         if (speculate) {
@@ -201,10 +269,57 @@ MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, 
             if (lane >= d) x ^= o;
         }
         const uint32_t value = last_value ^ x;
-        on_batch(k0, __uint_as_float(value), lane < cnt);
         last_value = __shfl_sync(0xffffffffu, value, cnt - 1);
+        return value;
     }
-    return __uint_as_float(last_value);
+
+    // Tries the next 256 values as one run of `0` codes; on success v holds this lane's eight values and the state has moved on.
+    MDB_WARP_FN bool wide(int lane, uint32_t (&v)[WIDE_RUN_PER_LANE]) {
+        if (first_raw) return false;
+        uint32_t x[WIDE_RUN_PER_LANE];
+        if (!wide_run_at(bits, p, width_in_force, trailing_zeros, lane, x)) return false;
+        uint32_t t = x[WIDE_RUN_PER_LANE - 1];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { // inclusive XOR scan of the lanes' totals
+            const uint32_t o = __shfl_up_sync(0xffffffffu, t, d);
+            if (lane >= d) t ^= o;
+        }
+        const uint32_t before = last_value ^ t ^ x[WIDE_RUN_PER_LANE - 1]; // the value before this lane's first one
+#pragma unroll
+        for (int j = 0; j < WIDE_RUN_PER_LANE; j++) v[j] = before ^ x[j];
+        last_value = __shfl_sync(0xffffffffu, v[WIDE_RUN_PER_LANE - 1], 31);
+        p += (uint64_t)WIDE_RUN * (1u + width_in_force);
+        return true;
+    }
+};
+
+template <typename OnBatch, typename OnWide = NoWideRuns>
+MDB_WARP_FN float warp_macaque_v_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, bool has_seed, float seed,
+                                                       uint32_t *stage_words, int lane, OnBatch &&on_batch, OnWide &&on_wide = NoWideRuns()) {
+    constexpr bool HAS_WIDE = !std::is_same<typename std::decay<OnWide>::type, NoWideRuns>::value;
+    int wide_pause = 0; // 32-value batches to go before the next wide attempt (the same in every lane)
+    WarpMacaqueDecoder dec;
+    dec.init(bytes, n_bytes, has_seed, seed, stage_words);
+    uint32_t k0 = 0;
+    while (k0 < count) {
+        if constexpr (HAS_WIDE) {
+            if (wide_pause == 0 && count - k0 >= WIDE_RUN) {
+                uint32_t v[WIDE_RUN_PER_LANE];
+                if (dec.wide(lane, v)) {
+                    on_wide(k0, v);
+                    k0 += WIDE_RUN;
+                    continue;
+                }
+                wide_pause = 8;
+            }
+            if (wide_pause > 0) wide_pause--;
+        }
+        const int cnt = (int)(count - k0 < 32u ? count - k0 : 32u);
+        const uint32_t value = dec.batch(cnt, lane);
+        on_batch(k0, __uint_as_float(value), lane < cnt);
+        k0 += 32;
+    }
+    return __uint_as_float(dec.last_value);
 }
 
 

@@ -321,6 +321,8 @@ void emu_fit_models(const int64_t *ts, const float *values, uint32_t n, uint8_t 
     }
 }
 
+static uint64_t g_emu_wide_runs = 0;
+extern "C" uint64_t emu_wide_runs() { return g_emu_wide_runs; }
 // warp_macaque_v_decode (mdb_macaque_warp.cuh) on one stream: out receives `count` values, *last_out the decoder's last value.
 void emu_warp_macaque_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t count, int has_seed, float seed, float *out, float *last_out) {
     std::vector<uint32_t> stage(STAGE_WORDS + 1);
@@ -328,6 +330,10 @@ void emu_warp_macaque_decode(const uint8_t *bytes, uint64_t n_bytes, uint32_t co
         const float last = warp_macaque_v_decode(bytes, n_bytes, count, has_seed != 0, seed, stage.data(), lane,
                                                  [&](uint32_t k0, float value, bool valid) {
                                                      if (valid) out[k0 + lane] = value;
+                                                 },
+                                                 [&](uint32_t k0, const uint32_t(&v)[WIDE_RUN_PER_LANE]) { // a verified run of 256 `0` codes
+                                                     g_emu_wide_runs += lane == 0;
+                                                     for (int j = 0; j < WIDE_RUN_PER_LANE; j++) std::memcpy(&out[k0 + WIDE_RUN_PER_LANE * lane + j], &v[j], 4);
                                                  });
         if (lane == 0) *last_out = last;
     });

@@ -168,3 +168,39 @@ def test_tma_tile_kernel_matches_oracle(oracle, kind, eb):
         assert_f32_bits_equal(dval.cpu().numpy(), wval, f"tma tile device {kind} {eb} shift {shift}")
     seg.free()
     ctx.close()
+
+
+@pytest.mark.parametrize("eb", [(0, 0.0), (2, 1e-4), (1, 0.05)], ids=["lossless", "rel1e-4", "abs0.05"])
+def test_block_per_row_macaque_decoder_matches_oracle(oracle, eb):
+    """k_macaque_block: a whole block decodes a very long MacaqueV row, 16 stretches of 256 fixed-width slots at a time, each
+    stretch proven by its own flag bits; where a run breaks (a repeated value, a window that widens) one warp walks on the
+    ordinary way.  The row length from which it is used is lowered ("block_row_min") so that rows of every length and kind
+    of break go through it: grid values and per-row f32 sums (one addition chain in stream order) are the oracle's bits."""
+    ctx = mc.Context(0)
+    ctx.set_option("block_row_min", 512)
+    rng = np.random.default_rng(5)
+    units = []
+    for u, n in enumerate([513, 4096, 4097, 9000, 40_000, 70_001]):
+        x = (100.0 + np.cumsum(rng.standard_normal(n))).astype(np.float32)
+        if u % 2:  # breaks: repeated values (`10` codes), an outlier that widens the window, a sign change
+            x[n // 3: n // 3 + 5] = x[n // 3]
+            x[n // 2] = np.float32(-3.0e30)
+            x[2 * n // 3] = np.float32(1e-30)
+        units.append(x)
+    vals = np.concatenate(units)
+    ts = np.concatenate([syn.regular_timestamps(len(u)) for u in units])
+    off = np.concatenate([[0], np.cumsum([len(u) for u in units])]).astype(np.uint64)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=4)
+    assert int(np.count_nonzero((want.model_type_id == 2) & (np.diff(want.values_off) > 1500))) >= 4  # long MacaqueV rows exist
+    host = mc.HostSegments(unit_seg_off=want.unit_seg_off, **{c: getattr(want, c) for c in mc._COLUMNS})
+    wts, wval, _ = oracle.grid(want, n_threads=4)
+    gts, gval = mc.grid(host, ctx=ctx)
+    assert np.array_equal(gts, wts)
+    assert_f32_bits_equal(gval, wval, f"block decoder grid {eb}")
+    assert_f32_bits_equal(mc.segment_sums(host, ctx), oracle.segment_sums(want, n_threads=4), f"block decoder sums {eb}", nan_payload_matters=False)
+    gc, gmn, gmx, gsm = mc.aggregate(host, want.unit_seg_off, ctx)
+    wc, wmn, wmx, wsm = oracle.aggregate(want, want.unit_seg_off, n_threads=4)
+    assert np.array_equal(gc, wc)
+    ok = np.isnan(wsm) & np.isnan(gsm) | (np.abs(gsm - wsm) <= 1e-12 * np.abs(wsm)) | (gsm == wsm)
+    assert ok.all()
+    ctx.close()

@@ -107,3 +107,33 @@ def test_warp_encoder_drains_its_stage(oracle):
         assert data == want.data and counted == len(data) and len(data) > 10 * 2048
         got, _ = emu.warp_macaque_decode(data, len(vals), misalign=5)
         assert got.tobytes() == oracle.macaque_v_grid(want.data, len(vals)).tobytes()
+
+
+def test_wide_runs_of_reuse_codes_are_taken_and_exact(oracle):
+    """Lossless high-entropy streams are fixed width after a warm-up (every code is `0` + the same number of bits): the
+    decoder proves 256 codes at a time from their flag bits alone and scans once per 256 values.  Streams where runs break
+    (a value repeated now and then, a window that has to widen) fall back to the 32-value batches and back."""
+    rng = np.random.default_rng(77)
+    lib = emu.lib()
+    lib.emu_wide_runs.restype = __import__("ctypes").c_uint64
+    walk = (100.0 + np.cumsum(rng.standard_normal(30_000))).astype(np.float32)
+    broken = walk.copy()
+    broken[5000:5003] = broken[4999]            # `10` codes inside a run
+    broken[12_000] = np.float32(-3.0e38)        # an XOR that needs a new window
+    noise = rng.uniform(-1e6, 1e6, 9000).astype(np.float32)
+    for name, vals, expect_wide in (("walk", walk, True), ("broken", broken, True), ("noise", noise, True), ("short", walk[:200], False)):
+        stream = oracle.macaque_v_compress((0, 0.0), vals)
+        for misalign in (0, 3):
+            before = lib.emu_wide_runs()
+            got, last = emu.warp_macaque_decode(stream.data, len(vals), misalign=misalign)
+            assert got.tobytes() == vals.tobytes(), (name, misalign)
+            assert np.float32(last).tobytes() == vals[-1:].tobytes()
+            assert (lib.emu_wide_runs() > before) == expect_wide, name
+    # a seeded (residual-style) stream and a lossy one (runs of `10` codes: never wide)
+    stream = oracle.macaque_v_compress((0, 0.0), walk[:5000], seed=np.float32(1.5))
+    got, _ = emu.warp_macaque_decode(stream.data, 5000, seed=np.float32(1.5))
+    assert got.tobytes() == walk[:5000].tobytes()
+    lossy = oracle.macaque_v_compress((2, 1.0), walk)
+    want = oracle.macaque_v_grid(lossy.data, len(walk))
+    got, _ = emu.warp_macaque_decode(lossy.data, len(walk))
+    assert got.tobytes() == want.tobytes()
