@@ -571,8 +571,7 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
                                                       const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ chunk_unit,
                                                       uint64_t n_chunks, const ChunkState *st, FittedModel *lists,
                                                       const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
-                                                      const uint8_t *__restrict__ unit_irregular) {
-    __shared__ __align__(16) double smem[4][128]; // per warp: two halves of (32 x terms, 32 y terms)
+                                                      const uint8_t *__restrict__ unit_irregular, uint2 *long_models, unsigned int *n_long) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint64_t g = (uint64_t)blockIdx.x * 4 + warp;
     if (g >= n_chunks) return;
@@ -587,7 +586,6 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
     const bool regular = !unit_irregular[u] && delta0 >= 0 && delta0 < (1ll << 31);
     const double delta_d = (double)delta0;
     FittedModel *list = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2);
-    double *sx = smem[warp];
     for (uint32_t k0 = 0; k0 < s.n_models; k0 += 32) {
         const uint32_t k = k0 + (uint32_t)lane;
         FittedModel m;
@@ -603,60 +601,87 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
             swing_finish_from_sums(m, num, den, uts, uval);
             list[k] = m;
         }
-        unsigned long_mask = __ballot_sync(FULL_MASK, is_long);
-        while (long_mask) { // the whole warp on one long model: 32 points per step, only the two running sums are chained
-            const int src = __ffs(long_mask) - 1;
-            long_mask &= long_mask - 1;
-            FittedModel lm = list[k0 + (uint32_t)src];
-            const int64_t t0 = uts[lm.start_index];
-            const double v0 = (double)uval[lm.start_index];
-            double num = 0.0, den = 0.0;
-            // Software pipeline over blocks of 32 points: while the two addition chains run over block b (their terms
-            // sit in one half of the shared buffer), the terms of block b + 1 are computed into the other half and the
-            // loads of blocks b + 2 and b + 3 are in flight.  Only the chains are serial: one rounding per point each.
-            const uint32_t p_first = lm.start_index + 2, p_last = lm.end_index;
-            auto load_t = [&](uint32_t i) { return i <= p_last ? uts[i] : (int64_t)0; };
-            auto load_v = [&](uint32_t i) { return i <= p_last ? uval[i] : 0.0f; };
-            auto put_terms = [&](int half, uint32_t i, int64_t t, float vf) {
-                double x = 0.0, y = 0.0;
-                if (i <= p_last) swing_mse_terms(t0, v0, t, (double)vf, x, y);
-                sx[half * 64 + lane] = x;
-                sx[half * 64 + 32 + lane] = y;
-            };
-            int64_t ta = load_t(p_first + lane), tb = load_t(p_first + 32 + lane), tc = load_t(p_first + 64 + lane);
-            float va = load_v(p_first + lane), vb = load_v(p_first + 32 + lane), vc = load_v(p_first + 64 + lane);
-            put_terms(0, p_first + lane, ta, va);
-            __syncwarp();
-            int half = 0;
-            for (uint32_t base = p_first; base <= p_last; base += 32) {
-                // next block's terms, and the loads three blocks ahead
-                put_terms(half ^ 1, base + 32 + lane, tb, vb);
-                tb = tc;
-                vb = vc;
-                tc = load_t(base + 96 + lane);
-                vc = load_v(base + 96 + lane);
-                const double *bx = sx + half * 64, *by = bx + 32;
-                if (p_last - base >= 31) {
-                    const double2 *bx2 = reinterpret_cast<const double2 *>(bx), *by2 = reinterpret_cast<const double2 *>(by);
-#pragma unroll
-                    for (int j = 0; j < 16; j++) { // 16-byte shared loads: two terms each
-                        const double2 xx = bx2[j], yy = by2[j];
-                        num = __dadd_rn(__dadd_rn(num, xx.x), xx.y);
-                        den = __dadd_rn(__dadd_rn(den, yy.x), yy.y);
-                    }
-                } else { // the last, partial block (adding a padding zero could flip the sign of a zero sum)
-                    const int cnt = (int)(p_last - base + 1);
-                    for (int j = 0; j < cnt; j++) {
-                        num = __dadd_rn(num, bx[j]);
-                        den = __dadd_rn(den, by[j]);
-                    }
-                }
-                half ^= 1;
-                __syncwarp();
-            }
-            swing_finish_from_sums(lm, num, den, uts, uval);
-            if (lane == 0) list[k0 + (uint32_t)src] = lm;
+        if (is_long) { // summed by k_swing_finish_long: one block per long model
+            const unsigned int slot = atomicAdd(n_long, 1u);
+            long_models[slot] = make_uint2((uint32_t)g, k);
         }
+    }
+}
+
+// A LONG pending Swing model (>= SWING_FINISH_LONG points, up to a whole unit): its two sums are chains of 10^6 dependent
+// f64 additions, and a dependent DADD takes 8.3 cycles on B200 (tools/microbench/fp64.cu), so the floor is ~4.4 ms per
+// 10^6 points however the work is arranged.  To get near it the chain must be nothing but the additions: warp 1 of the block
+// PRODUCES the terms (loads, conversions, two multiplications per point) for chunk c + 1 into one half of a shared buffer
+// while warp 0 CONSUMES chunk c from the other half -- 16-byte shared loads hoisted ahead of the chain, two DADD chains
+// interleaved -- one __syncthreads per 512 points.  (The former arrangement, one warp doing both in turn, took 31 cycles per
+// point.)  Order and operands of every addition are the reference's (swing.rs:180-193, 212-228).
+constexpr int SWING_LONG_CHUNK = 512;
+
+__global__ void __launch_bounds__(64) k_swing_finish_long(const int64_t *__restrict__ ts, const float *__restrict__ values,
+                                                          const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ chunk_unit, const ChunkState *st,
+                                                          FittedModel *lists, const uint64_t *__restrict__ list_base, const uint32_t *__restrict__ list_cap,
+                                                          const uint2 *__restrict__ long_models, const unsigned int *n_long) {
+    __shared__ __align__(16) double sx[2][SWING_LONG_CHUNK], sy[2][SWING_LONG_CHUNK];
+    if (blockIdx.x >= *n_long) return;
+    const uint2 item = long_models[blockIdx.x];
+    const uint64_t g = item.x;
+    const ChunkState s = st[g];
+    const uint32_t u = chunk_unit[g];
+    const int64_t *uts = ts + unit_off[u];
+    const float *uval = values + unit_off[u];
+    FittedModel *slot = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2) + item.y;
+    FittedModel m = *slot;
+    const int64_t t0 = uts[m.start_index];
+    const double v0 = (double)uval[m.start_index];
+    const uint32_t first = m.start_index + 2, last = m.end_index; // the first two points add no term
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_terms = last >= first ? last - first + 1 : 0;
+    const uint32_t n_chunks = (n_terms + SWING_LONG_CHUNK - 1) / SWING_LONG_CHUNK;
+    double num = 0.0, den = 0.0;
+    auto produce = [&](uint32_t c) { // (warp 1) terms of chunk c into half c & 1; entries past the model's end are not read back
+        const uint32_t base = first + c * SWING_LONG_CHUNK;
+        constexpr int PER_LANE = SWING_LONG_CHUNK / 32;
+        int64_t t[PER_LANE];
+        float v[PER_LANE];
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) { // every load of the chunk is in flight before the first one is used
+            const uint32_t i = base + (uint32_t)(q * 32 + lane);
+            t[q] = i <= last ? uts[i] : t0;
+            v[q] = i <= last ? uval[i] : 0.0f;
+        }
+#pragma unroll
+        for (int q = 0; q < PER_LANE; q++) {
+            double x, y;
+            swing_mse_terms(t0, v0, t[q], (double)v[q], x, y);
+            sx[c & 1][q * 32 + lane] = x;
+            sy[c & 1][q * 32 + lane] = y;
+        }
+    };
+    if (warp == 1 && n_chunks) produce(0);
+    __syncthreads();
+    for (uint32_t c = 0; c < n_chunks; c++) {
+        if (warp == 1) {
+            if (c + 1 < n_chunks) produce(c + 1);
+        } else {
+            const int cnt = (int)min((uint32_t)SWING_LONG_CHUNK, n_terms - c * SWING_LONG_CHUNK);
+            const double2 *bx = reinterpret_cast<const double2 *>(sx[c & 1]), *by = reinterpret_cast<const double2 *>(sy[c & 1]);
+            int j = 0;
+#pragma unroll 8
+            for (; j + 2 <= cnt; j += 2) { // every lane runs the same chain (uniform shared loads are broadcasts)
+                const double2 xx = bx[j >> 1], yy = by[j >> 1];
+                num = __dadd_rn(__dadd_rn(num, xx.x), xx.y);
+                den = __dadd_rn(__dadd_rn(den, yy.x), yy.y);
+            }
+            if (j < cnt) { // (adding a padding zero could flip the sign of a zero sum)
+                num = __dadd_rn(num, sx[c & 1][j]);
+                den = __dadd_rn(den, sy[c & 1][j]);
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        swing_finish_from_sums(m, num, den, uts, uval);
+        if (lane == 0) *slot = m;
     }
 }
 
@@ -892,6 +917,7 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
     const std::string n(name);
     if (n == "grid_tma_stores") ctx->grid_tma_stores = value != 0;
     else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
+    else if (n == "fit_wide") ctx->fit_wide = value != 0;
     else if (n == "block_row_warps") ctx->block_row_warps = (int)value;
     else if (n == "block_row_min") ctx->block_row_min = (uint32_t)std::max<int64_t>(512, value);
     else if (n == "lane_warmup") ctx->lane_warmup = (uint32_t)std::max<int64_t>(0, value);
@@ -1108,7 +1134,8 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         if (async_sched && G) {
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
             int blocks_per_sm = 0;
-            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, use_lanes ? k_spec_async<WarpFitWide> : k_spec_async<WarpFit>,
+            const bool wide_fit = use_lanes || ctx->fit_wide;
+            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, wide_fit ? k_spec_async<WarpFitWide> : k_spec_async<WarpFit>,
                                                                  CHAIN_WARPS * 32, 0));
             if (blocks_per_sm < 1) return bail(fail("compress: the chain kernel does not fit on this device"));
             const uint64_t n_blocks = std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, CHAIN_WARPS));
@@ -1136,7 +1163,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             const uint32_t n_initial = use_lanes ? 0u : (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G);
             LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, n_initial, units.p, queue.p);
             if (use_lanes) LAUNCH(ctx, k_sched_kick, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, units.p, queue.p, items.p);
-            if (use_lanes) // what the lanes left: stitching, and the long models they cut -- the engine with the wide steps
+            if (wide_fit) // what the lanes left: stitching, and the long models they cut -- the engine with the wide steps
                 LAUNCH(ctx, k_spec_async<WarpFitWide>, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
                        chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
             else
@@ -1195,8 +1222,20 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 
         // ---- rows
         LAUNCH(ctx, k_spec_finalize, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, unit_irregular.p);
-        if (G && ctx->fit_mode != 1)
-            LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p, unit_irregular.p);
+        if (G && ctx->fit_mode != 1) {
+            // pending Swing models: short ones one lane each; long ones are listed and get a block each (their number is only
+            // known on the device: as many blocks as there could be, all but the listed ones leave at once)
+            DBuf<uint2> long_models;
+            DBuf<unsigned int> n_long;
+            const uint64_t long_cap = (n_points - first) / SWING_FINISH_LONG + 1;
+            TRY_SG(long_models.alloc(long_cap, s));
+            TRY_SG(n_long.alloc(1, s));
+            TRY_SG(cudaMemsetAsync(n_long.p, 0, sizeof(unsigned int), s));
+            LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p, unit_irregular.p,
+                   long_models.p, n_long.p);
+            LAUNCH(ctx, k_swing_finish_long, (unsigned int)std::min<uint64_t>(long_cap, 1u << 20), 64, 0, d_ts, d_val, d_off, chunk_unit.p, st.p, lists.p,
+                   list_base.p, list_cap.p, long_models.p, n_long.p);
+        }
         if (G) LAUNCH(ctx, k_spec_count_rows, div_up(G, 128), 128, 0, st.p, G, lists.p, list_base.p, list_cap.p, rows.p);
         if (exclusive_scan<uint32_t>(ctx, rows.p, G, row_base.p)) return bail(MDBCU_FAILURE);
         LAUNCH(ctx, k_unit_seg_off, div_up(n_units + 1, 256), 256, 0, chunk_base.p, n_units, row_base.p, sg->unit_seg_off);

@@ -91,6 +91,7 @@ struct mdbcu_context {
     bool own_stream = false;
     uint64_t launches = 0;
     int sm_count = 148;
+    bool fit_wide = false;          // cooperative engine with the 512-point wide steps also when it runs alone (tuning)
     int block_row_warps = 4;        // warps per row of k_macaque_block (2, 4, 8 or 16)
     uint32_t block_row_min = 0;     // MacaqueV values from which a row is decoded by a whole block (set to BLOCK_ROW_MIN at creation)
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)

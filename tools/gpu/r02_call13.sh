@@ -1,0 +1,7 @@
+#!/bin/bash
+mkdir -p gpurun_out
+O=gpurun_out
+echo "== tests"; timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_fit_engines.py -m gpu -x -q -k "segmentation or long or medium" 2>&1 | tail -3
+B="python bench.py --steps 3 --warmup 2 --no-e2e --no-cpu-baseline"
+run() { name=$1; shift; timeout 300 $B "$@" > $O/r02m_$name.json 2> $O/r02m_$name.err; echo "$name rc=$?"; python tools/bench_brief.py $name < $O/r02m_$name.json 2>/dev/null || tail -3 $O/r02m_$name.err; }
+run cfg4 --config cfg4
