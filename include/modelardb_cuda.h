@@ -139,17 +139,20 @@ int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points);
 /* Number of chain rounds the last mdbcu_compress on this context needed (1 = no re-run at all; always
  * 1 with the asynchronous scheduler, which has no rounds). */
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
-/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (= 4), 1 one
+/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (4 when the units alone
+ * occupy the lanes, else 5), 1 one
  * thread per chain in global rounds, 2 one warp per chain (32 lanes fit 128 points per step,
  * csrc/mdb_fit_warp.cuh) in global rounds, 3 one warp per chain served from a device-side work queue
  * by persistent warps, each unit advancing its own exact frontier (csrc/mdb_compress.cuh,
  * sched_advance), 4 one LANE per chain for the bulk of the chains (every thread walks its own chunk point by point,
  * csrc/mdb_fit_lanes.cuh; regular units with finite values) followed by 3 for the exact stitching and for everything
- * the lanes leave alone.  Results are identical. */
+ * the lanes leave alone, 5 = 3 with the screened fit (csrc/mdb_fit_screen.cuh: Swing's comparisons decided in f32
+ * where they are certain and by the reference's own f64 operations where they are not; units with regular timestamps
+ * and a lossy bound, everything else falls to the exact engine inside the same kernel).  Results are identical. */
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine);
 
 /* Diagnostics: fit_next_model (compression.rs:280-301) at each of `starts` with the chosen engine
- * (1 one thread, 2 one warp); out receives n_starts records of 40 bytes {u32 start, u32 end, f32 min,
+ * (1 one thread, 2 one warp, 5 one warp with the screened fit); out receives n_starts records of 40 bytes {u32 start, u32 end, f32 min,
  * f32 max, f32 last, f32 bytes_per_value, i32 model_type_id, i32 values_len, i32 aborted, i32 irregular}.
  * Host space only.  Used by the tests to compare the two engines model by model. */
 int mdbcu_debug_fit_models(mdbcu_context *ctx, const int64_t *timestamps, const float *values, uint32_t n,

@@ -405,14 +405,21 @@ __global__ void __launch_bounds__(128) k_sched_kick(const uint64_t *__restrict__
 // claims it, runs its chain (the same spec_chain as the round scheme) and advances the unit.  A worker that finds
 // the queue empty EXITS: every later push is made by a worker that is still alive and pops right afterwards, so
 // nothing is ever stranded, and the SM slots of a draining kernel become free for other streams.
-template <typename Fit>
-__global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec_async(const int64_t *__restrict__ ts, const float *__restrict__ values,
+// The screened engine (mdb_fit_screen.cuh) needs far fewer registers per step than the exact one, whose code it only calls
+// on the rare fits it cannot decide (that code spills under this bound, which is the price of those fits): five blocks per SM.
+using WarpFitScreen = WarpFitScreenT<MDB_FIT_POINTS_PER_LANE>;
+#ifndef MDB_SCREEN_MIN_BLOCKS
+#define MDB_SCREEN_MIN_BLOCKS 5
+#endif
+// info: the units as the pre-pass (k_lanes_units, k_lanes_regular) saw them, or nullptr (only the screened engine looks)
+template <typename Fit, int MIN_BLOCKS>
+__global__ void __launch_bounds__(CHAIN_WARPS * 32, MIN_BLOCKS) k_spec_async(const int64_t *__restrict__ ts, const float *__restrict__ values,
                                                                  const uint64_t *__restrict__ unit_off, const uint8_t *__restrict__ eb_kind,
                                                                  const float *__restrict__ eb_value, const uint64_t *__restrict__ chunk_base,
                                                                  const uint32_t *__restrict__ chunk_unit, uint32_t chunk_len, ChunkState *st,
                                                                  FittedModel *lists, const uint64_t *__restrict__ list_base,
                                                                  const uint32_t *__restrict__ list_cap, UnitSched *units, SchedQueue *q, uint32_t *items,
-                                                                 uint32_t n_initial, uint32_t n_chunks) {
+                                                                 uint32_t n_initial, uint32_t n_chunks, const LaneUnit *__restrict__ info) {
     __shared__ double smem[CHAIN_WARPS][Fit::SMEM_DOUBLES];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     bool first = true, initial_phase = true;
@@ -475,7 +482,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MDB_CHAIN_MIN_BLOCKS) k_spec
         const uint32_t chunk_end = (uint64_t)chunk_start + chunk_len < n ? chunk_start + chunk_len : n;
         ChunkState s = load_shared_record(st + g);
         ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-        Fit fitter(eb, ts + a, values + a, n, smem[warp]);
+        Fit fitter(eb, ts + a, values + a, n, smem[warp], info ? info + u : nullptr);
 #ifdef MDB_FIT_COUNTERS
         const long long tc0 = clock64();
 #endif
@@ -930,9 +937,9 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
 
 int mdbcu_context_set_fit_engine(mdbcu_context *ctx, int engine) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
-    if (engine < 0 || engine > 4)
+    if (engine < 0 || engine > 5)
         return fail("fit engine must be 0 (automatic), 1 (one thread per chain, rounds), 2 (one warp per chain, rounds), 3 (one warp per chain, "
-                    "asynchronous scheduling) or 4 (one lane per chain, then 3 for the stitching)");
+                    "asynchronous scheduling), 4 (one lane per chain, then 3 for the stitching) or 5 (3 with the screened fit)");
     ctx->fit_mode = engine;
     return MDBCU_SUCCESS;
 }
@@ -1015,10 +1022,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         // walk alone, AFTER the lanes, cost more than they save (33 against 22 ms on the benchmark's mixed units): those
         // chains are the critical path either way, and the cooperative engine hides it behind the other units' work.
         bool use_lanes = ctx->fit_mode == 4 || (ctx->fit_mode == 0 && n_units * 4 >= (uint64_t)ctx->sm_count * 5 * LANES_WARPS * 32);
+        // The screened cooperative engine (mdb_fit_screen.cuh) needs the same per-unit facts: regular timestamps, bound kind.
+        bool use_screen = ctx->fit_mode == 5 || (ctx->fit_mode == 0 && !use_lanes);
         DBuf<LaneUnit> lane_units;
         DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
         unsigned int kind_units[4] = {0, 0, 0, 0};
-        if (use_lanes) {
+        if (use_lanes || use_screen) {
             TRY_SG(lane_units.alloc(n_units, s));
             TRY_SG(lane_words.alloc(4, s));
             TRY_SG(cudaMemsetAsync(lane_words.p, 0, 4 * sizeof(unsigned int), s));
@@ -1026,7 +1035,8 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             TRY_SG(post(ctx, 0, lane_words.p, 2));
             TRY_SG(sync_stream(ctx));
             std::memcpy(kind_units, ctx->mailbox, sizeof(kind_units));
-            use_lanes = kind_units[0] + kind_units[1] + kind_units[2] > 0;
+            use_lanes = use_lanes && kind_units[0] + kind_units[1] + kind_units[2] > 0;
+            use_screen = use_screen && kind_units[KIND_ABSOLUTE] + kind_units[KIND_RELATIVE] > 0; // (lossless fits are all ties: the exact engine's)
         }
         uint64_t resident_lanes = 0; // of the lane kernel (the smallest over the bound kinds present)
         int lane_blocks_per_sm[3] = {0, 0, 0};
@@ -1076,10 +1086,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         DBuf<FittedModel> lists;
         TRY_SG(lists.alloc(n_models_cap, s));
 
-        const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode == 3 || ctx->fit_mode == 4;
+        const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode >= 3;
+        if ((use_lanes || use_screen) && G) // every interval of every qualifying unit (coalesced, bandwidth bound)
+            LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
         if (use_lanes && G) {
             // ---- one lane per chunk: the bulk of the chains; what they leave open is stitched below
-            LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
             DBuf<uint32_t> lane_worklist;
             DBuf<uint2> lane_resume;
             DBuf<CompressCounters> lane_counters;
@@ -1134,9 +1145,12 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         if (async_sched && G) {
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
             int blocks_per_sm = 0;
-            const bool wide_fit = use_lanes || ctx->fit_wide;
-            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, wide_fit ? k_spec_async<WarpFitWide> : k_spec_async<WarpFit>,
-                                                                 CHAIN_WARPS * 32, 0));
+            const bool wide_fit = !use_screen && (use_lanes || ctx->fit_wide);
+            TRY_SG(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &blocks_per_sm,
+                use_screen ? k_spec_async<WarpFitScreen, MDB_SCREEN_MIN_BLOCKS>
+                           : (wide_fit ? k_spec_async<WarpFitWide, MDB_CHAIN_MIN_BLOCKS> : k_spec_async<WarpFit, MDB_CHAIN_MIN_BLOCKS>),
+                CHAIN_WARPS * 32, 0));
             if (blocks_per_sm < 1) return bail(fail("compress: the chain kernel does not fit on this device"));
             const uint64_t n_blocks = std::min<uint64_t>((uint64_t)ctx->sm_count * blocks_per_sm, div_up(G, CHAIN_WARPS));
             const uint64_t capacity = 3 * G + n_blocks * CHAIN_WARPS + 8;
@@ -1163,12 +1177,19 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             const uint32_t n_initial = use_lanes ? 0u : (uint32_t)std::min<uint64_t>(n_blocks * CHAIN_WARPS, G);
             LAUNCH(ctx, k_sched_units, div_up(n_units, 128), 128, 0, chunk_base.p, n_units, G, (uint32_t)capacity, n_initial, units.p, queue.p);
             if (use_lanes) LAUNCH(ctx, k_sched_kick, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, units.p, queue.p, items.p);
-            if (wide_fit) // what the lanes left: stitching, and the long models they cut -- the engine with the wide steps
-                LAUNCH(ctx, k_spec_async<WarpFitWide>, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
-                       chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
+            const LaneUnit *no_info = nullptr;
+            if (use_screen) // Swing's decisions screened in f32, the doubtful ones in the reference's f64 (mdb_fit_screen.cuh)
+                LAUNCH(ctx, (k_spec_async<WarpFitScreen, MDB_SCREEN_MIN_BLOCKS>), (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind,
+                       d_ebv, chunk_base.p, chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial,
+                       (uint32_t)G, lane_units.p);
+            else if (wide_fit) // what the lanes left: stitching, and the long models they cut -- the engine with the wide steps
+                LAUNCH(ctx, (k_spec_async<WarpFitWide, MDB_CHAIN_MIN_BLOCKS>), (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind,
+                       d_ebv, chunk_base.p, chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial,
+                       (uint32_t)G, no_info);
             else
-                LAUNCH(ctx, k_spec_async<WarpFit>, (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_base.p,
-                       chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial, (uint32_t)G);
+                LAUNCH(ctx, (k_spec_async<WarpFit, MDB_CHAIN_MIN_BLOCKS>), (unsigned int)n_blocks, CHAIN_WARPS * 32, 0, d_ts, d_val, d_off, d_kind,
+                       d_ebv, chunk_base.p, chunk_unit.p, chunk_len, st.p, lists.p, list_base.p, list_cap.p, units.p, queue.p, items.p, n_initial,
+                       (uint32_t)G, no_info);
             static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");
             TRY_SG(post(ctx, 0, queue.p, 4));
             TRY_SG(sync_stream(ctx));
@@ -1323,7 +1344,22 @@ __global__ void __launch_bounds__(32) k_debug_fit(const int64_t *ts, const float
     ErrorBound eb = make_error_bound(kind, value);
     bool aborted = false, irregular = false;
     FittedModel m;
-    if (engine == 2) {
+    if (engine == 5) { // the screened fit; the pre-pass over the unit (k_lanes_units, k_lanes_regular) is done here by the warp
+        __shared__ LaneUnit lu;
+        if (threadIdx.x == 0) lu = lane_unit_init(ts, n, eb);
+        __syncwarp();
+        bool bad = false;
+        if (lu.ok)
+            for (uint32_t i = threadIdx.x; i < n; i += 32) bad |= ts[i] != ts[0] + (int64_t)i * (ts[1] - ts[0]);
+        bad = __any_sync(FULL_MASK, bad);
+        if (threadIdx.x == 0 && bad) lu.irregular = 1;
+        __syncwarp();
+        WarpFitScreen f(eb, ts, values, n, smem, &lu);
+        f.begin(starts[k]);
+        m = f.fit(starts[k], budget_ends[k], aborted);
+        irregular = f.irregular();
+        if (!aborted && m.pending) swing_finish(m, ts, values);
+    } else if (engine == 2) {
         WarpFit f(eb, ts, values, n, smem);
         f.begin(starts[k]);
         m = f.fit(starts[k], budget_ends[k], aborted);

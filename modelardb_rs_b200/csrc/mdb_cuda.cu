@@ -28,6 +28,7 @@
 #include "mdb_compress.cuh"
 #include "mdb_fit_warp.cuh"
 #include "mdb_fit_lanes.cuh"
+#include "mdb_fit_screen.cuh"
 #include "mdb_grid.cuh"
 #include "mdb_macaque_warp.cuh"
 
@@ -100,7 +101,7 @@ struct mdbcu_context {
     bool lane_rounds_by_lanes = false; // repair rounds after the lanes' first pass: by lanes too, or (default) by the cooperative engine
     uint32_t lane_warmup = 4096;     // points a speculative lane chain starts before its chunk (LaneChain, mdb_fit_lanes.cuh)
     uint32_t last_rounds = 0;        // chain rounds of the last mdbcu_compress
-    int fit_mode = 0;                // 0 automatic (warp per chain), 1 thread per chain, 2 warp per chain
+    int fit_mode = 0;                // mdbcu_context_set_fit_engine
     // optional per-kernel CUDA-event timing (mdbcu_context_set_profiling)
     bool profiling = false;
     std::vector<KernelStat> stats;
@@ -111,7 +112,9 @@ struct mdbcu_context {
     Stager stager;                                       // pinned bounce ring for pageable caller memory
     std::vector<PinnedBlock> pinned_cache;               // reusable pinned blocks for library-owned host copies
 
-    size_t stat_index(const char *name) {
+    size_t stat_index(const char *raw) {
+        std::string name(raw); // (a template instance with two arguments is written in parentheses at the launch site)
+        if (name.size() >= 2 && name.front() == '(' && name.back() == ')') name = name.substr(1, name.size() - 2);
         for (size_t i = 0; i < stats.size(); i++)
             if (stats[i].name == name) return i;
         stats.push_back(KernelStat{name});

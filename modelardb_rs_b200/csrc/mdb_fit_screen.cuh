@@ -1,0 +1,474 @@
+// mdb_fit_screen.cuh -- fit_next_model (compression.rs:280-301) by one warp, 32 * P points per step, with Swing's
+// decisions SCREENED in f32 and only the doubtful ones evaluated in the reference's own f64 arithmetic.  Results are
+// bit-identical to the one-thread fit (mdb_compress.cuh) and to the exact cooperative engine (mdb_fit_warp.cuh), which this
+// engine contains and falls back on.
+//
+// Why.  The exact engine (WarpFitT) spends 58 % of its instructions on Swing: an exact f64 quotient pair for EVERY point,
+// f64 prefix scans over them, and a verification walk that re-evaluates the reference's comparisons for every point.  But
+// the outcome of a fit only depends on (1) where Swing rejects a point, and (2) the exact slopes of the LAST candidate that
+// tightened each bound.  Everything else is a chain of comparisons whose results are obvious for nearly every point.
+//
+// How.  On a unit with regular timestamps (t_i = t_0 + i * delta; checked once per unit by k_lanes_units / k_lanes_regular)
+// every line of a fit passes through its first point (t_0', v_0), so a line is its slope, and with dt = k * delta the four
+// comparisons of swing.rs:146-178 at point k are, in real arithmetic, comparisons between slopes per index:
+//     reject            <=>  lo_k / k > U   or   hi_k / k < L           (hi_k = v_k + dev_k - v_0, lo_k = v_k - dev_k - v_0)
+//     tighten the upper <=>  hi_k / k < U ;   tighten the lower <=>  lo_k / k > L
+// and U (L) is the running minimum (maximum) of the candidates hi_r / r (lo_r / r) that tightened.  The reference evaluates
+// them in f64 with roundings, so its decision equals the real-arithmetic one whenever the real difference exceeds a bound
+// on those roundings.  The screen computes hi_k and lo_k with the reference's own f64 operations (their error is the
+// reference's), converts them to f32 slopes (relative error 2^-22), scans the running minimum / maximum over the step in
+// f32, and compares with a tolerance tau_k that covers
+//     * the f32 errors of both slopes:                  2^-21 (|bound| + |candidate|)
+//     * the reference's roundings in slope * t + intercept and in the comparison:
+//                                                       2^-50 (|bound| * Tmax / delta + |v_0| + |v_k|) / k
+//       (derivation at tolerance()): with timestamps at epoch scale this is the larger term -- the reference's own
+//       evaluation is that noisy, which is why its decisions near the boundary can only be reproduced by its own operations.
+// A comparison whose |difference| exceeds tau_k is CERTAIN.  A step's points are accepted up to the first certain reject or
+// the first doubtful point; for the accepted stretch only the last tightening candidate of each bound is computed exactly
+// (one f64 division each, by the reference's formula); a doubtful point is then evaluated exactly as the reference does
+// (swing.rs:146-178 on the exact bounds), its decision is applied, and screening resumes after it.  By induction over the
+// points the sequence of bounds is the sequential one.  PMC-Mean keeps the exact scan form of the exact engine.
+//
+// A fit that needs more than a few exact evaluations (constant or exactly linear data: every comparison is a tie), a
+// non-finite or huge value, sums that are not exactly representable, a lossless bound, an irregular unit: the exact engine
+// runs the fit (fit_exact), and after a few such fits in a row the rest of the chain.
+#pragma once
+
+#if defined(__CUDACC__) || defined(MDB_WARP_EMU)
+
+#include "mdb_fit_lanes.cuh"
+
+namespace mdb {
+
+#ifdef MDB_WARP_EMU
+static unsigned long long g_screen_counters[8]; // [0] fits, [1] exact fits, [2] passes, [3] exact point evaluations, [4] exact candidates
+#define MDB_SCREEN_COUNT(i) do { if ((threadIdx.x & 31) == 0) g_screen_counters[i]++; } while (0)
+__device__ __forceinline__ float rcp_approx_f32(float x) { return 1.0f / x; }
+__device__ __forceinline__ float mdb_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
+#else
+__device__ unsigned long long g_screen_counters[8];
+#ifdef MDB_FIT_COUNTERS
+#define MDB_SCREEN_COUNT(i) do { if ((threadIdx.x & 31) == 0) atomicAdd(&g_screen_counters[i], 1ull); } while (0)
+#else
+#define MDB_SCREEN_COUNT(i) do { } while (0)
+#endif
+__device__ __forceinline__ float rcp_approx_f32(float x) {
+    float r;
+    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); // MUFU.RCP: at most 1 ulp off
+    return r;
+}
+__device__ __forceinline__ float mdb_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+#endif
+
+#ifndef MDB_SCREEN_MAX_EXACT_POINTS
+#define MDB_SCREEN_MAX_EXACT_POINTS 6 // exact point evaluations per fit before the exact engine takes the fit
+#endif
+
+template <int P> struct WarpFitScreenT {
+    using Exact = WarpFitT<P, false>;
+    static constexpr int STEP = 32 * P;
+    static constexpr int SMEM_DOUBLES = Exact::SMEM_DOUBLES;
+
+    Exact ex;           // the exact engine: constants, regularity tracking, and the fits this engine does not take
+    bool screen;        // this unit's fits may be screened
+    double t0u, delta;  // (double)ts[0], (double)(ts[1] - ts[0]) of the unit: (double)ts[i] = t0u + i * delta exactly
+    float kap;          // >= 3.1 * 2^-53 * max|t| / delta: the reference's line evaluation noise per unit of slope per index
+    uint32_t exact_run; // fits in a row that the exact engine had to take
+
+    __device__ __forceinline__ WarpFitScreenT(const ErrorBound &e, const int64_t *t, const float *v, uint32_t n_, double *smem_, const LaneUnit *lu)
+        : ex(e, t, v, n_, smem_), screen(false), t0u(0.0), delta(1.0), kap(0.0f), exact_run(0) {
+        if (lu != nullptr && n_ >= 2) {
+            const LaneUnit u = *lu;
+            // (lane_unit_init: positive interval below 2^31, |timestamps| < 2^53, an exact relative test; k_lanes_regular: every interval)
+            screen = u.ok && !u.irregular && (e.kind == KIND_RELATIVE || e.kind == KIND_ABSOLUTE);
+            t0u = u.t0d;
+            delta = u.delta_d;
+            const double t_last = __fma_rn((double)(n_ - 1), delta, t0u);
+            const double t_max = fmax(fabs(t0u), fabs(t_last));
+            // 3.1 u * t_max / delta, rounded up generously (the quotient and the conversion are within 2^-23 of the real value)
+            kap = __double2float_rn(__dmul_rn(__ddiv_rn(t_max, delta), SCREEN_C_KAP)) * 1.000001f;
+            screen = screen && kap < 1e30f && (e.kind != KIND_RELATIVE || ex.rel_exact_ok) && e.dev >= 0.0 && e.dev < 1e30;
+        }
+    }
+
+    __device__ __forceinline__ void begin(uint32_t cur) {
+        ex.begin(cur);
+        exact_run = 0;
+    }
+    __device__ __forceinline__ bool irregular() const { return ex.irregular(); }
+    __device__ __forceinline__ uint32_t skip_rejected(uint32_t from, uint32_t chunk_end, uint32_t budget_end) {
+        return ex.skip_rejected(from, chunk_end, budget_end);
+    }
+
+    // ---- the exact engine, out of line (its registers must not weigh on the screened step; see fit_scalar_impl) ----
+    struct ExactResult {
+        FittedModel m;
+        uint32_t max_seen;
+        bool irregular, aborted;
+    };
+    static __device__ __noinline__ ExactResult fit_exact_impl(ErrorBound eb, const int64_t *ts, const float *values, uint32_t n, double *smem,
+                                                              uint32_t start, uint32_t budget_end, uint32_t max_seen, int64_t delta0, bool irregular) {
+        Exact f(eb, ts, values, n, smem);
+        f.max_seen = max_seen;
+        f.delta0 = delta0;
+        f.irregular_ = irregular;
+        ExactResult r;
+        r.m = f.fit(start, budget_end, r.aborted);
+        r.max_seen = f.max_seen;
+        r.irregular = f.irregular_;
+        return r;
+    }
+    __device__ __forceinline__ FittedModel fit_exact(uint32_t start, uint32_t budget_end, bool &aborted) {
+        MDB_SCREEN_COUNT(1);
+        const ExactResult r = fit_exact_impl(ex.eb, ex.ts, ex.values, ex.n, ex.smem, start, budget_end, ex.max_seen, ex.delta0, ex.irregular_);
+        ex.max_seen = r.max_seen;
+        ex.irregular_ = r.irregular;
+        aborted = r.aborted;
+        if (exact_run < 0xFFFFu) exact_run++;
+        return r.m;
+    }
+
+    __device__ __forceinline__ FittedModel fit(uint32_t start, uint32_t budget_end, bool &aborted) {
+        // after three exact fits in a row the data is of the kind the screen cannot decide (ties everywhere): stay with the
+        // exact engine, and look again every 16 fits
+        if (!screen || (exact_run >= 3 && (exact_run & 15u) != 0u)) return fit_exact(start, budget_end, aborted);
+        if (ex.eb.kind == KIND_RELATIVE) return fit_s<KIND_RELATIVE>(start, budget_end, aborted);
+        return fit_s<KIND_ABSOLUTE>(start, budget_end, aborted);
+    }
+
+    // tau_k of the header comment, in slope-per-index units: tau = tw (|upper bound| + |lower bound|) + tz with
+    //     tw = C_F32 + kap / k,   tz = C_F32 (|upper candidate| + |lower candidate|) + e_val / k + floor.
+    // * C_F32 = 2^-20: every f32 slope is within 2^-21.3 of its real value (conversion of the numerator 2^-24, 1 / k within
+    //   2^-22, product 2^-24), and the difference of two of them is rounded once more (2^-24 of itself).
+    // * The reference evaluates up = RN(RN(U t) + RN(v0 - RN(U t0))) (swing.rs:146-149).  With M = |U| max|t| and u = 2^-53 the
+    //   four roundings add up to |up - line| <= 1.0001 u (3 M + |v0| + |line|); RN(up +- dev) then compares with v like the real
+    //   number unless they are within u |v|; and the numerators hi / lo of the candidate differ from the real v +- dev - v0 by at
+    //   most u (2 |v| + 2 dev + |v0|).  With |line| <= |D| + dev + |v| (D: the real difference that is being tested) a decision is
+    //   the real-arithmetic one if |D| > 1.0001 u (3 M + 2 |v0| + 3 dev + 4 |v|).  M = (slope per index) * max|t| / delta:
+    //   kap = 3.1 u max|t| / delta (the slope's f32 image is within 2^-21 of it), and with dev <= |v| for a relative bound
+    //   e_val = 4.1 u (|v0| + dev_abs + 2 max|v|) covers the rest.
+    // * floor: products that underflow in f32 (values of magnitude 1e-30) have an absolute, not a relative, error.
+    static constexpr float SCREEN_C_F32 = 9.5367431640625e-07f; // 2^-20
+    static constexpr float SCREEN_C_VAL = 4.552e-16f;           // 4.1 * 2^-53
+    static constexpr double SCREEN_C_KAP = 3.4417e-16;          // 3.1 * 2^-53
+
+    template <typename T> static __device__ __forceinline__ T pick(const T (&a)[P], int j) {
+        T x = a[0];
+#pragma unroll
+        for (int i = 1; i < P; i++)
+            if (i == j) x = a[i];
+        return x;
+    }
+
+    // (double)ts[i] and (double)(ts[i] - ts[j]) of a regular unit, from the indices (lane_feed: both are exact)
+    __device__ __forceinline__ double time_of(uint32_t i) const { return __fma_rn((double)i, delta, t0u); }
+
+    // The candidate slope the reference stores when point `idx` tightens a bound (swing.rs:151-178 -> 323-340): the line
+    // through (t0, v0) and (t, v + dev) (upper) or (t, v - dev) (lower).  Every lane computes it (uniform).
+    template <int KIND> __device__ __forceinline__ double exact_candidate(uint32_t start, uint32_t idx, double v0, bool upper) const {
+        MDB_SCREEN_COUNT(4);
+        const double vd = (double)ex.values[idx];
+        const double dev = max_dev_k<KIND>(ex.eb, vd);
+        const double target = upper ? __dadd_rn(vd, dev) : __dsub_rn(vd, dev);
+        const double dt = __dmul_rn((double)(idx - start), delta);
+        return v0 == target ? 0.0 : __ddiv_rn(__dsub_rn(target, v0), dt);
+    }
+
+    template <int KIND> __device__ __forceinline__ FittedModel fit_s(uint32_t start, uint32_t budget_end, bool &aborted) {
+        const int lane = threadIdx.x & 31;
+        const int p0 = lane * P;
+        const uint32_t n = ex.n;
+        const float *values = ex.values;
+        const uint32_t limit = budget_end < n ? budget_end : n;
+        aborted = false;
+        MDB_SCREEN_COUNT(0);
+
+        // PMC-Mean state (pmc_mean.rs:31-53)
+        bool pmc_ok = true;
+        float p_mn = __uint_as_float(0x7fc00000u), p_mx = p_mn;
+        double p_sum = 0.0;
+        uint32_t p_len = 0;
+        int p_umax = 0, p_umin = 0x7fffffff; // largest / smallest non-zero |value| summed so far, as bit patterns
+        // Swing state (swing.rs:34-80): exact slopes, and their f32 images per index for the screen
+        bool swing_ok = true;
+        double v0 = 0.0;
+        uint32_t iu = 0, il = 0; // the points whose candidates are the bounds in force (valid from the second point on)
+        float Ub = __uint_as_float(0x7f800000u), Lb = __uint_as_float(0xff800000u);
+        float a0 = 0.0f; // |v0|
+        uint32_t s_len = 0;
+        int exact_points = 0;
+
+        uint32_t base = start;
+        float vn[P];
+#pragma unroll
+        for (int j = 0; j < P; j++) {
+            const uint32_t idx = start + (uint32_t)(p0 + j);
+            vn[j] = idx < limit ? values[idx] : 0.0f;
+        }
+
+        while (pmc_ok || swing_ok) {
+            if (base >= limit) { // out of points: the end of the data, or the budget of a speculative chain
+                aborted = limit < n;
+                break;
+            }
+            const int cnt = (int)((limit - base) < (uint32_t)STEP ? (limit - base) : (uint32_t)STEP);
+            float v[P];
+            double vd[P];
+            int umax = 0, umin = 0x7fffffff;
+#pragma unroll
+            for (int j = 0; j < P; j++) {
+                v[j] = vn[j];
+                const uint32_t idx = base + (uint32_t)(STEP + p0 + j);
+                vn[j] = idx < limit ? values[idx] : 0.0f;
+                vd[j] = (double)v[j];
+                const int bits = (int)(__float_as_uint(v[j]) & 0x7fffffffu);
+                if (p0 + j < cnt) {
+                    umax = max(umax, bits);
+                    if (bits != 0) umin = min(umin, bits);
+                }
+            }
+            umax = __reduce_max_sync(FULL_MASK, umax);
+            umin = __reduce_min_sync(FULL_MASK, umin);
+            // NaN, infinity, or a magnitude at which the f32 screen could overflow (1e37): the exact engine takes the fit
+            if (umax >= 0x7cf0bdc2) return fit_exact(start, budget_end, aborted);
+            const float vmax = __uint_as_float((uint32_t)umax);
+
+            // ------------------------------------------------------------------ PMC-Mean (exact: the scan form of WarpFitT::fit_k)
+            if (pmc_ok) {
+                float lmn[P], lmx[P];
+                double lS[P];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    lmn[j] = j ? rust_minf(lmn[j - 1], v[j]) : v[0];
+                    lmx[j] = j ? rust_maxf(lmx[j - 1], v[j]) : v[0];
+                    const double x = (p0 + j < cnt) ? vd[j] : 0.0;
+                    lS[j] = j ? __dadd_rn(lS[j - 1], x) : x;
+                }
+                // every addend is a multiple of 2^q and every partial sum is below 2^(emax + 1 + len_bits): all of them are exact
+                // iff that span fits into 53 bits, and then the order of the additions does not matter (mdb_fit_warp.cuh)
+                const int n_umax = max(p_umax, umax), n_umin = min(p_umin, umin);
+                const uint32_t total_len = p_len + (uint32_t)cnt;
+                const int len_bits = 32 - __clz((int)total_len);
+                const int emax = max(n_umax >> 23, 1) - 127, q = max(n_umin >> 23, 1) - 127 - 23;
+                const bool exact = n_umax == 0 || (emax + 1 + len_bits - q) <= 53;
+                if (!exact) return fit_exact(start, budget_end, aborted);
+                float amn = lmn[P - 1], amx = lmx[P - 1];
+                double aS = lS[P - 1];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const float omn = __shfl_up_sync(FULL_MASK, amn, d), omx = __shfl_up_sync(FULL_MASK, amx, d);
+                    const double oS = __shfl_up_sync(FULL_MASK, aS, d);
+                    if (lane >= d) {
+                        amn = rust_minf(omn, amn);
+                        amx = rust_maxf(omx, amx);
+                        aS = __dadd_rn(oS, aS);
+                    }
+                }
+                float pmn = __shfl_up_sync(FULL_MASK, amn, 1), pmx = __shfl_up_sync(FULL_MASK, amx, 1);
+                double pS = __shfl_up_sync(FULL_MASK, aS, 1);
+                if (lane == 0) { pmn = p_mn; pmx = p_mx; pS = p_sum; }
+                else { pmn = rust_minf(p_mn, pmn); pmx = rust_maxf(p_mx, pmx); pS = __dadd_rn(p_sum, pS); }
+                float mn[P], mx[P];
+                double S[P];
+                int fail_p = IDX_INF;
+#pragma unroll
+                for (int j = P - 1; j >= 0; j--) {
+                    mn[j] = rust_minf(pmn, lmn[j]);
+                    mx[j] = rust_maxf(pmx, lmx[j]);
+                    S[j] = __dadd_rn(pS, lS[j]);
+                    const uint32_t len_l = p_len + (uint32_t)(p0 + j) + 1;
+                    const float avg = __double2float_rn(ddiv_fast_in_range(S[j], (double)len_l)); // pmc_mean.rs:63
+                    bool ok;
+                    if (KIND == KIND_RELATIVE) {
+                        ok = ex.within_relative(mn[j], avg) & ex.within_relative(mx[j], avg);
+                    } else {
+                        bool no_division_here = false;
+                        ok = within_bound_k<KIND, true>(ex.eb, mn[j], avg, no_division_here) & within_bound_k<KIND, true>(ex.eb, mx[j], avg, no_division_here);
+                    }
+                    if ((p0 + j < cnt) && !ok) fail_p = p0 + j;
+                }
+                fail_p = __reduce_min_sync(FULL_MASK, fail_p);
+                const int accepted = fail_p < cnt ? fail_p : cnt;
+                if (fail_p < cnt) pmc_ok = false;
+                if (accepted > 0) {
+                    const int owner = (accepted - 1) / P, jj = (accepted - 1) % P;
+                    float smn = mn[0], smx = mx[0];
+                    double sS = S[0];
+#pragma unroll
+                    for (int j = 1; j < P; j++)
+                        if (j == jj) { smn = mn[j]; smx = mx[j]; sS = S[j]; }
+                    p_mn = __shfl_sync(FULL_MASK, smn, owner);
+                    p_mx = __shfl_sync(FULL_MASK, smx, owner);
+                    p_sum = __shfl_sync(FULL_MASK, sS, owner);
+                    p_len += (uint32_t)accepted;
+                }
+                p_umax = n_umax;
+                p_umin = n_umin;
+            }
+
+            // ------------------------------------------------------------------ Swing (screened)
+            if (swing_ok) {
+                int lo = 0; // first point of the step not yet processed
+                const uint32_t kb = base - start; // points of the fit before this step
+                if (s_len == 0) { // swing.rs:106-112: the first point is stored
+                    v0 = __shfl_sync(FULL_MASK, vd[0], 0);
+                    a0 = fabsf(__shfl_sync(FULL_MASK, v[0], 0));
+                    s_len = 1;
+                    lo = 1;
+                }
+                // candidate slopes per index: the reference's own numerators (swing.rs:151-178 -> 323-340) over k, in f32;
+                // tolerance(): tau = tw * (|upper bound| + |lower bound|) + tz
+                const float dev_abs = KIND == KIND_ABSOLUTE ? __fmul_rn(__double2float_rn(ex.eb.dev), 1.000001f) : 0.0f;
+                const float e_val = __fmul_rn(__fadd_rn(__fadd_rn(a0, dev_abs), __fadd_rn(vmax, vmax)), SCREEN_C_VAL);
+                float su[P], sl[P], tw[P], tz[P];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    const double dev = max_dev_k<KIND>(ex.eb, vd[j]);
+                    const double hi = __dsub_rn(__dadd_rn(vd[j], dev), v0), lw = __dsub_rn(__dsub_rn(vd[j], dev), v0);
+                    const float rk = rcp_approx_f32((float)(kb + (uint32_t)(p0 + j)));
+                    su[j] = __fmul_rn(__double2float_rn(hi), rk);
+                    sl[j] = __fmul_rn(__double2float_rn(lw), rk);
+                    tw[j] = mdb_fmaf(rk, kap, SCREEN_C_F32);
+                    tz[j] = mdb_fmaf(__fadd_rn(fabsf(su[j]), fabsf(sl[j])), SCREEN_C_F32, mdb_fmaf(rk, e_val, 1e-37f));
+                }
+                const float inf = __uint_as_float(0x7f800000u);
+
+                while (lo < cnt && swing_ok) {
+                    MDB_SCREEN_COUNT(2);
+                    const bool has_state = s_len >= 2; // bounds exist (swing.rs:126-143 sets them at the second point)
+                    // running minimum of the upper / maximum of the lower candidates over the points [lo, cnt)
+                    float am = inf, ax = -inf;
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        const bool in = (p0 + j >= lo) && (p0 + j < cnt);
+                        am = fminf(am, in ? su[j] : inf);
+                        ax = fmaxf(ax, in ? sl[j] : -inf);
+                    }
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        const float om = __shfl_up_sync(FULL_MASK, am, d), ox = __shfl_up_sync(FULL_MASK, ax, d);
+                        if (lane >= d) {
+                            am = fminf(am, om);
+                            ax = fmaxf(ax, ox);
+                        }
+                    }
+                    float ru = __shfl_up_sync(FULL_MASK, am, 1), rl = __shfl_up_sync(FULL_MASK, ax, 1);
+                    if (lane == 0) { ru = inf; rl = -inf; }
+                    if (has_state) { ru = fminf(ru, Ub); rl = fmaxf(rl, Lb); }
+                    // this lane's points against the bounds the screen assumes before each of them
+                    unsigned rej_m = 0, unc_m = 0; // this lane's points that are certainly rejected / doubtful
+                    unsigned rec_u = 0, rec_l = 0; // ... at which the screen tightens the upper / the lower bound
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        const int p = p0 + j;
+                        const bool in = p >= lo && p < cnt;
+                        const bool check = in && (has_state || p > lo); // (the second point of a fit sets both bounds untested)
+                        const float tau = mdb_fmaf(tw[j], __fadd_rn(fabsf(ru), fabsf(rl)), tz[j]);
+                        const float a = __fsub_rn(sl[j], ru), b = __fsub_rn(rl, su[j]); // > 0: rejected (above the upper / below the lower line)
+                        const float c = __fsub_rn(ru, su[j]), d = __fsub_rn(sl[j], rl); // > 0: tightens the upper / the lower bound
+                        const bool certain = fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) > tau;
+                        const bool rej = fmaxf(a, b) > 0.0f;
+                        if (check && !certain) unc_m |= 1u << j;
+                        if (check && certain && rej) rej_m |= 1u << j;
+                        // (what follows a reject or a doubtful point is discarded below: only points before `stop` count)
+                        if (in && (!check || c > 0.0f)) { ru = su[j]; rec_u |= 1u << j; }
+                        if (in && (!check || d > 0.0f)) { rl = sl[j]; rec_l |= 1u << j; }
+                    }
+                    const int first_rej = __reduce_min_sync(FULL_MASK, rej_m ? p0 + __ffs((int)rej_m) - 1 : IDX_INF);
+                    const int first_unc = __reduce_min_sync(FULL_MASK, unc_m ? p0 + __ffs((int)unc_m) - 1 : IDX_INF);
+                    const int stop = min(min(first_rej, first_unc), cnt); // the points [lo, stop) are accepted as the screen assumed
+                    // the last tightening candidate of each bound within [lo, stop): its index (the exact slope is computed
+                    // when it is needed: for a doubtful point, or when the fit ends) and its f32 image
+                    {
+                        const int keep = stop - p0; // this lane's points before `stop`: j < keep
+                        const unsigned km = keep >= P ? (1u << P) - 1u : (keep > 0 ? (1u << keep) - 1u : 0u);
+                        const unsigned mu = rec_u & km, ml = rec_l & km;
+                        const int gu = __reduce_max_sync(FULL_MASK, mu ? p0 + 31 - __clz((int)mu) : -1);
+                        const int gl = __reduce_max_sync(FULL_MASK, ml ? p0 + 31 - __clz((int)ml) : -1);
+                        if (gu >= 0) {
+                            iu = base + (uint32_t)gu;
+                            Ub = __shfl_sync(FULL_MASK, pick(su, gu % P), gu / P);
+                        }
+                        if (gl >= 0) {
+                            il = base + (uint32_t)gl;
+                            Lb = __shfl_sync(FULL_MASK, pick(sl, gl % P), gl / P);
+                        }
+                    }
+                    s_len += (uint32_t)(stop - lo);
+                    lo = stop;
+                    if (stop < cnt) {
+                        if (first_rej <= first_unc) {
+                            swing_ok = false; // certainly rejected
+                        } else {
+                            // a doubtful point: the reference's own tests (swing.rs:146-178) on the exact bounds
+                            MDB_SCREEN_COUNT(3);
+                            if (++exact_points > MDB_SCREEN_MAX_EXACT_POINTS) return fit_exact(start, budget_end, aborted);
+                            const uint32_t idx = base + (uint32_t)stop;
+                            const double us = exact_candidate<KIND>(start, iu, v0, true), ls = exact_candidate<KIND>(start, il, v0, false);
+                            const double t0d = time_of(start);
+                            const double vdp = (double)values[idx], tdp = time_of(idx);
+                            const double dvp = max_dev_k<KIND>(ex.eb, vdp);
+                            const double up = __dadd_rn(__dmul_rn(us, tdp), icpt_of(us, v0, t0d));
+                            const double lw = __dadd_rn(__dmul_rn(ls, tdp), icpt_of(ls, v0, t0d));
+                            if ((__dadd_rn(up, dvp) < vdp) | (__dsub_rn(lw, dvp) > vdp)) {
+                                swing_ok = false;
+                            } else {
+                                if (__dsub_rn(up, dvp) > vdp) {
+                                    iu = idx;
+                                    Ub = __shfl_sync(FULL_MASK, pick(su, stop % P), stop / P);
+                                }
+                                if (__dadd_rn(lw, dvp) < vdp) {
+                                    il = idx;
+                                    Lb = __shfl_sync(FULL_MASK, pick(sl, stop % P), stop / P);
+                                }
+                                s_len += 1;
+                                lo = stop + 1;
+                            }
+                        }
+                    }
+                }
+            }
+            base += (uint32_t)cnt; // cnt < STEP only when `limit` cut the step short
+        }
+
+        FittedModel m;
+        m.start_index = start;
+        m.pending = 0;
+        m.pad = 0;
+        m.lower_slope = m.upper_slope = 0.0;
+        exact_run = 0;
+        if (aborted) {
+            m.end_index = start;
+            m.min_value = m.max_value = m.model_last_value = 0.0f;
+            m.bytes_per_value = 1e30f;
+            m.model_type_id = PMC_MEAN;
+            m.values_len = 0;
+            return m;
+        }
+        const float pmc_bpv = __fdiv_rn(29.0f, (float)p_len);   // pmc_mean.rs:83-87
+        const float swing_bpv = __fdiv_rn(30.0f, (float)s_len); // swing.rs:236-239
+        if (swing_bpv < pmc_bpv) {
+            // boundaries and bounds are final; Swing::model (swing.rs:246-259) is completed by swing_finish
+            m.model_type_id = SWING;
+            m.end_index = start + s_len - 1;
+            m.min_value = m.max_value = m.model_last_value = 0.0f;
+            m.values_len = 0;
+            m.bytes_per_value = swing_bpv;
+            m.pending = 1;
+            m.lower_slope = s_len >= 2 ? exact_candidate<KIND>(start, il, v0, false) : (double)__uint_as_float(0x7fc00000u);
+            m.upper_slope = s_len >= 2 ? exact_candidate<KIND>(start, iu, v0, true) : (double)__uint_as_float(0x7fc00000u);
+        } else {
+            const float value = canonical_nan(__double2float_rn(__ddiv_rn(p_sum, (double)p_len))); // pmc_mean.rs:91-93
+            m.model_type_id = PMC_MEAN;
+            m.end_index = start + p_len - 1;
+            m.min_value = m.max_value = m.model_last_value = value;
+            m.values_len = 0;
+            m.bytes_per_value = pmc_bpv;
+        }
+        return m;
+    }
+};
+
+} // namespace mdb
+
+#endif // __CUDACC__ || MDB_WARP_EMU

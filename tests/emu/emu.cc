@@ -20,6 +20,7 @@
 #include "warp_emu.h"
 #include "../../modelardb_rs_b200/csrc/mdb_fit_warp.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_fit_lanes.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_fit_screen.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_macaque_warp.cuh"
 
 using namespace mdb;
@@ -34,8 +35,31 @@ struct EmuSegments {
 
 // One chain of one chunk with the chosen engine: 1 = the one-thread fit, 2 = the warp-cooperative fit (every lane runs
 // spec_chain on its own copy of the chunk state, as the lanes of k_spec_chain_warp / k_spec_async do; lane 0's copy is kept).
+using WarpFitScreen = WarpFitScreenT<MDB_FIT_POINTS_PER_LANE>;
+// k_lanes_units + k_lanes_regular for one unit: what the screened engine (mdb_fit_screen.cuh) is told about it
+static LaneUnit emu_lane_unit(const ErrorBound &eb, const int64_t *uts, uint32_t n) {
+    LaneUnit lu = lane_unit_init(uts, n, eb);
+    if (lu.ok)
+        for (uint32_t i = 0; i < n; i++)
+            if (uts[i] != uts[0] + (int64_t)i * (uts[1] - uts[0])) { lu.irregular = 1; break; }
+    return lu;
+}
 static void emu_run_chain(int engine, const ErrorBound &eb, const int64_t *uts, const float *uval, uint32_t n, uint32_t chunk_end,
                           uint32_t budget, ChunkState &st, FittedModel *lists, uint32_t cap) {
+    if (engine == 5) {
+        std::vector<double> smem(WarpFitScreen::SMEM_DOUBLES);
+        const LaneUnit lu = emu_lane_unit(eb, uts, n);
+        const ChunkState before = st;
+        ChunkState after = st;
+        warp_emu::run([&](int lane) {
+            ChunkState mine = before;
+            WarpFitScreen fitter(eb, uts, uval, n, smem.data(), &lu);
+            spec_chain(fitter, (uint32_t)lane, 32u, n, chunk_end, budget, mine, lists, cap);
+            if (lane == 0) after = mine;
+        });
+        st = after;
+        return;
+    }
     if (engine != 2) {
         ScalarFit fitter(eb, uts, uval, n);
         spec_chain(fitter, 0u, 1u, n, chunk_end, budget, st, lists, cap);
@@ -283,6 +307,7 @@ void emu_set_lane_rounds(uint32_t rounds) { g_emu_lane_rounds = rounds; }
 uint64_t emu_lane_reruns() { return g_emu_lane_reruns; }
 void emu_lane_counters(uint64_t *chunks, uint64_t *bailed) { *chunks = g_emu_lane_chunks; *bailed = g_emu_lane_bailed; }
 uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
+void emu_screen_counters(uint64_t *out8, int clear) { for (int i = 0; i < 8; i++) { out8[i] = g_screen_counters[i]; if (clear) g_screen_counters[i] = 0; } }
 
 // mdbcu_debug_fit_models on the host: fit_next_model at each start with either engine (records of 40 bytes).
 struct EmuDebugFit {
@@ -297,7 +322,17 @@ void emu_fit_models(const int64_t *ts, const float *values, uint32_t n, uint8_t 
     for (uint32_t k = 0; k < n_starts; k++) {
         FittedModel m;
         bool aborted = false, irregular = false;
-        if (engine == 2) {
+        if (engine == 5) {
+            const LaneUnit lu = emu_lane_unit(eb, ts, n);
+            warp_emu::run([&](int lane) {
+                WarpFitScreen f(eb, ts, values, n, smem.data(), &lu);
+                f.begin(starts[k]);
+                bool ab = false;
+                FittedModel mm = f.fit(starts[k], budget_ends[k], ab);
+                if (!ab && mm.pending) swing_finish(mm, ts, values);
+                if (lane == 0) { m = mm; aborted = ab; irregular = f.irregular(); }
+            });
+        } else if (engine == 2) {
             warp_emu::run([&](int lane) {
                 WarpFit f(eb, ts, values, n, smem.data());
                 f.begin(starts[k]);

@@ -45,6 +45,8 @@ def lib():
     L.emu_lane_counters.argtypes = [vp, vp]
     L.emu_lane_counters.restype = None
     L.emu_division_mismatches.restype = u64
+    L.emu_screen_counters.argtypes = [vp, C.c_int]
+    L.emu_screen_counters.restype = None
     L.emu_fit_models.argtypes = [vp, vp, C.c_uint32, C.c_uint8, C.c_float, C.c_int, vp, vp, C.c_uint32, vp]
     L.emu_fit_models.restype = None
     L.emu_segments_len.argtypes = [vp]
@@ -109,6 +111,14 @@ def fit_models(ts, values, eb, engine, starts, budget_ends, library=None):
 def division_mismatches() -> int:
     """Emulated fast-path quotients (ddiv_fast*) that differed from the host's a / b so far."""
     return int(lib().emu_division_mismatches())
+
+
+def screen_counters(clear=True):
+    """Event counters of the screened engine (csrc/mdb_fit_screen.cuh): fits, fits the exact engine took, passes, exact point
+    evaluations, exact candidates."""
+    out = (C.c_uint64 * 8)()
+    lib().emu_screen_counters(out, 1 if clear else 0)
+    return dict(zip(("fits", "exact_fits", "passes", "exact_points", "exact_candidates"), list(out)[:5]))
 
 
 def lane_counters():

@@ -99,7 +99,7 @@ def test_device_space_matches_host_space(oracle, ctx, case):
     seg.free()
 
 
-@pytest.mark.parametrize("engine", [1, 2, 3, 4], ids=["thread-per-chain", "warp-per-chain", "warp-per-chain-async", "lane-per-chain"])
+@pytest.mark.parametrize("engine", [1, 2, 3, 4, 5], ids=["thread-per-chain", "warp-per-chain", "warp-per-chain-async", "lane-per-chain", "screened"])
 @pytest.mark.parametrize("chunk_len", [8, 64, 1000, 4096])
 def test_parallel_segmentation_is_independent_of_chunk_length(oracle, chunk_len, engine):
     """The chunked, speculative, fixpoint-stitched segmentation (csrc/mdb_compress.cuh) must yield exactly
