@@ -406,10 +406,10 @@ __global__ void __launch_bounds__(128) k_sched_kick(const uint64_t *__restrict__
 // the queue empty EXITS: every later push is made by a worker that is still alive and pops right afterwards, so
 // nothing is ever stranded, and the SM slots of a draining kernel become free for other streams.
 // The screened engine (mdb_fit_screen.cuh) needs far fewer registers per step than the exact one, whose code it only calls
-// on the rare fits it cannot decide (that code spills under this bound, which is the price of those fits): five blocks per SM.
+// on the rare fits it cannot decide (that code spills under this bound, which is the price of those fits): four blocks per SM (measured: 13.2 ms against 15.5 ms with five, whose 96 registers make the step itself spill).
 using WarpFitScreen = WarpFitScreenT<MDB_FIT_POINTS_PER_LANE>;
 #ifndef MDB_SCREEN_MIN_BLOCKS
-#define MDB_SCREEN_MIN_BLOCKS 5
+#define MDB_SCREEN_MIN_BLOCKS 4
 #endif
 // info: the units as the pre-pass (k_lanes_units, k_lanes_regular) saw them, or nullptr (only the screened engine looks)
 template <typename Fit, int MIN_BLOCKS>

@@ -54,7 +54,7 @@ __device__ unsigned long long g_screen_counters[8];
 #endif
 __device__ __forceinline__ float rcp_approx_f32(float x) {
     float r;
-    asm("rcp.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); // MUFU.RCP: at most 1 ulp off
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); // one MUFU.RCP, at most 1 ulp off (the arguments are point counts: no subnormals)
     return r;
 }
 __device__ __forceinline__ float mdb_fmaf(float a, float b, float c) { return __fmaf_rn(a, b, c); }
@@ -165,13 +165,15 @@ template <int P> struct WarpFitScreenT {
 
     // The candidate slope the reference stores when point `idx` tightens a bound (swing.rs:151-178 -> 323-340): the line
     // through (t0, v0) and (t, v + dev) (upper) or (t, v - dev) (lower).  Every lane computes it (uniform).
-    template <int KIND> __device__ __forceinline__ double exact_candidate(uint32_t start, uint32_t idx, double v0, bool upper) const {
+    // k: the point's index within the fit (> 0), v: its value.  The operands of the division are in the range in which
+    // ddiv_fast_in_range is the correctly rounded quotient (mdb_fit_warp.cuh: finite f32 values, a time difference >= 1).
+    template <int KIND> __device__ __forceinline__ double exact_candidate(uint32_t k, float v, double v0, bool upper) const {
         MDB_SCREEN_COUNT(4);
-        const double vd = (double)ex.values[idx];
+        const double vd = (double)v;
         const double dev = max_dev_k<KIND>(ex.eb, vd);
         const double target = upper ? __dadd_rn(vd, dev) : __dsub_rn(vd, dev);
-        const double dt = __dmul_rn((double)(idx - start), delta);
-        return v0 == target ? 0.0 : __ddiv_rn(__dsub_rn(target, v0), dt);
+        const double dt = __dmul_rn((double)k, delta);
+        return v0 == target ? 0.0 : ddiv_fast_in_range(__dsub_rn(target, v0), dt);
     }
 
     template <int KIND> __device__ __forceinline__ FittedModel fit_s(uint32_t start, uint32_t budget_end, bool &aborted) {
@@ -188,15 +190,17 @@ template <int P> struct WarpFitScreenT {
         float p_mn = __uint_as_float(0x7fc00000u), p_mx = p_mn;
         double p_sum = 0.0;
         uint32_t p_len = 0;
-        int p_umax = 0, p_umin = 0x7fffffff; // largest / smallest non-zero |value| summed so far, as bit patterns
+        unsigned p_umax = 0u, p_umin1 = 0xffffffffu; // largest |value| summed so far / smallest non-zero one minus one, as bit patterns
         // Swing state (swing.rs:34-80): exact slopes, and their f32 images per index for the screen
         bool swing_ok = true;
         double v0 = 0.0;
-        uint32_t iu = 0, il = 0; // the points whose candidates are the bounds in force (valid from the second point on)
+        uint32_t iu = 1, il = 1; // the points (index within the fit) whose candidates are the bounds in force (valid from the second point on)
+        float vu = 0.0f, vl = 0.0f; // ... and their values
         float Ub = __uint_as_float(0x7f800000u), Lb = __uint_as_float(0xff800000u);
         float a0 = 0.0f; // |v0|
         uint32_t s_len = 0;
         int exact_points = 0;
+        bool calm = false; // the previous step moved no bound (then a quiet step is likely)
 
         uint32_t base = start;
         float vn[P];
@@ -214,24 +218,23 @@ template <int P> struct WarpFitScreenT {
             const int cnt = (int)((limit - base) < (uint32_t)STEP ? (limit - base) : (uint32_t)STEP);
             float v[P];
             double vd[P];
-            int umax = 0, umin = 0x7fffffff;
+            // largest |value| of the step as a bit pattern, and (for PMC-Mean's sums) the smallest non-zero one minus one: slots past
+            // `limit` hold 0.0f, which is neutral for both (0 - 1 wraps to the largest unsigned number)
+            unsigned umax = 0u, umin1 = 0xffffffffu;
 #pragma unroll
             for (int j = 0; j < P; j++) {
                 v[j] = vn[j];
                 const uint32_t idx = base + (uint32_t)(STEP + p0 + j);
                 vn[j] = idx < limit ? values[idx] : 0.0f;
                 vd[j] = (double)v[j];
-                const int bits = (int)(__float_as_uint(v[j]) & 0x7fffffffu);
-                if (p0 + j < cnt) {
-                    umax = max(umax, bits);
-                    if (bits != 0) umin = min(umin, bits);
-                }
+                const unsigned bits = __float_as_uint(v[j]) & 0x7fffffffu;
+                umax = max(umax, bits);
+                umin1 = min(umin1, bits - 1u);
             }
             umax = __reduce_max_sync(FULL_MASK, umax);
-            umin = __reduce_min_sync(FULL_MASK, umin);
-            // NaN, infinity, or a magnitude at which the f32 screen could overflow (1e37): the exact engine takes the fit
-            if (umax >= 0x7cf0bdc2) return fit_exact(start, budget_end, aborted);
-            const float vmax = __uint_as_float((uint32_t)umax);
+            // NaN, infinity, or a magnitude (1e28) at which the f32 screen could overflow: the exact engine takes the fit
+            if (umax >= 0x6e013f39u) return fit_exact(start, budget_end, aborted);
+            const float vmax = __uint_as_float(umax);
 
             // ------------------------------------------------------------------ PMC-Mean (exact: the scan form of WarpFitT::fit_k)
             if (pmc_ok) {
@@ -246,11 +249,11 @@ template <int P> struct WarpFitScreenT {
                 }
                 // every addend is a multiple of 2^q and every partial sum is below 2^(emax + 1 + len_bits): all of them are exact
                 // iff that span fits into 53 bits, and then the order of the additions does not matter (mdb_fit_warp.cuh)
-                const int n_umax = max(p_umax, umax), n_umin = min(p_umin, umin);
+                const unsigned n_umax = max(p_umax, umax), n_umin1 = min(p_umin1, __reduce_min_sync(FULL_MASK, umin1));
                 const uint32_t total_len = p_len + (uint32_t)cnt;
                 const int len_bits = 32 - __clz((int)total_len);
-                const int emax = max(n_umax >> 23, 1) - 127, q = max(n_umin >> 23, 1) - 127 - 23;
-                const bool exact = n_umax == 0 || (emax + 1 + len_bits - q) <= 53;
+                const int emax = max((int)(n_umax >> 23), 1) - 127, q = max((int)((n_umin1 + 1u) >> 23), 1) - 127 - 23;
+                const bool exact = n_umax == 0u || (emax + 1 + len_bits - q) <= 53;
                 if (!exact) return fit_exact(start, budget_end, aborted);
                 float amn = lmn[P - 1], amx = lmx[P - 1];
                 double aS = lS[P - 1];
@@ -303,7 +306,7 @@ template <int P> struct WarpFitScreenT {
                     p_len += (uint32_t)accepted;
                 }
                 p_umax = n_umax;
-                p_umin = n_umin;
+                p_umin1 = n_umin1;
             }
 
             // ------------------------------------------------------------------ Swing (screened)
@@ -316,113 +319,160 @@ template <int P> struct WarpFitScreenT {
                     s_len = 1;
                     lo = 1;
                 }
-                // candidate slopes per index: the reference's own numerators (swing.rs:151-178 -> 323-340) over k, in f32;
-                // tolerance(): tau = tw * (|upper bound| + |lower bound|) + tz
                 const float dev_abs = KIND == KIND_ABSOLUTE ? __fmul_rn(__double2float_rn(ex.eb.dev), 1.000001f) : 0.0f;
                 const float e_val = __fmul_rn(__fadd_rn(__fadd_rn(a0, dev_abs), __fadd_rn(vmax, vmax)), SCREEN_C_VAL);
-                float su[P], sl[P], tw[P], tz[P];
-#pragma unroll
-                for (int j = 0; j < P; j++) {
-                    const double dev = max_dev_k<KIND>(ex.eb, vd[j]);
-                    const double hi = __dsub_rn(__dadd_rn(vd[j], dev), v0), lw = __dsub_rn(__dsub_rn(vd[j], dev), v0);
-                    const float rk = rcp_approx_f32((float)(kb + (uint32_t)(p0 + j)));
-                    su[j] = __fmul_rn(__double2float_rn(hi), rk);
-                    sl[j] = __fmul_rn(__double2float_rn(lw), rk);
-                    tw[j] = mdb_fmaf(rk, kap, SCREEN_C_F32);
-                    tz[j] = mdb_fmaf(__fadd_rn(fabsf(su[j]), fabsf(sl[j])), SCREEN_C_F32, mdb_fmaf(rk, e_val, 1e-37f));
-                }
                 const float inf = __uint_as_float(0x7f800000u);
+                // Quiet step.  Inside a long model most steps change nothing: every point lies strictly inside the cone, i.e.
+                // its candidate interval [lo_k / k, hi_k / k] contains [L, U] with room to spare -- then it neither rejects nor
+                // tightens.  In value space that is hi_k - k U > T and k L - lo_k > T, tested in plain f32 (no division, no
+                // scan) against one tolerance for the whole step: T = k tau_k of tolerance() at the step's largest k, plus the
+                // f32 errors of this test itself (hi_k, lo_k within 2^-22 (|v0| + |v| + dev), k U within 2^-24 of itself).  The two
+                // reject tests follow: lo_k < k L - T <= k U - T needs U >= L, which holds for the f32 images (checked) and
+                // therefore for the exact bounds up to 2^-21 (|U| + |L|), which T also covers.
+                // Tried after a step in which nothing happened; a step that is not quiet takes the normal path below.
+                bool quiet = false;
+                if (calm && lo == 0 && s_len >= 2 && cnt == STEP && Ub >= Lb) {
+                    const float kmaxf = (float)(kb + (uint32_t)STEP);
+                    const float w_b = __fadd_rn(fabsf(Ub), fabsf(Lb));
+                    const float a_v = __fadd_rn(__fadd_rn(a0, vmax), KIND == KIND_ABSOLUTE ? dev_abs : vmax);
+                    const float t_q = __fmul_rn(__fadd_rn(mdb_fmaf(w_b, mdb_fmaf(kmaxf, 1.6e-6f, kap), mdb_fmaf(a_v, 2.4e-6f, e_val)), __fmul_rn(kmaxf, 1e-37f)), 1.000001f);
+                    const float v0f = __double2float_rn(v0), c32 = __double2float_rn(ex.eb.dev);
+                    bool busy = false;
+#pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        const float w = __fsub_rn(v[j], v0f);
+                        const float dv = KIND == KIND_RELATIVE ? __fmul_rn(fabsf(v[j]), c32) : c32;
+                        const float kf = (float)(kb + (uint32_t)(p0 + j));
+                        const float x = mdb_fmaf(-kf, Ub, __fadd_rn(w, dv)), y = mdb_fmaf(kf, Lb, -__fsub_rn(w, dv));
+                        busy |= !(fminf(x, y) > t_q);
+                    }
+                    quiet = !__any_sync(FULL_MASK, busy);
+                    if (quiet) {
+                        MDB_SCREEN_COUNT(5);
+                        s_len += (uint32_t)cnt;
+                    }
+                }
+                if (!quiet) {
+                    calm = true; // until a bound moves or the accepted stretch ends inside the step
+                    // candidate slopes per index: the reference's own numerators (swing.rs:151-178 -> 323-340) over k, in f32;
+                    // tolerance(): tau = tw * (|upper bound| + |lower bound|) + tz.  Slots that are not points of this fit's step
+                    // (the fit's first point, slots past the data) become NEUTRAL candidates (+inf / -inf): they never reject,
+                    // never tighten, and all four differences are infinite, so the loops below need no masks.
+                    float su[P], sl[P], tw[P], tz[P];
+    #pragma unroll
+                    for (int j = 0; j < P; j++) {
+                        const double dev = max_dev_k<KIND>(ex.eb, vd[j]);
+                        const double hi = __dsub_rn(__dadd_rn(vd[j], dev), v0), lw = __dsub_rn(__dsub_rn(vd[j], dev), v0);
+                        const uint32_t k = kb + (uint32_t)(p0 + j);
+                        const float rk = k ? rcp_approx_f32((float)k) : 0.0f;
+                        const float u = __fmul_rn(__double2float_rn(hi), rk), l = __fmul_rn(__double2float_rn(lw), rk);
+                        tw[j] = mdb_fmaf(rk, kap, SCREEN_C_F32);
+                        tz[j] = mdb_fmaf(__fadd_rn(fabsf(u), fabsf(l)), SCREEN_C_F32, mdb_fmaf(rk, e_val, 1e-37f));
+                        const bool real = (p0 + j >= lo) && (p0 + j < cnt);
+                        su[j] = real ? u : inf;
+                        sl[j] = real ? l : -inf;
+                    }
 
-                while (lo < cnt && swing_ok) {
-                    MDB_SCREEN_COUNT(2);
-                    const bool has_state = s_len >= 2; // bounds exist (swing.rs:126-143 sets them at the second point)
-                    // running minimum of the upper / maximum of the lower candidates over the points [lo, cnt)
-                    float am = inf, ax = -inf;
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        const bool in = (p0 + j >= lo) && (p0 + j < cnt);
-                        am = fminf(am, in ? su[j] : inf);
-                        ax = fmaxf(ax, in ? sl[j] : -inf);
-                    }
-#pragma unroll
-                    for (int d = 1; d < 32; d <<= 1) {
-                        const float om = __shfl_up_sync(FULL_MASK, am, d), ox = __shfl_up_sync(FULL_MASK, ax, d);
-                        if (lane >= d) {
-                            am = fminf(am, om);
-                            ax = fmaxf(ax, ox);
+                    while (lo < cnt && swing_ok) {
+                        MDB_SCREEN_COUNT(2);
+                        // running minimum of the upper / maximum of the lower candidates over the step
+                        float am = fminf(su[0], su[1]), ax = fmaxf(sl[0], sl[1]);
+    #pragma unroll
+                        for (int j = 2; j < P; j++) {
+                            am = fminf(am, su[j]);
+                            ax = fmaxf(ax, sl[j]);
                         }
-                    }
-                    float ru = __shfl_up_sync(FULL_MASK, am, 1), rl = __shfl_up_sync(FULL_MASK, ax, 1);
-                    if (lane == 0) { ru = inf; rl = -inf; }
-                    if (has_state) { ru = fminf(ru, Ub); rl = fmaxf(rl, Lb); }
-                    // this lane's points against the bounds the screen assumes before each of them
-                    unsigned rej_m = 0, unc_m = 0; // this lane's points that are certainly rejected / doubtful
-                    unsigned rec_u = 0, rec_l = 0; // ... at which the screen tightens the upper / the lower bound
-#pragma unroll
-                    for (int j = 0; j < P; j++) {
-                        const int p = p0 + j;
-                        const bool in = p >= lo && p < cnt;
-                        const bool check = in && (has_state || p > lo); // (the second point of a fit sets both bounds untested)
-                        const float tau = mdb_fmaf(tw[j], __fadd_rn(fabsf(ru), fabsf(rl)), tz[j]);
-                        const float a = __fsub_rn(sl[j], ru), b = __fsub_rn(rl, su[j]); // > 0: rejected (above the upper / below the lower line)
-                        const float c = __fsub_rn(ru, su[j]), d = __fsub_rn(sl[j], rl); // > 0: tightens the upper / the lower bound
-                        const bool certain = fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) > tau;
-                        const bool rej = fmaxf(a, b) > 0.0f;
-                        if (check && !certain) unc_m |= 1u << j;
-                        if (check && certain && rej) rej_m |= 1u << j;
-                        // (what follows a reject or a doubtful point is discarded below: only points before `stop` count)
-                        if (in && (!check || c > 0.0f)) { ru = su[j]; rec_u |= 1u << j; }
-                        if (in && (!check || d > 0.0f)) { rl = sl[j]; rec_l |= 1u << j; }
-                    }
-                    const int first_rej = __reduce_min_sync(FULL_MASK, rej_m ? p0 + __ffs((int)rej_m) - 1 : IDX_INF);
-                    const int first_unc = __reduce_min_sync(FULL_MASK, unc_m ? p0 + __ffs((int)unc_m) - 1 : IDX_INF);
-                    const int stop = min(min(first_rej, first_unc), cnt); // the points [lo, stop) are accepted as the screen assumed
-                    // the last tightening candidate of each bound within [lo, stop): its index (the exact slope is computed
-                    // when it is needed: for a doubtful point, or when the fit ends) and its f32 image
-                    {
-                        const int keep = stop - p0; // this lane's points before `stop`: j < keep
-                        const unsigned km = keep >= P ? (1u << P) - 1u : (keep > 0 ? (1u << keep) - 1u : 0u);
-                        const unsigned mu = rec_u & km, ml = rec_l & km;
-                        const int gu = __reduce_max_sync(FULL_MASK, mu ? p0 + 31 - __clz((int)mu) : -1);
-                        const int gl = __reduce_max_sync(FULL_MASK, ml ? p0 + 31 - __clz((int)ml) : -1);
-                        if (gu >= 0) {
-                            iu = base + (uint32_t)gu;
-                            Ub = __shfl_sync(FULL_MASK, pick(su, gu % P), gu / P);
+    #pragma unroll
+                        for (int d = 1; d < 32; d <<= 1) {
+                            const float om = __shfl_up_sync(FULL_MASK, am, d), ox = __shfl_up_sync(FULL_MASK, ax, d);
+                            if (lane >= d) {
+                                am = fminf(am, om);
+                                ax = fmaxf(ax, ox);
+                            }
                         }
-                        if (gl >= 0) {
-                            il = base + (uint32_t)gl;
-                            Lb = __shfl_sync(FULL_MASK, pick(sl, gl % P), gl / P);
+                        float ru = __shfl_up_sync(FULL_MASK, am, 1), rl = __shfl_up_sync(FULL_MASK, ax, 1);
+                        if (lane == 0) { ru = inf; rl = -inf; }
+                        ru = fminf(ru, Ub); // (+inf / -inf until the second point of the fit has set the bounds, swing.rs:126-143)
+                        rl = fmaxf(rl, Lb);
+                        // this lane's points against the bounds the screen assumes before each of them
+                        unsigned ev_m = 0, rj_m = 0;   // this lane's points that end the accepted stretch / of those, the certain rejects
+                        unsigned rec_u = 0, rec_l = 0; // ... at which the screen tightens the upper / the lower bound
+    #pragma unroll
+                        for (int j = 0; j < P; j++) {
+                            // (|bounds| capped: the second point of a fit meets infinite bounds, tightens both untested, and must count as
+                            // certain; real slopes stay below 5e28 because every |value| is below 1e28, and tw is at most 3.2)
+                            const float tau = mdb_fmaf(tw[j], fminf(__fadd_rn(fabsf(ru), fabsf(rl)), 1e30f), tz[j]);
+                            const float a = __fsub_rn(sl[j], ru), b = __fsub_rn(rl, su[j]); // > 0: rejected (above the upper / below the lower line)
+                            const float c = __fsub_rn(ru, su[j]), d = __fsub_rn(sl[j], rl); // > 0: tightens the upper / the lower bound
+                            const bool certain = fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) > tau;
+                            const bool rej = fmaxf(a, b) > 0.0f;
+                            if (!certain || rej) ev_m |= 1u << j;
+                            if (certain && rej) rj_m |= 1u << j;
+                            // (what follows the first such point is discarded below: only points before `stop` count)
+                            if (c > 0.0f) { ru = su[j]; rec_u |= 1u << j; }
+                            if (d > 0.0f) { rl = sl[j]; rec_l |= 1u << j; }
                         }
-                    }
-                    s_len += (uint32_t)(stop - lo);
-                    lo = stop;
-                    if (stop < cnt) {
-                        if (first_rej <= first_unc) {
-                            swing_ok = false; // certainly rejected
-                        } else {
-                            // a doubtful point: the reference's own tests (swing.rs:146-178) on the exact bounds
-                            MDB_SCREEN_COUNT(3);
-                            if (++exact_points > MDB_SCREEN_MAX_EXACT_POINTS) return fit_exact(start, budget_end, aborted);
-                            const uint32_t idx = base + (uint32_t)stop;
-                            const double us = exact_candidate<KIND>(start, iu, v0, true), ls = exact_candidate<KIND>(start, il, v0, false);
-                            const double t0d = time_of(start);
-                            const double vdp = (double)values[idx], tdp = time_of(idx);
-                            const double dvp = max_dev_k<KIND>(ex.eb, vdp);
-                            const double up = __dadd_rn(__dmul_rn(us, tdp), icpt_of(us, v0, t0d));
-                            const double lw = __dadd_rn(__dmul_rn(ls, tdp), icpt_of(ls, v0, t0d));
-                            if ((__dadd_rn(up, dvp) < vdp) | (__dsub_rn(lw, dvp) > vdp)) {
-                                swing_ok = false;
+                        const int first_ev = __reduce_min_sync(FULL_MASK, ev_m ? p0 + __ffs((int)ev_m) - 1 : IDX_INF);
+                        const int stop = min(first_ev, cnt); // the points [lo, stop) are accepted as the screen assumed
+                        // the last tightening candidate of each bound within [lo, stop): its index and value (the exact slope is
+                        // computed when it is needed: for a doubtful point, or when the fit ends) and its f32 image
+                        {
+                            const int keep = stop - p0; // this lane's points before `stop`: j < keep
+                            const unsigned km = keep >= P ? (1u << P) - 1u : (keep > 0 ? (1u << keep) - 1u : 0u);
+                            const unsigned mu = rec_u & km, ml = rec_l & km;
+                            const int gu = __reduce_max_sync(FULL_MASK, mu ? p0 + 31 - __clz((int)mu) : -1);
+                            const int gl = __reduce_max_sync(FULL_MASK, ml ? p0 + 31 - __clz((int)ml) : -1);
+                            if (gu >= 0 || gl >= 0 || stop < cnt) calm = false;
+                            if (gu >= 0) {
+                                iu = kb + (uint32_t)gu;
+                                Ub = __shfl_sync(FULL_MASK, pick(su, gu % P), gu / P);
+                                vu = __shfl_sync(FULL_MASK, pick(v, gu % P), gu / P);
+                            }
+                            if (gl >= 0) {
+                                il = kb + (uint32_t)gl;
+                                Lb = __shfl_sync(FULL_MASK, pick(sl, gl % P), gl / P);
+                                vl = __shfl_sync(FULL_MASK, pick(v, gl % P), gl / P);
+                            }
+                        }
+                        s_len += (uint32_t)(stop - lo);
+                        lo = stop;
+                        if (stop < cnt) {
+                            const int owner = stop / P, jo = stop % P;
+                            if (__shfl_sync(FULL_MASK, (rj_m >> jo) & 1u, owner)) {
+                                swing_ok = false; // certainly rejected
                             } else {
-                                if (__dsub_rn(up, dvp) > vdp) {
-                                    iu = idx;
-                                    Ub = __shfl_sync(FULL_MASK, pick(su, stop % P), stop / P);
+                                // a doubtful point: the reference's own tests (swing.rs:146-178) on the exact bounds
+                                MDB_SCREEN_COUNT(3);
+                                if (++exact_points > MDB_SCREEN_MAX_EXACT_POINTS || s_len < 2) return fit_exact(start, budget_end, aborted);
+                                const uint32_t idx = base + (uint32_t)stop;
+                                const float vp = __shfl_sync(FULL_MASK, pick(v, jo), owner);
+                                const double us = exact_candidate<KIND>(iu, vu, v0, true), ls = exact_candidate<KIND>(il, vl, v0, false);
+                                const double t0d = time_of(start);
+                                const double vdp = (double)vp, tdp = time_of(idx);
+                                const double dvp = max_dev_k<KIND>(ex.eb, vdp);
+                                const double up = __dadd_rn(__dmul_rn(us, tdp), icpt_of(us, v0, t0d));
+                                const double lw = __dadd_rn(__dmul_rn(ls, tdp), icpt_of(ls, v0, t0d));
+                                if ((__dadd_rn(up, dvp) < vdp) | (__dsub_rn(lw, dvp) > vdp)) {
+                                    swing_ok = false;
+                                } else {
+                                    if (__dsub_rn(up, dvp) > vdp) {
+                                        iu = idx - start;
+                                        vu = vp;
+                                        Ub = __shfl_sync(FULL_MASK, pick(su, jo), owner);
+                                    }
+                                    if (__dadd_rn(lw, dvp) < vdp) {
+                                        il = idx - start;
+                                        vl = vp;
+                                        Lb = __shfl_sync(FULL_MASK, pick(sl, jo), owner);
+                                    }
+                                    s_len += 1;
+                                    lo = stop + 1;
+                                    // the points up to and including this one are done: neutral for the next pass
+    #pragma unroll
+                                    for (int j = 0; j < P; j++) {
+                                        if (p0 + j < lo) { su[j] = inf; sl[j] = -inf; }
+                                    }
                                 }
-                                if (__dadd_rn(lw, dvp) < vdp) {
-                                    il = idx;
-                                    Lb = __shfl_sync(FULL_MASK, pick(sl, stop % P), stop / P);
-                                }
-                                s_len += 1;
-                                lo = stop + 1;
                             }
                         }
                     }
@@ -455,8 +505,8 @@ template <int P> struct WarpFitScreenT {
             m.values_len = 0;
             m.bytes_per_value = swing_bpv;
             m.pending = 1;
-            m.lower_slope = s_len >= 2 ? exact_candidate<KIND>(start, il, v0, false) : (double)__uint_as_float(0x7fc00000u);
-            m.upper_slope = s_len >= 2 ? exact_candidate<KIND>(start, iu, v0, true) : (double)__uint_as_float(0x7fc00000u);
+            m.lower_slope = s_len >= 2 ? exact_candidate<KIND>(il, vl, v0, false) : (double)__uint_as_float(0x7fc00000u);
+            m.upper_slope = s_len >= 2 ? exact_candidate<KIND>(iu, vu, v0, true) : (double)__uint_as_float(0x7fc00000u);
         } else {
             const float value = canonical_nan(__double2float_rn(__ddiv_rn(p_sum, (double)p_len))); // pmc_mean.rs:91-93
             m.model_type_id = PMC_MEAN;

@@ -221,6 +221,18 @@ static inline int __reduce_max_sync(unsigned, int v) {
     return m;
 }
 
+static inline unsigned __reduce_min_sync(unsigned, unsigned v) {
+    const uint64_t *slots = warp_emu::rendezvous(v);
+    unsigned m = 0xffffffffu;
+    for (int l = 0; l < warp_emu::LANES; l++) m = std::min(m, warp_emu::read_slot<unsigned>(slots, l));
+    return m;
+}
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    const uint64_t *slots = warp_emu::rendezvous(v);
+    unsigned m = 0u;
+    for (int l = 0; l < warp_emu::LANES; l++) m = std::max(m, warp_emu::read_slot<unsigned>(slots, l));
+    return m;
+}
 static inline int __double2hiint(double d) { uint64_t u; std::memcpy(&u, &d, 8); return (int)(u >> 32); }
 static inline double __hiloint2double(int hi, int lo) {
     uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
