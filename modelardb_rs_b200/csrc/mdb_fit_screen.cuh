@@ -187,7 +187,7 @@ template <int P> struct WarpFitScreenT {
 
         // PMC-Mean state (pmc_mean.rs:31-53)
         bool pmc_ok = true;
-        float p_mn = __uint_as_float(0x7fc00000u), p_mx = p_mn;
+        float p_mn = __uint_as_float(0x7f800000u), p_mx = __uint_as_float(0xff800000u); // (+inf / -inf: replaced by the first value like the reference's NaN)
         double p_sum = 0.0;
         uint32_t p_len = 0;
         unsigned p_umax = 0u, p_umin1 = 0xffffffffu; // largest |value| summed so far / smallest non-zero one minus one, as bit patterns
@@ -237,15 +237,17 @@ template <int P> struct WarpFitScreenT {
             const float vmax = __uint_as_float(umax);
 
             // ------------------------------------------------------------------ PMC-Mean (exact: the scan form of WarpFitT::fit_k)
+            // Every value here is finite, so f32::min / f32::max (pmc_mean.rs:59-60) are fminf / fmaxf up to the sign of a zero,
+            // which nothing that leaves this function depends on: the tests below treat +0 and -0 alike, and the model is the
+            // mean.  Slots past `limit` hold 0.0f: they come after every real point in the prefix order and add nothing to a sum.
             if (pmc_ok) {
                 float lmn[P], lmx[P];
                 double lS[P];
 #pragma unroll
                 for (int j = 0; j < P; j++) {
-                    lmn[j] = j ? rust_minf(lmn[j - 1], v[j]) : v[0];
-                    lmx[j] = j ? rust_maxf(lmx[j - 1], v[j]) : v[0];
-                    const double x = (p0 + j < cnt) ? vd[j] : 0.0;
-                    lS[j] = j ? __dadd_rn(lS[j - 1], x) : x;
+                    lmn[j] = j ? fminf(lmn[j - 1], v[j]) : v[0];
+                    lmx[j] = j ? fmaxf(lmx[j - 1], v[j]) : v[0];
+                    lS[j] = j ? __dadd_rn(lS[j - 1], vd[j]) : vd[0];
                 }
                 // every addend is a multiple of 2^q and every partial sum is below 2^(emax + 1 + len_bits): all of them are exact
                 // iff that span fits into 53 bits, and then the order of the additions does not matter (mdb_fit_warp.cuh)
@@ -258,52 +260,47 @@ template <int P> struct WarpFitScreenT {
                 float amn = lmn[P - 1], amx = lmx[P - 1];
                 double aS = lS[P - 1];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    const float omn = __shfl_up_sync(FULL_MASK, amn, d), omx = __shfl_up_sync(FULL_MASK, amx, d);
+                for (int d = 1; d < 32; d <<= 1) { // (a lane below d receives its own value back: harmless for min / max)
+                    amn = fminf(amn, __shfl_up_sync(FULL_MASK, amn, d));
+                    amx = fmaxf(amx, __shfl_up_sync(FULL_MASK, amx, d));
                     const double oS = __shfl_up_sync(FULL_MASK, aS, d);
-                    if (lane >= d) {
-                        amn = rust_minf(omn, amn);
-                        amx = rust_maxf(omx, amx);
-                        aS = __dadd_rn(oS, aS);
-                    }
+                    if (lane >= d) aS = __dadd_rn(oS, aS);
                 }
                 float pmn = __shfl_up_sync(FULL_MASK, amn, 1), pmx = __shfl_up_sync(FULL_MASK, amx, 1);
                 double pS = __shfl_up_sync(FULL_MASK, aS, 1);
                 if (lane == 0) { pmn = p_mn; pmx = p_mx; pS = p_sum; }
-                else { pmn = rust_minf(p_mn, pmn); pmx = rust_maxf(p_mx, pmx); pS = __dadd_rn(p_sum, pS); }
-                float mn[P], mx[P];
+                else { pmn = fminf(p_mn, pmn); pmx = fmaxf(p_mx, pmx); pS = __dadd_rn(p_sum, pS); }
+                float mn_last = 0.0f, mx_last = 0.0f;
                 double S[P];
-                int fail_p = IDX_INF;
+                int fail_p = IDX_INF; // (a failure in a slot past cnt is no failure: compared with cnt below)
 #pragma unroll
                 for (int j = P - 1; j >= 0; j--) {
-                    mn[j] = rust_minf(pmn, lmn[j]);
-                    mx[j] = rust_maxf(pmx, lmx[j]);
+                    const float mn = fminf(pmn, lmn[j]), mx = fmaxf(pmx, lmx[j]);
+                    if (j == P - 1) { mn_last = mn; mx_last = mx; }
                     S[j] = __dadd_rn(pS, lS[j]);
                     const uint32_t len_l = p_len + (uint32_t)(p0 + j) + 1;
                     const float avg = __double2float_rn(ddiv_fast_in_range(S[j], (double)len_l)); // pmc_mean.rs:63
                     bool ok;
                     if (KIND == KIND_RELATIVE) {
-                        ok = ex.within_relative(mn[j], avg) & ex.within_relative(mx[j], avg);
+                        ok = ex.within_relative(mn, avg) & ex.within_relative(mx, avg);
                     } else {
                         bool no_division_here = false;
-                        ok = within_bound_k<KIND, true>(ex.eb, mn[j], avg, no_division_here) & within_bound_k<KIND, true>(ex.eb, mx[j], avg, no_division_here);
+                        ok = within_bound_k<KIND, true>(ex.eb, mn, avg, no_division_here) & within_bound_k<KIND, true>(ex.eb, mx, avg, no_division_here);
                     }
-                    if ((p0 + j < cnt) && !ok) fail_p = p0 + j;
+                    if (!ok) fail_p = p0 + j;
                 }
                 fail_p = __reduce_min_sync(FULL_MASK, fail_p);
-                const int accepted = fail_p < cnt ? fail_p : cnt;
-                if (fail_p < cnt) pmc_ok = false;
-                if (accepted > 0) {
-                    const int owner = (accepted - 1) / P, jj = (accepted - 1) % P;
-                    float smn = mn[0], smx = mx[0];
-                    double sS = S[0];
-#pragma unroll
-                    for (int j = 1; j < P; j++)
-                        if (j == jj) { smn = mn[j]; smx = mx[j]; sS = S[j]; }
-                    p_mn = __shfl_sync(FULL_MASK, smn, owner);
-                    p_mx = __shfl_sync(FULL_MASK, smx, owner);
-                    p_sum = __shfl_sync(FULL_MASK, sS, owner);
-                    p_len += (uint32_t)accepted;
+                if (fail_p >= cnt) { // every point of the step is accepted (after a step cut short by `limit` the state is not used again)
+                    p_mn = __shfl_sync(FULL_MASK, mn_last, 31);
+                    p_mx = __shfl_sync(FULL_MASK, mx_last, 31);
+                    p_sum = __shfl_sync(FULL_MASK, S[P - 1], 31);
+                    p_len += (uint32_t)cnt;
+                } else { // PMC-Mean ends here: only its length and sum are still needed
+                    pmc_ok = false;
+                    if (fail_p > 0) {
+                        p_sum = __shfl_sync(FULL_MASK, pick(S, (fail_p - 1) % P), (fail_p - 1) / P);
+                        p_len += (uint32_t)fail_p;
+                    }
                 }
                 p_umax = n_umax;
                 p_umin1 = n_umin1;
@@ -384,44 +381,45 @@ template <int P> struct WarpFitScreenT {
                         }
     #pragma unroll
                         for (int d = 1; d < 32; d <<= 1) {
-                            const float om = __shfl_up_sync(FULL_MASK, am, d), ox = __shfl_up_sync(FULL_MASK, ax, d);
-                            if (lane >= d) {
-                                am = fminf(am, om);
-                                ax = fmaxf(ax, ox);
-                            }
+                            am = fminf(am, __shfl_up_sync(FULL_MASK, am, d)); // (a lane below d receives its own value back)
+                            ax = fmaxf(ax, __shfl_up_sync(FULL_MASK, ax, d));
                         }
                         float ru = __shfl_up_sync(FULL_MASK, am, 1), rl = __shfl_up_sync(FULL_MASK, ax, 1);
                         if (lane == 0) { ru = inf; rl = -inf; }
                         ru = fminf(ru, Ub); // (+inf / -inf until the second point of the fit has set the bounds, swing.rs:126-143)
                         rl = fmaxf(rl, Lb);
-                        // this lane's points against the bounds the screen assumes before each of them
-                        unsigned ev_m = 0, rj_m = 0;   // this lane's points that end the accepted stretch / of those, the certain rejects
-                        unsigned rec_u = 0, rec_l = 0; // ... at which the screen tightens the upper / the lower bound
-    #pragma unroll
+                        // this lane's points against the bounds the screen assumes before each of them, up to the lane's first
+                        // EVENT: a point that is certainly rejected, or doubtful.  (What a lane computes after its first event,
+                        // or at and after another lane's earlier one, is discarded: only points before `stop` count.)
+                        int ev_j = P;             // this lane's first event
+                        bool ev_certain = false;  // ... is a certain reject
+                        int pos_u = -1, pos_l = -1; // this lane's last point before its first event that tightens the upper / the lower bound
+#pragma unroll
                         for (int j = 0; j < P; j++) {
                             // (|bounds| capped: the second point of a fit meets infinite bounds, tightens both untested, and must count as
                             // certain; real slopes stay below 5e28 because every |value| is below 1e28, and tw is at most 3.2)
                             const float tau = mdb_fmaf(tw[j], fminf(__fadd_rn(fabsf(ru), fabsf(rl)), 1e30f), tz[j]);
                             const float a = __fsub_rn(sl[j], ru), b = __fsub_rn(rl, su[j]); // > 0: rejected (above the upper / below the lower line)
                             const float c = __fsub_rn(ru, su[j]), d = __fsub_rn(sl[j], rl); // > 0: tightens the upper / the lower bound
-                            const bool certain = fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))) > tau;
-                            const bool rej = fmaxf(a, b) > 0.0f;
-                            if (!certain || rej) ev_m |= 1u << j;
-                            if (certain && rej) rj_m |= 1u << j;
-                            // (what follows the first such point is discarded below: only points before `stop` count)
-                            if (c > 0.0f) { ru = su[j]; rec_u |= 1u << j; }
-                            if (d > 0.0f) { rl = sl[j]; rec_l |= 1u << j; }
+                            const float margin = __fsub_rn(fminf(fminf(fabsf(a), fabsf(b)), fminf(fabsf(c), fabsf(d))), tau); // > 0: all four are certain
+                            // an event: doubtful (margin <= 0) or rejected (a or b > 0; a zero there is doubtful anyway)
+                            const bool event = fmaxf(-margin, fmaxf(a, b)) >= 0.0f;
+                            const bool first = event && ev_j == P;
+                            if (first) { ev_j = j; ev_certain = margin > 0.0f; }
+                            const bool live = ev_j == P;
+                            if (live && c > 0.0f) pos_u = j;
+                            if (live && d > 0.0f) pos_l = j;
+                            ru = fminf(ru, su[j]); // (tightens iff c > 0)
+                            rl = fmaxf(rl, sl[j]);
                         }
-                        const int first_ev = __reduce_min_sync(FULL_MASK, ev_m ? p0 + __ffs((int)ev_m) - 1 : IDX_INF);
+                        const int first_ev = __reduce_min_sync(FULL_MASK, ev_j < P ? p0 + ev_j : IDX_INF);
                         const int stop = min(first_ev, cnt); // the points [lo, stop) are accepted as the screen assumed
                         // the last tightening candidate of each bound within [lo, stop): its index and value (the exact slope is
                         // computed when it is needed: for a doubtful point, or when the fit ends) and its f32 image
                         {
-                            const int keep = stop - p0; // this lane's points before `stop`: j < keep
-                            const unsigned km = keep >= P ? (1u << P) - 1u : (keep > 0 ? (1u << keep) - 1u : 0u);
-                            const unsigned mu = rec_u & km, ml = rec_l & km;
-                            const int gu = __reduce_max_sync(FULL_MASK, mu ? p0 + 31 - __clz((int)mu) : -1);
-                            const int gl = __reduce_max_sync(FULL_MASK, ml ? p0 + 31 - __clz((int)ml) : -1);
+                            const bool mine = p0 < stop; // (then this lane's points before its first event lie before `stop`)
+                            const int gu = __reduce_max_sync(FULL_MASK, mine && pos_u >= 0 ? p0 + pos_u : -1);
+                            const int gl = __reduce_max_sync(FULL_MASK, mine && pos_l >= 0 ? p0 + pos_l : -1);
                             if (gu >= 0 || gl >= 0 || stop < cnt) calm = false;
                             if (gu >= 0) {
                                 iu = kb + (uint32_t)gu;
@@ -438,7 +436,7 @@ template <int P> struct WarpFitScreenT {
                         lo = stop;
                         if (stop < cnt) {
                             const int owner = stop / P, jo = stop % P;
-                            if (__shfl_sync(FULL_MASK, (rj_m >> jo) & 1u, owner)) {
+                            if (__shfl_sync(FULL_MASK, ev_certain ? 1 : 0, owner)) {
                                 swing_ok = false; // certainly rejected
                             } else {
                                 // a doubtful point: the reference's own tests (swing.rs:146-178) on the exact bounds
