@@ -139,8 +139,8 @@ int mdbcu_context_set_lane_warmup(mdbcu_context *ctx, uint32_t points);
 /* Number of chain rounds the last mdbcu_compress on this context needed (1 = no re-run at all; always
  * 1 with the asynchronous scheduler, which has no rounds). */
 uint32_t mdbcu_context_last_compress_rounds(const mdbcu_context *ctx);
-/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (4 when the units alone
- * occupy the lanes, else 5), 1 one
+/* Which fit_next_model engine runs the chains and how they are scheduled: 0 automatic (5; 3 when no unit has
+ * a lossy bound), 1 one
  * thread per chain in global rounds, 2 one warp per chain (32 lanes fit 128 points per step,
  * csrc/mdb_fit_warp.cuh) in global rounds, 3 one warp per chain served from a device-side work queue
  * by persistent warps, each unit advancing its own exact frontier (csrc/mdb_compress.cuh,

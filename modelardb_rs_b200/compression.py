@@ -111,7 +111,7 @@ class Context:
         _native.check(_native.lib().mdbcu_context_set_lane_warmup(self._h, points))
 
     def set_fit_engine(self, engine: int):
-        """0 automatic (4 when the units alone occupy the lanes, else 5), 1 one thread per chain in rounds, 2 one warp per
+        """0 automatic (5; 3 when no unit has a lossy bound), 1 one thread per chain in rounds, 2 one warp per
         chain in rounds, 3 one warp per chain with the asynchronous scheduler, 4 one lane per chain for the bulk of the
         chains and 3 for the stitching, 5 = 3 with the screened fit (csrc/mdb_fit_screen.cuh); results are identical."""
         _native.check(_native.lib().mdbcu_context_set_fit_engine(self._h, engine))

@@ -1014,16 +1014,15 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
 
     if (n_units) {
         // ---- chunks
-        // One lane per chain (mdb_fit_lanes.cuh) if any unit qualifies: decided first, because the chunks are shorter then.
-        // Automatic choice (measured on B200, round 2): with units enough to occupy the lanes by themselves (100 000 series of
-        // 10 000 points: 14.3 ms against 20.2 ms per 10^9 points) the lanes win -- no speculation, no stitching.  With few long
-        // units they win on units whose models are a few hundred points (17.0 against 20.4 ms, homogeneous sine + noise), but a
-        // handful of units with models of many thousands of points, which the lanes cut and the cooperative engine then has to
-        // walk alone, AFTER the lanes, cost more than they save (33 against 22 ms on the benchmark's mixed units): those
-        // chains are the critical path either way, and the cooperative engine hides it behind the other units' work.
-        bool use_lanes = ctx->fit_mode == 4 || (ctx->fit_mode == 0 && n_units * 4 >= (uint64_t)ctx->sm_count * 5 * LANES_WARPS * 32);
-        // The screened cooperative engine (mdb_fit_screen.cuh) needs the same per-unit facts: regular timestamps, bound kind.
-        bool use_screen = ctx->fit_mode == 5 || (ctx->fit_mode == 0 && !use_lanes);
+        // Engines (mdbcu_context_set_fit_engine).  Automatic = the screened cooperative fit (mdb_fit_screen.cuh) whenever a unit
+        // has a lossy bound, else the exact cooperative fit; both under the asynchronous scheduler.  Measured on B200 per 10^9
+        // points, chain kernel only (round 2): 1000 series x 10^6 points, 1 %: exact 17.8 ms, screened 10.7 ms; 100 000 series x
+        // 10^4 points, 1 %: one lane per chain (mdb_fit_lanes.cuh, engine 4) 13.1 ms, screened 8.7 ms; 5 % bound (models of
+        // thousands of points): exact 20.0 ms, screened 23.3 ms -- the one case the automatic choice loses.
+        // The lanes (engine 4) are decided first, because their chunks are shorter.
+        bool use_lanes = ctx->fit_mode == 4;
+        // The screened engine needs the same per-unit facts as the lanes: regular timestamps, bound kind.
+        bool use_screen = ctx->fit_mode == 5 || ctx->fit_mode == 0;
         DBuf<LaneUnit> lane_units;
         DBuf<unsigned int> lane_words; // [0..2] qualifying units per bound kind, [3] the chunk counter
         unsigned int kind_units[4] = {0, 0, 0, 0};

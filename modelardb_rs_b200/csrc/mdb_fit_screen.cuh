@@ -41,7 +41,7 @@
 namespace mdb {
 
 #ifdef MDB_WARP_EMU
-static unsigned long long g_screen_counters[8]; // [0] fits, [1] exact fits, [2] passes, [3] exact point evaluations, [4] exact candidates
+static unsigned long long g_screen_counters[8]; // [0] fits, [1] exact fits, [2] passes, [3] exact point evaluations, [4] exact candidates, [5] quiet steps, [6] second rounds
 #define MDB_SCREEN_COUNT(i) do { if ((threadIdx.x & 31) == 0) g_screen_counters[i]++; } while (0)
 __device__ __forceinline__ float rcp_approx_f32(float x) { return 1.0f / x; }
 __device__ __forceinline__ float mdb_fmaf(float a, float b, float c) { return std::fmaf(a, b, c); }
@@ -74,9 +74,10 @@ template <int P> struct WarpFitScreenT {
     double t0u, delta;  // (double)ts[0], (double)(ts[1] - ts[0]) of the unit: (double)ts[i] = t0u + i * delta exactly
     float kap;          // >= 3.1 * 2^-53 * max|t| / delta: the reference's line evaluation noise per unit of slope per index
     uint32_t exact_run; // fits in a row that the exact engine had to take
+    bool pmc_close;     // PMC-Mean won the last fit or came close: follow it exactly from the start of the next one (see fit_s)
 
     __device__ __forceinline__ WarpFitScreenT(const ErrorBound &e, const int64_t *t, const float *v, uint32_t n_, double *smem_, const LaneUnit *lu)
-        : ex(e, t, v, n_, smem_), screen(false), t0u(0.0), delta(1.0), kap(0.0f), exact_run(0) {
+        : ex(e, t, v, n_, smem_), screen(false), t0u(0.0), delta(1.0), kap(0.0f), exact_run(0), pmc_close(false) {
         if (lu != nullptr && n_ >= 2) {
             const LaneUnit u = *lu;
             // (lane_unit_init: positive interval below 2^31, |timestamps| < 2^53, an exact relative test; k_lanes_regular: every interval)
@@ -201,8 +202,23 @@ template <int P> struct WarpFitScreenT {
         uint32_t s_len = 0;
         int exact_points = 0;
         bool calm = false; // the previous step moved no bound (then a quiet step is likely)
+        // PMC-Mean, bounded.  Swing wins 19 fits out of 20 on noisy data, and then PMC-Mean's length only matters as "shorter
+        // than 29/30 of Swing's" (types.rs:88-98).  So PMC-Mean is first only BOUNDED from above: a point accepted by it has
+        // min and max within the bound of the mean, hence max - min <= bound(|min| + |max|) (relative; 2 * bound absolute),
+        // with the reference's roundings (2^-23) covered by the 2^-20 in `yq`.  The first point at which the running range
+        // exceeds that is certainly rejected, so p_len <= its index: a running min / max and one comparison per point, no
+        // sum, no division.  Only if that bound does not decide the choice of the model is PMC-Mean followed exactly, in a
+        // second round over the fit's points (and, while it stays close, from the start of the next fits: pmc_close).
+        bool cheap = !pmc_close;
+        bool p_dead = false;   // (bounded) a point has certainly been rejected ...
+        uint32_t p_bound = 0;  // ... so at most this many were accepted
+        float c_mn = __uint_as_float(0x7f800000u), c_mx = __uint_as_float(0xff800000u);
+        const float yq = KIND == KIND_RELATIVE ? __fmul_rn(__double2float_rn(ex.rel_mid), 1.000002f) : __fmul_rn(ex.eb.value, 2.000002f);
+        bool swing_by_bound = false;
 
         uint32_t base = start;
+        for (;;) { // one round; a second one (PMC-Mean alone, exactly) if the bound does not decide
+        base = start;
         float vn[P];
 #pragma unroll
         for (int j = 0; j < P; j++) {
@@ -210,7 +226,7 @@ template <int P> struct WarpFitScreenT {
             vn[j] = idx < limit ? values[idx] : 0.0f;
         }
 
-        while (pmc_ok || swing_ok) {
+        while ((!cheap && pmc_ok) || swing_ok) {
             if (base >= limit) { // out of points: the end of the data, or the budget of a speculative chain
                 aborted = limit < n;
                 break;
@@ -240,7 +256,43 @@ template <int P> struct WarpFitScreenT {
             // Every value here is finite, so f32::min / f32::max (pmc_mean.rs:59-60) are fminf / fmaxf up to the sign of a zero,
             // which nothing that leaves this function depends on: the tests below treat +0 and -0 alike, and the model is the
             // mean.  Slots past `limit` hold 0.0f: they come after every real point in the prefix order and add nothing to a sum.
-            if (pmc_ok) {
+            if (cheap && !p_dead) { // the bound (see above)
+                float lmn[P], lmx[P];
+#pragma unroll
+                for (int j = 0; j < P; j++) {
+                    lmn[j] = j ? fminf(lmn[j - 1], v[j]) : v[0];
+                    lmx[j] = j ? fmaxf(lmx[j - 1], v[j]) : v[0];
+                }
+                float amn = lmn[P - 1], amx = lmx[P - 1];
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    amn = fminf(amn, __shfl_up_sync(FULL_MASK, amn, d));
+                    amx = fmaxf(amx, __shfl_up_sync(FULL_MASK, amx, d));
+                }
+                float pmn = __shfl_up_sync(FULL_MASK, amn, 1), pmx = __shfl_up_sync(FULL_MASK, amx, 1);
+                if (lane == 0) { pmn = c_mn; pmx = c_mx; }
+                else { pmn = fminf(c_mn, pmn); pmx = fmaxf(c_mx, pmx); }
+                int dead_j = P;
+                float mn_last = 0.0f, mx_last = 0.0f;
+#pragma unroll
+                for (int j = P - 1; j >= 0; j--) {
+                    const float mn = fminf(pmn, lmn[j]), mx = fmaxf(pmx, lmx[j]);
+                    if (j == P - 1) { mn_last = mn; mx_last = mx; }
+                    const float range = __fsub_rn(mx, mn);
+                    const bool dead = KIND == KIND_RELATIVE ? range > __fmul_rn(yq, __fadd_rn(fabsf(mn), fabsf(mx))) : range > yq;
+                    if (dead) dead_j = j;
+                }
+                // (slots past `limit` hold 0.0f and may look rejected: they come after every real point and are not counted)
+                const int first_dead = __reduce_min_sync(FULL_MASK, dead_j < P ? p0 + dead_j : IDX_INF);
+                if (first_dead < cnt) {
+                    p_dead = true;
+                    p_bound = (base - start) + (uint32_t)first_dead;
+                } else {
+                    c_mn = __shfl_sync(FULL_MASK, mn_last, 31);
+                    c_mx = __shfl_sync(FULL_MASK, mx_last, 31);
+                }
+            }
+            if (!cheap && pmc_ok) {
                 float lmn[P], lmx[P];
                 double lS[P];
 #pragma unroll
@@ -478,6 +530,17 @@ template <int P> struct WarpFitScreenT {
             }
             base += (uint32_t)cnt; // cnt < STEP only when `limit` cut the step short
         }
+        if (aborted || !cheap) break;
+        // Swing has ended (or the data has).  PMC-Mean accepted at most p_bound points: if even that many lose against Swing
+        // (the comparison of types.rs:88-98; 29 / len falls with len), Swing is the model whatever PMC-Mean's length is.
+        if (p_dead && __fdiv_rn(30.0f, (float)s_len) < __fdiv_rn(29.0f, (float)p_bound)) {
+            swing_by_bound = true;
+            break;
+        }
+        MDB_SCREEN_COUNT(6);
+        cheap = false;     // second round: PMC-Mean alone and exactly, from the fit's first point
+        swing_ok = false;  // (Swing's results stay as they are)
+        }
 
         FittedModel m;
         m.start_index = start;
@@ -493,8 +556,10 @@ template <int P> struct WarpFitScreenT {
             m.values_len = 0;
             return m;
         }
-        const float pmc_bpv = __fdiv_rn(29.0f, (float)p_len);   // pmc_mean.rs:83-87
+        const float pmc_bpv = swing_by_bound ? 1e30f : __fdiv_rn(29.0f, (float)p_len); // pmc_mean.rs:83-87
         const float swing_bpv = __fdiv_rn(30.0f, (float)s_len); // swing.rs:236-239
+        // follow PMC-Mean exactly from the start of the next fit while it wins or stays within a quarter of winning
+        pmc_close = !swing_by_bound && !(swing_bpv < __fdiv_rn(29.0f, __fmul_rn((float)p_len, 1.25f)));
         if (swing_bpv < pmc_bpv) {
             // boundaries and bounds are final; Swing::model (swing.rs:246-259) is completed by swing_finish
             m.model_type_id = SWING;

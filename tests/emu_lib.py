@@ -115,10 +115,10 @@ def division_mismatches() -> int:
 
 def screen_counters(clear=True):
     """Event counters of the screened engine (csrc/mdb_fit_screen.cuh): fits, fits the exact engine took, passes, exact point
-    evaluations, exact candidates."""
+    evaluations, exact candidates, quiet steps, second rounds (PMC-Mean followed exactly after its bound did not decide)."""
     out = (C.c_uint64 * 8)()
     lib().emu_screen_counters(out, 1 if clear else 0)
-    return dict(zip(("fits", "exact_fits", "passes", "exact_points", "exact_candidates"), list(out)[:5]))
+    return dict(zip(("fits", "exact_fits", "passes", "exact_points", "exact_candidates", "quiet_steps", "pmc_second_rounds"), list(out)[:7]))
 
 
 def lane_counters():
