@@ -190,6 +190,18 @@ int mdbcu_grid_count(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments
 int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments,
                int64_t *timestamps_out, float *values_out, uint64_t capacity, uint64_t *n_points);
 
+/* grid() with the query's time predicate pushed in.  The reference selects segments by start_time / end_time
+ * (crates/modelardb_storage/src/query/time_series_table.rs:290-373), reconstructs every data point of them and then
+ * prunes by the predicate (grid_exec.rs:366-387).  Here rows that end before t_lo or start after t_hi are never
+ * reconstructed, and of the others only the data points with t_lo <= timestamp <= t_hi are written, rows in order:
+ * the same points GridStream yields for the predicate `t_lo <= timestamp AND timestamp <= t_hi`.
+ * point_off (n_segments + 1, nullable) receives the exclusive prefix sum of the points written per row (0 for pruned
+ * rows); *n_points (host) their number.  With both outputs null the call only counts; otherwise it fails if more than
+ * `capacity` points lie in the range. */
+int mdbcu_grid_range(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, int64_t t_lo,
+                     int64_t t_hi, uint64_t *point_off, int64_t *timestamps_out, float *values_out,
+                     uint64_t capacity, uint64_t *n_points);
+
 /* ---- K3: aggregates ------------------------------------------------------------------------ */
 
 /* Per-row `sum` exactly as models/mod.rs:129-184 computes it (f32). */

@@ -493,6 +493,41 @@ def grid(segments, timestamps_out=None, values_out=None, ctx: Optional[Context] 
     return timestamps_out[: n.value], values_out[: n.value]
 
 
+def grid_range(segments, t_lo: int, t_hi: int, ctx: Optional[Context] = None, with_point_off: bool = False):
+    """grid() with the time predicate `t_lo <= timestamp <= t_hi` evaluated on the device (mdbcu_grid_range): rows outside
+    the range are never reconstructed, of the others only the points inside it come back.  The reference prunes after
+    reconstructing everything (grid_exec.rs:366-387).  Returns (timestamps, values[, point_off]); point_off is the
+    exclusive prefix sum of the points returned per row of the batch."""
+    ctx = ctx or getattr(segments, "ctx", None) or default_context()
+    v, space = _view_of(segments)
+    # capacity: the points of the rows that meet the range (len() per row is cheap: no point is reconstructed for it)
+    row_off, total = grid_count(segments, ctx)
+    if hasattr(segments, "start_time") and v.n_segments:
+        keep = (segments.end_time >= t_lo) & (segments.start_time <= t_hi)
+        bound = int((row_off[1:] - row_off[:-1])[keep].sum())
+    else:  # (an owned batch: its columns are only reachable through the view)
+        bound = int(total)
+    if space == HOST:
+        ts_out, val_out = np.empty(bound, np.int64), np.empty(bound, np.float32)
+        point_off = np.empty(v.n_segments + 1, np.uint64) if with_point_off else None
+    else:
+        import torch
+        dev = f"cuda:{ctx.device}"
+        ts_out = torch.empty(bound, dtype=torch.int64, device=dev)
+        val_out = torch.empty(bound, dtype=torch.float32, device=dev)
+        point_off = torch.empty(v.n_segments + 1, dtype=torch.int64, device=dev) if with_point_off else None
+    n = C.c_uint64()
+    _order_streams(space)
+    if bound == 0:  # nothing meets the range: the call still fills point_off
+        _native.check(_native.lib().mdbcu_grid_range(ctx._h, space, C.byref(v), int(t_lo), int(t_hi), _ptr(point_off), None, None, 0, C.byref(n)))
+    else:
+        _native.check(_native.lib().mdbcu_grid_range(ctx._h, space, C.byref(v), int(t_lo), int(t_hi), _ptr(point_off), _ptr(ts_out), _ptr(val_out),
+                                                     bound, C.byref(n)))
+    if with_point_off:
+        return ts_out[: n.value], val_out[: n.value], point_off
+    return ts_out[: n.value], val_out[: n.value]
+
+
 def segment_sums(segments, ctx: Optional[Context] = None):
     """sum() per row (models/mod.rs:129-184)."""
     ctx = ctx or getattr(segments, "ctx", None) or default_context()

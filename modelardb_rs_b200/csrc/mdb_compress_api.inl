@@ -923,6 +923,7 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
     if (!name) return fail("set_option: name is null");
     const std::string n(name);
     if (n == "grid_tma_stores") ctx->grid_tma_stores = value != 0;
+    else if (n == "grid_tile_scan") ctx->grid_tile_scan = value != 0;
     else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
     else if (n == "fit_wide") ctx->fit_wide = value != 0;
     else if (n == "block_row_warps") ctx->block_row_warps = (int)value;

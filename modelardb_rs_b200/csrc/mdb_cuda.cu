@@ -97,6 +97,7 @@ struct mdbcu_context {
     uint32_t block_row_min = 0;     // MacaqueV values from which a row is decoded by a whole block (set to BLOCK_ROW_MIN at creation)
     uint32_t lane_rows_min = 24576; // long MacaqueV rows per batch from which one thread owns a row (LANE_ROWS_MIN)
     uint32_t chunk_len_override = 0; // 0: choose_chunk_len() decides
+    bool grid_tile_scan = false;     // k_grid_tile (rows of a tile by head flags + max-scan) instead of k_grid_tile_search (binary search per quad)
     bool grid_tma_stores = false;    // k_grid_tile_tma (tiles staged in shared memory, stored by the TMA engine) instead of k_grid_tile: measured slower, see there
     bool lane_rounds_by_lanes = false; // repair rounds after the lanes' first pass: by lanes too, or (default) by the cooperative engine
     uint32_t lane_warmup = 4096;     // points a speculative lane chain starts before its chunk (LaneChain, mdb_fit_lanes.cuh)
@@ -879,6 +880,82 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__res
     }
 }
 
+
+// Tiles with their rows found by BINARY SEARCH.  k_grid_tile's head flags + block-wide max-scan give every point its row in
+// O(1), but cost ~40 of its 64 thread instructions per point, and every tile pays three dependent global round trips
+// (first row, point offsets, descriptors) with little work to hide them behind (ncu, round 2: issue slots half used,
+// long_scoreboard the top stall).  Here a block takes TILE_GROUP consecutive tiles at once: the rows overlapping them are
+// tile_first[b] .. tile_first[b + TILE_GROUP] (about forty on the benchmark); their point offsets are staged in shared
+// memory once, each QUAD of four consecutive points finds its row with log2(rows) probes, and a thread's
+// TILE_GROUP * 2 quads have their descriptor loads and stores in flight together.
+constexpr int TILE_GROUP = 4;
+__global__ void __launch_bounds__(TILE_THREADS) k_grid_tile_search(const SegDesc *__restrict__ desc, const uint64_t *__restrict__ point_off,
+                                                                   const uint32_t *__restrict__ tile_first, uint64_t n_segments, uint32_t n_tiles,
+                                                                   uint64_t total, int64_t *__restrict__ ts_out, float *__restrict__ val_out) {
+    __shared__ uint64_t po_s[TILE + 2]; // point offsets of the rows overlapping the span, and the end of the last one
+    const int tid = threadIdx.x;
+    const uint32_t tile0 = blockIdx.x * TILE_GROUP;
+    const bool vector_ok = ((reinterpret_cast<uintptr_t>(val_out) | reinterpret_cast<uintptr_t>(ts_out)) & 15) == 0;
+    uint32_t t_lo = tile0, t_hi = min(tile0 + (uint32_t)TILE_GROUP, n_tiles); // the tiles [t_lo, t_hi) are done together
+    while (t_lo < t_hi) {
+        const uint64_t s0 = tile_first[t_lo];
+        uint64_t s_last = t_hi < n_tiles ? (uint64_t)tile_first[t_hi] : n_segments - 1; // (may start at the next span's first point)
+        if (s_last - s0 + 1 > (uint64_t)TILE + 1) { // more rows than the staging area holds (rows of a few points): one tile at a time
+            t_hi = t_lo + 1;
+            s_last = t_hi < n_tiles ? (uint64_t)tile_first[t_hi] : n_segments - 1; // (rows have >= 1 point: at most TILE + 1 now)
+        }
+        const int nr = (int)(s_last - s0) + 1; // rows s0 .. s0 + nr - 1
+        const uint64_t span_start = (uint64_t)t_lo * TILE, span_end = min(total, (uint64_t)t_hi * TILE);
+        __syncthreads(); // (the previous span's offsets have been read by everybody)
+        for (int i = tid; i <= nr; i += TILE_THREADS) po_s[i] = point_off[s0 + i];
+        __syncthreads();
+        for (uint64_t gp = span_start + 4 * (uint64_t)tid; gp < span_end; gp += 4 * TILE_THREADS) {
+            int i = 0, hi = nr; // largest i in [0, nr) with po_s[i] <= gp
+            while (hi - i > 1) {
+                const int mid = (i + hi) >> 1;
+                if (po_s[mid] <= gp) i = mid;
+                else hi = mid;
+            }
+            if (vector_ok && gp + 3 < span_end && gp + 3 < po_s[i + 1]) { // the four points lie in row i
+                const SegDesc d = desc[s0 + i];
+                if (!(d.flags & F_REGULAR)) continue; // timestamps and values of this row come from k_grid_sequential
+                const uint32_t j = (uint32_t)(gp - po_s[i]);
+                const int64_t t0 = d.start + (int64_t)j * d.interval;
+                const int64_t t1 = t0 + d.interval, t2 = t1 + d.interval, t3 = t2 + d.interval;
+                reinterpret_cast<longlong2 *>(ts_out + gp)[0] = make_longlong2(t0, t1);
+                reinterpret_cast<longlong2 *>(ts_out + gp)[1] = make_longlong2(t2, t3);
+                if (d.flags & F_TILE_VALUES) {
+                    if (j + 3 < d.model_len) {
+                        float4 v;
+                        if ((d.flags & F_TYPE_MASK) == PMC_MEAN) {
+                            v.x = v.y = v.z = v.w = (float)d.a;                                  // pmc_mean.rs:104-108
+                        } else {
+                            v.x = swing_value(d.a, d.b, t0);                                     // swing.rs:304-319
+                            v.y = swing_value(d.a, d.b, t1);
+                            v.z = swing_value(d.a, d.b, t2);
+                            v.w = swing_value(d.a, d.b, t3);
+                        }
+                        *reinterpret_cast<float4 *>(val_out + gp) = v;
+                    } else { // the model part ends inside the quad: the rest are residual values (k_grid_sequential)
+                        for (int q = 0; q < 4; q++)
+                            if (j + q < d.model_len)
+                                val_out[gp + q] = (d.flags & F_TYPE_MASK) == PMC_MEAN ? (float)d.a : swing_value(d.a, d.b, t0 + q * d.interval);
+                    }
+                }
+                continue;
+            }
+            for (int q = 0; q < 4; q++) {
+                if (gp + q < span_end) {
+                    while (gp + q >= po_s[i + 1]) i++; // (rows have >= 1 point: at most three steps)
+                    grid_point(desc[s0 + i], (uint32_t)(gp + q - po_s[i]), ts_out, val_out, gp + q);
+                }
+            }
+        }
+        t_lo = t_hi;
+        t_hi = min(tile0 + (uint32_t)TILE_GROUP, n_tiles);
+    }
+}
+
 // ---- the same tile, staged in shared memory and written by the TMA engine ------------------------------------------
 // k_grid_tile's stores are issued by the threads themselves: three 16-byte STG per four points, each waiting in the LSU
 // pipe behind the descriptor loads of the same thread.  Here a block assembles the whole tile (2048 timestamps = 16 KiB,
@@ -1625,6 +1702,40 @@ int mdbcu_grid_count(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments
     return MDBCU_SUCCESS;
 }
 
+// The launches of grid(): every point of every row of `v` (device memory) into d_ts / d_val (device memory, pl.total entries).
+static int grid_on_device(mdbcu_context *ctx, const SegmentsView &v, GridPlan &pl, int64_t *d_ts, float *d_val) {
+    cudaStream_t s = ctx->stream;
+    const uint64_t S = v.n_segments;
+    unsigned int n_tiles = div_up(pl.total, TILE);
+    DBuf<uint32_t> tile_first;
+    CUDA_TRY(tile_first.alloc(n_tiles, s));
+    LAUNCH(ctx, k_grid_tile_index, div_up(S, 256), 256, 0, pl.point_off.p, S, tile_first.p);
+    if ((((uintptr_t)d_ts | (uintptr_t)d_val) & 15) == 0 && ctx->grid_tma_stores) {
+        int per_sm = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_tile_tma, TILE_THREADS, 0));
+        const unsigned int blocks = std::min<unsigned int>(n_tiles, (unsigned int)(ctx->sm_count * std::max(per_sm, 1)));
+        LAUNCH(ctx, k_grid_tile_tma, blocks, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, n_tiles, d_ts, d_val);
+    } else if (ctx->grid_tile_scan) {
+        LAUNCH(ctx, k_grid_tile, n_tiles, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, d_ts, d_val);
+    } else {
+        LAUNCH(ctx, k_grid_tile_search, div_up(n_tiles, TILE_GROUP), TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, n_tiles, pl.total, d_ts,
+               d_val);
+    }
+    if (pl.h_status.n_seq)
+        LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, v, pl.desc.p, pl.point_off.p, pl.worklist.p,
+               (uint32_t)pl.h_status.n_seq, d_ts, d_val);
+    if (pl.h_status.n_wide >= ctx->lane_rows_min)
+        LAUNCH(ctx, k_grid_macaque_lanes, div_up(pl.h_status.n_wide, 128), 128, 0, v, pl.desc.p, pl.point_off.p, pl.worklist.p + (S - 1),
+               (uint32_t)pl.h_status.n_wide, d_val);
+    else if (pl.h_status.n_wide) {
+        LAUNCH(ctx, k_grid_macaque_warp, div_up(pl.h_status.n_wide, WIDE_WARPS), WIDE_WARPS * 32, 0, v, pl.desc.p, pl.point_off.p,
+               pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, ctx->block_row_min, d_val);
+        launch_macaque_block<false>(ctx, std::min<unsigned int>(pl.h_status.n_wide, (unsigned int)ctx->sm_count * 16), v, pl.worklist.p + (S - 1), -1,
+                                    (const unsigned int *)nullptr, (uint32_t)pl.h_status.n_wide, pl.point_off.p, d_val);
+    }
+    return MDBCU_SUCCESS;
+}
+
 int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, int64_t *timestamps_out, float *values_out,
                uint64_t capacity, uint64_t *n_points) {
     if (check_ctx(ctx)) return MDBCU_FAILURE;
@@ -1637,7 +1748,6 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
     if (pl.total == 0) return MDBCU_SUCCESS;
     if (!timestamps_out || !values_out) return fail("grid: output pointer is null");
     cudaStream_t s = ctx->stream;
-    uint64_t S = st.view.n_segments;
 
     int64_t *d_ts = timestamps_out;
     float *d_val = values_out;
@@ -1649,34 +1759,264 @@ int mdbcu_grid(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view 
         d_ts = ts_buf.p;
         d_val = val_buf.p;
     }
-    unsigned int n_tiles = div_up(pl.total, TILE);
-    DBuf<uint32_t> tile_first;
-    CUDA_TRY(tile_first.alloc(n_tiles, s));
-    LAUNCH(ctx, k_grid_tile_index, div_up(S, 256), 256, 0, pl.point_off.p, S, tile_first.p);
-    if ((((uintptr_t)d_ts | (uintptr_t)d_val) & 15) == 0 && ctx->grid_tma_stores) {
-        int per_sm = 0;
-        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_grid_tile_tma, TILE_THREADS, 0));
-        const unsigned int blocks = std::min<unsigned int>(n_tiles, (unsigned int)(ctx->sm_count * std::max(per_sm, 1)));
-        LAUNCH(ctx, k_grid_tile_tma, blocks, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, n_tiles, d_ts, d_val);
-    } else {
-        LAUNCH(ctx, k_grid_tile, n_tiles, TILE_THREADS, 0, pl.desc.p, pl.point_off.p, tile_first.p, S, pl.total, d_ts, d_val);
-    }
-    if (pl.h_status.n_seq)
-        LAUNCH(ctx, k_grid_sequential, div_up(pl.h_status.n_seq, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p,
-               (uint32_t)pl.h_status.n_seq, d_ts, d_val);
-    if (pl.h_status.n_wide >= ctx->lane_rows_min)
-        LAUNCH(ctx, k_grid_macaque_lanes, div_up(pl.h_status.n_wide, 128), 128, 0, st.view, pl.desc.p, pl.point_off.p, pl.worklist.p + (S - 1),
-               (uint32_t)pl.h_status.n_wide, d_val);
-    else if (pl.h_status.n_wide) {
-        LAUNCH(ctx, k_grid_macaque_warp, div_up(pl.h_status.n_wide, WIDE_WARPS), WIDE_WARPS * 32, 0, st.view, pl.desc.p, pl.point_off.p,
-               pl.worklist.p + (S - 1), (uint32_t)pl.h_status.n_wide, ctx->block_row_min, d_val);
-        launch_macaque_block<false>(ctx, std::min<unsigned int>(pl.h_status.n_wide, (unsigned int)ctx->sm_count * 16), st.view, pl.worklist.p + (S - 1), -1,
-                                    (const unsigned int *)nullptr, (uint32_t)pl.h_status.n_wide, pl.point_off.p, d_val);
-    }
+    if (grid_on_device(ctx, st.view, pl, d_ts, d_val)) return MDBCU_FAILURE;
     CUDA_TRY(cudaGetLastError());
     if (space == MDBCU_HOST) {
         CUDA_TRY(d2h_bytes(ctx, timestamps_out, d_ts, pl.total * sizeof(int64_t)));
         CUDA_TRY(d2h_bytes(ctx, values_out, d_val, pl.total * sizeof(float)));
+    }
+    CUDA_TRY(sync_stream(ctx));
+    return MDBCU_SUCCESS;
+}
+
+
+// ---- grid with the query's time predicate pushed in -------------------------------------------------------------------
+// The reference reconstructs every data point of every segment and then prunes by the predicate (grid_exec.rs:366-387: "for
+// simplicity, all data points are reconstructed and then pruned by time"); segments are selected by start_time / end_time
+// before that (time_series_table.rs:290-373).  Here both happen on the device and before any point leaves it:
+//   k_range_select   one thread per row: does [start_time, end_time] meet [t_lo, t_hi]?          -> scan -> kept row ids
+//   k_range_lengths / k_range_gather   the kept rows as a dense batch of their own (byte columns copied: ~30 bytes a row)
+//   grid_plan + grid_on_device         the ordinary K2 over that batch, into scratch
+//   k_range_clip     one thread per kept row: timestamps within a row ascend, so the points inside the range are one index
+//                    range, found by two binary searches in the row's reconstructed timestamps  -> scan -> output offsets
+//   k_range_copy     one warp per kept row: that index range to its place in the output
+// Rows outside the range cost one comparison; only the rows straddling t_lo or t_hi are reconstructed beyond what is returned.
+__global__ void __launch_bounds__(256) k_range_select(SegmentsView v, int64_t t_lo, int64_t t_hi, uint32_t *keep) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= v.n_segments) return;
+    keep[s] = (v.end_time[s] >= t_lo && v.start_time[s] <= t_hi) ? 1u : 0u;
+}
+__global__ void __launch_bounds__(256) k_range_lengths(SegmentsView v, const uint32_t *keep, const uint64_t *kidx, uint32_t *rows, uint32_t *tl,
+                                                       uint32_t *vl, uint32_t *rl, Status *status) {
+    const uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= v.n_segments || !keep[s]) return;
+    const uint64_t k = kidx[s];
+    rows[k] = (uint32_t)s;
+    const uint64_t a = v.timestamps_off[s + 1] - v.timestamps_off[s], b = v.values_off[s + 1] - v.values_off[s],
+                   c = v.residuals_off[s + 1] - v.residuals_off[s];
+    // (offsets that run backwards, or a row of more than 4 GiB: load_row would refuse it too)
+    if (v.timestamps_off[s + 1] < v.timestamps_off[s] || v.values_off[s + 1] < v.values_off[s] || v.residuals_off[s + 1] < v.residuals_off[s] ||
+        (a | b | c) > 0xFFFFFFF0ull)
+        report_bad(status, s);
+    tl[k] = (uint32_t)a;
+    vl[k] = (uint32_t)b;
+    rl[k] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(128) k_range_gather(SegmentsView v, const uint32_t *rows, uint64_t n_kept, int8_t *type, int64_t *start, int64_t *end,
+                                                      float *mn, float *mx, const uint64_t *t_off, uint8_t *t_data, const uint64_t *v_off, uint8_t *v_data,
+                                                      const uint64_t *r_off, uint8_t *r_data) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_kept) return;
+    const uint64_t s = rows[k];
+    type[k] = v.model_type_id[s];
+    start[k] = v.start_time[s];
+    end[k] = v.end_time[s];
+    mn[k] = v.min_value[s];
+    mx[k] = v.max_value[s];
+    const uint8_t *src = v.timestamps_data + v.timestamps_off[s];
+    for (uint64_t i = 0, n = t_off[k + 1] - t_off[k]; i < n; i++) t_data[t_off[k] + i] = src[i];
+    src = v.values_data + v.values_off[s];
+    if (v_off[k + 1] - v_off[k] < 4096) // (longer ones: k_range_gather_long)
+        for (uint64_t i = 0, n = v_off[k + 1] - v_off[k]; i < n; i++) v_data[v_off[k] + i] = src[i];
+    src = v.residuals_data + v.residuals_off[s];
+    for (uint64_t i = 0, n = r_off[k + 1] - r_off[k]; i < n; i++) r_data[r_off[k] + i] = src[i];
+}
+// Long rows (a MacaqueV row can hold a whole series) have their bytes copied by a block each.
+__global__ void __launch_bounds__(256) k_range_gather_long(SegmentsView v, const uint32_t *rows, uint64_t n_kept, const uint64_t *v_off, uint8_t *v_data) {
+    for (uint64_t k = blockIdx.x; k < n_kept; k += gridDim.x) {
+        const uint64_t n = v_off[k + 1] - v_off[k];
+        if (n < 4096) continue;
+        const uint8_t *src = v.values_data + v.values_off[rows[k]];
+        for (uint64_t i = threadIdx.x; i < n; i += blockDim.x) v_data[v_off[k] + i] = src[i];
+    }
+}
+__global__ void __launch_bounds__(256) k_range_clip(const uint64_t *point_off, const int64_t *ts, uint64_t n_kept, int64_t t_lo, int64_t t_hi, uint32_t *first,
+                                                    uint32_t *count) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_kept) return;
+    const int64_t *row = ts + point_off[k];
+    const uint32_t n = (uint32_t)(point_off[k + 1] - point_off[k]);
+    uint32_t lo = 0, hi = n; // first index with row[i] >= t_lo
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (row[mid] < t_lo) lo = mid + 1;
+        else hi = mid;
+    }
+    const uint32_t a = lo;
+    hi = n; // first index with row[i] > t_hi
+    while (lo < hi) {
+        const uint32_t mid = lo + (hi - lo) / 2;
+        if (row[mid] <= t_hi) lo = mid + 1;
+        else hi = mid;
+    }
+    first[k] = a;
+    count[k] = lo - a;
+}
+constexpr uint64_t RANGE_LONG_ROW = 16384;
+__global__ void __launch_bounds__(128) k_range_copy(const uint64_t *point_off, const uint32_t *first, const uint64_t *out_off, uint64_t n_kept,
+                                                    const int64_t *ts, const float *val, int64_t *ts_out, float *val_out) {
+    const uint64_t k = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (k >= n_kept) return;
+    const int lane = threadIdx.x & 31;
+    const uint64_t src = point_off[k] + first[k], dst = out_off[k], n = min(out_off[k + 1] - dst, RANGE_LONG_ROW); // (the rest: k_range_copy_long)
+    for (uint64_t i = lane; i < n; i += 32) {
+        ts_out[dst + i] = ts[src + i];
+        val_out[dst + i] = val[src + i];
+    }
+}
+// Rows of more than RANGE_LONG_ROW points: the rest is copied by a block (one warp would take a 10^6-point row alone).
+__global__ void __launch_bounds__(256) k_range_copy_long(const uint64_t *point_off, const uint32_t *first, const uint64_t *out_off, uint64_t n_kept,
+                                                         const int64_t *ts, const float *val, int64_t *ts_out, float *val_out) {
+    for (uint64_t k = blockIdx.x; k < n_kept; k += gridDim.x) {
+        const uint64_t src = point_off[k] + first[k], dst = out_off[k], n = out_off[k + 1] - dst;
+        if (n <= RANGE_LONG_ROW) continue;
+        for (uint64_t i = RANGE_LONG_ROW + threadIdx.x; i < n; i += blockDim.x) {
+            ts_out[dst + i] = ts[src + i];
+            val_out[dst + i] = val[src + i];
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_range_row_counts(const uint32_t *rows, const uint32_t *count, uint64_t n_kept, uint32_t *per_row) {
+    const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k < n_kept) per_row[rows[k]] = count[k];
+}
+
+int mdbcu_grid_range(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_view *segments, int64_t t_lo, int64_t t_hi, uint64_t *point_off,
+                     int64_t *timestamps_out, float *values_out, uint64_t capacity, uint64_t *n_points) {
+    if (check_ctx(ctx)) return MDBCU_FAILURE;
+    StagedSegments st;
+    if (stage_segments(ctx, space, segments, st)) return MDBCU_FAILURE;
+    cudaStream_t s = ctx->stream;
+    const uint64_t S = st.view.n_segments;
+    if (n_points) *n_points = 0;
+    auto give_point_off = [&](const uint64_t *d_off) -> int { // (d_off == nullptr: all zero)
+        if (!point_off) return MDBCU_SUCCESS;
+        const size_t bytes = (S + 1) * sizeof(uint64_t);
+        if (!d_off) {
+            if (space == MDBCU_HOST) std::memset(point_off, 0, bytes);
+            else CUDA_TRY(cudaMemsetAsync(point_off, 0, bytes, s));
+        } else if (space == MDBCU_HOST) {
+            CUDA_TRY(d2h_bytes(ctx, point_off, d_off, bytes));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(point_off, d_off, bytes, cudaMemcpyDeviceToDevice, s));
+        }
+        return MDBCU_SUCCESS;
+    };
+    if (S == 0 || t_lo > t_hi) {
+        if (give_point_off(nullptr)) return MDBCU_FAILURE;
+        CUDA_TRY(sync_stream(ctx));
+        return MDBCU_SUCCESS;
+    }
+    // ---- the rows that meet the range, as a batch of their own
+    DBuf<uint32_t> keep, rows, tl, vl, rl;
+    DBuf<uint64_t> kidx;
+    DBuf<Status> status;
+    CUDA_TRY(keep.alloc(S, s));
+    CUDA_TRY(kidx.alloc(S + 1, s));
+    if (new_status(ctx, status)) return MDBCU_FAILURE;
+    LAUNCH(ctx, k_range_select, div_up(S, 256), 256, 0, st.view, t_lo, t_hi, keep.p);
+    if (exclusive_scan<uint32_t>(ctx, keep.p, S, kidx.p)) return MDBCU_FAILURE;
+    CUDA_TRY(post(ctx, 0, kidx.p + S, 1));
+    CUDA_TRY(sync_stream(ctx));
+    const uint64_t K = ctx->mailbox[0];
+    if (K == 0) {
+        if (give_point_off(nullptr)) return MDBCU_FAILURE;
+        CUDA_TRY(sync_stream(ctx));
+        return MDBCU_SUCCESS;
+    }
+    CUDA_TRY(rows.alloc(K, s));
+    CUDA_TRY(tl.alloc(K, s));
+    CUDA_TRY(vl.alloc(K, s));
+    CUDA_TRY(rl.alloc(K, s));
+    LAUNCH(ctx, k_range_lengths, div_up(S, 256), 256, 0, st.view, keep.p, kidx.p, rows.p, tl.p, vl.p, rl.p, status.p);
+    StagedSegments sub;
+    CUDA_TRY(sub.model_type_id.alloc(K, s));
+    CUDA_TRY(sub.start_time.alloc(K, s));
+    CUDA_TRY(sub.end_time.alloc(K, s));
+    CUDA_TRY(sub.min_value.alloc(K, s));
+    CUDA_TRY(sub.max_value.alloc(K, s));
+    CUDA_TRY(sub.ts_off.alloc(K + 1, s));
+    CUDA_TRY(sub.val_off.alloc(K + 1, s));
+    CUDA_TRY(sub.res_off.alloc(K + 1, s));
+    if (exclusive_scan<uint32_t>(ctx, tl.p, K, sub.ts_off.p)) return MDBCU_FAILURE;
+    if (exclusive_scan<uint32_t>(ctx, vl.p, K, sub.val_off.p)) return MDBCU_FAILURE;
+    if (exclusive_scan<uint32_t>(ctx, rl.p, K, sub.res_off.p)) return MDBCU_FAILURE;
+    CUDA_TRY(post(ctx, 0, sub.ts_off.p + K, 1));
+    CUDA_TRY(post(ctx, 1, sub.val_off.p + K, 1));
+    CUDA_TRY(post(ctx, 2, sub.res_off.p + K, 1));
+    {
+        Status h;
+        if (read_status(ctx, status.p, h, "segment row (offsets)")) return MDBCU_FAILURE; // (synchronises the stream)
+    }
+    const uint64_t tb = ctx->mailbox[0], vb = ctx->mailbox[1], rb = ctx->mailbox[2];
+    CUDA_TRY(sub.ts_data.alloc(tb ? tb : 1, s));
+    CUDA_TRY(sub.val_data.alloc(vb ? vb : 1, s));
+    CUDA_TRY(sub.res_data.alloc(rb ? rb : 1, s));
+    LAUNCH(ctx, k_range_gather, div_up(K, 128), 128, 0, st.view, rows.p, K, sub.model_type_id.p, sub.start_time.p, sub.end_time.p, sub.min_value.p,
+           sub.max_value.p, sub.ts_off.p, sub.ts_data.p, sub.val_off.p, sub.val_data.p, sub.res_off.p, sub.res_data.p);
+    LAUNCH(ctx, k_range_gather_long, (unsigned int)std::min<uint64_t>(K, (uint64_t)ctx->sm_count * 8), 256, 0, st.view, rows.p, K, sub.val_off.p,
+           sub.val_data.p);
+    sub.view.n_segments = K;
+    sub.view.model_type_id = sub.model_type_id.p;
+    sub.view.start_time = sub.start_time.p;
+    sub.view.end_time = sub.end_time.p;
+    sub.view.min_value = sub.min_value.p;
+    sub.view.max_value = sub.max_value.p;
+    sub.view.timestamps_off = sub.ts_off.p;
+    sub.view.timestamps_data = sub.ts_data.p;
+    sub.view.values_off = sub.val_off.p;
+    sub.view.values_data = sub.val_data.p;
+    sub.view.residuals_off = sub.res_off.p;
+    sub.view.residuals_data = sub.res_data.p;
+    // ---- their points (scratch), the index range of each row inside [t_lo, t_hi], and those ranges to the output
+    GridPlan pl;
+    if (grid_plan(ctx, sub.view, pl)) return MDBCU_FAILURE;
+    DBuf<int64_t> ts_s;
+    DBuf<float> val_s;
+    CUDA_TRY(ts_s.alloc(pl.total ? pl.total : 1, s));
+    CUDA_TRY(val_s.alloc(pl.total ? pl.total : 1, s));
+    if (pl.total && grid_on_device(ctx, sub.view, pl, ts_s.p, val_s.p)) return MDBCU_FAILURE;
+    DBuf<uint32_t> first, count, per_row;
+    DBuf<uint64_t> out_off, row_off;
+    CUDA_TRY(first.alloc(K, s));
+    CUDA_TRY(count.alloc(K, s));
+    CUDA_TRY(out_off.alloc(K + 1, s));
+    LAUNCH(ctx, k_range_clip, div_up(K, 256), 256, 0, pl.point_off.p, ts_s.p, K, t_lo, t_hi, first.p, count.p);
+    if (exclusive_scan<uint32_t>(ctx, count.p, K, out_off.p)) return MDBCU_FAILURE;
+    CUDA_TRY(post(ctx, 0, out_off.p + K, 1));
+    if (point_off) {
+        CUDA_TRY(per_row.alloc(S, s));
+        CUDA_TRY(row_off.alloc(S + 1, s));
+        CUDA_TRY(cudaMemsetAsync(per_row.p, 0, S * sizeof(uint32_t), s));
+        LAUNCH(ctx, k_range_row_counts, div_up(K, 256), 256, 0, rows.p, count.p, K, per_row.p);
+        if (exclusive_scan<uint32_t>(ctx, per_row.p, S, row_off.p)) return MDBCU_FAILURE;
+        if (give_point_off(row_off.p)) return MDBCU_FAILURE;
+    }
+    CUDA_TRY(sync_stream(ctx));
+    const uint64_t N = ctx->mailbox[0];
+    if (n_points) *n_points = N;
+    if (!timestamps_out && !values_out) return MDBCU_SUCCESS; // a count
+    if (N > capacity) return fail("grid_range: " + std::to_string(N) + " data points lie in the range, capacity is " + std::to_string(capacity));
+    if (N == 0) return MDBCU_SUCCESS;
+    if (!timestamps_out || !values_out) return fail("grid_range: output pointer is null");
+    int64_t *d_ts = timestamps_out;
+    float *d_val = values_out;
+    DBuf<int64_t> ts_buf;
+    DBuf<float> val_buf;
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(ts_buf.alloc(N, s));
+        CUDA_TRY(val_buf.alloc(N, s));
+        d_ts = ts_buf.p;
+        d_val = val_buf.p;
+    }
+    LAUNCH(ctx, k_range_copy, div_up(K * 32, 128), 128, 0, pl.point_off.p, first.p, out_off.p, K, ts_s.p, val_s.p, d_ts, d_val);
+    if (N > RANGE_LONG_ROW)
+        LAUNCH(ctx, k_range_copy_long, (unsigned int)std::min<uint64_t>(K, (uint64_t)ctx->sm_count * 8), 256, 0, pl.point_off.p, first.p, out_off.p, K, ts_s.p,
+               val_s.p, d_ts, d_val);
+    CUDA_TRY(cudaGetLastError());
+    if (space == MDBCU_HOST) {
+        CUDA_TRY(d2h_bytes(ctx, timestamps_out, d_ts, N * sizeof(int64_t)));
+        CUDA_TRY(d2h_bytes(ctx, values_out, d_val, N * sizeof(float)));
     }
     CUDA_TRY(sync_stream(ctx));
     return MDBCU_SUCCESS;

@@ -92,6 +92,8 @@ class GridStream:
 
     input: an iterable of (segments, tags) where `segments` is a HostSegments / CompressedSegments batch and `tags` a
     sequence of per-row tag arrays (one array per tag column, possibly none).
+    time_range / device_time_clip: the time predicate pushed down -- whole segments outside (lo, hi) are skipped, and with
+    device_time_clip the points outside it are dropped inside the grid kernels' call (mdbcu_grid_range).
     predicate: optional function (timestamps, values) -> bool mask applied to every reconstructed batch, the
     reference's `maybe_predicate` (all points are reconstructed, then pruned: grid_exec.rs:368-386).
     tag_runs: hand out every tag column as (values, run_lengths) instead of one string per created row (SURVEY 8(f2):
@@ -105,7 +107,7 @@ class GridStream:
     def __init__(self, input: Iterable[Tuple[object, Sequence[np.ndarray]]], batch_size: int, n_tag_columns: int = 0,
                  predicate: Optional[Callable[[np.ndarray, np.ndarray], np.ndarray]] = None, ctx: Optional[mc.Context] = None,
                  time_range: Optional[Tuple[Optional[int], Optional[int]]] = None, tag_runs: bool = False,
-                 limit: Optional[int] = None):
+                 limit: Optional[int] = None, device_time_clip: bool = False):
         if batch_size <= 0:
             raise ValueError("batch_size must be positive")
         if limit is not None:
@@ -122,6 +124,11 @@ class GridStream:
         # the push-down the reference applies to its Parquet scan (time_series_table.rs:290-373), SURVEY 8(f2).  The
         # caller's predicate must imply the range; points of the surviving segments are still pruned by it.
         self.time_range = time_range
+        # With device_time_clip the range is ALSO evaluated point by point inside the grid call (mdbcu_grid_range): of the
+        # surviving segments only the points with lo <= timestamp <= hi are reconstructed into the output and copied back,
+        # instead of all of them (grid_exec.rs:366-387 prunes after reconstruction).  Since the predicate implies the range
+        # the stream's output is unchanged.
+        self.device_time_clip = device_time_clip
         self.tag_runs = tag_runs
         self.segments_skipped = 0
         self.ctx = ctx
@@ -155,6 +162,10 @@ class GridStream:
                 tags = [np.asarray(t, object)[keep] for t in tags]
         if len(host) == 0:
             point_off, ts, vals = np.zeros(1, np.uint64), np.zeros(0, np.int64), np.zeros(0, np.float32)
+        elif self.device_time_clip and self.time_range is not None:
+            lo, hi = self.time_range
+            ts, vals, point_off = mc.grid_range(host, -(2 ** 63) if lo is None else lo, 2 ** 63 - 1 if hi is None else hi, self.ctx,
+                                                with_point_off=True)
         else:
             point_off, _ = mc.grid_count(host, self.ctx)
             if self.limit is not None and self.predicate is None:

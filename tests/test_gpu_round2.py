@@ -1,5 +1,7 @@
 """GPU parity tests added in round 2: the device's own rewrite position for every f32, caller offsets that run
 backwards or out of range, and two BASELINE.json configs at their exact / slab size against the oracle."""
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -142,15 +144,19 @@ def test_config2_slab_of_1000_series_matches_oracle(oracle, ctx):
     seg.free()
 
 
-@pytest.mark.parametrize("kind,eb", [("sine", (2, 1.0)), ("mixed", (2, 5.0)), ("walk", (2, 1.0)), ("sine", (0, 0.0))])
-def test_tma_tile_kernel_matches_oracle(oracle, kind, eb):
-    """k_grid_tile_tma (tiles staged in shared memory and stored by the TMA engine, metadata prefetched with cp.async; an
-    option, the per-thread stores are the default) writes the same points as the oracle: PMC-Mean / Swing rows of every
-    length, residual tails and MacaqueV rows that the serial kernels overwrite afterwards, a last tile that is not a multiple
-    of four points, and -- device space -- outputs that are not 16-byte aligned (which take the plain kernel)."""
+@pytest.mark.parametrize("tile_kernel", ["search", "scan", "tma"])
+@pytest.mark.parametrize("kind,eb", [("sine", (2, 1.0)), ("mixed", (2, 5.0)), ("walk", (2, 1.0)), ("sine", (0, 0.0)), ("sine", (2, 0.02))])
+def test_tile_kernels_match_oracle(oracle, kind, eb, tile_kernel):
+    """The three tile kernels of K2 -- k_grid_tile_search (rows of a tile by binary search per quad; the default), k_grid_tile
+    (head flags + block-wide max-scan) and k_grid_tile_tma (tiles staged in shared memory and stored by the TMA engine,
+    metadata prefetched with cp.async) -- write the same points as the oracle: PMC-Mean / Swing rows of every length (a 0.02 %
+    bound gives hundreds of short rows per tile), residual tails and MacaqueV rows that the serial kernels overwrite
+    afterwards, a last tile that is not a multiple of four points, and -- device space -- outputs that are not 16-byte
+    aligned."""
     import torch
     ctx = mc.Context(0)
-    ctx.set_option("grid_tma_stores", 1)
+    ctx.set_option("grid_tma_stores", 1 if tile_kernel == "tma" else 0)
+    ctx.set_option("grid_tile_scan", 1 if tile_kernel == "scan" else 0)
     ts, vals, off = syn.multi_series(7, 30_001, 19, kind)
     want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
     wts, wval, _ = oracle.grid(want, n_threads=8)
@@ -203,4 +209,95 @@ def test_block_per_row_macaque_decoder_matches_oracle(oracle, eb):
     assert np.array_equal(gc, wc)
     ok = np.isnan(wsm) & np.isnan(gsm) | (np.abs(gsm - wsm) <= 1e-12 * np.abs(wsm)) | (gsm == wsm)
     assert ok.all()
+    ctx.close()
+
+
+# ---- the time predicate inside the grid call (mdbcu_grid_range) -----------------------------------------------------------
+
+def _range_cases(ts):
+    t0, t1 = int(ts.min()), int(ts.max())
+    span = t1 - t0
+    return [(t0, t1), (t0 - 10, t1 + 10), (t0 + span // 3, t0 + span // 3 + span // 7), (t0 + 5, t0 + 5), (t0 + span // 2, t0 + span // 2 + 1),
+            (t1, t1 + 100), (t0 - 100, t0), (t1 + 1, t1 + 50), (t0 - 50, t0 - 1), (t0 + 10, t0 + 9), (-(2 ** 63), 2 ** 63 - 1)]
+
+
+@pytest.mark.parametrize("kind,eb,irregular", [("sine", (2, 1.0), False), ("mixed", (2, 5.0), False), ("walk", (0, 0.0), False),
+                                              ("mixed", (1, 0.5), True), ("walk", (2, 1.0), True)])
+def test_grid_range_equals_grid_then_filter(oracle, kind, eb, irregular):
+    """mdbcu_grid_range returns exactly the points the reference keeps when it reconstructs everything and then prunes by
+    `t_lo <= timestamp <= t_hi` (grid_exec.rs:366-387), in the same order, with the per-row counts -- for PMC-Mean / Swing /
+    MacaqueV rows, residual tails, regular and irregular timestamps, host and device space, ranges that cut rows, hit a
+    single point, cover everything or nothing."""
+    import torch
+    ctx = mc.Context(0)
+    ts, vals, off = syn.multi_series(5, 20_011, 23, kind, irregular=irregular)
+    want = oracle.compress(ts, vals, off, eb=eb, n_threads=8)
+    wts, wval, wpo = oracle.grid(want, n_threads=8)
+    row_of_point = np.repeat(np.arange(len(want)), np.diff(wpo).astype(np.int64))
+    host = mc.HostSegments(unit_seg_off=want.unit_seg_off, **{c: getattr(want, c) for c in mc._COLUMNS})
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx)
+    for lo, hi in _range_cases(ts):
+        keep = (wts >= lo) & (wts <= hi)
+        counts = np.bincount(row_of_point[keep], minlength=len(want))
+        gts, gval, gpo = mc.grid_range(host, lo, hi, ctx, with_point_off=True)
+        assert np.array_equal(gts, wts[keep]), (lo, hi)
+        assert_f32_bits_equal(gval, wval[keep], f"grid_range host {kind} {eb} [{lo}, {hi}]")
+        assert np.array_equal(np.diff(gpo).astype(np.int64), counts), (lo, hi)
+        dts, dval, dpo = mc.grid_range(seg, lo, hi, ctx, with_point_off=True)
+        assert np.array_equal(dts.cpu().numpy(), wts[keep]), (lo, hi)
+        assert_f32_bits_equal(dval.cpu().numpy(), wval[keep], f"grid_range device {kind} {eb} [{lo}, {hi}]")
+        assert np.array_equal(np.diff(dpo.cpu().numpy()), counts), (lo, hi)
+    n = ctypes.c_uint64()
+    v = host.view()
+    _native.check(_native.lib().mdbcu_grid_range(ctx._h, mc.HOST, ctypes.byref(v), int(wts[3]), int(wts[-3]), None, None, None, 0, ctypes.byref(n)))  # a count
+    assert n.value == int(((wts >= wts[3]) & (wts <= wts[-3])).sum())
+    with pytest.raises(mc.ModelarDbCudaError, match="capacity"):
+        out_t, out_v = np.empty(2, np.int64), np.empty(2, np.float32)
+        _native.check(_native.lib().mdbcu_grid_range(ctx._h, mc.HOST, ctypes.byref(v), int(wts.min()), int(wts.max()), None, out_t.ctypes.data,
+                                                     out_v.ctypes.data, 2, ctypes.byref(n)))
+    seg.free()
+    ctx.close()
+
+
+def test_grid_range_on_long_rows(oracle):
+    """Rows of 10^5 MacaqueV values (copied by a block each) and whole-series PMC-Mean rows, cut in the middle."""
+    ctx = mc.Context(0)
+    n = 150_000
+    ts = np.tile(syn.regular_timestamps(n), 3)
+    rng = np.random.default_rng(5)
+    vals = np.concatenate([(100 + np.cumsum(rng.standard_normal(n))).astype(np.float32), np.full(n, 7.5, np.float32),
+                           (50 + 0.001 * np.arange(n)).astype(np.float32)])
+    off = np.array([0, n, 2 * n, 3 * n], np.uint64)
+    for eb in ((0, 0.0), (2, 1.0)):
+        want = oracle.compress(ts, vals, off, eb=eb, n_threads=4)
+        wts, wval, _ = oracle.grid(want, n_threads=4)
+        host = mc.HostSegments(unit_seg_off=want.unit_seg_off, **{c: getattr(want, c) for c in mc._COLUMNS})
+        lo, hi = int(ts[n // 3]), int(ts[n - n // 5])
+        keep = (wts >= lo) & (wts <= hi)
+        gts, gval = mc.grid_range(host, lo, hi, ctx)
+        assert np.array_equal(gts, wts[keep])
+        assert_f32_bits_equal(gval, wval[keep], f"grid_range long rows {eb}")
+    ctx.close()
+
+
+def test_grid_stream_with_the_time_predicate_on_the_device(oracle):
+    """GridStream(time_range=..., device_time_clip=True): the same batches as evaluating the predicate on the host after
+    reconstructing every point, which is what the reference does."""
+    ctx = mc.Context(0)
+    ts, vals, off = syn.multi_series(6, 9_000, 31, "mixed")
+    seg = mc.compress(ts, vals, off, mc.ErrorBound(2, 5.0), ctx).to_host()
+    tags = [np.array([f"s{u}" for u in np.repeat(np.arange(6), np.diff(seg.unit_seg_off).astype(np.int64))], object)]
+    lo, hi = int(ts[1234]), int(ts[7000])
+
+    def predicate(t, v):
+        return (t >= lo) & (t <= hi)
+
+    def batches(**kw):
+        return list(ops.GridStream([(seg, tags)], batch_size=4096, n_tag_columns=1, predicate=predicate, ctx=ctx, **kw))
+
+    a = batches()
+    b = batches(time_range=(lo, hi), device_time_clip=True)
+    assert len(a) == len(b) and len(a) > 1
+    for x, y in zip(a, b):
+        assert np.array_equal(x[0], y[0]) and np.array_equal(x[1].view(np.uint32), y[1].view(np.uint32)) and np.array_equal(x[2], y[2])
     ctx.close()
