@@ -561,11 +561,15 @@ def main():
         "k_grid_tile": seg_bytes + 12 * n,            # reads the segments; writes 12 B per point
         "k_grid_sequential": seg_bytes + 12 * n,
         "k_agg_segments": seg_bytes,
+        "k_agg_groups": seg_bytes,
+        "k_agg_groups_warp": seg_bytes,
         "k_compress_emit": seg_bytes,
+        "k_lanes_regular": 8 * n,                     # reads every timestamp once
     }
     # The chain kernel runs once per fixpoint round; its unit of work is one SLAB (one step), so every
     # kernel is accounted per step: algorithmic bytes of one slab / device time the kernel took in one step.
     algo_bytes["k_spec_chain_warp"] = algo_bytes["k_spec_async"] = algo_bytes["k_spec_lanes"] = algo_bytes["k_spec_chain"]
+    algo_bytes["k_grid_tile_search"] = algo_bytes["k_grid_tile_tma"] = algo_bytes["k_grid_tile"]
 
     def algo_of(kernel):  # template instances report as e.g. "k_spec_async<WarpFit>"
         return algo_bytes.get(kernel.split("<")[0], 12 * n)
@@ -587,9 +591,13 @@ def main():
                     "algorithmic_bytes_per_step": ab, "kernel_ms_per_step": per_step_ms[dominant],
                     "launches_per_step": kstats[dominant][1] / prof_steps, "peak_source": peak_src,
                     "kernel_share_of_step": per_step_ms[dominant] / ms_per_step,
+                    "algorithmic_bytes_note": "SURVEY.md 8(d) per-point figure of the stage (compress: 12 B read per point + 28 B per model); the "
+                                              "screened chain kernel itself reads only the 4 B values, the 8 B timestamps are read once by "
+                                              "k_lanes_regular (listed with its own fraction)" if dominant.startswith("k_spec_async<WarpFitScreen") else None,
                     "all_kernels_ms_per_step": dict(sorted(per_step_ms.items(), key=lambda kv: -kv[1]))}
         for k in per_step_ms:
-            if k.split("<")[0] in ("k_grid_tile", "k_spec_async", "k_spec_lanes", "k_spec_chain", "k_spec_chain_warp", "k_agg_segments", "k_agg_groups") \
+            if k.split("<")[0] in ("k_grid_tile", "k_grid_tile_search", "k_grid_tile_tma", "k_spec_async", "k_spec_lanes", "k_spec_chain", "k_spec_chain_warp",
+                                   "k_agg_segments", "k_agg_groups", "k_lanes_regular") \
                     and per_step_ms[k] > 0:
                 a_ = algo_of(k) / (per_step_ms[k] / 1000.0) / 1e9
                 roofline[f"{k}_GBps"] = a_

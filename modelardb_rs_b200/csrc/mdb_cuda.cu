@@ -888,7 +888,10 @@ __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile(const SegDesc *__res
 // tile_first[b] .. tile_first[b + TILE_GROUP] (about forty on the benchmark); their point offsets are staged in shared
 // memory once, each QUAD of four consecutive points finds its row with log2(rows) probes, and a thread's
 // TILE_GROUP * 2 quads have their descriptor loads and stores in flight together.
-constexpr int TILE_GROUP = 4;
+#ifndef MDB_TILE_GROUP
+#define MDB_TILE_GROUP 4
+#endif
+constexpr int TILE_GROUP = MDB_TILE_GROUP;
 __global__ void __launch_bounds__(TILE_THREADS) k_grid_tile_search(const SegDesc *__restrict__ desc, const uint64_t *__restrict__ point_off,
                                                                    const uint32_t *__restrict__ tile_first, uint64_t n_segments, uint32_t n_tiles,
                                                                    uint64_t total, int64_t *__restrict__ ts_out, float *__restrict__ val_out) {
