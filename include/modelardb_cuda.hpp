@@ -237,6 +237,23 @@ inline void grid(Context &ctx, const CompressedSegmentBatch &batch, std::vector<
     if (point_off_out) *point_off_out = std::move(point_off);
 }
 
+// grid() with the predicate `t_lo <= timestamp AND timestamp <= t_hi` evaluated inside the call (mdbcu_grid_range): the
+// reference reconstructs every point of the selected segments and prunes afterwards (grid_exec.rs:366-387).  APPENDS the
+// surviving points; point_off_out receives their exclusive prefix sum per row (0 points for rows outside the range).
+inline void grid_range(Context &ctx, const CompressedSegmentBatch &batch, int64_t t_lo, int64_t t_hi, std::vector<int64_t> &timestamp_builder,
+                       std::vector<float> &value_builder, std::vector<uint64_t> *point_off_out = nullptr) {
+    const mdbcu_segments_view v = batch.view();
+    uint64_t n = 0;
+    check(mdbcu_grid_range(ctx.get(), MDBCU_HOST, &v, t_lo, t_hi, nullptr, nullptr, nullptr, 0, &n)); // a count
+    const uint64_t before = timestamp_builder.size();
+    timestamp_builder.resize(before + n);
+    value_builder.resize(before + n);
+    std::vector<uint64_t> point_off(batch.num_rows() + 1, 0);
+    check(mdbcu_grid_range(ctx.get(), MDBCU_HOST, &v, t_lo, t_hi, point_off.data(), n ? timestamp_builder.data() + before : nullptr,
+                           n ? value_builder.data() + before : nullptr, n, &n));
+    if (point_off_out) *point_off_out = std::move(point_off);
+}
+
 // grid_exec.rs:197-430: leftovers of the current batch + the points of the next segment batch, handed out in slices
 // of batch_size rows; `tags` of a segment batch (one value per row and tag column) are repeated for every created row.
 class GridStream {

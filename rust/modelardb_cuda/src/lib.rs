@@ -85,6 +85,9 @@ pub mod ffi {
                                 point_off: *mut u64, total: *mut u64) -> c_int;
         pub fn mdbcu_grid(ctx: *mut MdbcuContext, space: c_int, segments: *const MdbcuSegmentsView,
                           timestamps_out: *mut i64, values_out: *mut f32, capacity: u64, n_points: *mut u64) -> c_int;
+        pub fn mdbcu_grid_range(ctx: *mut MdbcuContext, space: c_int, segments: *const MdbcuSegmentsView, t_lo: i64, t_hi: i64,
+                                point_off: *mut u64, timestamps_out: *mut i64, values_out: *mut f32, capacity: u64,
+                                n_points: *mut u64) -> c_int;
         // K3 aggregates
         pub fn mdbcu_segment_sums(ctx: *mut MdbcuContext, space: c_int, segments: *const MdbcuSegmentsView,
                                   sums_out: *mut f32) -> c_int;
@@ -353,6 +356,26 @@ pub fn grid_batch(ctx: &mut Context, segments: &SegmentColumns) -> Result<(Vec<i
     let mut n = 0u64;
     check(unsafe {
         ffi::mdbcu_grid(ctx.raw, ffi::MDBCU_HOST, &view, timestamps.as_mut_ptr(), values.as_mut_ptr(), total, &mut n)
+    })?;
+    Ok((timestamps, values, point_off))
+}
+
+/// `grid` with the predicate `t_lo <= timestamp AND timestamp <= t_hi` evaluated inside the call: `GridStream` prunes after
+/// reconstructing every data point (`grid_exec.rs:366-387`), here rows outside the range are never reconstructed and only the
+/// points inside it come back.  Returns (timestamps, values, exclusive prefix sum of the points returned per row).
+pub fn grid_range(ctx: &mut Context, segments: &SegmentColumns, t_lo: i64, t_hi: i64) -> Result<(Vec<i64>, Vec<f32>, Vec<u64>)> {
+    let view = segments.view();
+    let mut n = 0u64;
+    check(unsafe {
+        ffi::mdbcu_grid_range(ctx.raw, ffi::MDBCU_HOST, &view, t_lo, t_hi, std::ptr::null_mut(), std::ptr::null_mut(),
+                              std::ptr::null_mut(), 0, &mut n) // a count
+    })?;
+    let mut timestamps = vec![0i64; n as usize];
+    let mut values = vec![0f32; n as usize];
+    let mut point_off = vec![0u64; segments.len() + 1];
+    check(unsafe {
+        ffi::mdbcu_grid_range(ctx.raw, ffi::MDBCU_HOST, &view, t_lo, t_hi, point_off.as_mut_ptr(), timestamps.as_mut_ptr(),
+                              values.as_mut_ptr(), n, &mut n)
     })?;
     Ok((timestamps, values, point_off))
 }

@@ -97,6 +97,38 @@ int mdbcu_grid(mdbcu_context *, mdbcu_space, const mdbcu_segments_view *segments
     return MDBCU_SUCCESS;
 }
 
+// (the oracle reconstructs everything and prunes afterwards, as the reference does: grid_exec.rs:366-387)
+int mdbcu_grid_range(mdbcu_context *, mdbcu_space, const mdbcu_segments_view *segments, int64_t t_lo, int64_t t_hi, uint64_t *point_off,
+                     int64_t *timestamps_out, float *values_out, uint64_t capacity, uint64_t *n_points) {
+    const mdbo_segments_view v = as_oracle(segments);
+    std::vector<uint64_t> off(segments->n_segments + 1, 0);
+    const uint64_t total = mdbo_grid_count(&v, off.data(), 1);
+    if (total == ~0ull) return fail("grid_range: malformed segment row");
+    std::vector<int64_t> ts(total);
+    std::vector<float> val(total);
+    mdbo_grid(&v, ts.data(), val.data(), total, 1);
+    uint64_t n = 0;
+    for (uint64_t i = 0; i < total; i++) n += ts[i] >= t_lo && ts[i] <= t_hi;
+    if (n_points) *n_points = n;
+    if (point_off) {
+        point_off[0] = 0;
+        for (uint64_t r = 0; r < segments->n_segments; r++) {
+            uint64_t c = 0;
+            for (uint64_t i = off[r]; i < off[r + 1]; i++) c += ts[i] >= t_lo && ts[i] <= t_hi;
+            point_off[r + 1] = point_off[r] + c;
+        }
+    }
+    if (!timestamps_out && !values_out) return MDBCU_SUCCESS;
+    if (n > capacity) return fail("grid_range: capacity too small");
+    uint64_t k = 0;
+    for (uint64_t i = 0; i < total; i++)
+        if (ts[i] >= t_lo && ts[i] <= t_hi) {
+            timestamps_out[k] = ts[i];
+            values_out[k++] = val[i];
+        }
+    return MDBCU_SUCCESS;
+}
+
 int mdbcu_segment_sums(mdbcu_context *, mdbcu_space, const mdbcu_segments_view *segments, float *sums_out) {
     const mdbo_segments_view v = as_oracle(segments);
     mdbo_segment_sums(&v, sums_out, 1);

@@ -90,6 +90,21 @@ int main() {
     mdbo_grid(&want, want_ts.data(), want_val.data(), total, 4);
     CHECK(grid_ts == want_ts && grid_ts == ts, "grid timestamps");
     CHECK(same_bytes(grid_val, want_val.data(), total), "grid values bit-identical");
+    { // the time predicate inside the call (mdbcu_grid_range) against grid-then-filter (grid_exec.rs:366-387)
+        const int64_t t_lo = ts[n / 3], t_hi = ts[n + n / 2]; // from inside the first unit to the middle of the second (timestamps repeat per unit)
+        std::vector<int64_t> r_ts, f_ts;
+        std::vector<float> r_val, f_val;
+        std::vector<uint64_t> r_off;
+        mc::grid_range(ctx, batch, t_lo, t_hi, r_ts, r_val, &r_off);
+        for (uint64_t i = 0; i < total; i++)
+            if (want_ts[i] >= t_lo && want_ts[i] <= t_hi) {
+                f_ts.push_back(want_ts[i]);
+                f_val.push_back(want_val[i]);
+            }
+        CHECK(r_ts == f_ts && !f_ts.empty() && f_ts.size() < total, "grid_range timestamps");
+        CHECK(same_bytes(r_val, f_val.data(), f_val.size()), "grid_range values bit-identical");
+        CHECK(r_off.size() == batch.num_rows() + 1 && r_off.back() == f_ts.size(), "grid_range point offsets");
+    }
     const std::vector<float> sums = mc::sum(ctx, batch);
     std::vector<float> want_sums(want.n_segments);
     mdbo_segment_sums(&want, want_sums.data(), 4);

@@ -23,6 +23,39 @@ def test_header_symbols_match_binding_list():
     assert declared == set(_native.SYMBOLS)
 
 
+def _c_declarations(text):
+    """name -> number of parameters, for every `mdbcu_*(...)` declaration in a C header."""
+    out = {}
+    for name, args in re.findall(r"\b(mdbcu_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*;", re.sub(r"/\*.*?\*/", "", text, flags=re.S)):
+        args = args.strip()
+        out[name] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def _rust_declarations(text):
+    """name -> number of parameters, for every `pub fn mdbcu_*(...)` inside an extern block of Rust source."""
+    out = {}
+    for name, args in re.findall(r"pub fn (mdbcu_[a-z_0-9]+)\s*\(([^;{]*?)\)\s*(?:->[^;]*)?;", re.sub(r"//[^\n]*", "", text)):
+        args = args.strip()
+        out[name] = 0 if args == "" else len([a for a in args.split(",") if a.strip()])
+    return out
+
+
+@pytest.mark.parametrize("path", ["rust/modelardb_cuda/src/lib.rs", "INTEGRATION.md"])
+def test_rust_extern_block_lists_every_entry_point_of_the_header(path):
+    """The reference-side binding (rust/: the FFI crate as files; INTEGRATION.md: the same block in the text) cannot be
+    compiled here (no cargo / rustc), so at least its declarations are held against the header: every entry point, with the
+    header's number of arguments."""
+    header = _c_declarations(open(os.path.join(ROOT, "include", "modelardb_cuda.h")).read())
+    rust = _rust_declarations(open(os.path.join(ROOT, path)).read())
+    assert set(header) == set(_native.SYMBOLS)
+    missing = sorted(set(header) - set(rust))
+    assert not missing, f"{path} does not declare {missing}"
+    wrong = {n: (rust[n], header[n]) for n in header if rust[n] != header[n]}
+    assert not wrong, f"{path}: argument counts differ from the header (rust, header): {wrong}"
+    assert not sorted(set(rust) - set(header)), f"{path} declares entry points the header does not have"
+
+
 def test_library_exports_every_declared_symbol(lib):
     for name in _native.SYMBOLS:
         assert hasattr(lib, name), f"{name} is not exported by libmodelardb_cuda.so"
