@@ -178,6 +178,11 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self):
+        """The timed region starts here: samples that arrived before belong to the warm-up (nvidia-smi needs about a second
+        before its first line, so it is started before the warm-up steps)."""
+        self.first = len(self.lines)
+
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -188,7 +193,11 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        first = getattr(self, "first", 0)
+        timed = self.lines[first:]
+        # a timed region shorter than nvidia-smi's sampling period: the last samples of the warm-up (same load), and say so
+        source = "timed region" if timed else "warm-up steps right before the timed region (it was shorter than a sampling period)"
+        for line in (timed or self.lines[-3:]):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
@@ -201,7 +210,7 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "sampled_during": source, "reasons": sorted(reasons)}
 
 
 # ----------------------------------------------------------------------------------------------- CPU arm
@@ -408,13 +417,14 @@ def main():
             dist.barrier(device_ids=[local_rank])
         torch.cuda.synchronize()
 
+    clocks = ClockSampler(local_rank)
+    clocks.start()
     step(False, measure_segments=True)  # sizes of the compressed output, outside every timed region
     for _ in range(args.warmup):
         step(False)
     barrier()
     launches0 = ctx.launch_count
-    clocks = ClockSampler(local_rank)
-    clocks.start()
+    clocks.mark()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
