@@ -202,6 +202,21 @@ int mdbcu_grid_range(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments
                      int64_t t_hi, uint64_t *point_off, int64_t *timestamps_out, float *values_out,
                      uint64_t capacity, uint64_t *n_points);
 
+/* ---- the front end of try_compress_multivariate_time_series --------------------------------- */
+
+/* The row order `sort_time_series_by_tags_and_time` establishes (compression.rs:110-141: lexsort_to_indices over the tag
+ * columns, then the timestamp column, ascending): series_code[i] is the dense code of row i's tag tuple, codes ordered
+ * like the tuples (the tag strings stay with the host); order_out[k] = index of the row that comes k-th.  A stable LSD
+ * radix sort on the device over the bytes of (timestamp - min timestamp) and of the code that actually differ; rows
+ * with equal tags and timestamp keep their input order (the reference leaves it unspecified). */
+int mdbcu_sort_rows(mdbcu_context *ctx, mdbcu_space space, const uint32_t *series_code, const int64_t *timestamps,
+                    uint64_t n, uint32_t *order_out);
+/* compute::take_arrays of the same function: out[k] = in[order[k]] for the timestamp column (nullable) and n_fields field
+ * columns. */
+int mdbcu_take_rows(mdbcu_context *ctx, mdbcu_space space, const uint32_t *order, uint64_t n,
+                    const int64_t *timestamps_in, int64_t *timestamps_out, const float *const *fields_in,
+                    float *const *fields_out, uint32_t n_fields);
+
 /* ---- K3: aggregates ------------------------------------------------------------------------ */
 
 /* Per-row `sum` exactly as models/mod.rs:129-184 computes it (f32). */

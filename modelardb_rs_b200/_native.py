@@ -21,7 +21,7 @@ SYMBOLS = (
     "mdbcu_context_set_chunk_len", "mdbcu_context_set_lane_warmup", "mdbcu_context_set_option", "mdbcu_context_last_compress_rounds", "mdbcu_context_set_fit_engine", "mdbcu_debug_fit_models", "mdbcu_debug_counters",
     "mdbcu_debug_rewrite_position_steps",
     "mdbcu_compress", "mdbcu_segments_len", "mdbcu_segments_get", "mdbcu_segments_free",
-    "mdbcu_grid_count", "mdbcu_grid", "mdbcu_grid_range", "mdbcu_segment_sums", "mdbcu_aggregate",
+    "mdbcu_grid_count", "mdbcu_grid", "mdbcu_grid_range", "mdbcu_sort_rows", "mdbcu_take_rows", "mdbcu_segment_sums", "mdbcu_aggregate",
     "mdbcu_shard_units", "mdbcu_comm_unique_id", "mdbcu_comm_create", "mdbcu_comm_create_all", "mdbcu_comm_destroy",
     "mdbcu_comm_world", "mdbcu_comm_rank", "mdbcu_aggregate_sharded", "mdbcu_aggregate_all_sharded",
 )
@@ -108,6 +108,10 @@ def lib():
     L.mdbcu_grid.restype = i32
     L.mdbcu_grid_range.argtypes = [vp, i32, C.POINTER(SegmentsView), C.c_int64, C.c_int64, vp, vp, vp, u64, C.POINTER(u64)]
     L.mdbcu_grid_range.restype = i32
+    L.mdbcu_sort_rows.argtypes = [vp, i32, vp, vp, u64, vp]
+    L.mdbcu_sort_rows.restype = i32
+    L.mdbcu_take_rows.argtypes = [vp, i32, vp, u64, vp, vp, vp, vp, C.c_uint32]
+    L.mdbcu_take_rows.restype = i32
     L.mdbcu_segment_sums.argtypes = [vp, i32, C.POINTER(SegmentsView), vp]
     L.mdbcu_segment_sums.restype = i32
     L.mdbcu_aggregate.argtypes = [vp, i32, C.POINTER(SegmentsView), vp, u64, vp, vp, vp, vp]

@@ -363,7 +363,35 @@ def try_compress_univariate_time_series(uncompressed_timestamps, uncompressed_va
         seg.free()
 
 
-def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_columns: Sequence[np.ndarray]):
+def sort_rows(series_code, timestamps, ctx: Optional[Context] = None):
+    """The permutation `lexsort_to_indices` yields for (tag tuple code, timestamp) (compression.rs:110-141), computed by a
+    stable radix sort on the device (mdbcu_sort_rows); rows with equal keys keep their input order."""
+    ctx = ctx or default_context()
+    code = np.ascontiguousarray(series_code, np.uint32)
+    ts = np.ascontiguousarray(timestamps, np.int64)
+    if len(code) != len(ts):
+        raise ValueError("one code per row")
+    order = np.empty(len(ts), np.uint32)
+    _native.check(_native.lib().mdbcu_sort_rows(ctx._h, HOST, _ptr(code), _ptr(ts), len(ts), _ptr(order)))
+    return order
+
+
+def take_rows(order, timestamps, field_columns: Sequence[np.ndarray], ctx: Optional[Context] = None):
+    """`take_arrays` of the same function on the device: (timestamps[order], [field[order] for every field column])."""
+    ctx = ctx or default_context()
+    order = np.ascontiguousarray(order, np.uint32)
+    ts = np.ascontiguousarray(timestamps, np.int64)
+    fields = [np.ascontiguousarray(f, np.float32) for f in field_columns]
+    n = len(order)
+    ts_out = np.empty(n, np.int64)
+    outs = [np.empty(n, np.float32) for _ in fields]
+    ins_p = (C.c_void_p * max(1, len(fields)))(*[f.ctypes.data for f in fields])
+    outs_p = (C.c_void_p * max(1, len(fields)))(*[o.ctypes.data for o in outs])
+    _native.check(_native.lib().mdbcu_take_rows(ctx._h, HOST, _ptr(order), n, _ptr(ts), _ptr(ts_out), ins_p, outs_p, len(fields)))
+    return ts_out, outs
+
+
+def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_columns: Sequence[np.ndarray], device_ctx: Optional[Context] = None):
     """The host part of try_compress_multivariate_time_series (compression.rs:42-141): sort the rows by all tags and then
     time (`sort_time_series_by_tags_and_time`, :110-141), split them into time series where any tag changes (:64-93),
     and lay the (series, field) pairs out as the units of ONE compress call, series-major and field-minor -- the
@@ -371,7 +399,10 @@ def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_co
 
     Returns (unit_timestamps, unit_values, unit_off, unit_series, unit_field, series_tags): unit u is
     unit_*[unit_off[u]:unit_off[u+1]], belongs to series unit_series[u] (tags series_tags[unit_series[u]]) and to field
-    column unit_field[u]."""
+    column unit_field[u].
+
+    device_ctx: sort and gather on the GPU (mdbcu_sort_rows / mdbcu_take_rows: the tag strings stay here, every row gets the
+    dense code of its tag tuple) instead of numpy's lexsort; the result is the same."""
     ts = np.ascontiguousarray(timestamps, np.int64)
     n = len(ts)
     fields = [np.ascontiguousarray(f, np.float32) for f in field_columns]
@@ -386,9 +417,20 @@ def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_co
         values, codes = np.unique(np.asarray(t, dtype=str), return_inverse=True)
         tag_codes.append(codes)
         tag_values.append(values)
-    order = np.lexsort([ts] + tag_codes[::-1])  # np.lexsort: the LAST key is the primary one
-    ts = ts[order]
-    tag_codes = [c[order] for c in tag_codes]
+    if device_ctx is not None:
+        if tag_codes:  # the rank of every row's tag tuple among the tuples (np.unique sorts rows lexicographically)
+            _, tuple_code = np.unique(np.stack(tag_codes, axis=1), axis=0, return_inverse=True)
+            tuple_code = np.asarray(tuple_code).reshape(-1)
+        else:
+            tuple_code = np.zeros(n, np.int64)
+        order = sort_rows(tuple_code.astype(np.uint32), ts, device_ctx)
+        ts, fields = take_rows(order, ts, fields, device_ctx)
+        tag_codes = [c[order] for c in tag_codes]
+        order = None  # (the columns are already in sorted order)
+    else:
+        order = np.lexsort([ts] + tag_codes[::-1])  # np.lexsort: the LAST key is the primary one
+        ts = ts[order]
+        tag_codes = [c[order] for c in tag_codes]
     new_series = np.zeros(n, bool)
     new_series[0] = True
     for c in tag_codes:
@@ -405,17 +447,18 @@ def plan_multivariate(timestamps, tag_columns: Sequence[Sequence[str]], field_co
     total = int(unit_off[-1])
     row = np.repeat(np.repeat(starts, n_fields) - unit_off[:-1].astype(np.int64), unit_len) + np.arange(total)
     field_of_row = np.repeat(unit_field, unit_len)
-    field_matrix = np.stack([f[order] for f in fields])
+    field_matrix = np.stack([f if order is None else f[order] for f in fields])
     return ts[row], field_matrix[field_of_row, row], unit_off, unit_series, unit_field, series_tags
 
 
 def try_compress_multivariate_time_series(timestamps, tag_columns: Sequence[Sequence[str]], field_columns: Sequence[np.ndarray],
-                                          error_bounds: Sequence[ErrorBound], ctx: Optional[Context] = None):
+                                          error_bounds: Sequence[ErrorBound], ctx: Optional[Context] = None, device_sort: bool = True):
     """compression.rs:42-107 with the per-series loop replaced by one batched kernel call: returns, in the reference's
     order, one (tag_values, field_column_index, HostSegments) triple per (time series, field column)."""
     if len(error_bounds) != len(field_columns):
         raise ValueError("one error bound per field column")
-    u_ts, u_val, unit_off, unit_series, unit_field, series_tags = plan_multivariate(timestamps, tag_columns, field_columns)
+    u_ts, u_val, unit_off, unit_series, unit_field, series_tags = plan_multivariate(
+        timestamps, tag_columns, field_columns, device_ctx=(ctx or default_context()) if device_sort else None)
     n_units = len(unit_series)
     if n_units == 0:
         return []

@@ -535,6 +535,29 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MIN_BLOCKS) k_spec_async(con
 #endif
 constexpr uint32_t SWING_FINISH_LONG = MDB_SWING_FINISH_LONG;
 
+// (Used for LONG models only.  For the short ones of k_swing_finish four accumulators per lane were measured on B200 and gained
+// nothing -- 1.5 ms for the order-free pass against 1.95 ms for the serial one per 10^9 points: a lane per model is bound by
+// its scattered 16-byte loads, not by the two addition chains -- while every model that failed the test paid twice.)
+// When are the two error sums independent of the ORDER of their additions?  When every partial sum, in any order, is exactly
+// representable -- then no addition rounds.  On a regular unit a numerator term is (v_k - v0) * dt_k with dt_k = k * delta an
+// integer <= D = K * delta (K = points after the first), and every value is a multiple of q = 2^(emin - 23), emin the smallest
+// exponent among the model's non-zero values: so v_k - v0 is a multiple of q below 2^(emax + 2), the product is a multiple of q
+// below 2^(emax + 2) D, and any sum of up to K of them stays below 2^(bits(K) + emax + 2 + bits(D)): all of these are exact
+// doubles iff that exponent exceeds emin - 23 by at most 53.  A denominator term is the integer dt_k^2 <= D^2: sums of up to K
+// of them are exact iff bits(K) + 2 bits(D) <= 53.  (umax / umin1: the largest |value| and the smallest non-zero |value| minus
+// one as bit patterns, v0 included; zeros are multiples of anything.)
+__device__ __forceinline__ bool swing_sums_order_free(unsigned umax, unsigned umin1, uint32_t K, double delta_d) {
+    if (umax >= 0x7f800000u) return false; // (a NaN or an infinity: never in a pending model, but then nothing is exact)
+    const double D = __dmul_rn((double)K, delta_d);
+    if (!(D >= 1.0)) return false;
+    const int bits_d = ((__double2hiint(D) >> 20) & 0x7ff) - 1022; // floor(log2 D) + 1 (a rounded-up D only errs on the safe side)
+    const int bits_k = 32 - __clz((int)K);
+    if (bits_k + 2 * bits_d > 53) return false;
+    if (umax == 0u) return true; // every value is zero: every term is skipped
+    const int emax = max((int)(umax >> 23), 1) - 127, emin = max((int)((umin1 + 1u) >> 23), 1) - 127;
+    return bits_k + emax + 2 + bits_d - (emin - 23) <= 53;
+}
+
 __device__ __forceinline__ void swing_sums_one_lane(const int64_t *__restrict__ uts, const float *__restrict__ uval, bool regular, double delta_d,
                                                     uint32_t start, uint32_t end, double &num, double &den) {
     const double v0 = (double)uval[start];
@@ -615,6 +638,81 @@ __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict_
     }
 }
 
+// A LONG pending Swing model whose sums are order free (swing_sums_order_free): one block adds the terms in parallel --
+// coalesced loads, a partial sum per thread, a shuffle tree -- instead of a chain of 10^6 dependent additions.  Models whose
+// sums are not order free (or units with irregular timestamps) are left pending for k_swing_finish_long below.
+__global__ void __launch_bounds__(256) k_swing_finish_long_par(const int64_t *__restrict__ ts, const float *__restrict__ values,
+                                                               const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ chunk_unit,
+                                                               const ChunkState *st, FittedModel *lists, const uint64_t *__restrict__ list_base,
+                                                               const uint32_t *__restrict__ list_cap, const uint8_t *__restrict__ unit_irregular,
+                                                               const uint2 *__restrict__ long_models, const unsigned int *n_long) {
+    __shared__ double s_num[8], s_den[8];
+    __shared__ unsigned s_max[8], s_min[8];
+    for (unsigned int item_i = blockIdx.x; item_i < *n_long; item_i += gridDim.x) {
+        const uint2 item = long_models[item_i];
+        const uint64_t g = item.x;
+        const ChunkState s = st[g];
+        const uint32_t u = chunk_unit[g];
+        const uint64_t a = unit_off[u];
+        const uint32_t n = (uint32_t)(unit_off[u + 1] - a);
+        const int64_t *uts = ts + a;
+        const float *uval = values + a;
+        const int64_t delta0 = n >= 2 ? uts[1] - uts[0] : 0;
+        const bool regular = !unit_irregular[u] && delta0 >= 0 && delta0 < (1ll << 31);
+        if (!regular) continue; // (uniform: the whole block skips the model)
+        FittedModel *slot = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2) + item.y;
+        FittedModel m = *slot;
+        const double delta_d = (double)delta0, v0 = (double)uval[m.start_index];
+        // what is known before a value is read: the denominator's condition, and the numerator's with the narrowest
+        // conceivable values (a spread of 16 bits between the largest difference and the quantum).  With microsecond
+        // timestamps a millisecond apart a model of 4096 points already fails it, and the block leaves at no cost.
+        {
+            const uint32_t K = m.end_index - m.start_index;
+            const double D = __dmul_rn((double)K, delta_d);
+            const int bits_d = D >= 1.0 ? ((__double2hiint(D) >> 20) & 0x7ff) - 1022 : 64, bits_k = 32 - __clz((int)K);
+            if (bits_k + 2 * bits_d > 53 || bits_k + bits_d + 16 > 53) continue; // (uniform)
+        }
+        double num = 0.0, den = 0.0;
+        unsigned umax = 0u, umin1 = 0xffffffffu;
+        for (uint32_t i = m.start_index + threadIdx.x; i <= m.end_index; i += blockDim.x) {
+            const float vf = uval[i];
+            const unsigned b = __float_as_uint(vf) & 0x7fffffffu;
+            umax = max(umax, b);
+            umin1 = min(umin1, b - 1u);
+            if (i >= m.start_index + 2) { // the first two points add no term
+                const double v = (double)vf, dt = __dmul_rn((double)(i - m.start_index), delta_d);
+                if (!(v0 == v)) {
+                    num = __dadd_rn(num, __dmul_rn(__dsub_rn(v, v0), dt));
+                    den = __dadd_rn(den, __dmul_rn(dt, dt));
+                }
+            }
+        }
+#pragma unroll
+        for (int d = 16; d >= 1; d >>= 1) {
+            num = __dadd_rn(num, __shfl_xor_sync(0xffffffffu, num, d));
+            den = __dadd_rn(den, __shfl_xor_sync(0xffffffffu, den, d));
+        }
+        umax = __reduce_max_sync(0xffffffffu, umax);
+        umin1 = __reduce_min_sync(0xffffffffu, umin1);
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        __syncthreads(); // (the previous model's partials have been read)
+        if (lane == 0) { s_num[warp] = num; s_den[warp] = den; s_max[warp] = umax; s_min[warp] = umin1; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            for (int w = 1; w < 8; w++) {
+                num = __dadd_rn(num, s_num[w]);
+                den = __dadd_rn(den, s_den[w]);
+                umax = max(umax, s_max[w]);
+                umin1 = min(umin1, s_min[w]);
+            }
+            if (swing_sums_order_free(umax, umin1, m.end_index - m.start_index, delta_d)) {
+                swing_finish_from_sums(m, num, den, uts, uval);
+                *slot = m; // (pending is cleared: k_swing_finish_long skips it)
+            }
+        }
+    }
+}
+
 // A LONG pending Swing model (>= SWING_FINISH_LONG points, up to a whole unit): its two sums are chains of 10^6 dependent
 // f64 additions, and a dependent DADD takes 8.3 cycles on B200 (tools/microbench/fp64.cu), so the floor is ~4.4 ms per
 // 10^6 points however the work is arranged.  To get near it the chain must be nothing but the additions: warp 1 of the block
@@ -638,6 +736,7 @@ __global__ void __launch_bounds__(64) k_swing_finish_long(const int64_t *__restr
     const float *uval = values + unit_off[u];
     FittedModel *slot = lists + list_base[g] + (size_t)s.buf * (list_cap[g] / 2) + item.y;
     FittedModel m = *slot;
+    if (!m.pending) return; // its sums were order free: k_swing_finish_long_par has added them
     const int64_t t0 = uts[m.start_index];
     const double v0 = (double)uval[m.start_index];
     const uint32_t first = m.start_index + 2, last = m.end_index; // the first two points add no term
@@ -1254,6 +1353,8 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             TRY_SG(cudaMemsetAsync(n_long.p, 0, sizeof(unsigned int), s));
             LAUNCH(ctx, k_swing_finish, div_up(G, 4), 128, 0, d_ts, d_val, d_off, chunk_unit.p, G, st.p, lists.p, list_base.p, list_cap.p, unit_irregular.p,
                    long_models.p, n_long.p);
+            LAUNCH(ctx, k_swing_finish_long_par, (unsigned int)std::min<uint64_t>(long_cap, (uint64_t)ctx->sm_count * 8), 256, 0, d_ts, d_val, d_off,
+                   chunk_unit.p, st.p, lists.p, list_base.p, list_cap.p, unit_irregular.p, long_models.p, n_long.p);
             LAUNCH(ctx, k_swing_finish_long, (unsigned int)std::min<uint64_t>(long_cap, 1u << 20), 64, 0, d_ts, d_val, d_off, chunk_unit.p, st.p, lists.p,
                    list_base.p, list_cap.p, long_models.p, n_long.p);
         }

@@ -2215,3 +2215,4 @@ int mdbcu_segments_get(mdbcu_segments *sg, mdbcu_space space, mdbcu_segments_vie
 
 #include "mdb_compress_api.inl"
 #include "mdb_comm.inl"
+#include "mdb_sort.inl"

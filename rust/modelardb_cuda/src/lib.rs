@@ -88,6 +88,11 @@ pub mod ffi {
         pub fn mdbcu_grid_range(ctx: *mut MdbcuContext, space: c_int, segments: *const MdbcuSegmentsView, t_lo: i64, t_hi: i64,
                                 point_off: *mut u64, timestamps_out: *mut i64, values_out: *mut f32, capacity: u64,
                                 n_points: *mut u64) -> c_int;
+        pub fn mdbcu_sort_rows(ctx: *mut MdbcuContext, space: c_int, series_code: *const u32, timestamps: *const i64, n: u64,
+                               order_out: *mut u32) -> c_int;
+        pub fn mdbcu_take_rows(ctx: *mut MdbcuContext, space: c_int, order: *const u32, n: u64, timestamps_in: *const i64,
+                               timestamps_out: *mut i64, fields_in: *const *const f32, fields_out: *const *mut f32,
+                               n_fields: u32) -> c_int;
         // K3 aggregates
         pub fn mdbcu_segment_sums(ctx: *mut MdbcuContext, space: c_int, segments: *const MdbcuSegmentsView,
                                   sums_out: *mut f32) -> c_int;

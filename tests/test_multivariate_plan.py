@@ -68,3 +68,50 @@ def test_multivariate_compress_matches_per_series_oracle(oracle):
         sl = slice(s * n, (s + 1) * n)
         want = oracle.compress(ts[sl], (f0, f1)[f][sl], eb=[(2, 1.0), (0, 0.0)][f])
         assert_segments_equal(seg, want, f"series {s} field {f}")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,n_codes,ts_kind", [(1, 1, "distinct"), (257, 3, "distinct"), (5000, 70000, "dups"), (100_003, 300, "distinct"),
+                                               (40_000, 1, "equal"), (33_333, 1000, "negative"), (2_000_000, 5000, "dups")])
+def test_device_sort_equals_numpy_lexsort(n, n_codes, ts_kind):
+    """mdbcu_sort_rows: the stable radix sort by (tag tuple code, timestamp) against np.lexsort (also stable), for sizes
+    around the block boundaries, codes needing one to three bytes, duplicate / equal / negative timestamps; and
+    mdbcu_take_rows against numpy's fancy indexing."""
+    rng = np.random.default_rng(n + n_codes)
+    code = rng.integers(0, n_codes, n).astype(np.uint32)
+    if ts_kind == "distinct":
+        ts = (rng.permutation(n).astype(np.int64) * 13 + 1_700_000_000_000)
+    elif ts_kind == "dups":
+        ts = rng.integers(0, max(2, n // 50), n).astype(np.int64) + 1_700_000_000_000_000
+    elif ts_kind == "equal":
+        ts = np.full(n, 42, np.int64)
+    else:
+        ts = rng.integers(-2 ** 62, 2 ** 62, n).astype(np.int64)
+    ctx = mc.Context(0)
+    order = mc.sort_rows(code, ts, ctx)
+    want = np.lexsort([ts, code])
+    assert np.array_equal(order, want.astype(np.uint32))
+    f0, f1 = rng.standard_normal(n).astype(np.float32), rng.uniform(0, 1, n).astype(np.float32)
+    t_out, (g0, g1) = mc.take_rows(order, ts, [f0, f1], ctx)
+    assert np.array_equal(t_out, ts[want]) and np.array_equal(g0, f0[want]) and np.array_equal(g1, f1[want])
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [0, 1, 2])
+def test_device_plan_equals_host_plan(seed):
+    """plan_multivariate with the sort and the gather on the device gives the arrays of the host plan (which is checked
+    against the reference's loop above)."""
+    rng = np.random.default_rng(seed)
+    n = 20_000
+    tag_a = rng.choice(["north", "south", "east", "Zeta", "älv"], n)
+    tag_b = rng.choice(["t1", "t10", "t2"], n)
+    ts = rng.permutation(n).astype(np.int64) * 7 + 1000
+    fields = [rng.standard_normal(n).astype(np.float32), rng.uniform(0, 1, n).astype(np.float32)]
+    ctx = mc.Context(0)
+    host = mc.plan_multivariate(ts, [tag_a, tag_b], fields)
+    dev = mc.plan_multivariate(ts, [tag_a, tag_b], fields, device_ctx=ctx)
+    for a, b in zip(host[:5], dev[:5]):
+        assert np.array_equal(a, b)
+    assert host[5] == dev[5]
+    ctx.close()
