@@ -1311,6 +1311,9 @@ __device__ __forceinline__ GroupAgg block_reduce_in_order(GroupAgg a) {
     return r; // valid in thread 0
 }
 
+#ifndef MDB_AGG_SLICE
+#define MDB_AGG_SLICE 2048
+#endif
 // Block (part, group) of the fused aggregate: see k_agg_find_wide above.
 __global__ void __launch_bounds__(AGG_THREADS) k_agg_groups(SegmentsView v, const uint64_t *group_off, uint64_t n_groups, uint32_t parts,
                                                             const float *wide_sum, GroupAgg *partial, Status *status) {
@@ -2096,10 +2099,10 @@ int mdbcu_aggregate(mdbcu_context *ctx, mdbcu_space space, const mdbcu_segments_
 
     // Shape of the reduction: a function of the batch alone (never of the device), so that the tree -- and with it the last
     // bits of SUM -- is the same everywhere.  Small groups: one warp each.  Large groups: blocks of 256 threads over slices of
-    // ~2048 rows (parts per group), then a fold of the parts.
+    // ~MDB_AGG_SLICE rows (parts per group), then a fold of the parts.
     const uint64_t avg_rows = S / n_groups + 1;
     const bool warp_groups = avg_rows < 512;
-    const uint32_t parts = warp_groups ? 1u : (uint32_t)std::min<uint64_t>(1024, (avg_rows + 2047) / 2048);
+    const uint32_t parts = warp_groups ? 1u : (uint32_t)std::min<uint64_t>(1024, (avg_rows + MDB_AGG_SLICE - 1) / MDB_AGG_SLICE);
     DBuf<GroupAgg> partial;
     if (!warp_groups) {
         CUDA_TRY(partial.alloc(n_groups * parts, s));
