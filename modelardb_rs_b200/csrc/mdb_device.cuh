@@ -64,11 +64,14 @@ MDB_DEV float rust_maxf(float a, float b) { return (a != a) ? b : (b > a ? b : a
 MDB_DEV double rust_mind(double a, double b) { return (a != a) ? b : (b < a ? b : a); }
 MDB_DEV double rust_maxd(double a, double b) { return (a != a) ? b : (b > a ? b : a); }
 
-// The sign and payload of a NaN PRODUCED BY ARITHMETIC are unspecified in Rust and differ between x86
-// SSE (propagates the quieted operand, 0x7fc00000 for the usual input NaN) and the GPU (0x7fffffff).
-// Model parameters and sums that come out NaN are canonicalised to 0x7fc00000, which is what the
-// reference yields on x86-64 for default-NaN inputs; NaNs that are bit COPIES of input values
-// (MacaqueV-coded values) keep their payload exactly.
+// The sign and payload of a NaN PRODUCED BY ARITHMETIC are unspecified in Rust and differ between machines: x86 SSE propagates
+// the quieted payload of a NaN operand (0x7fc00000 for the usual f32::NAN input) and GENERATES the default NaN with the sign bit
+// set (inf - inf, 0 * inf: 0xffc00000); the GPU generates 0x7fffffff.  Model parameters and sums that come out NaN are
+// canonicalised to 0x7fc00000 here.  That equals the reference on x86-64 when the NaN comes from a default-NaN input, and
+// differs from it in sign / payload when the NaN is generated (a MacaqueV row's f32 sum over +inf and -inf) or when an input NaN
+// carries another payload: NaN-NESS is identical, NaN sign and payload of computed values are the one documented exception to
+// bit-identity (the tests compare them with nan_payload_matters=False).  NaNs that are bit COPIES of input
+// values (MacaqueV-coded values) keep their payload exactly.
 MDB_DEV float canonical_nan(float x) { return (x != x) ? __uint_as_float(0x7fc00000u) : x; }
 
 // models/mod.rs:92-95

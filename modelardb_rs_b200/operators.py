@@ -4,7 +4,9 @@ kernels through the C-ABI (modelardb_rs_b200.compression):
   * GridStream            crates/modelardb_storage/src/query/grid_exec.rs:197-430   
   * Model*Accumulator     crates/modelardb_storage/src/optimizer/model_simple_aggregates.rs:336-618   (row a23)
 
-Same names, same state machines and the same results as the Rust operators; the per-row loops of the reference
+Same names, same state machines and the same results as the Rust operators (COUNT / MIN / MAX and every reconstructed point
+bit for bit; the f64 SUM / AVG within 1e-12 relative, because the row sums are added in a fixed tree instead of one after the
+other: include/modelardb_cuda.h, mdbcu_aggregate); the per-row loops of the reference
 (`modelardb_compression::grid` / `sum` / `len` once per segment) are replaced by ONE batched call per segment batch.
 The reference's toolchain is not in this image, so these are Python where the reference is Rust; INTEGRATION.md
 shows the Rust call sites that would bind the same C-ABI entry points.
