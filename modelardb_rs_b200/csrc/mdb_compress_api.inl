@@ -159,6 +159,13 @@ __global__ void __launch_bounds__(128) k_lanes_units(const int64_t *__restrict__
 }
 
 constexpr int REGULAR_THREADS = 256;
+// Units that passed lane_unit_init but turned out irregular: when the check below runs BESIDE the chain kernel (see
+// mdbcu_compress), chains of such a unit may have been screened under a wrong assumption and the chains are redone.
+__global__ void __launch_bounds__(256) k_lanes_late(const LaneUnit *info, uint64_t n_units, unsigned int *count) {
+    const uint64_t u = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (u < n_units && info[u].ok && info[u].irregular) atomicAdd(count, 1u);
+}
+
 __global__ void __launch_bounds__(REGULAR_THREADS) k_lanes_regular(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off,
                                                                    const uint64_t *__restrict__ chunk_base, const uint32_t *__restrict__ chunk_unit,
                                                                    uint32_t chunk_len, LaneUnit *info) {
@@ -1023,6 +1030,7 @@ int mdbcu_context_set_option(mdbcu_context *ctx, const char *name, int64_t value
     const std::string n(name);
     if (n == "grid_tma_stores") ctx->grid_tma_stores = value != 0;
     else if (n == "grid_tile_scan") ctx->grid_tile_scan = value != 0;
+    else if (n == "overlap_regular_check") ctx->overlap_regular_check = value != 0;
     else if (n == "lane_rows_min") ctx->lane_rows_min = (uint32_t)std::max<int64_t>(1, value);
     else if (n == "fit_wide") ctx->fit_wide = value != 0;
     else if (n == "block_row_warps") ctx->block_row_warps = (int)value;
@@ -1093,7 +1101,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     mdbcu_segments *sg = new mdbcu_segments();
     sg->ctx = ctx;
     sg->n_units = n_units;
-    auto bail = [&](int rc) { mdbcu_segments_free(sg); return rc; };
+    auto bail = [&](int rc) {
+        if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream); // (a check still running there reads buffers this scope frees)
+        mdbcu_segments_free(sg);
+        return rc;
+    };
 #define TRY_SG(expr)                                                                                \
     do {                                                                                            \
         cudaError_t e_ = (expr);                                                                    \
@@ -1186,8 +1198,26 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(lists.alloc(n_models_cap, s));
 
         const bool async_sched = ctx->fit_mode == 0 || ctx->fit_mode >= 3;
-        if ((use_lanes || use_screen) && G) // every interval of every qualifying unit (coalesced, bandwidth bound)
+        // Every interval of every qualifying unit (coalesced, bandwidth bound: 1.1 ms per 10^9 points).  The screened chain
+        // kernel does not read a timestamp and is nowhere near the memory bandwidth, so the check runs BESIDE it on a second
+        // stream: the chains assume what lane_unit_init saw (first interval, last timestamp), and if the check then finds an
+        // irregular interval inside such a unit -- which costs it its `ok` -- the chains are simply run again, with the exact
+        // engine.  (With per-kernel profiling on, everything stays on one stream so that the kernels can be timed.)
+        const bool overlap_check = use_screen && !use_lanes && G && !ctx->profiling && ctx->overlap_regular_check;
+        if (overlap_check) {
+            if (!ctx->aux_stream) {
+                TRY_SG(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+                TRY_SG(cudaEventCreateWithFlags(&ctx->aux_ready, cudaEventDisableTiming));
+                TRY_SG(cudaEventCreateWithFlags(&ctx->aux_done, cudaEventDisableTiming));
+            }
+            TRY_SG(cudaEventRecord(ctx->aux_ready, s));
+            TRY_SG(cudaStreamWaitEvent(ctx->aux_stream, ctx->aux_ready, 0));
+            k_lanes_regular<<<(unsigned int)G, REGULAR_THREADS, 0, ctx->aux_stream>>>(d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
+            ctx->launches++;
+            TRY_SG(cudaEventRecord(ctx->aux_done, ctx->aux_stream));
+        } else if ((use_lanes || use_screen) && G) {
             LAUNCH(ctx, k_lanes_regular, (unsigned int)G, REGULAR_THREADS, 0, d_ts, d_off, chunk_base.p, chunk_unit.p, chunk_len, lane_units.p);
+        }
         if (use_lanes && G) {
             // ---- one lane per chunk: the bulk of the chains; what they leave open is stitched below
             DBuf<uint32_t> lane_worklist;
@@ -1241,7 +1271,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             }
             TRY_SG(cudaGetLastError());
         }
-        if (async_sched && G) {
+        for (int attempt = 0; async_sched && G && attempt < 2; attempt++) {
+            if (attempt == 1) { // the overlapped check found an irregular unit among the screened ones: again, exactly
+                use_screen = false;
+                LAUNCH(ctx, k_spec_init, div_up(n_units, 128), 128, 0, d_off, n_units, chunk_base.p, chunk_len, st.p, chunk_unit.p, list_cap.p);
+            }
             // ---- one persistent kernel: work queue of chunks, per-unit frontiers (sched_advance)
             int blocks_per_sm = 0;
             const bool wide_fit = !use_screen && (use_lanes || ctx->fit_wide);
@@ -1291,6 +1325,13 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
                        (uint32_t)G, no_info);
             static_assert(sizeof(SchedQueue) == 32, "SchedQueue is posted as four words");
             TRY_SG(post(ctx, 0, queue.p, 4));
+            const bool check_late = overlap_check && attempt == 0;
+            if (check_late) { // the regularity check has finished by now, or is waited for here
+                TRY_SG(cudaStreamWaitEvent(s, ctx->aux_done, 0));
+                TRY_SG(cudaMemsetAsync(lane_words.p + 3, 0, sizeof(unsigned int), s));
+                LAUNCH(ctx, k_lanes_late, div_up(n_units, 256), 256, 0, lane_units.p, n_units, lane_words.p + 3);
+                TRY_SG(post(ctx, 4, lane_words.p + 2, 1)); // (words 2 and 3 of lane_words as one 64-bit word: the count is the high half)
+            }
             TRY_SG(sync_stream(ctx));
             TRY_SG(cudaGetLastError());
             SchedQueue hq;
@@ -1298,6 +1339,7 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
             if (hq.finished != 1 || hq.units_done != hq.live_units)
                 return bail(fail("compress: chain scheduler stopped early (internal error)"));
             ctx->last_rounds = 1;
+            if (!check_late || (ctx->mailbox[4] >> 32) == 0) break;
         }
 
         // ---- rounds: the chains of the chunks in the worklist, then the per-unit walk that builds the next worklist

@@ -90,6 +90,11 @@ struct mdbcu_context {
     int device = 0;
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    // a second stream for work that only has to be finished by the end of a call (compress: the regularity check of the
+    // timestamps, which is bandwidth bound, beside the chain kernel, which is not), and the two events that order it
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t aux_ready = nullptr, aux_done = nullptr;
+    bool overlap_regular_check = true;
     uint64_t launches = 0;
     int sm_count = 148;
     bool fit_wide = false;          // cooperative engine with the 512-point wide steps also when it runs alone (tuning)
@@ -1620,6 +1625,12 @@ void mdbcu_context_destroy(mdbcu_context *ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    if (ctx->aux_ready) cudaEventDestroy(ctx->aux_ready);
+    if (ctx->aux_done) cudaEventDestroy(ctx->aux_done);
     if (ctx->mailbox) cudaFreeHost(ctx->mailbox);
     if (ctx->stager.base) cudaFreeHost(ctx->stager.base);
     for (cudaEvent_t ev : ctx->stager.done)

@@ -301,3 +301,23 @@ def test_grid_stream_with_the_time_predicate_on_the_device(oracle):
     for x, y in zip(a, b):
         assert np.array_equal(x[0], y[0]) and np.array_equal(x[1].view(np.uint32), y[1].view(np.uint32)) and np.array_equal(x[2], y[2])
     ctx.close()
+
+
+@pytest.mark.parametrize("overlap", [1, 0])
+def test_a_unit_that_only_looks_regular_is_compressed_exactly(oracle, overlap):
+    """The regularity check of the timestamps runs beside the screened chain kernel (mdbcu_compress, `overlap_regular_check`):
+    the chains assume what the first interval and the last timestamp say.  A unit whose first interval and last timestamp are
+    those of a regular unit but which has a shifted timestamp inside must still come out as the oracle's -- the chains are run
+    again with the exact engine -- and so must the regular units beside it."""
+    ctx = mc.Context(0)
+    ctx.set_option("overlap_regular_check", overlap)
+    n = 30_000
+    ts, vals, off = syn.multi_series(4, n, 41, "sine")
+    ts = ts.copy()
+    ts[n + 12_345] += 1          # unit 1: one timestamp a millisecond late (first interval and last timestamp untouched)
+    ts[3 * n + 2] += 3           # unit 3: the third point already
+    for eb in ((2, 1.0), (1, 0.5)):
+        want = oracle.compress(ts, vals, off, eb=eb, n_threads=4)
+        got = mc.compress(ts, vals, off, mc.ErrorBound(*eb), ctx).to_host()
+        assert_segments_equal(got, want, f"looks regular, overlap={overlap}, eb={eb}")
+    ctx.close()
