@@ -56,7 +56,7 @@ def parse_args():
     p.add_argument("--e2e-series", type=int, default=100, help="series per slab of the host-buffer (e2e) measurement")
     p.add_argument("--e2e-steps", type=int, default=5, help="slabs per worker in the timed e2e region")
     p.add_argument("--e2e-workers", type=int, default=0,
-                   help="host threads pipelining slabs (one context each); 0 = host cores / ranks, between 2 and 8 (measured on B200, "
+                   help="host threads pipelining slabs (one context each); 0 = up to 8 on one GPU, 4 per rank otherwise (measured on B200, "
                         "round 2: 4 workers x 200 series 3.45 G points/s, 6 x 100 3.56, 8 x 100 3.60)")
     p.add_argument("--e2e-stages", default="all", choices=["all", "compress", "grid"], help="diagnostics: time one half of the e2e slab alone")
     p.add_argument("--e2e-up-gate", type=int, default=2, help="workers allowed at once in the upload-heavy call (compress)")
@@ -462,7 +462,11 @@ def main():
         # own context (stream) and its own pinned buffers -- keep H2D of one slab, kernels of another and D2H
         # of a third in flight (the calls are blocking but release the GIL; PCIe is full duplex).
         es, esteps = min(args.e2e_series, n_series), args.e2e_steps
-        workers = args.e2e_workers or max(2, min(8, (os.cpu_count() or 8) // max(1, world)))
+        # one GPU: up to 8 workers (sweep above); several ranks share the host's cores and links, and keep the 4 workers and the
+        # slab sizes their lines were measured with
+        workers = args.e2e_workers or (max(2, min(8, os.cpu_count() or 8)) if world == 1 else 4)
+        if world > 1:
+            es = min(n_series, 2 * es)
         if world > 2:  # every rank pins 24 B/point x workers of host memory: keep the box's total near the 2-rank figure
             es = max(8, es * 2 // world)
         en = es * n_points
