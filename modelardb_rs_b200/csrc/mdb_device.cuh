@@ -14,7 +14,8 @@
 #define MDB_DEV_NOINLINE __device__ __noinline__
 #else
 // Host build of the per-thread bodies, used ONLY by tests/emu (a debugging harness that steps the
-// kernels' thread functions in a loop on this GPU-less build container).  Not part of the product.
+// kernels' thread functions in a loop on this GPU-less build container).  Not part of the product: the
+// shim lives in tests/emu/ and is only on the include path of the emulator's own build.
 #include "mdb_host_shim.h"
 #define MDB_DEV inline
 #define MDB_DEV_NOINLINE inline

@@ -1,4 +1,4 @@
-// mdb_host_shim.h -- host stand-ins for the CUDA intrinsics used by the per-thread kernel bodies, so
+// mdb_host_shim.h (tests/emu/; found through -I by the emulator build only) -- host stand-ins for the CUDA intrinsics used by the per-thread kernel bodies, so
 // that tests/emu can step those bodies on the GPU-less build container (g++ -ffp-contract=off).
 // NOT used by the product library: libmodelardb_cuda.so is compiled by nvcc and never sees this file.
 #pragma once

@@ -21,10 +21,10 @@ def lib():
     global _lib
     if _lib is not None:
         return _lib
-    deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+    deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h"), os.path.join(_HERE, "emu", "mdb_host_shim.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
     if not os.path.exists(_SO) or any(os.path.getmtime(d) > os.path.getmtime(_SO) for d in deps):
         subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
-                               "-x", "c++", _SRC, "-o", _SO])
+                               "-I", os.path.join(_HERE, "emu"), "-x", "c++", _SRC, "-o", _SO])
     L = C.CDLL(_SO)
     vp, u64 = C.c_void_p, C.c_uint64
     L.emu_compress.argtypes = [vp, vp, vp, u64, vp, vp, C.c_uint32, vp]
@@ -80,10 +80,10 @@ def variant(*defines):
     if key not in _variants:
         lib()  # (builds the default library first, so compile errors show up there)
         so = os.path.join(_HERE, "emu", "libmdb_emu_" + "_".join(d.replace("=", "-") for d in defines) + ".so")
-        deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
+        deps = [_SRC, os.path.join(_HERE, "emu", "warp_emu.h"), os.path.join(_HERE, "emu", "mdb_host_shim.h")] + [os.path.join(_CSRC, f) for f in os.listdir(_CSRC) if f.endswith((".cuh", ".h"))]
         if not os.path.exists(so) or any(os.path.getmtime(d) > os.path.getmtime(so) for d in deps):
-            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math"] +
-                                  ["-D" + d for d in defines] + ["-x", "c++", _SRC, "-o", so])
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math",
+                                   "-I", os.path.join(_HERE, "emu")] + ["-D" + d for d in defines] + ["-x", "c++", _SRC, "-o", so])
         L = C.CDLL(so)
         L.emu_fit_models.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint8, C.c_float, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]
         L.emu_fit_models.restype = None
