@@ -13,10 +13,10 @@
 //   k_spec_count_rows  rows per chunk                                            -> scan -> row_base
 //   k_spec_records     SegRecord of every row in final order (byte lengths by running the encoders on a counter);
 //                      long MacaqueV rows are only listed ...
-//   k_records_macaque_warp   ... and sized by a whole warp, 32 values at a time (warp_macaque_v_encode)
+//   k_records_macaque_warp   ... and encoded ONCE by a whole warp, 32 values at a time (warp_macaque_v_encode), into a staging area
 //   k_compress_gather  row metadata columns + per-row byte lengths               -> 3 scans -> offsets
 //   k_compress_emit    MacaqueTS / MacaqueV byte columns at their final offsets (short rows, one thread each)
-//   k_emit_macaque_warp      the value bytes of the long MacaqueV rows
+//   k_copy_macaque_warp      the value bytes of the long MacaqueV rows from the staging area to their final offsets
 
 struct CompressCounters { // device-resident, read back once per round
     unsigned int dirty;
@@ -904,33 +904,16 @@ __global__ void __launch_bounds__(128) k_spec_records(const int64_t *__restrict_
 
 // ---- long MacaqueV rows encoded by a whole warp: warp_macaque_v_encode, WarpCodeCounter, WarpCodeWriter (mdb_macaque_warp.cuh)
 
+// A long MacaqueV row is encoded ONCE (round 2; before, once on a bit counter to size it and once more to write it): its bytes
+// go to a staging area whose slot for the row follows from where the row's points lie in the input -- a code is at most 45
+// bits, so the row of the points [p, q] needs fewer than 6 (q - p + 1) bytes (rows here have at least 256 values) and gets the
+// bytes from round_up(6 p, 16) on -- and k_copy_macaque_warp moves them to their final offset once that is known.
+__device__ __forceinline__ uint64_t wide_slot(uint64_t first_point) { return (6 * first_point + 15) & ~(uint64_t)15; }
+
 __global__ void __launch_bounds__(WIDE_WARPS * 32) k_records_macaque_warp(const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
                                                                            const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
                                                                            const uint32_t *__restrict__ row_unit, const uint32_t *__restrict__ wide_rows,
-                                                                           const unsigned int *n_wide_ptr, SegRecord *recs) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_wide = *n_wide_ptr;
-    for (uint32_t w = blockIdx.x * WIDE_WARPS + warp; w < n_wide; w += gridDim.x * WIDE_WARPS) {
-        const uint32_t r = wide_rows[w];
-        const uint32_t u = row_unit[r];
-        const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
-        const uint32_t lo = recs[r].start_index, hi = recs[r].res_end_index;
-        WarpCodeCounter c;
-        float mn, mx;
-        warp_macaque_v_encode(eb, values + unit_off[u], lo, hi, c, lane, mn, mx);
-        if (lane == 0) {
-            recs[r].val_len = (uint32_t)c.bytes();
-            recs[r].min_value = mn;
-            recs[r].max_value = mx;
-        }
-    }
-}
-
-__global__ void __launch_bounds__(WIDE_WARPS * 32) k_emit_macaque_warp(const float *__restrict__ values, const uint64_t *__restrict__ unit_off,
-                                                                        const uint8_t *__restrict__ eb_kind, const float *__restrict__ eb_value,
-                                                                        const uint32_t *__restrict__ row_unit, const uint32_t *__restrict__ wide_rows,
-                                                                        const unsigned int *n_wide_ptr, const SegRecord *__restrict__ recs,
-                                                                        const uint64_t *__restrict__ val_off, uint8_t *val_data) {
+                                                                           const unsigned int *n_wide_ptr, SegRecord *recs, uint8_t *wide_tmp) {
     __shared__ uint32_t stage[WIDE_WARPS][STAGE_WORDS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_wide = *n_wide_ptr;
@@ -938,13 +921,51 @@ __global__ void __launch_bounds__(WIDE_WARPS * 32) k_emit_macaque_warp(const flo
         const uint32_t r = wide_rows[w];
         const uint32_t u = row_unit[r];
         const ErrorBound eb = make_error_bound(eb_kind[u], eb_value[u]);
+        const uint32_t lo = recs[r].start_index, hi = recs[r].res_end_index;
+        uint8_t *slot = wide_tmp + wide_slot(unit_off[u] + lo);
         WarpCodeWriter sink;
-        sink.init(val_data + val_off[r], stage[warp], lane);
+        sink.init(slot, stage[warp], lane);
+        sink.word_stores = true;
         float mn, mx;
-        warp_macaque_v_encode(eb, values + unit_off[u], recs[r].start_index, recs[r].res_end_index, sink, lane, mn, mx);
+        warp_macaque_v_encode(eb, values + unit_off[u], lo, hi, sink, lane, mn, mx);
         sink.finish();
+        if (lane == 0) {
+            recs[r].val_len = (uint32_t)(sink.out - slot);
+            recs[r].min_value = mn;
+            recs[r].max_value = mx;
+        }
+        __syncwarp();
     }
 }
+
+// The staged bytes of every long MacaqueV row to their final place (arbitrary byte alignment): a block per row (a row can be
+// megabytes: a lossless series is one row), whole words assembled from two aligned source words by a funnel shift.
+constexpr int COPY_THREADS = 256;
+__global__ void __launch_bounds__(COPY_THREADS) k_copy_macaque_warp(const uint64_t *__restrict__ unit_off, const uint32_t *__restrict__ row_unit,
+                                                                        const uint32_t *__restrict__ wide_rows, const unsigned int *n_wide_ptr,
+                                                                        const SegRecord *__restrict__ recs, const uint8_t *__restrict__ wide_tmp,
+                                                                        const uint64_t *__restrict__ val_off, uint8_t *val_data) {
+    const uint32_t lane = threadIdx.x; // (of the block)
+    const uint32_t n_wide = *n_wide_ptr;
+    for (uint32_t w = blockIdx.x; w < n_wide; w += gridDim.x) {
+        const uint32_t r = wide_rows[w];
+        const uint8_t *src = wide_tmp + wide_slot(unit_off[row_unit[r]] + recs[r].start_index);
+        uint8_t *dst = val_data + val_off[r];
+        const uint32_t n = recs[r].val_len;
+        const uint32_t head = min(n, (uint32_t)((4 - (reinterpret_cast<uintptr_t>(dst) & 3)) & 3)); // bytes up to the first aligned word of dst
+        if (lane < head) dst[lane] = src[lane];
+        const uint32_t n_words = (n - head) >> 2;
+        const uint32_t *src_w = reinterpret_cast<const uint32_t *>(src); // (16-byte aligned)
+        uint32_t *dst_w = reinterpret_cast<uint32_t *>(dst + head);
+        const uint32_t shift = 8 * (head & 3), first = head >> 2;         // dst word i = source bytes head + 4 i .. + 3
+        for (uint32_t i = lane; i < n_words; i += COPY_THREADS) {
+            const uint32_t a = src_w[first + i], b = shift ? src_w[first + i + 1] : 0u; // (the slot has room past the row's bytes)
+            dst_w[i] = __funnelshift_r(a, b, shift);
+        }
+        for (uint32_t i = head + 4 * n_words + lane; i < n; i += COPY_THREADS) dst[i] = src[i];
+    }
+}
+
 
 // One thread per row: metadata columns and the byte lengths of the three binary columns.
 __global__ void __launch_bounds__(256) k_compress_gather(const int64_t *__restrict__ ts, const uint64_t *__restrict__ unit_off,
@@ -1119,9 +1140,11 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     uint64_t S = 0;
     DBuf<SegRecord> recs;
     DBuf<uint32_t> row_unit, wide_rows; // wide_rows: long MacaqueV rows, sized and written by a whole warp
-    DBuf<unsigned int> n_wide;
-    TRY_SG(n_wide.alloc(1, s));
-    TRY_SG(cudaMemsetAsync(n_wide.p, 0, sizeof(unsigned int), s));
+    DBuf<unsigned int> n_wide; // (two words: posted to the host as one 64-bit word)
+    DBuf<uint8_t> wide_tmp;    // staging area of the long MacaqueV rows' bytes
+    uint32_t n_wide_host = 0;
+    TRY_SG(n_wide.alloc(2, s));
+    TRY_SG(cudaMemsetAsync(n_wide.p, 0, 2 * sizeof(unsigned int), s));
     ctx->last_rounds = 0;
 
     if (n_units) {
@@ -1411,12 +1434,18 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
         TRY_SG(row_unit.alloc(S, s));
         const uint32_t lanes = (uint32_t)std::min<uint64_t>(32, std::max<uint64_t>(1, div_up(G, (uint64_t)ctx->sm_count * 32)));
         TRY_SG(wide_rows.alloc(S, s));
-        TRY_SG(cudaMemsetAsync(n_wide.p, 0, sizeof(unsigned int), s));
+        TRY_SG(cudaMemsetAsync(n_wide.p, 0, 2 * sizeof(unsigned int), s));
         if (G && S) {
             LAUNCH(ctx, k_spec_records, div_up(G, 4), 128, 0, d_ts, d_val, d_off, d_kind, d_ebv, chunk_unit.p, G, st.p, lists.p,
                    list_base.p, list_cap.p, unit_irregular.p, row_base.p, recs.p, row_unit.p, wide_rows.p, n_wide.p);
-            LAUNCH(ctx, k_records_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0,
-                   d_val, d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p);
+            TRY_SG(post(ctx, 0, n_wide.p, 1));
+            TRY_SG(sync_stream(ctx));
+            n_wide_host = (uint32_t)ctx->mailbox[0];
+            if (n_wide_host) { // long MacaqueV rows: encoded once, into a staging area (see k_records_macaque_warp)
+                TRY_SG(wide_tmp.alloc(6 * (size_t)n_points + 64, s));
+                LAUNCH(ctx, k_records_macaque_warp, std::min<unsigned int>(div_up(n_wide_host, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32,
+                       0, d_val, d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p, wide_tmp.p);
+            }
         }
         // the scratch above is released (stream-ordered) when this scope ends
     } else {
@@ -1458,8 +1487,9 @@ int mdbcu_compress(mdbcu_context *ctx, mdbcu_space space, const int64_t *timesta
     if (S) {
         LAUNCH(ctx, k_compress_emit, div_up(S, 64), 64, 0, d_ts, d_val, d_off, d_kind, d_ebv, recs.p, row_unit.p, S, sg->ts_off, sg->ts_data,
                sg->val_off, sg->val_data, sg->res_off, sg->res_data);
-        LAUNCH(ctx, k_emit_macaque_warp, std::min<unsigned int>(div_up(S, WIDE_WARPS), (unsigned int)ctx->sm_count * 8), WIDE_WARPS * 32, 0, d_val,
-               d_off, d_kind, d_ebv, row_unit.p, wide_rows.p, n_wide.p, recs.p, sg->val_off, sg->val_data);
+        if (n_wide_host)
+            LAUNCH(ctx, k_copy_macaque_warp, std::min<unsigned int>(n_wide_host, (unsigned int)ctx->sm_count * 32), COPY_THREADS, 0,
+                   d_off, row_unit.p, wide_rows.p, n_wide.p, recs.p, wide_tmp.p, sg->val_off, sg->val_data);
     }
     TRY_SG(cudaGetLastError());
     TRY_SG(sync_stream(ctx));

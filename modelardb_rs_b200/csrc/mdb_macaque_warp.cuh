@@ -354,8 +354,19 @@ struct WarpCodeWriter {
         for (int i = lane; i < STAGE_WORDS; i += 32) stage[i] = 0;
         __syncwarp();
     }
+    bool word_stores = false; // `out` is 4-byte aligned and stays so (drains write whole words): store words, not bytes
     MDB_WARP_FN void write_bytes(uint32_t n_bytes) {
-        for (uint32_t i = (uint32_t)lane; i < n_bytes; i += 32) out[i] = (uint8_t)(stage[i >> 2] >> (24 - 8 * (i & 3)));
+        uint32_t done = 0;
+        if (word_stores) { // the stage holds the stream MSB first: a stored word is the stage word with its bytes reversed
+            const uint32_t n_words = n_bytes >> 2;
+            uint32_t *out_w = reinterpret_cast<uint32_t *>(out);
+            for (uint32_t i = (uint32_t)lane; i < n_words; i += 32) {
+                const uint32_t x = stage[i];
+                out_w[i] = (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24);
+            }
+            done = n_words * 4;
+        }
+        for (uint32_t i = done + (uint32_t)lane; i < n_bytes; i += 32) out[i] = (uint8_t)(stage[i >> 2] >> (24 - 8 * (i & 3)));
         out += n_bytes;
     }
     MDB_WARP_FN void drain() { // whole words leave; the partial word moves to the front
