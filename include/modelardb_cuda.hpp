@@ -274,6 +274,10 @@ public:
         // Segments that end before the first or start after the second are not reconstructed at all (the push-down the
         // reference applies to its Parquet scan, time_series_table.rs:290-373); the predicate must imply the range.
         std::optional<int64_t> time_range_start, time_range_end;
+        // With a time range: ALSO drop the points outside it inside the reconstruction call (grid_range) instead of
+        // reconstructing every point of the surviving segments and pruning afterwards (grid_exec.rs:366-387).  Since the
+        // predicate implies the range the stream's rows are unchanged; only rows_created() shrinks.
+        bool device_time_clip = false;
         // batch_size becomes min(limit, batch_size) as in the reference (grid_exec.rs:239-246); the stream also ends after
         // `limit` rows and, without a predicate, reconstructs only the leading segments needed to reach it.
         std::optional<size_t> limit;
@@ -368,7 +372,13 @@ private:
         next.tags.resize(current_.tags.size());
         for (size_t c = 0; c < current_.tags.size(); c++) next.tags[c].assign(current_.tags[c].begin() + offset_, current_.tags[c].end());
         point_off.assign(1, 0);
-        if (segments->num_rows()) grid(ctx_, *segments, next.timestamps, next.values, &point_off);
+        if (segments->num_rows()) {
+            if (options_.device_time_clip && (options_.time_range_start || options_.time_range_end))
+                grid_range(ctx_, *segments, options_.time_range_start.value_or(std::numeric_limits<int64_t>::min()),
+                           options_.time_range_end.value_or(std::numeric_limits<int64_t>::max()), next.timestamps, next.values, &point_off);
+            else
+                grid(ctx_, *segments, next.timestamps, next.values, &point_off);
+        }
         rows_created_ += point_off.back();
         for (size_t c = 0; c < next.tags.size(); c++)
             for (size_t row = 0; row < segments->num_rows(); row++)

@@ -196,6 +196,42 @@ int main() {
         CHECK(b_ts == expect_ts && same_bytes(b_val, expect_val.data(), expect_val.size()) && b_tag == expect_tag, "time range pushed down: same rows");
         CHECK(a_skipped == 0 && a_created == total && b_skipped > 0 && b_created < total, "segments outside the range are never reconstructed");
 
+        // the same range evaluated per point inside the reconstruction call: only the rows of the answer are ever created
+        for (int with_predicate = 0; with_predicate < 2; with_predicate++) {
+            mc::GridStream::Options clipped_options = pushed_options;
+            clipped_options.device_time_clip = true;
+            if (!with_predicate) clipped_options.predicate = nullptr;
+            std::vector<int64_t> c_ts;
+            std::vector<float> c_val;
+            std::vector<std::string> c_tag;
+            size_t c_skipped;
+            uint64_t c_created;
+            const bool c_ok = run(clipped_options, c_ts, c_val, c_tag, c_skipped, c_created);
+            CHECK(c_ok && c_ts == expect_ts && same_bytes(c_val, expect_val.data(), expect_val.size()) && c_tag == expect_tag, "time range clipped in the grid call: same rows");
+            CHECK(c_skipped == b_skipped && c_created == expect_ts.size(), "clipped: no row outside the range is created");
+        }
+        {   // a half-open range clips one side only
+            mc::GridStream::Options half;
+            half.batch_size = 5000;
+            half.time_range_start = lo;
+            half.device_time_clip = true;
+            std::vector<int64_t> h_ts;
+            std::vector<float> h_val;
+            std::vector<std::string> h_tag;
+            size_t h_skipped;
+            uint64_t h_created;
+            const bool h_ok = run(half, h_ts, h_val, h_tag, h_skipped, h_created);
+            size_t expect_rows = 0;
+            bool same = true;
+            for (size_t i = 0; i < want_ts.size(); i++)
+                if (want_ts[i] >= lo) {
+                    same = same && expect_rows < h_ts.size() && h_ts[expect_rows] == want_ts[i] && h_tag[expect_rows] == want_tag[i] &&
+                           std::memcmp(&h_val[expect_rows], &want_val[i], 4) == 0;
+                    expect_rows++;
+                }
+            CHECK(h_ok && same && h_ts.size() == expect_rows && h_created == expect_rows, "clipped with a start only");
+        }
+
         for (size_t limit : {size_t(1), size_t(4097), size_t(30000)}) {
             mc::GridStream::Options options;
             options.batch_size = 4096;
