@@ -537,6 +537,7 @@ __global__ void __launch_bounds__(CHAIN_WARPS * 32, MIN_BLOCKS) k_spec_async(con
 // differences are k * interval and the timestamps are not read at all.  Models longer than
 // SWING_FINISH_LONG points would leave the other 31 lanes waiting: those are summed by the whole warp instead
 // (coalesced loads, terms in parallel, the additions chained through shared memory).
+#include "mdb_swing_sums.cuh" // swing_sums_one_lane
 #ifndef MDB_SWING_FINISH_LONG
 #define MDB_SWING_FINISH_LONG 4096
 #endif
@@ -563,45 +564,6 @@ __device__ __forceinline__ bool swing_sums_order_free(unsigned umax, unsigned um
     if (umax == 0u) return true; // every value is zero: every term is skipped
     const int emax = max((int)(umax >> 23), 1) - 127, emin = max((int)((umin1 + 1u) >> 23), 1) - 127;
     return bits_k + emax + 2 + bits_d - (emin - 23) <= 53;
-}
-
-__device__ __forceinline__ void swing_sums_one_lane(const int64_t *__restrict__ uts, const float *__restrict__ uval, bool regular, double delta_d,
-                                                    uint32_t start, uint32_t end, double &num, double &den) {
-    const double v0 = (double)uval[start];
-    num = 0.0;
-    den = 0.0;
-    uint32_t i = start + 2; // the first two points add no term
-    if (regular) {
-        // t[i] - t[start] = k * interval exactly; k and the interval are exact doubles, so the rounded product is
-        // the same double as the conversion of the integer difference
-        double kd = 2.0;
-        auto term = [&](float vf) {
-            const double v = (double)vf;
-            const double dt = __dmul_rn(kd, delta_d);
-            const bool eq = equal_or_nan(v0, v);
-            const double x = __dmul_rn(__dsub_rn(v, v0), dt), y = __dmul_rn(dt, dt);
-            num = __dadd_rn(num, eq ? 0.0 : x);
-            den = __dadd_rn(den, eq ? 0.0 : y);
-            kd = __dadd_rn(kd, 1.0);
-        };
-        for (; i <= end && (reinterpret_cast<uintptr_t>(uval + i) & 15); i++) term(uval[i]);
-        for (; i + 3 <= end; i += 4) {
-            const float4 q = __ldg(reinterpret_cast<const float4 *>(uval + i));
-            term(q.x);
-            term(q.y);
-            term(q.z);
-            term(q.w);
-        }
-        for (; i <= end; i++) term(uval[i]);
-    } else {
-        const int64_t t0 = uts[start];
-        for (; i <= end; i++) {
-            double x, y;
-            swing_mse_terms(t0, v0, uts[i], (double)uval[i], x, y);
-            num = __dadd_rn(num, x);
-            den = __dadd_rn(den, y);
-        }
-    }
 }
 
 __global__ void __launch_bounds__(128) k_swing_finish(const int64_t *__restrict__ ts, const float *__restrict__ values,

@@ -14,6 +14,7 @@
 #include "../../modelardb_rs_b200/csrc/mdb_aggregate.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_compress.cuh"
 #include "../../modelardb_rs_b200/csrc/mdb_grid.cuh"
+#include "../../modelardb_rs_b200/csrc/mdb_swing_sums.cuh"
 
 // The warp-cooperative fit (mdb_fit_warp.cuh) on the host: 32 fibers per warp, see warp_emu.h.
 #define MDB_WARP_EMU
@@ -308,6 +309,23 @@ uint64_t emu_lane_reruns() { return g_emu_lane_reruns; }
 void emu_lane_counters(uint64_t *chunks, uint64_t *bailed) { *chunks = g_emu_lane_chunks; *bailed = g_emu_lane_bailed; }
 uint64_t emu_division_mismatches() { return g_emu_division_mismatches; }
 void emu_screen_counters(uint64_t *out8, int clear) { for (int i = 0; i < 8; i++) { out8[i] = g_screen_counters[i]; if (clear) g_screen_counters[i] = 0; } }
+
+// The body of k_swing_finish for the model [start, end] of one unit, and the plain loop of swing_finish (mdb_compress.cuh) beside it.
+void emu_swing_sums(const int64_t *ts, const float *values, int regular, uint32_t start, uint32_t end, double *out4) {
+    const double delta_d = (double)(ts[1] - ts[0]);
+    swing_sums_one_lane(ts, values, regular != 0, delta_d, start, end, out4[0], out4[1]);
+    const int64_t t0 = ts[start];
+    const double v0 = (double)values[start];
+    double num = 0.0, den = 0.0;
+    for (uint32_t i = start + 2; i <= end; i++) {
+        double x, y;
+        swing_mse_terms(t0, v0, ts[i], (double)values[i], x, y);
+        num = __dadd_rn(num, x);
+        den = __dadd_rn(den, y);
+    }
+    out4[2] = num;
+    out4[3] = den;
+}
 
 // mdbcu_debug_fit_models on the host: fit_next_model at each start with either engine (records of 40 bytes).
 struct EmuDebugFit {
